@@ -1,0 +1,110 @@
+"""Devices and compute mode.  Mirrors compyute/backend.py:26-178 for the in-scope surface.
+
+``cpu`` tensors hold NumPy arrays and exist only as host staging (creation, ``to_numpy``); every hot-path
+Function requires ``cuda`` tensors and raises ``DeviceError`` otherwise — there is no CPU fallback.
+Unlike the reference, ``import cupy`` is not required (CuPy is not in this image): device memory is owned by
+torch's caching allocator and handed to the C ABI as raw pointers.
+"""
+
+from __future__ import annotations
+
+import os
+from contextlib import contextmanager
+from dataclasses import dataclass
+
+from . import _lib
+
+__all__ = ["Device", "cpu", "cuda", "DeviceError", "gpu_available", "synchronize", "use_device", "select_device",
+           "compute_mode", "get_compute_mode", "set_compute_mode"]
+
+
+class DeviceError(Exception):
+    """Tensors on mismatching / unsupported devices (backend.py:15)."""
+
+
+@dataclass(frozen=True, repr=False)
+class Device:
+    t: str
+    index: int = 0
+
+    def __repr__(self) -> str:
+        return f'Device("{self.t}:{self.index}")' if self.t == "cuda" else 'Device("cpu")'
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+cpu = Device("cpu")
+
+
+def _local_cuda_index() -> int:
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+class _Cuda(Device):
+    """The process's CUDA device (one process per GPU: index = LOCAL_RANK)."""
+
+    def __init__(self):
+        super().__init__("cuda", _local_cuda_index())
+
+
+cuda = _Cuda()
+
+
+def gpu_available() -> bool:
+    """backend.py:102-114"""
+    import torch
+    return torch.cuda.is_available()
+
+
+def synchronize() -> None:
+    """backend.py:124-128"""
+    import torch
+    torch.cuda.synchronize()
+
+
+_default_device = None
+
+
+def select_device(device):
+    """backend.py:131-144: explicit device, else the context default, else cpu."""
+    return device or _default_device or cpu
+
+
+@contextmanager
+def use_device(device: Device):
+    """backend.py:147-166"""
+    global _default_device
+    prev, _default_device = _default_device, device
+    try:
+        yield
+    finally:
+        _default_device = prev
+
+
+# ---- compute mode of the contractions (Conv2D / Linear): "fp32" exact FFMA, "tf32" / "bf16" tcgen05
+_MODES = {"fp32": _lib.MODE_FP32, "tf32": _lib.MODE_TF32, "bf16": _lib.MODE_BF16}
+_mode = _MODES[os.environ.get("COMPYUTE_B200_MODE", "fp32")]
+
+
+def get_compute_mode() -> int:
+    return _mode
+
+
+def set_compute_mode(mode: str | int) -> None:
+    global _mode
+    _mode = _MODES[mode] if isinstance(mode, str) else int(mode)
+
+
+@contextmanager
+def compute_mode(mode: str | int):
+    """``with compute_mode("bf16"):`` — same kind of global switch as ``use_dtype`` (typing.py:133-139)."""
+    prev = _mode
+    set_compute_mode(mode)
+    try:
+        yield
+    finally:
+        set_compute_mode(prev)

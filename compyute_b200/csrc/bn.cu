@@ -1,0 +1,311 @@
+// BatchNorm 1-D / 2-D forward (train, eval) and backward over x viewed as (N, C, HW) — HBM-bound.
+// Reference: compyute/nn/functional/normalization_funcs.py:10-177.
+//
+// Training forward = 3 launches: partial statistics (grid C x S) -> finalize (per channel, fixed-order
+// merge: deterministic) -> apply.  x is read twice, y written once: 12 B/elem algorithmic.
+// Backward = partial sums (Σdy, Σdy·x̂) -> finalize (dw, db, coefficients) -> apply: reads dy, x twice each,
+// writes dx: 20 B/elem.  x̂ is recomputed from (x, mean, rstd) instead of being cached like the reference does.
+//
+// Variance: shifted sums Σ(x-K), Σ(x-K)² with K = first element of the channel, so the single pass does not
+// suffer E[x²]-E[x]² cancellation when |mean| >> std.
+#include "common.cuh"
+
+namespace cpt {
+
+constexpr int BN_THREADS = 256;
+
+// partial sums for channel c = blockIdx.x, split s = blockIdx.y.  MODE 0: stats (a = x-K, b = (x-K)²);
+// MODE 1: backward (a = dy, b = dy * x̂).
+template <int MODE, int VEC>
+__global__ void __launch_bounds__(BN_THREADS) bn_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 float2* __restrict__ partial, int N, int C, int HW) {
+  __shared__ float sh[32];
+  const int c = blockIdx.x, S = gridDim.y, s = blockIdx.y;
+  const int HWv = HW / VEC;
+  const int64_t items = (int64_t)N * HWv;
+  const int64_t per = (items + S - 1) / S;
+  const int64_t lo = per * s, hi = (lo + per < items) ? lo + per : items;
+  float k0, k1;
+  if (MODE == 0) { k0 = __ldg(x + (int64_t)c * HW); k1 = 0.f; }
+  else { k0 = __ldg(mean + c); k1 = __ldg(rstd + c); }
+  float sa = 0.f, sb = 0.f;
+  for (int64_t it = lo + threadIdx.x; it < hi; it += BN_THREADS) {
+    const int64_t n = it / HWv;
+    const int j = (int)(it - n * HWv);
+    const int64_t off = (n * C + c) * (int64_t)HW + (int64_t)j * VEC;
+    float xv[VEC], gv[VEC];
+    if (VEC == 4) {
+      float4 v = ld_stream(reinterpret_cast<const float4*>(x + off));
+      xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
+      if (MODE == 1) {
+        float4 g = ld_stream(reinterpret_cast<const float4*>(dy + off));
+        gv[0] = g.x; gv[1] = g.y; gv[2] = g.z; gv[3] = g.w;
+      }
+    } else {
+      xv[0] = x[off];
+      if (MODE == 1) gv[0] = dy[off];
+    }
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) {
+      if (MODE == 0) {
+        const float d = xv[u] - k0;
+        sa += d;
+        sb = fmaf(d, d, sb);
+      } else {
+        sa += gv[u];
+        sb = fmaf(gv[u], (xv[u] - k0) * k1, sb);
+      }
+    }
+  }
+  sa = block_sum(sa, sh);
+  sb = block_sum(sb, sh);
+  if (threadIdx.x == 0) partial[(int64_t)c * S + s] = make_float2(sa, sb);
+}
+
+// HW == 1 (BatchNorm1D on (N, C)): threads map across channels so loads stay coalesced.
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_partial_hw1_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             float2* __restrict__ partial, int N, int C) {
+  __shared__ float sa_s[8][33], sb_s[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx, S = gridDim.y, s = blockIdx.y;
+  float sa = 0.f, sb = 0.f;
+  if (c < C) {
+    float k0, k1;
+    if (MODE == 0) { k0 = __ldg(x + c); k1 = 0.f; }
+    else { k0 = __ldg(mean + c); k1 = __ldg(rstd + c); }
+    for (int n = s * 8 + ty; n < N; n += S * 8) {
+      const float xv = x[(int64_t)n * C + c];
+      if (MODE == 0) {
+        const float d = xv - k0;
+        sa += d;
+        sb = fmaf(d, d, sb);
+      } else {
+        const float g = dy[(int64_t)n * C + c];
+        sa += g;
+        sb = fmaf(g, (xv - k0) * k1, sb);
+      }
+    }
+  }
+  sa_s[ty][tx] = sa;
+  sb_s[ty][tx] = sb;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int r = 1; r < 8; ++r) { sa += sa_s[r][tx]; sb += sb_s[r][tx]; }
+    partial[(int64_t)c * S + s] = make_float2(sa, sb);
+  }
+}
+
+__global__ void bn_fwd_finalize_kernel(const float* __restrict__ x, const float2* __restrict__ partial, int S,
+                                       const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                       float* __restrict__ rmean_out, float* __restrict__ rvar_out,
+                                       float* __restrict__ save_mean, float* __restrict__ save_rstd, int C, int HW,
+                                       float count, float m, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sa = 0.f, sb = 0.f;
+  for (int s = 0; s < S; ++s) {  // fixed order -> run-to-run deterministic
+    const float2 p = partial[(int64_t)c * S + s];
+    sa += p.x;
+    sb += p.y;
+  }
+  const float k0 = x[(int64_t)c * HW];
+  const float dm = sa / count;
+  const float mean = k0 + dm;
+  float var = sb / count - dm * dm;  // biased (ddof = 0), used for normalisation
+  var = fmaxf(var, 0.f);
+  save_mean[c] = mean;
+  save_rstd[c] = 1.0f / sqrtf(var + eps);
+  // running stats use the unbiased variance (normalization_funcs.py:147); count == 1 -> nan like numpy
+  const float var_unbiased = var * count / (count - 1.0f);
+  rmean_out[c] = rmean[c] * (1.0f - m) + mean * m;
+  rvar_out[c] = rvar[c] * (1.0f - m) + var_unbiased * m;
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                     float* __restrict__ save_mean, float* __restrict__ save_rstd, int C, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  save_mean[c] = rmean[c];
+  save_rstd[c] = 1.0f / sqrtf(rvar[c] + eps);
+}
+
+// y = w * ((x - mean) * rstd) + b
+template <int VEC>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ b, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, float* __restrict__ y,
+                                                       int64_t items, int C, int HWv) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += stride) {
+    const int c = (int)((it / HWv) % C);
+    const float mu = __ldg(mean + c), rs = __ldg(rstd + c), ww = __ldg(w + c), bb = __ldg(b + c);
+    if (VEC == 4) {
+      float4 v = ld_stream(reinterpret_cast<const float4*>(x) + it);
+      v.x = fmaf(ww, (v.x - mu) * rs, bb);
+      v.y = fmaf(ww, (v.y - mu) * rs, bb);
+      v.z = fmaf(ww, (v.z - mu) * rs, bb);
+      v.w = fmaf(ww, (v.w - mu) * rs, bb);
+      st_stream(reinterpret_cast<float4*>(y) + it, v);
+    } else {
+      y[it] = fmaf(ww, (x[it] - mu) * rs, bb);
+    }
+  }
+}
+
+// per channel: dw = Σ dy x̂, db = Σ dy, coef = (A, Bc, Cc) with dx = A*dy - Bc - x̂*Cc
+__global__ void bn_bwd_finalize_kernel(const float2* __restrict__ partial, int S, const float* __restrict__ w,
+                                       const float* __restrict__ rstd, float* __restrict__ dw, float* __restrict__ db,
+                                       float* __restrict__ coef, int C, float count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sa = 0.f, sb = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float2 p = partial[(int64_t)c * S + s];
+    sa += p.x;
+    sb += p.y;
+  }
+  db[c] = sa;
+  dw[c] = sb;
+  // reference: w / (std * n) * (n * dy - dy_sum - x_norm * dy_x_norm_sum)
+  const float g = w[c] * rstd[c] / count;
+  coef[3 * c + 0] = g;
+  coef[3 * c + 1] = sa;
+  coef[3 * c + 2] = sb;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ coef, float* __restrict__ dx,
+                                                           int64_t items, int C, int HWv, float count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += stride) {
+    const int c = (int)((it / HWv) % C);
+    const float mu = __ldg(mean + c), rs = __ldg(rstd + c);
+    const float g = __ldg(coef + 3 * c), s1 = __ldg(coef + 3 * c + 1), s2 = __ldg(coef + 3 * c + 2);
+    if (VEC == 4) {
+      const float4 xv = ld_stream(reinterpret_cast<const float4*>(x) + it);
+      const float4 gv = ld_stream(reinterpret_cast<const float4*>(dy) + it);
+      float4 o;
+      o.x = g * (count * gv.x - s1 - (xv.x - mu) * rs * s2);
+      o.y = g * (count * gv.y - s1 - (xv.y - mu) * rs * s2);
+      o.z = g * (count * gv.z - s1 - (xv.z - mu) * rs * s2);
+      o.w = g * (count * gv.w - s1 - (xv.w - mu) * rs * s2);
+      st_stream(reinterpret_cast<float4*>(dx) + it, o);
+    } else {
+      dx[it] = g * (count * dy[it] - s1 - (x[it] - mu) * rs * s2);
+    }
+  }
+}
+
+static int bn_splits(int N, int C, int HW) {
+  // aim for >= 4 CTAs per SM in total, each with at least ~4K elements
+  const int64_t per_channel = (int64_t)N * HW;
+  int64_t want = ((int64_t)sm_count() * 4 + C - 1) / C;
+  int64_t maxs = per_channel / 4096;
+  if (maxs < 1) maxs = 1;
+  if (want > maxs) want = maxs;
+  if (want > 64) want = 64;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+static int bn_check(const char* name, int N, int C, int HW) {
+  CPT_REQUIRE(N > 0 && C > 0 && HW > 0, CPT_ERR_INVALID, "%s: non-positive dimension", name);
+  return CPT_OK;
+}
+
+template <int MODE>
+static void launch_partial(const float* x, const float* dy, const float* mean, const float* rstd, float2* partial, int N,
+                           int C, int HW, int S, cudaStream_t st) {
+  if (HW == 1) {
+    dim3 grid((C + 31) / 32, S);
+    bn_partial_hw1_kernel<MODE><<<grid, 256, 0, st>>>(x, dy, mean, rstd, partial, N, C);
+  } else if (HW % 4 == 0 && aligned16(x) && (MODE == 0 || aligned16(dy))) {
+    bn_partial_kernel<MODE, 4><<<dim3(C, S), BN_THREADS, 0, st>>>(x, dy, mean, rstd, partial, N, C, HW);
+  } else {
+    bn_partial_kernel<MODE, 1><<<dim3(C, S), BN_THREADS, 0, st>>>(x, dy, mean, rstd, partial, N, C, HW);
+  }
+}
+
+}  // namespace cpt
+
+using namespace cpt;
+
+extern "C" {
+
+size_t cpt_bn_workspace_size(int N, int C, int HW) {
+  if (N <= 0 || C <= 0 || HW <= 0) return 0;
+  // partials [C][S] float2 + coef [C][3]
+  return (size_t)C * 64 * sizeof(float2) + (size_t)C * 3 * sizeof(float) + 256;
+}
+
+int cpt_bn_fwd_train(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,
+                     float* rmean_out, float* rvar_out, float* save_mean, float* save_rstd, int N, int C, int HW,
+                     float m, float eps, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = bn_check("bn_fwd_train", N, C, HW)) return e;
+  CPT_REQUIRE(ws && ws_bytes >= cpt_bn_workspace_size(N, C, HW), CPT_ERR_WORKSPACE, "bn_fwd_train: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int S = (HW == 1) ? (int)((N / 8 / 64 > 0) ? ((N / 8 / 64 > 64) ? 64 : N / 8 / 64) : 1) : bn_splits(N, C, HW);
+  float2* partial = reinterpret_cast<float2*>(ws);
+  launch_partial<0>(x, nullptr, nullptr, nullptr, partial, N, C, HW, S, st);
+  CPT_LAUNCH_CHECK("bn_stats");
+  const float count = (float)((int64_t)N * HW);
+  bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(x, partial, S, rmean, rvar, rmean_out, rvar_out, save_mean,
+                                                          save_rstd, C, HW, count, m, eps);
+  CPT_LAUNCH_CHECK("bn_fwd_finalize");
+  const int64_t total = (int64_t)N * C * HW;
+  if (HW % 4 == 0 && aligned16(x) && aligned16(y)) {
+    bn_apply_kernel<4><<<ew_grid(total / 4, 256), 256, 0, st>>>(x, w, b, save_mean, save_rstd, y, total / 4, C, HW / 4);
+  } else {
+    bn_apply_kernel<1><<<ew_grid(total, 256), 256, 0, st>>>(x, w, b, save_mean, save_rstd, y, total, C, HW);
+  }
+  CPT_LAUNCH_CHECK("bn_apply");
+  return CPT_OK;
+}
+
+int cpt_bn_fwd_eval(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,
+                    float* save_mean, float* save_rstd, int N, int C, int HW, float eps, void* stream) {
+  if (int e = bn_check("bn_fwd_eval", N, C, HW)) return e;
+  cudaStream_t st = as_stream(stream);
+  bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(rmean, rvar, save_mean, save_rstd, C, eps);
+  CPT_LAUNCH_CHECK("bn_eval_stats");
+  const int64_t total = (int64_t)N * C * HW;
+  if (HW % 4 == 0 && aligned16(x) && aligned16(y)) {
+    bn_apply_kernel<4><<<ew_grid(total / 4, 256), 256, 0, st>>>(x, w, b, save_mean, save_rstd, y, total / 4, C, HW / 4);
+  } else {
+    bn_apply_kernel<1><<<ew_grid(total, 256), 256, 0, st>>>(x, w, b, save_mean, save_rstd, y, total, C, HW);
+  }
+  CPT_LAUNCH_CHECK("bn_apply");
+  return CPT_OK;
+}
+
+int cpt_bn_bwd(const float* x, const float* dy, const float* w, const float* save_mean, const float* save_rstd,
+               float* dx, float* dw, float* db, int N, int C, int HW, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = bn_check("bn_bwd", N, C, HW)) return e;
+  CPT_REQUIRE(ws && ws_bytes >= cpt_bn_workspace_size(N, C, HW), CPT_ERR_WORKSPACE, "bn_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int S = (HW == 1) ? (int)((N / 8 / 64 > 0) ? ((N / 8 / 64 > 64) ? 64 : N / 8 / 64) : 1) : bn_splits(N, C, HW);
+  float2* partial = reinterpret_cast<float2*>(ws);
+  float* coef = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + (size_t)C * 64 * sizeof(float2));
+  launch_partial<1>(x, dy, save_mean, save_rstd, partial, N, C, HW, S, st);
+  CPT_LAUNCH_CHECK("bn_bwd_partial");
+  const float count = (float)((int64_t)N * HW);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, S, w, save_rstd, dw, db, coef, C, count);
+  CPT_LAUNCH_CHECK("bn_bwd_finalize");
+  const int64_t total = (int64_t)N * C * HW;
+  if (HW % 4 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx)) {
+    bn_bwd_apply_kernel<4><<<ew_grid(total / 4, 256), 256, 0, st>>>(x, dy, save_mean, save_rstd, coef, dx, total / 4, C,
+                                                                   HW / 4, count);
+  } else {
+    bn_bwd_apply_kernel<1><<<ew_grid(total, 256), 256, 0, st>>>(x, dy, save_mean, save_rstd, coef, dx, total, C, HW, count);
+  }
+  CPT_LAUNCH_CHECK("bn_bwd_apply");
+  return CPT_OK;
+}
+
+}  // extern "C"

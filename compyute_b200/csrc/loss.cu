@@ -1,0 +1,144 @@
+// Softmax cross-entropy forward/backward, accuracy count, dropout — small memory-bound kernels that
+// close the train step on the device.  Reference: compyute/nn/functional/loss_funcs.py:53-69,
+// activation_funcs.py:276-284 (softmax), metric_funcs.py:10-25, regularization_funcs.py:11-32.
+#include "common.cuh"
+
+namespace cpt {
+
+// one warp per row (NC up to a few thousand); probs = exp(x - max) / Σ; loss += -log(p_t + eta) / B
+__global__ void __launch_bounds__(256) softmax_ce_fwd_kernel(const float* __restrict__ logits, const int32_t* __restrict__ targets,
+                                                             float* __restrict__ probs, float* __restrict__ loss, int B,
+                                                             int NC, float eta) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float* x = logits + (int64_t)row * NC;
+  float* p = probs + (int64_t)row * NC;
+  float mx = -INFINITY;
+  for (int j = lane; j < NC; j += 32) mx = fmaxf(mx, x[j]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < NC; j += 32) {
+    const float e = expf(x[j] - mx);
+    p[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  for (int j = lane; j < NC; j += 32) p[j] = p[j] / sum;
+  __syncwarp();
+  if (lane == 0) {
+    const int t = targets[row];
+    const float pt = (t >= 0 && t < NC) ? p[t] : 0.f;
+    atomicAdd(loss, -logf(pt + eta) / (float)B);
+  }
+}
+
+__global__ void __launch_bounds__(256) softmax_ce_bwd_kernel(const float* __restrict__ probs, const int32_t* __restrict__ targets,
+                                                             float* __restrict__ dlogits, int64_t total, int NC, float bsz) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t row = i / NC;
+    const int j = (int)(i - row * NC);
+    const float onehot = (__ldg(targets + row) == j) ? 1.f : 0.f;
+    dlogits[i] = (probs[i] - onehot) / bsz;  // loss_funcs.py:69
+  }
+}
+
+__global__ void __launch_bounds__(256) accuracy_kernel(const float* __restrict__ logits, const int32_t* __restrict__ targets,
+                                                       int* __restrict__ correct, int B, int NC) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float* x = logits + (int64_t)row * NC;
+  float best = -INFINITY;
+  int arg = NC;
+  for (int j = lane; j < NC; j += 32) {
+    const float v = x[j];
+    if (v > best) { best = v; arg = j; }  // first maximum within the lane's stride
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }  // numpy argmax: first occurrence
+  }
+  if (lane == 0 && arg == targets[row]) atomicAdd(correct, 1);
+}
+
+// counter-based RNG (splitmix64 finaliser over (seed, index)): stateless, reproducible, one draw per element
+__device__ __forceinline__ float u01(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f);  // 24 random bits -> [0, 1)
+}
+
+__global__ void __launch_bounds__(256) dropout_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                          int8_t* __restrict__ mask, int64_t n, float keep, uint64_t seed) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int8_t mk = u01(seed, (uint64_t)i) < keep ? 1 : 0;  // bernoulli(1-p): random() < p_keep (random.py:264)
+    mask[i] = mk;
+    y[i] = x[i] * (float)mk / keep;  // regularization_funcs.py:22
+  }
+}
+
+__global__ void __launch_bounds__(256) dropout_bwd_kernel(const float* __restrict__ dy, const int8_t* __restrict__ mask,
+                                                          float* __restrict__ dx, int64_t n, float keep) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dx[i] = dy[i] * (float)mask[i] / keep;
+}
+
+}  // namespace cpt
+
+using namespace cpt;
+
+extern "C" {
+
+int cpt_softmax_ce_fwd(const float* logits, const int32_t* targets, float* probs, float* loss, int B, int NC, float eta,
+                       void* stream) {
+  CPT_REQUIRE(B > 0 && NC > 0 && logits && targets && probs && loss, CPT_ERR_INVALID, "softmax_ce_fwd: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  CPT_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  softmax_ce_fwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(logits, targets, probs, loss, B, NC, eta);
+  CPT_LAUNCH_CHECK("softmax_ce_fwd");
+  return CPT_OK;
+}
+
+int cpt_softmax_ce_bwd(const float* probs, const int32_t* targets, float* dlogits, int B, int NC, void* stream) {
+  CPT_REQUIRE(B > 0 && NC > 0 && probs && targets && dlogits, CPT_ERR_INVALID, "softmax_ce_bwd: bad arguments");
+  const int64_t total = (int64_t)B * NC;
+  softmax_ce_bwd_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(probs, targets, dlogits, total, NC,
+                                                                          (float)B);
+  CPT_LAUNCH_CHECK("softmax_ce_bwd");
+  return CPT_OK;
+}
+
+int cpt_accuracy_count(const float* logits, const int32_t* targets, int* correct, int B, int NC, void* stream) {
+  CPT_REQUIRE(B > 0 && NC > 0 && logits && targets && correct, CPT_ERR_INVALID, "accuracy_count: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  CPT_CUDA(cudaMemsetAsync(correct, 0, sizeof(int), st));
+  accuracy_kernel<<<(B + 7) / 8, 256, 0, st>>>(logits, targets, correct, B, NC);
+  CPT_LAUNCH_CHECK("accuracy_count");
+  return CPT_OK;
+}
+
+int cpt_dropout_fwd(const float* x, float* y, int8_t* mask, int64_t n, float p, uint64_t seed, void* stream) {
+  CPT_REQUIRE(n >= 0 && x && y && mask && p >= 0.f && p < 1.f, CPT_ERR_INVALID, "dropout_fwd: bad arguments");
+  if (n == 0) return CPT_OK;
+  dropout_fwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, y, mask, n, 1.0f - p, seed);
+  CPT_LAUNCH_CHECK("dropout_fwd");
+  return CPT_OK;
+}
+
+int cpt_dropout_bwd(const float* dy, const int8_t* mask, float* dx, int64_t n, float p, void* stream) {
+  CPT_REQUIRE(n >= 0 && dy && dx && mask && p >= 0.f && p < 1.f, CPT_ERR_INVALID, "dropout_bwd: bad arguments");
+  if (n == 0) return CPT_OK;
+  dropout_bwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(dy, mask, dx, n, 1.0f - p);
+  CPT_LAUNCH_CHECK("dropout_bwd");
+  return CPT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,611 @@
+// Host side of the tensor-core back end: TMA descriptor construction (tiled + im2col), operand staging
+// kernels (NCHW fp32 -> NHWC bf16/tf32, weight re-layout, casts), and the per-op drivers that launch
+// tc_kernel<> for Conv2D fprop / dgrad / wgrad and Linear fwd / dgrad / wgrad.
+#include <cuda_bf16.h>
+
+#include "simt_gemm.cuh"
+#include "tc.cuh"
+#include "tc_kernel.cuh"
+
+namespace cpt {
+namespace tc {
+
+// ------------------------------------------------------------------ driver entry points (no -lcuda needed)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+
+static int load_driver() {
+  if (g_encode_tiled && g_encode_im2col) return CPT_OK;
+  void* f1 = nullptr;
+  void* f2 = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CPT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f1, cudaEnableDefault, &q));
+  CPT_REQUIRE(f1 && q == cudaDriverEntryPointSuccess, CPT_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  CPT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f2, cudaEnableDefault, &q));
+  CPT_REQUIRE(f2 && q == cudaDriverEntryPointSuccess, CPT_ERR_CUDA, "cuTensorMapEncodeIm2col not available");
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(f1);
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(f2);
+  return CPT_OK;
+}
+
+static inline int esize(int mode) { return mode == CPT_MODE_BF16 ? 2 : 4; }
+static inline int kc_of(int mode) { return 128 / esize(mode); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// 2-D tiled map over a row-major [rows][cols] matrix with `pitch` elements per row; box = (box_cols, box_rows)
+static int make_map_2d(CUtensorMap* m, const void* base, int mode, uint64_t cols, uint64_t rows, uint64_t pitch, int box_cols,
+                       int box_rows) {
+  if (int e = load_driver()) return e;
+  const int es = esize(mode);
+  CPT_REQUIRE(((uintptr_t)base & 15) == 0 && (pitch * es) % 16 == 0, CPT_ERR_UNSUPPORTED,
+              "TMA needs 16-byte aligned base and row pitch (pitch=%llu elems)", (unsigned long long)pitch);
+  CPT_REQUIRE(box_cols * es == 128 && box_rows >= 1 && box_rows <= 256, CPT_ERR_INVALID, "bad TMA box %dx%d", box_cols, box_rows);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch * es};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(m, mode == CPT_MODE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                              const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CPT_REQUIRE(r == CUDA_SUCCESS, CPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) cols=%llu rows=%llu pitch=%llu box=%dx%d", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch, box_cols, box_rows);
+  return CPT_OK;
+}
+
+// im2col map over a channels-last activation tensor (N, H, W, C) [C innermost, Cp channels per pixel].
+// Bounding box of the *base pixel* in input coordinates: [lower, extent - 1 + upper] per spatial dim, walked with
+// `stride`; the filter-tap offset is added per load (PTX {off_w, off_h}).  Out-of-bounds reads are zero-filled.
+static int make_map_im2col(CUtensorMap* m, const void* base, int mode, int Cp, int W, int H, int N, int lower, int upper_w,
+                           int upper_h, int stride, int channels_per_pixel, int pixels_per_column) {
+  if (int e = load_driver()) return e;
+  const int es = esize(mode);
+  CPT_REQUIRE(((uintptr_t)base & 15) == 0 && ((size_t)Cp * es) % 16 == 0, CPT_ERR_UNSUPPORTED, "im2col TMA alignment");
+  CPT_REQUIRE(lower >= -128 && lower <= 127 && upper_w >= -128 && upper_w <= 127 && upper_h >= -128 && upper_h <= 127,
+              CPT_ERR_UNSUPPORTED, "im2col corner out of the 8-bit range");
+  CPT_REQUIRE(stride >= 1 && stride <= 8, CPT_ERR_UNSUPPORTED, "im2col traversal stride %d unsupported", stride);
+  cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)Cp * es, (cuuint64_t)W * Cp * es, (cuuint64_t)H * W * Cp * es};
+  int lo[2] = {lower, lower};
+  int hi[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(m, mode == CPT_MODE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                               const_cast<void*>(base), dims, strides, lo, hi, (cuuint32_t)channels_per_pixel,
+                               (cuuint32_t)pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CPT_REQUIRE(r == CUDA_SUCCESS, CPT_ERR_CUDA,
+              "cuTensorMapEncodeIm2col failed (%d) C=%d W=%d H=%d N=%d lo=%d hi=%d,%d stride=%d cpp=%d ppc=%d", (int)r, Cp, W, H, N,
+              lower, upper_w, upper_h, stride, channels_per_pixel, pixels_per_column);
+  // Known driver issue (also worked around by CUTLASS, copy_traits_sm90_im2col.hpp): for tensors < 128 KiB the
+  // encoder sets a descriptor bit that makes small im2col loads fault; clear it.
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  if (drv <= 13010 && (size_t)Cp * W * H * N * es < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+  return CPT_OK;
+}
+
+// ------------------------------------------------------------------ staging kernels
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// NCHW fp32 -> NHWC (C padded to Cp) bf16 / tf32-rounded fp32.  Tile = 64 channels x 32 pixels through smem:
+// reads are 128 B per channel row, writes 128 B (bf16) / 256 B (fp32) per pixel.  8 B/elem (bf16: 6 B/elem).
+template <bool BF16>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW,
+                                                           int Cp, float* __restrict__ chan_sum) {
+  __shared__ float tile[64][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 64, b = blockIdx.z;
+  const float* s = src + (int64_t)b * C * HW;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = ty + 8 * i, c = c0 + r, px = p0 + tx;
+    float v = 0.f;
+    if (c < C && px < HW) v = s[(int64_t)c * HW + px];
+    tile[r][tx] = v;
+    if (chan_sum) {
+      const float t = warp_sum(v);
+      if (tx == 0 && c < C) atomicAdd(chan_sum + c, t);
+    }
+  }
+  __syncthreads();
+  const int ch = c0 + 2 * tx;
+  if (ch < Cp) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pp = ty + 8 * i, px = p0 + pp;
+      if (px < HW) {
+        const float v0 = tile[2 * tx][pp], v1 = tile[2 * tx + 1][pp];
+        const int64_t o = ((int64_t)b * HW + px) * Cp + ch;
+        if (BF16) {
+          *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(dst) + o) = __floats2bfloat162_rn(v0, v1);
+        } else {
+          *reinterpret_cast<float2*>(reinterpret_cast<float*>(dst) + o) = make_float2(round_tf32(v0), round_tf32(v1));
+        }
+      }
+    }
+  }
+}
+
+// w (Co, Ci, K, K) fp32 -> fprop weight matrix [Co][T][Ck] (zero padded, Ck = round_up(Ci, KC))
+template <bool BF16>
+__global__ void w_fprop_kernel(const float* __restrict__ w, void* __restrict__ dst, int Co, int Ci, int T, int Ck) {
+  const int64_t n = (int64_t)Co * T * Ck;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Ck);
+    const int64_t r = i / Ck;
+    const int tap = (int)(r % T), co = (int)(r / T);
+    const float v = c < Ci ? w[((int64_t)co * Ci + c) * T + tap] : 0.f;
+    if (BF16) reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(dst)[i] = round_tf32(v);
+  }
+}
+// dgrad weight matrix [Ci][T][Cok] with both spatial axes flipped: w'[ci][t][co] = w[co][ci][T-1-t]
+template <bool BF16>
+__global__ void w_dgrad_kernel(const float* __restrict__ w, void* __restrict__ dst, int Co, int Ci, int T, int Cok) {
+  const int64_t n = (int64_t)Ci * T * Cok;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cok);
+    const int64_t r = i / Cok;
+    const int tap = (int)(r % T), ci = (int)(r / T);
+    const float v = co < Co ? w[((int64_t)co * Ci + ci) * T + (T - 1 - tap)] : 0.f;
+    if (BF16) reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(dst)[i] = round_tf32(v);
+  }
+}
+// dw[co][ci][tap] = Σ_split partial[split][co][tap][ci]   (fixed order)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Co, int Ci, int T, int splits) {
+  const int64_t n = (int64_t)Co * Ci * T;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Ci);
+    const int64_t r = i / Ci;
+    const int tap = (int)(r % T), co = (int)(r / T);
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * n + i];
+    dw[((int64_t)co * Ci + ci) * T + tap] = s;
+  }
+}
+// [R][C] fp32 -> [R][Cp] bf16 (zero padded columns)
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t R, int C, int Cp) {
+  const int64_t n = R * (Cp / 2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (Cp / 2);
+    const int c = (int)(i - r * (Cp / 2)) * 2;
+    const float v0 = c < C ? src[r * C + c] : 0.f, v1 = (c + 1) < C ? src[r * C + c + 1] : 0.f;
+    *reinterpret_cast<__nv_bfloat162*>(dst + r * Cp + c) = __floats2bfloat162_rn(v0, v1);
+  }
+}
+
+// ------------------------------------------------------------------ kernel launch
+__device__ int g_tc_status = 0;
+
+template <bool BF16, bool A_MN, bool B_MN, int BN, int OP>
+static int launch_inst(const TcParams& p, cudaStream_t st) {
+  using S = StageCfg<BN>;
+  static bool configured = false;
+  auto kern = tc_kernel<BF16, A_MN, B_MN, BN, OP>;
+  if (!configured) {
+    CPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
+    configured = true;
+  }
+  const int total = p.m_tiles * p.n_tiles * p.z_tiles;
+  int grid = total < sm_count() ? total : sm_count();
+  if (grid < 1) return CPT_OK;
+  kern<<<grid, 256, S::SMEM_BYTES, st>>>(p);
+  CPT_LAUNCH_CHECK("tc_kernel");
+  return CPT_OK;
+}
+
+template <bool A_MN, bool B_MN, int OP>
+static int launch_bn(const TcParams& p, int mode, int BN, cudaStream_t st) {
+  const bool bf = mode == CPT_MODE_BF16;
+  if (BN == 256) return bf ? launch_inst<true, A_MN, B_MN, 256, OP>(p, st) : launch_inst<false, A_MN, B_MN, 256, OP>(p, st);
+  if (BN == 128) return bf ? launch_inst<true, A_MN, B_MN, 128, OP>(p, st) : launch_inst<false, A_MN, B_MN, 128, OP>(p, st);
+  return bf ? launch_inst<true, A_MN, B_MN, 64, OP>(p, st) : launch_inst<false, A_MN, B_MN, 64, OP>(p, st);
+}
+
+static int pick_bn(int64_t n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
+
+static int get_status_ptr(int** ptr) {
+  CPT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(ptr), g_tc_status));
+  return CPT_OK;
+}
+
+// splits so that tiles*splits fills whole waves of the persistent grid; every split keeps >= min_iters iterations
+static int pick_splits(int tiles, int k_iters, int min_iters) {
+  const int sms = sm_count();
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 64; ++s) {
+    if (s > 1 && k_iters / s < min_iters) break;
+    const int total = tiles * s;
+    const int waves = (total + sms - 1) / sms;
+    const double eff = (double)total / ((double)waves * sms);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+// ------------------------------------------------------------------ Conv2D
+struct G {
+  int B, Ci, H, W, Co, K, P, S, D, Ho, Wo, T;
+};
+static G geom(const cpt_conv2d_desc* d) {
+  G g{d->B, d->Ci, d->H, d->W, d->Co, d->K, d->pad, d->stride, d->dil, 0, 0, d->K * d->K};
+  const int keff = d->dil * (d->K - 1) + 1;
+  g.Ho = (d->H + 2 * d->pad - keff) / d->stride + 1;
+  g.Wo = (d->W + 2 * d->pad - keff) / d->stride + 1;
+  return g;
+}
+static size_t cl_bytes(int B, int C, int H, int W, int mode) {
+  return align_up((size_t)B * H * W * round_up(C, 8) * esize(mode), 1024);
+}
+static size_t wmat_bytes(int rows, int T, int C, int mode) {
+  return align_up((size_t)rows * T * round_up(C, kc_of(mode)) * esize(mode), 1024);
+}
+static bool dgrad_tc_ok(const G& g) { return g.S == 1 && (g.K - 1) * g.D - g.P >= 0 && (g.K - 1) * g.D - g.P <= 127; }
+
+static int wgrad_splits(const G& g, int mode) {
+  const int bk = kc_of(mode);
+  const int k_iters = (int)(((int64_t)g.B * g.Ho * g.Wo + bk - 1) / bk);
+  const int tiles = ((g.Ci + 127) / 128) * ((g.Co + pick_bn(g.Co) - 1) / pick_bn(g.Co)) * g.T;
+  return pick_splits(tiles, k_iters, 8);
+}
+
+int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, int mode, float* chan_sum, cudaStream_t st) {
+  const int Cp = round_up(C, 8), HW = H * W;
+  dim3 grid((HW + 31) / 32, (Cp + 63) / 64, B);
+  CPT_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CPT_ERR_UNSUPPORTED, "to_channels_last: grid too large");
+  if (mode == CPT_MODE_BF16) nchw_to_nhwc_kernel<true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum);
+  else nchw_to_nhwc_kernel<false><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum);
+  CPT_LAUNCH_CHECK("nchw_to_nhwc");
+  return CPT_OK;
+}
+
+// fprop-form implicit GEMM: out[b, n, p, q] = Σ_{tap, c} act_cl[b, p*s - P + j*d, q*s - P + kk*d, c] * wmat[n][tap][c]
+static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Win, const void* wmat, int Ncols, int K, int pad,
+                            int stride, int dil, int Hout, int Wout, const float* bias, float* out, int mode, cudaStream_t st) {
+  const int kc = kc_of(mode), Cp = round_up(Cact, 8), Ck = round_up(Cact, kc), T = K * K;
+  const int BN = pick_bn(Ncols);
+  TcParams p{};
+  const int upper = pad - (K - 1) * dil;  // CUTLASS detail.hpp compute_upper_corner_whd (fprop)
+  if (int e = make_map_im2col(&p.tmA, act_cl, mode, Cp, Win, Hin, B, -pad, upper, upper, stride, kc, 128)) return e;
+  if (int e = make_map_2d(&p.tmB, wmat, mode, (uint64_t)T * Ck, Ncols, (uint64_t)T * Ck, kc, BN)) return e;
+  p.out = out;
+  p.bias = bias;
+  p.bias_mode = bias ? BIAS_COL : BIAS_NONE;
+  if (int e = get_status_ptr(&p.status)) return e;
+  const int64_t M = (int64_t)B * Hout * Wout;
+  p.M = (int)M;
+  p.N = Ncols;
+  p.m_tiles = (int)((M + 127) / 128);
+  p.n_tiles = (Ncols + BN - 1) / BN;
+  p.z_tiles = 1;
+  p.cchunks = Ck / kc;
+  p.k_iters_total = T * p.cchunks;
+  p.k_iters_per_split = p.k_iters_total;
+  p.col_stride = (long long)Hout * Wout;
+  p.lane_is_pixel = 1;
+  p.px_per_img = Hout * Wout;
+  p.img_stride = (long long)Ncols * Hout * Wout;
+  p.Wo = Wout;
+  p.conv_stride = stride;
+  p.pad = pad;
+  p.dil = dil;
+  p.Kw = K;
+  p.taps = T;
+  p.wk_cols = Ck;
+  return launch_bn<false, false, OP_CONV>(p, mode, BN, st);
+}
+
+int conv_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w, const float* bias, float* y, int mode, void* ws,
+                  size_t ws_bytes, cudaStream_t st) {
+  const G g = geom(d);
+  const size_t need = wmat_bytes(g.Co, g.T, g.Ci, mode);
+  CPT_REQUIRE(ws && ws_bytes >= need, CPT_ERR_WORKSPACE, "conv2d_fprop_cl: workspace too small (%zu < %zu)", ws_bytes, need);
+  const int Ck = round_up(g.Ci, kc_of(mode));
+  const int64_t n = (int64_t)g.Co * g.T * Ck;
+  if (mode == CPT_MODE_BF16) w_fprop_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Ck);
+  else w_fprop_kernel<false><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Ck);
+  CPT_LAUNCH_CHECK("w_fprop");
+  return conv_im2col_gemm(x_cl, g.B, g.Ci, g.H, g.W, ws, g.Co, g.K, g.P, g.S, g.D, g.Ho, g.Wo, bias, y, mode, st);
+}
+
+int conv_dgrad_cl(const cpt_conv2d_desc* d, const void* dy_cl, const float* w, float* dx, int mode, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  const G g = geom(d);
+  CPT_REQUIRE(dgrad_tc_ok(g), CPT_ERR_UNSUPPORTED, "conv2d_dgrad_cl: stride %d / padding %d not supported on the tensor-core path",
+              g.S, g.P);
+  const size_t need = wmat_bytes(g.Ci, g.T, g.Co, mode);
+  CPT_REQUIRE(ws && ws_bytes >= need, CPT_ERR_WORKSPACE, "conv2d_dgrad_cl: workspace too small (%zu < %zu)", ws_bytes, need);
+  const int Cok = round_up(g.Co, kc_of(mode));
+  const int64_t n = (int64_t)g.Ci * g.T * Cok;
+  if (mode == CPT_MODE_BF16) w_dgrad_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Cok);
+  else w_dgrad_kernel<false><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Cok);
+  CPT_LAUNCH_CHECK("w_dgrad");
+  // dx = full correlation of dy with the flipped filter: an fprop over dy with padding (K-1)d - P, stride 1
+  return conv_im2col_gemm(dy_cl, g.B, g.Co, g.Ho, g.Wo, ws, g.Ci, g.K, (g.K - 1) * g.D - g.P, 1, g.D, g.H, g.W, nullptr, dx, mode, st);
+}
+
+int conv_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl, float* dw, int mode, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  const G g = geom(d);
+  const int kc = kc_of(mode), bk = kc;
+  const int splits_req = wgrad_splits(g, mode);
+  const int64_t pixels = (int64_t)g.B * g.Ho * g.Wo;
+  const int k_iters = (int)((pixels + bk - 1) / bk);
+  const int kps = (k_iters + splits_req - 1) / splits_req;
+  const int splits = (k_iters + kps - 1) / kps;  // no empty split
+  const size_t need = align_up((size_t)splits * g.Co * g.T * g.Ci * sizeof(float), 1024);
+  CPT_REQUIRE(ws && ws_bytes >= need, CPT_ERR_WORKSPACE, "conv2d_wgrad_cl: workspace too small (%zu < %zu)", ws_bytes, need);
+  const int BN = pick_bn(g.Co);
+  TcParams p{};
+  const int upper = g.P - (g.K - 1) * g.D;
+  // A: x_cl through im2col, lanes = input channels (MN-major), reduction = output pixels
+  if (int e = make_map_im2col(&p.tmA, x_cl, mode, round_up(g.Ci, 8), g.W, g.H, g.B, -g.P, upper, upper, g.S, kc, bk)) return e;
+  // B: dy_cl as [pixels][Cop], columns = output channels (MN-major)
+  const int Cop = round_up(g.Co, 8);
+  if (int e = make_map_2d(&p.tmB, dy_cl, mode, Cop, (uint64_t)pixels, Cop, kc, bk)) return e;
+  p.out = reinterpret_cast<float*>(ws);
+  p.bias = nullptr;
+  p.bias_mode = BIAS_NONE;
+  if (int e = get_status_ptr(&p.status)) return e;
+  p.M = g.Ci;
+  p.N = g.Co;
+  p.m_tiles = (g.Ci + 127) / 128;
+  p.n_tiles = (g.Co + BN - 1) / BN;
+  p.z_tiles = g.T * splits;
+  p.k_iters_total = k_iters;
+  p.k_iters_per_split = kps;
+  p.col_stride = (long long)g.T * g.Ci;
+  p.split_stride = (long long)g.Co * g.T * g.Ci;
+  p.tap_stride = g.Ci;
+  p.lane_is_pixel = 0;
+  p.px_per_img = g.Ho * g.Wo;
+  p.Wo = g.Wo;
+  p.conv_stride = g.S;
+  p.pad = g.P;
+  p.dil = g.D;
+  p.Kw = g.K;
+  p.taps = g.T;
+  if (int e = launch_bn<true, true, OP_WGRAD>(p, mode, BN, st)) return e;
+  const int64_t n = (int64_t)g.Co * g.Ci * g.T;
+  wgrad_reduce_kernel<<<ew_grid(n, 256), 256, 0, st>>>(reinterpret_cast<float*>(ws), dw, g.Co, g.Ci, g.T, splits);
+  CPT_LAUNCH_CHECK("wgrad_reduce");
+  return CPT_OK;
+}
+
+size_t conv_workspace_size(int op, const cpt_conv2d_desc* d, int mode) {
+  const G g = geom(d);
+  if (op == CPT_OP_FPROP) return cl_bytes(g.B, g.Ci, g.H, g.W, mode) + wmat_bytes(g.Co, g.T, g.Ci, mode) + 1024;
+  if (op == CPT_OP_DGRAD) {
+    if (!dgrad_tc_ok(g)) return 1024;
+    return cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode) + wmat_bytes(g.Ci, g.T, g.Co, mode) + 1024;
+  }
+  const size_t part = align_up((size_t)wgrad_splits(g, mode) * g.Co * g.T * g.Ci * sizeof(float), 1024);
+  return cl_bytes(g.B, g.Ci, g.H, g.W, mode) + cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode) + part + 1024;
+}
+
+int conv_fprop(const cpt_conv2d_desc* d, const float* x, const float* w, const float* bias, float* y, int mode, void* ws,
+               size_t ws_bytes, cudaStream_t st) {
+  const G g = geom(d);
+  CPT_REQUIRE(ws && ws_bytes >= conv_workspace_size(CPT_OP_FPROP, d, mode), CPT_ERR_WORKSPACE, "conv2d_fprop: workspace too small");
+  const size_t xb = cl_bytes(g.B, g.Ci, g.H, g.W, mode);
+  if (int e = to_channels_last(x, ws, g.B, g.Ci, g.H, g.W, mode, nullptr, st)) return e;
+  return conv_fprop_cl(d, ws, w, bias, y, mode, reinterpret_cast<char*>(ws) + xb, ws_bytes - xb, st);
+}
+
+int conv_dgrad(const cpt_conv2d_desc* d, const float* dy, const float* w, float* dx, int mode, void* ws, size_t ws_bytes,
+               cudaStream_t st) {
+  const G g = geom(d);
+  if (!dgrad_tc_ok(g))  // strided dgrad: exact FFMA path (more accurate than the requested mode, never less)
+    return cpt_conv2d_dgrad(d, dy, w, dx, CPT_MODE_FP32, ws, ws_bytes, st);
+  CPT_REQUIRE(ws && ws_bytes >= conv_workspace_size(CPT_OP_DGRAD, d, mode), CPT_ERR_WORKSPACE, "conv2d_dgrad: workspace too small");
+  const size_t yb = cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode);
+  if (int e = to_channels_last(dy, ws, g.B, g.Co, g.Ho, g.Wo, mode, nullptr, st)) return e;
+  return conv_dgrad_cl(d, ws, w, dx, mode, reinterpret_cast<char*>(ws) + yb, ws_bytes - yb, st);
+}
+
+int conv_wgrad(const cpt_conv2d_desc* d, const float* x, const float* dy, float* dw, float* db, int mode, void* ws,
+               size_t ws_bytes, cudaStream_t st) {
+  const G g = geom(d);
+  CPT_REQUIRE(ws && ws_bytes >= conv_workspace_size(CPT_OP_WGRAD, d, mode), CPT_ERR_WORKSPACE, "conv2d_wgrad: workspace too small");
+  char* base = reinterpret_cast<char*>(ws);
+  const size_t xb = cl_bytes(g.B, g.Ci, g.H, g.W, mode), yb = cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode);
+  if (int e = to_channels_last(x, base, g.B, g.Ci, g.H, g.W, mode, nullptr, st)) return e;
+  if (db) CPT_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * g.Co, st));
+  if (int e = to_channels_last(dy, base + xb, g.B, g.Co, g.Ho, g.Wo, mode, db, st)) return e;  // db fused into the staging pass
+  return conv_wgrad_cl(d, base, base + xb, dw, mode, base + xb + yb, ws_bytes - xb - yb, st);
+}
+
+// ------------------------------------------------------------------ Linear (lanes = the output's contiguous dim)
+static size_t cast_bytes(int64_t R, int C) { return align_up((size_t)R * round_up(C, 8) * 2, 1024); }
+
+static int cast_to_bf16(const float* src, void* dst, int64_t R, int C, cudaStream_t st) {
+  const int Cp = round_up(C, 8);
+  cast_bf16_kernel<<<ew_grid(R * (Cp / 2), 256), 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), R, C, Cp);
+  CPT_LAUNCH_CHECK("cast_bf16");
+  return CPT_OK;
+}
+
+static bool tf32_direct_ok(const void* a, const void* b, int In, int Out) {
+  return In % 4 == 0 && Out % 4 == 0 && aligned16(a) && aligned16(b);
+}
+
+size_t linear_workspace_size(int op, int64_t N, int In, int Out, int mode) {
+  size_t s = 1024;
+  if (mode == CPT_MODE_BF16) {
+    if (op == CPT_OP_FPROP) s += cast_bytes(N, In) + cast_bytes(Out, In);
+    else if (op == CPT_OP_DGRAD) s += cast_bytes(N, Out) + cast_bytes(Out, In);
+    else s += cast_bytes(N, In) + cast_bytes(N, Out);
+  }
+  if (op == CPT_OP_WGRAD) {
+    // split-K partials + db partials
+    s += align_up((size_t)16 * Out * In * sizeof(float), 1024);  // up to 16 split-K partials
+    s += align_up((size_t)Out * 64 * sizeof(float), 256);
+  }
+  return s;
+}
+
+int linear_fwd(const float* x, const float* w, const float* bias, float* y, int64_t N, int In, int Out, int mode, void* ws,
+               size_t ws_bytes, cudaStream_t st) {
+  const void* xa = x;
+  const void* wa = w;
+  int pitch = In;
+  if (mode == CPT_MODE_BF16) {
+    CPT_REQUIRE(ws && ws_bytes >= linear_workspace_size(CPT_OP_FPROP, N, In, Out, mode), CPT_ERR_WORKSPACE, "linear_fwd: workspace too small");
+    char* base = reinterpret_cast<char*>(ws);
+    if (int e = cast_to_bf16(x, base, N, In, st)) return e;
+    if (int e = cast_to_bf16(w, base + cast_bytes(N, In), Out, In, st)) return e;
+    xa = base; wa = base + cast_bytes(N, In); pitch = round_up(In, 8);
+  } else if (!tf32_direct_ok(x, w, In, 4)) {
+    return cpt_linear_fwd(x, w, bias, y, N, In, Out, CPT_MODE_FP32, ws, ws_bytes, st);
+  }
+  const int kc = kc_of(mode), BN = pick_bn(N);
+  TcParams p{};
+  // y[n][o]: lanes = o.  A = w [Out][In] K-major, B = x [N][In] K-major
+  if (int e = make_map_2d(&p.tmA, wa, mode, In, Out, pitch, kc, 128)) return e;
+  if (int e = make_map_2d(&p.tmB, xa, mode, In, (uint64_t)N, pitch, kc, BN)) return e;
+  p.out = y; p.bias = bias; p.bias_mode = bias ? BIAS_LANE : BIAS_NONE;
+  if (int e = get_status_ptr(&p.status)) return e;
+  p.M = Out; p.N = (int)N;
+  p.m_tiles = (Out + 127) / 128; p.n_tiles = (int)((N + BN - 1) / BN); p.z_tiles = 1;
+  p.k_iters_total = (In + kc - 1) / kc; p.k_iters_per_split = p.k_iters_total;
+  p.col_stride = Out; p.taps = 1;
+  return launch_bn<false, false, OP_GEMM>(p, mode, BN, st);
+}
+
+int linear_dgrad(const float* dy, const float* w, float* dx, int64_t N, int In, int Out, int mode, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+  const void* ga = dy;
+  const void* wa = w;
+  int gpitch = Out, wpitch = In;
+  if (mode == CPT_MODE_BF16) {
+    CPT_REQUIRE(ws && ws_bytes >= linear_workspace_size(CPT_OP_DGRAD, N, In, Out, mode), CPT_ERR_WORKSPACE, "linear_dgrad: workspace too small");
+    char* base = reinterpret_cast<char*>(ws);
+    if (int e = cast_to_bf16(dy, base, N, Out, st)) return e;
+    if (int e = cast_to_bf16(w, base + cast_bytes(N, Out), Out, In, st)) return e;
+    ga = base; wa = base + cast_bytes(N, Out); gpitch = round_up(Out, 8); wpitch = round_up(In, 8);
+  } else if (!tf32_direct_ok(dy, w, In, Out)) {
+    return cpt_linear_dgrad(dy, w, dx, N, In, Out, CPT_MODE_FP32, ws, ws_bytes, st);
+  }
+  const int kc = kc_of(mode), BN = pick_bn(N);
+  TcParams p{};
+  // dx[n][i]: lanes = i.  A(m=i, k=o) = w[o][i]: MN-major over the [Out][In] matrix; B = dy [N][Out] K-major
+  if (int e = make_map_2d(&p.tmA, wa, mode, In, Out, wpitch, kc, kc)) return e;
+  if (int e = make_map_2d(&p.tmB, ga, mode, Out, (uint64_t)N, gpitch, kc, BN)) return e;
+  p.out = dx; p.bias = nullptr; p.bias_mode = BIAS_NONE;
+  if (int e = get_status_ptr(&p.status)) return e;
+  p.M = In; p.N = (int)N;
+  p.m_tiles = (In + 127) / 128; p.n_tiles = (int)((N + BN - 1) / BN); p.z_tiles = 1;
+  p.k_iters_total = (Out + kc - 1) / kc; p.k_iters_per_split = p.k_iters_total;
+  p.col_stride = In; p.taps = 1;
+  return launch_bn<true, false, OP_GEMM>(p, mode, BN, st);
+}
+
+int linear_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t N, int In, int Out, int mode, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+  CPT_REQUIRE(ws && ws_bytes >= linear_workspace_size(CPT_OP_WGRAD, N, In, Out, mode), CPT_ERR_WORKSPACE, "linear_wgrad: workspace too small");
+  char* base = reinterpret_cast<char*>(ws);
+  const void* xa = x;
+  const void* ga = dy;
+  int xpitch = In, gpitch = Out;
+  size_t off = 0;
+  if (mode == CPT_MODE_BF16) {
+    if (int e = cast_to_bf16(x, base, N, In, st)) return e;
+    if (int e = cast_to_bf16(dy, base + cast_bytes(N, In), N, Out, st)) return e;
+    xa = base; ga = base + cast_bytes(N, In); xpitch = round_up(In, 8); gpitch = round_up(Out, 8);
+    off = cast_bytes(N, In) + cast_bytes(N, Out);
+  } else if (!tf32_direct_ok(x, dy, In, Out)) {
+    return cpt_linear_wgrad(x, dy, dw, db, N, In, Out, CPT_MODE_FP32, ws, ws_bytes, st);
+  }
+  const int kc = kc_of(mode), bk = kc, BN = pick_bn(Out);
+  const int k_iters = (int)((N + bk - 1) / bk);
+  const int tiles = ((In + 127) / 128) * ((Out + BN - 1) / BN);
+  int splits_req = pick_splits(tiles, k_iters, 8);
+  if (splits_req > 16) splits_req = 16;
+  const int kps = (k_iters + splits_req - 1) / splits_req;
+  const int splits = (k_iters + kps - 1) / kps;
+  float* partial = reinterpret_cast<float*>(base + off);
+  const size_t part_bytes = align_up((size_t)(splits > 1 ? splits : 0) * Out * In * sizeof(float), 1024);
+  TcParams p{};
+  // dw[o][i]: lanes = i.  A(m=i, k=n) = x[n][i] MN-major; B(col=o, k=n) = dy[n][o] MN-major
+  if (int e = make_map_2d(&p.tmA, xa, mode, In, (uint64_t)N, xpitch, kc, bk)) return e;
+  if (int e = make_map_2d(&p.tmB, ga, mode, Out, (uint64_t)N, gpitch, kc, bk)) return e;
+  p.out = splits > 1 ? partial : dw; p.bias = nullptr; p.bias_mode = BIAS_NONE;
+  if (int e = get_status_ptr(&p.status)) return e;
+  p.M = In; p.N = Out;
+  p.m_tiles = (In + 127) / 128; p.n_tiles = (Out + BN - 1) / BN; p.z_tiles = splits;
+  p.k_iters_total = k_iters; p.k_iters_per_split = kps;
+  p.col_stride = In; p.split_stride = (long long)Out * In; p.taps = 1;
+  if (int e = launch_bn<true, true, OP_GEMM>(p, mode, BN, st)) return e;
+  if (splits > 1) {
+    launch_reduce_splits(partial, dw, (int64_t)Out * In, splits, st);
+    CPT_LAUNCH_CHECK("linear_wgrad reduce");
+  }
+  if (db) return channel_sum(dy, db, (int)N, Out, 1, base + off + part_bytes, st);
+  return CPT_OK;
+}
+
+}  // namespace tc
+}  // namespace cpt
+
+using namespace cpt;
+
+extern "C" {
+
+size_t cpt_channels_last_bytes(int B, int C, int H, int W, int mode) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || mode == CPT_MODE_FP32) return 0;
+  return tc::cl_bytes(B, C, H, W, mode);
+}
+
+int cpt_to_channels_last(const float* src, void* dst, int B, int C, int H, int W, int mode, float* chan_sum, void* stream) {
+  CPT_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, CPT_ERR_INVALID, "to_channels_last: bad arguments");
+  CPT_REQUIRE(mode == CPT_MODE_TF32 || mode == CPT_MODE_BF16, CPT_ERR_INVALID, "to_channels_last: mode must be TF32 or BF16");
+  return tc::to_channels_last(src, dst, B, C, H, W, mode, chan_sum, as_stream(stream));
+}
+
+static int check_tc(const cpt_conv2d_desc* d, int mode, const char* who) {
+  CPT_REQUIRE(d && d->B > 0 && d->Ci > 0 && d->H > 0 && d->W > 0 && d->Co > 0 && d->K > 0 && d->pad >= 0 && d->stride >= 1 &&
+                  d->dil >= 1,
+              CPT_ERR_INVALID, "%s: bad descriptor", who);
+  CPT_REQUIRE(mode == CPT_MODE_TF32 || mode == CPT_MODE_BF16, CPT_ERR_INVALID, "%s: mode must be TF32 or BF16", who);
+  return CPT_OK;
+}
+
+int cpt_conv2d_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w, const float* bias, float* y, int mode,
+                        void* ws, size_t ws_bytes, void* stream) {
+  if (int e = check_tc(d, mode, "conv2d_fprop_cl")) return e;
+  return tc::conv_fprop_cl(d, x_cl, w, bias, y, mode, ws, ws_bytes, as_stream(stream));
+}
+int cpt_conv2d_dgrad_cl(const cpt_conv2d_desc* d, const void* dy_cl, const float* w, float* dx, int mode, void* ws,
+                        size_t ws_bytes, void* stream) {
+  if (int e = check_tc(d, mode, "conv2d_dgrad_cl")) return e;
+  return tc::conv_dgrad_cl(d, dy_cl, w, dx, mode, ws, ws_bytes, as_stream(stream));
+}
+int cpt_conv2d_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl, float* dw, int mode, void* ws,
+                        size_t ws_bytes, void* stream) {
+  if (int e = check_tc(d, mode, "conv2d_wgrad_cl")) return e;
+  return tc::conv_wgrad_cl(d, x_cl, dy_cl, dw, mode, ws, ws_bytes, as_stream(stream));
+}
+
+// Debug/test helper: synchronises the device and returns the pipeline-timeout flag of the tensor-core kernels
+// (0 = healthy), clearing it.
+int cpt_tc_check_status(void) {
+  int v = 0, zero = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(&v, tc::g_tc_status, sizeof(int)) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(tc::g_tc_status, &zero, sizeof(int));
+  return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,267 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM convolution kernel for sm_100a.
+//
+//   warp 0 (1 lane)  TMA producer: tiled 2-D or im2col 4-D loads into a ring of 128B-swizzled smem stages
+//   warp 1 (1 lane)  MMA issuer:   tcgen05.mma (M=128, N=BN, fp32 accumulate in TMEM), tcgen05.commit
+//   warp 2           TMEM allocator (2 x BN columns: double-buffered accumulator)
+//   warps 4-7        epilogue: tcgen05.ld -> registers -> (bias) -> global, overlapped with the next tile
+//
+// The GEMM "M" (TMEM lane) dimension is always mapped onto the output's CONTIGUOUS dimension (pixels for
+// NCHW conv outputs, the feature dimension for row-major Linear outputs, Ci for wgrad partials) so that the
+// epilogue's 32-lane stores are 128-byte coalesced without a shared-memory transpose.
+#pragma once
+#include "tc_ptx.cuh"
+
+namespace cpt {
+namespace tc {
+
+enum { OP_GEMM = 0, OP_CONV = 1, OP_WGRAD = 2 };
+enum { BIAS_NONE = 0, BIAS_COL = 1, BIAS_LANE = 2 };
+
+struct alignas(64) TcParams {
+  CUtensorMap tmA;  // operand A (M side)
+  CUtensorMap tmB;  // operand B (N side)
+  float* out;
+  const float* bias;
+  int* status;      // device int: set non-zero on a pipeline timeout
+  int bias_mode;
+  int M, N;         // valid extents of the lane / column dimensions
+  int m_tiles, n_tiles, z_tiles;  // z = split (GEMM), 1 (CONV), tap * split (WGRAD)
+  int k_iters_total;              // k iterations of the whole reduction (GEMM / WGRAD) or per tile (CONV)
+  int k_iters_per_split;
+  // epilogue addressing: dst = out + z_off + lane_off(m) + col * col_stride
+  long long col_stride, split_stride, tap_stride;
+  int lane_is_pixel;              // 1: m -> (image b, pixel pq): lane_off = b * img_stride + pq
+  int px_per_img;                 // Ho*Wo (CONV lanes, WGRAD reduction)
+  long long img_stride;
+  // convolution geometry (im2col coordinates)
+  int Wo, conv_stride, pad, dil, Kw, taps, cchunks, wk_cols;  // wk_cols: weight-matrix columns per tap (padded C)
+};
+
+template <bool BF16>
+struct Elem {
+  static constexpr int BYTES = BF16 ? 2 : 4;
+  static constexpr int KC = 128 / BYTES;      // elements per 128-byte swizzle row: 64 bf16 / 32 tf32
+  static constexpr int UMMA_K = 32 / BYTES;   // 16 bf16 / 8 tf32
+  static constexpr int BK = KC;               // reduction elements per stage (also k-rows of an MN-major stage)
+};
+
+template <int BN>
+struct StageCfg {
+  static constexpr int A_BYTES = 128 * 128;   // 128 lanes x 128 B (K-major) == (128/KC chunks) x BK rows x 128 B
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <bool BF16, bool A_MN, bool B_MN, int BN, int OP>
+__global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcParams p) {
+  using E = Elem<BF16>;
+  using S = StageCfg<BN>;
+  constexpr int STAGES = S::STAGES;
+  constexpr uint32_t IDESC = make_idesc(BF16, A_MN, B_MN, 128, BN);
+  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr uint32_t CHUNK_BYTES = E::BK * 128;  // one MN-major chunk: BK k-rows x 128 B
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto a_smem = [&](int s) { return smem_base + s * S::STAGE_BYTES; };
+  auto b_smem = [&](int s) { return smem_base + s * S::STAGE_BYTES + S::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.z_tiles;
+
+  auto tile_k_iters = [&](int z) -> int {
+    if (OP == OP_CONV) return p.k_iters_total;
+    const int split = (OP == OP_WGRAD) ? z / p.taps : z;
+    const int rem = p.k_iters_total - split * p.k_iters_per_split;
+    return rem < p.k_iters_per_split ? rem : p.k_iters_per_split;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // =========================== TMA producer ===========================
+    int stage = 0;
+    uint32_t phase = 0;
+    bool ok = true;
+    for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+      const int m_tile = t % p.m_tiles, r = t / p.m_tiles, n_tile = r % p.n_tiles, z = r / p.n_tiles;
+      const int m0 = m_tile * 128, n0 = n_tile * BN;
+      const int iters = tile_k_iters(z);
+      int cw = 0, ch = 0, cn = 0, tap = 0, k_begin = 0;
+      if (OP == OP_CONV) {
+        const int b = m0 / p.px_per_img, rem = m0 - b * p.px_per_img, py = rem / p.Wo, qx = rem - py * p.Wo;
+        cw = qx * p.conv_stride - p.pad;
+        ch = py * p.conv_stride - p.pad;
+        cn = b;
+      } else if (OP == OP_WGRAD) {
+        tap = z % p.taps;
+        k_begin = (z / p.taps) * p.k_iters_per_split;
+      } else {
+        k_begin = z * p.k_iters_per_split;
+      }
+      for (int i = 0; i < iters; ++i) {
+        if (!mbar_wait(empty_bar(stage), phase ^ 1)) { atomicExch(p.status, 1); ok = false; break; }
+        mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
+        const uint32_t fb = full_bar(stage), sa = a_smem(stage), sb = b_smem(stage);
+        if (OP == OP_CONV) {
+          // A: 128 output pixels x KC channels of filter tap (j, kk); B: weights [Co][tap][C] rows n0.., K-major
+          const int tp = i / p.cchunks, cc = i - tp * p.cchunks;
+          const int j = tp / p.Kw, kk = tp - j * p.Kw;
+          tma_load_im2col_4d(&p.tmA, fb, sa, cc * E::KC, cw, ch, cn, (uint16_t)(kk * p.dil), (uint16_t)(j * p.dil));
+          tma_load_2d(&p.tmB, fb, sb, tp * p.wk_cols + cc * E::KC, n0);
+        } else if (OP == OP_WGRAD) {
+          // reduction over output pixels: chunk of BK pixels starting at flattened pixel k0
+          const int k0 = (k_begin + i) * E::BK;
+          const int b = k0 / p.px_per_img, rem = k0 - b * p.px_per_img, py = rem / p.Wo, qx = rem - py * p.Wo;
+          const int j = tap / p.Kw, kk = tap - j * p.Kw;
+#pragma unroll
+          for (int c = 0; c < 128 / E::KC; ++c)
+            tma_load_im2col_4d(&p.tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, qx * p.conv_stride - p.pad,
+                               py * p.conv_stride - p.pad, b, (uint16_t)(kk * p.dil), (uint16_t)(j * p.dil));
+#pragma unroll
+          for (int c = 0; c < BN / E::KC; ++c) tma_load_2d(&p.tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, k0);
+        } else {
+          const int kidx = k_begin + i;
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < 128 / E::KC; ++c)
+              tma_load_2d(&p.tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, kidx * E::BK);
+          } else {
+            tma_load_2d(&p.tmA, fb, sa, kidx * E::KC, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / E::KC; ++c)
+              tma_load_2d(&p.tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, kidx * E::BK);
+          } else {
+            tma_load_2d(&p.tmB, fb, sb, kidx * E::KC, n0);
+          }
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // =========================== MMA issuer ===========================
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    bool ok = true;
+    for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+      const int z = (t / p.m_tiles) / p.n_tiles;
+      const int iters = tile_k_iters(z);
+      if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1)) { atomicExch(p.status, 2); break; }
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int i = 0; i < iters; ++i) {
+        if (!mbar_wait(full_bar(stage), phase)) { atomicExch(p.status, 3); ok = false; break; }
+        tc_fence_after();
+        const uint32_t sa = a_smem(stage), sb = b_smem(stage);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          // K-major: advance 32 B inside the 128-B swizzle row; MN-major: advance UMMA_K k-rows (x128 B)
+          const uint64_t da = A_MN ? make_smem_desc(sa + s * (E::UMMA_K * 128), CHUNK_BYTES, 1024)
+                                   : make_smem_desc(sa + s * 32, 16, 1024);
+          const uint64_t db = B_MN ? make_smem_desc(sb + s * (E::UMMA_K * 128), CHUNK_BYTES, 1024)
+                                   : make_smem_desc(sb + s * 32, 16, 1024);
+          umma<BF16>(d_tmem, da, db, IDESC, (uint32_t)((i | s) != 0));
+        }
+        umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull_bar(acc));      // accumulator complete -> epilogue
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue ===========================
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m_tile = t % p.m_tiles, r = t / p.m_tiles, n_tile = r % p.n_tiles, z = r / p.n_tiles;
+      const int m = m_tile * 128 + ew * 32 + lane, n0 = n_tile * BN;
+      const int iters = tile_k_iters(z);
+      long long z_off = 0;
+      if (OP == OP_WGRAD) z_off = (long long)(z / p.taps) * p.split_stride + (long long)(z % p.taps) * p.tap_stride;
+      else if (OP == OP_GEMM) z_off = (long long)z * p.split_stride;
+      long long lane_off = m;
+      if (p.lane_is_pixel) {
+        const int b = m / p.px_per_img;
+        lane_off = (long long)b * p.img_stride + (m - b * p.px_per_img);
+      }
+      const bool m_ok = m < p.M;
+      const float lane_bias = (p.bias_mode == BIAS_LANE && m_ok) ? __ldg(p.bias + m) : 0.f;
+      bool ok = mbar_wait(tfull_bar(acc), acc_phase);
+      if (!ok) { atomicExch(p.status, 4); break; }
+      tc_fence_after();
+      float* dst = p.out + z_off + lane_off;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+        if (iters > 0) {
+          tmem_ld_32x32(taddr, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if (m_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = n0 + c * 32 + j;
+            if (col < p.N) {
+              float val = __uint_as_float(v[j]) + lane_bias;
+              if (p.bias_mode == BIAS_COL) val += __ldg(p.bias + col);
+              dst[(long long)col * p.col_stride] = val;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+}  // namespace cpt

@@ -1,0 +1,110 @@
+"""Conv2D forward/backward on the B200 kernels.  API of compyute/nn/functional/convolution_funcs.py:218-291.
+
+``Conv2DFn.forward(cache, x, f, b, padding, stride, dilation)`` / ``.backward(cache, dy) -> (dx, df, db|None)``.
+The reference evaluates dilate → pad → window view → einsum (and flips/pads again in backward); here each pass
+is one implicit-GEMM launch (``cpt_conv2d_fprop/_dgrad/_wgrad``), exact FFMA in "fp32" mode, tcgen05 in
+"tf32"/"bf16" mode.  One cache tuple is pushed instead of the reference's four.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from ... import _lib
+from ...backend import get_compute_mode
+from ...tensors import DeviceArray, ShapeError, Tensor, f32ptr, require_cuda, stream_ptr, workspace
+from .functions import Function, FunctionCache, PseudoCache
+
+__all__ = ["conv2d", "Conv2DFn"]
+
+
+def _desc(x_shape, f_shape, padding: int, stride: int, dilation: int) -> _lib.ConvDesc:
+    B, Ci, H, W = x_shape
+    Co, Ci_f, K, K2 = f_shape
+    if Ci_f != Ci:
+        raise ShapeError(f"Filter expects {Ci_f} input channels, input has {Ci}.")
+    if K != K2:
+        raise ShapeError("Only square kernels are supported (like the reference).")
+    return _lib.ConvDesc(B, Ci, H, W, Co, K, int(padding), int(stride), int(dilation))
+
+
+def _out_hw(d: _lib.ConvDesc) -> tuple[int, int]:
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.lib().cpt_conv2d_out_shape(ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo)))
+    return ho.value, wo.value
+
+
+class Conv2DFn(Function):
+    """2-D cross-correlation, NCHW x OIHW (convolution_funcs.py:218-254)."""
+
+    @staticmethod
+    def forward(cache: FunctionCache, x: Tensor, f: Tensor, b: Optional[Tensor], padding: int, stride: int,
+                dilation: int) -> Tensor:
+        if x.ndim != 4:
+            raise ShapeError(f"Expected input to be 4D, got {x.ndim}D.")
+        require_cuda(x, f, b)
+        L = _lib.lib()
+        d = _desc(x.shape, f.shape, padding, stride, dilation)
+        ho, wo = _out_hw(d)
+        mode = get_compute_mode()
+        y = DeviceArray.empty((d.B, d.Co, ho, wo), np.float32)
+        st = stream_ptr()
+        x_cl = None
+        if mode == _lib.MODE_FP32:
+            ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_FPROP, ctypes.byref(d), mode))
+            _lib.check(L.cpt_conv2d_fprop(ctypes.byref(d), f32ptr(x), f32ptr(f), f32ptr(b), y.ptr, mode, ws, wsb, st))
+        else:
+            # stage x once as channels-last; kept in the cache so wgrad does not convert it again
+            x_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Ci, d.H, d.W, mode),), np.uint8)
+            _lib.check(L.cpt_to_channels_last(f32ptr(x), x_cl.ptr, d.B, d.Ci, d.H, d.W, mode, None, st))
+            ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_FPROP, ctypes.byref(d), mode))
+            _lib.check(L.cpt_conv2d_fprop_cl(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, mode, ws, wsb, st))
+        cache.push(x, f, b is not None, d, mode, x_cl)
+        return Tensor(y)
+
+    @staticmethod
+    def backward(cache: FunctionCache, dy: Tensor, df_out: Optional[DeviceArray] = None,
+                 db_out: Optional[DeviceArray] = None) -> tuple[Tensor, Tensor, Optional[Tensor]]:
+        """``df_out``/``db_out``: optional preallocated gradient slots (flat DP arena); extension of the reference API."""
+        x, f, has_bias, d, mode, x_cl = cache.pop()
+        require_cuda(dy)
+        L = _lib.lib()
+        st = stream_ptr()
+        dref = ctypes.byref(d)
+        dx = DeviceArray.empty(x.shape, np.float32)
+        df = df_out.reshape(f.shape) if df_out is not None else DeviceArray.empty(f.shape, np.float32)
+        db = None
+        if has_bias:
+            db = db_out.reshape((d.Co,)) if db_out is not None else DeviceArray.empty((d.Co,), np.float32)
+        dbp = db.ptr if db is not None else None
+        ho, wo = dy.shape[2], dy.shape[3]
+        tc_dgrad = mode != _lib.MODE_FP32 and d.stride == 1 and 0 <= (d.K - 1) * d.dil - d.pad <= 127
+        if mode == _lib.MODE_FP32:
+            ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_DGRAD, dref, mode))
+            _lib.check(L.cpt_conv2d_dgrad(dref, f32ptr(dy), f32ptr(f), dx.ptr, mode, ws, wsb, st))
+            ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_WGRAD, dref, mode))
+            _lib.check(L.cpt_conv2d_wgrad(dref, f32ptr(x), f32ptr(dy), df.ptr, dbp, mode, ws, wsb, st))
+        else:
+            # dy staged once (db fused into the staging pass), shared by dgrad and wgrad
+            dy_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Co, ho, wo, mode),), np.uint8)
+            if db is not None:
+                db.fill(0.0)
+            _lib.check(L.cpt_to_channels_last(f32ptr(dy), dy_cl.ptr, d.B, d.Co, ho, wo, mode, dbp, st))
+            if tc_dgrad:
+                ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_DGRAD, dref, mode))
+                _lib.check(L.cpt_conv2d_dgrad_cl(dref, dy_cl.ptr, f32ptr(f), dx.ptr, mode, ws, wsb, st))
+            else:  # strided dgrad has no tensor-core kernel yet: exact path
+                ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_DGRAD, dref, _lib.MODE_FP32))
+                _lib.check(L.cpt_conv2d_dgrad(dref, f32ptr(dy), f32ptr(f), dx.ptr, _lib.MODE_FP32, ws, wsb, st))
+            ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_WGRAD, dref, mode))
+            _lib.check(L.cpt_conv2d_wgrad_cl(dref, x_cl.ptr, dy_cl.ptr, df.ptr, mode, ws, wsb, st))
+        return Tensor(dx), Tensor(df), (Tensor(db) if db is not None else None)
+
+
+def conv2d(x: Tensor, f: Tensor, b: Optional[Tensor] = None, padding: int = 0, stride: int = 1,
+           dilation: int = 1) -> Tensor:
+    """User-level wrapper (convolution_funcs.py:257-291)."""
+    return Conv2DFn.forward(PseudoCache(), x, f, b, padding, stride, dilation)

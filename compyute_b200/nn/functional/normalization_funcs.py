@@ -1,0 +1,87 @@
+"""BatchNorm 1-D / 2-D.  API of compyute/nn/functional/normalization_funcs.py:10-224."""
+
+from __future__ import annotations
+
+import numpy as np
+
+from ... import _lib
+from ...tensors import DeviceArray, ShapeError, Tensor, f32ptr, require_cuda, stream_ptr, workspace
+from .functions import Function, FunctionCache, PseudoCache
+
+__all__ = ["batchnorm1d", "batchnorm2d", "BatchNorm1DFn", "BatchNorm2DFn"]
+
+
+def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW):
+    require_cuda(x, rmean, rvar, w, b)
+    L = _lib.lib()
+    st = stream_ptr()
+    y = DeviceArray.empty(x.shape, np.float32)
+    save_mean = DeviceArray.empty((C,), np.float32)
+    save_rstd = DeviceArray.empty((C,), np.float32)
+    if training:
+        new_rmean = DeviceArray.empty((C,), np.float32)
+        new_rvar = DeviceArray.empty((C,), np.float32)
+        ws, wsb = workspace(L.cpt_bn_workspace_size(N, C, HW))
+        _lib.check(L.cpt_bn_fwd_train(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, new_rmean.ptr,
+                                      new_rvar.ptr, save_mean.ptr, save_rstd.ptr, N, C, HW, float(m), float(eps), ws, wsb, st))
+        rmean, rvar = Tensor(new_rmean), Tensor(new_rvar)
+    else:
+        _lib.check(L.cpt_bn_fwd_eval(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, save_mean.ptr,
+                                     save_rstd.ptr, N, C, HW, float(eps), st))
+    # the reference caches (w, dims, std, x_norm); x_norm is recomputed from (x, mean, rstd) in backward instead
+    cache.push(x, w, save_mean, save_rstd, (N, C, HW))
+    return Tensor(y), rmean, rvar
+
+
+def _bn_backward(cache, dy, dw_out=None, db_out=None):
+    x, w, save_mean, save_rstd, (N, C, HW) = cache.pop()
+    require_cuda(dy)
+    L = _lib.lib()
+    dx = DeviceArray.empty(x.shape, np.float32)
+    dw = dw_out.reshape((C,)) if dw_out is not None else DeviceArray.empty((C,), np.float32)
+    db = db_out.reshape((C,)) if db_out is not None else DeviceArray.empty((C,), np.float32)
+    ws, wsb = workspace(L.cpt_bn_workspace_size(N, C, HW))
+    _lib.check(L.cpt_bn_bwd(f32ptr(x), f32ptr(dy), f32ptr(w), save_mean.ptr, save_rstd.ptr, dx.ptr, dw.ptr, db.ptr, N, C, HW,
+                            ws, wsb, stream_ptr()))
+    return Tensor(dx), Tensor(dw), Tensor(db)
+
+
+class BatchNorm2DFn(Function):
+    """(:120-177) statistics over (0, 2, 3)."""
+
+    @staticmethod
+    def forward(cache: FunctionCache, x: Tensor, rmean: Tensor, rvar: Tensor, w: Tensor, b: Tensor, m: float, eps: float,
+                training: bool) -> tuple[Tensor, Tensor, Tensor]:
+        if x.ndim != 4:
+            raise ShapeError(f"Expected input to be 4D, got {x.ndim}D.")
+        B, C, H, W = x.shape
+        return _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, B, C, H * W)
+
+    @staticmethod
+    def backward(cache: FunctionCache, dy: Tensor, dw_out=None, db_out=None) -> tuple[Tensor, Tensor, Tensor]:
+        return _bn_backward(cache, dy, dw_out, db_out)
+
+
+class BatchNorm1DFn(Function):
+    """(:10-70) statistics over (0,) for 2-D input, (0, 2) for 3-D input."""
+
+    @staticmethod
+    def forward(cache: FunctionCache, x: Tensor, rmean: Tensor, rvar: Tensor, w: Tensor, b: Tensor, m: float, eps: float,
+                training: bool) -> tuple[Tensor, Tensor, Tensor]:
+        if x.ndim not in {2, 3}:
+            raise ShapeError(f"Expected input to be 2D or 3D, got {x.ndim}D.")
+        N, C = x.shape[0], x.shape[1]
+        HW = x.shape[2] if x.ndim == 3 else 1
+        return _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW)
+
+    @staticmethod
+    def backward(cache: FunctionCache, dy: Tensor, dw_out=None, db_out=None) -> tuple[Tensor, Tensor, Tensor]:
+        return _bn_backward(cache, dy, dw_out, db_out)
+
+
+def batchnorm1d(x, rmean, rvar, w, b, m: float = 0.1, eps: float = 1e-5, training: bool = False):
+    return BatchNorm1DFn.forward(PseudoCache(), x, rmean, rvar, w, b, m, eps, training)
+
+
+def batchnorm2d(x, rmean, rvar, w, b, m: float = 0.1, eps: float = 1e-5, training: bool = False):
+    return BatchNorm2DFn.forward(PseudoCache(), x, rmean, rvar, w, b, m, eps, training)

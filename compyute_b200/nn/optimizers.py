@@ -1,0 +1,192 @@
+"""Optimizers with a fused multi-tensor step and batch-sharded data parallelism.
+
+API of compyute/nn/optimizers.py:14-92 (``Optimizer``), :95-176 (``SGD``), :179-271 (``Adam``), :274-362 (``AdamW``):
+same constructor arguments, ``step() / reset_grads() / get_state_dict() / load_state_dict()``, ``t`` starting at 1,
+state layout ``{i: {"m": Tensor, "v": Tensor}}``.  What changes is *how* a step runs:
+
+* one kernel launch updates every parameter (``cpt_adam_step`` / ``cpt_sgd_step`` over a device pointer table)
+  instead of ~12 launches and ~10 temporaries per parameter;
+* gradients live in one flat fp32 arena (``Parameter.grad_slot`` views; layers write dW/db straight into it), so
+  in data-parallel mode ``step()`` issues ONE sum all-reduce (NCCL over NVLink) on the arena and folds the 1/world
+  averaging into the update kernel's ``grad_scale`` (local CE gradients are already means over the local shard,
+  loss_funcs.py:69).
+
+``lr`` and ``t`` stay plain Python attributes read at every step, so LR schedulers keep working (Appendix A.17).
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Any, Iterable, Optional
+
+import numpy as np
+
+from .. import _lib, distributed
+from ..tensors import DeviceArray, Tensor, stream_ptr
+from .parameter import Parameter
+
+__all__ = ["Optimizer", "SGD", "Adam", "AdamW"]
+
+
+class Optimizer:
+    """Optimizer base class (optimizers.py:14-92)."""
+
+    _state_keys: tuple[str, ...] = ()
+
+    def __init__(self, parameters: Optional[Iterable[Parameter]] = None, lr: float = 1e-3) -> None:
+        self.lr = lr
+        self.t = 1
+        self._parameters: list[Parameter] = []
+        self._state: dict[int, dict[str, Tensor]] = {}
+        self._arena: Optional[DeviceArray] = None
+        self._table_dev: Optional[DeviceArray] = None
+        self._table_key: Optional[bytes] = None
+        if parameters is not None:
+            self.set_parameters(parameters)
+
+    # ---- reference API -------------------------------------------------------------------------
+    def set_parameters(self, parameters: Iterable[Parameter]) -> None:
+        """De-duplicates by ``p.ptr`` (optimizers.py:36-53) and lays out the flat gradient arena."""
+        seen: set[int] = set()
+        self._parameters = []
+        for p in parameters:
+            if p.ptr in seen:
+                continue
+            self._parameters.append(p)
+            seen.add(p.ptr)
+        self._state = {i: {} for i in range(len(self._parameters))}
+        self._build_arena()
+
+    def get_state_dict(self) -> dict[str, dict[Any, Any]]:
+        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key"}
+        return {"state": self._state, "vars": {k: v for k, v in vars(self).items() if k not in skip}}
+
+    def load_state_dict(self, state_dict: dict[str, dict[Any, Any]]) -> None:
+        self._state = state_dict["state"]
+        for k, v in state_dict["vars"].items():
+            setattr(self, k, v)
+        self._table_key = None
+
+    def reset_grads(self) -> None:
+        """``p.grad = None`` (optimizers.py:85-88); arena slots are simply overwritten by the next backward."""
+        for p in self._parameters:
+            p.grad = None
+
+    def step(self) -> None:
+        raise NotImplementedError
+
+    # ---- arena / pointer table -----------------------------------------------------------------
+    def _build_arena(self) -> None:
+        """One fp32 buffer holding every gradient, 64-element aligned slots.  Only for cuda parameters."""
+        self._arena = None
+        cuda_params = [p for p in self._parameters if isinstance(p.data, DeviceArray)]
+        if not cuda_params or len(cuda_params) != len(self._parameters):
+            return
+        offs, total = [], 0
+        for p in cuda_params:
+            offs.append(total)
+            total += (p.size + 63) // 64 * 64
+        self._arena = DeviceArray.zeros((total,), np.float32)
+        flat = self._arena._buf
+        for p, o in zip(cuda_params, offs):
+            p.grad_slot = DeviceArray(flat[o:o + p.size], p.shape, np.float32)
+
+    def _gather_grads_into_arena(self) -> None:
+        """A gradient that was assigned by hand (not written into its slot by a layer) is copied into the arena so
+        that the single all-reduce covers it."""
+        for p in self._parameters:
+            if p.grad is not None and p.grad_slot is not None and p.grad.data.ptr != p.grad_slot.ptr:
+                p.grad_slot.copy_from(p.grad.data)
+                p.grad = Tensor(p.grad_slot)
+
+    def _state_array(self, i: int, key: str, like: Parameter) -> DeviceArray:
+        st = self._state[i]
+        if key not in st:  # the reference starts from python 0.0 (optimizers.py:164, 256, 261): a zero buffer is identical
+            st[key] = Tensor(DeviceArray.zeros(like.shape, np.float32))
+        elif not isinstance(st[key].data, DeviceArray):
+            st[key] = st[key].to_device(like.device)
+        return st[key].data
+
+    def _table(self, keys: tuple[str, ...]) -> tuple[int, int, int]:
+        """Builds/refreshes the device pointer table; returns (table ptr, entries, max elements)."""
+        n = len(self._parameters)
+        entries = (_lib.ParamEntry * max(n, 1))()
+        max_n = 0
+        for i, p in enumerate(self._parameters):
+            if not isinstance(p.data, DeviceArray):
+                raise TypeError("compyute_b200 optimizers update cuda parameters only (no CPU fallback).")
+            e = entries[i]
+            e.p = p.data.ptr
+            if p.grad is None:
+                e.n = 0  # skipped like `if p.grad is None: continue`
+                continue
+            e.g = p.grad.data.ptr
+            e.m = self._state_array(i, keys[0], p).ptr if len(keys) > 0 else None
+            e.v = self._state_array(i, keys[1], p).ptr if len(keys) > 1 else None
+            e.n = p.size
+            max_n = max(max_n, p.size)
+        raw = bytes(entries)
+        if raw != self._table_key:  # pointers are stable with the arena: the upload happens once, not per step
+            host = np.frombuffer(raw, dtype=np.uint8).copy()
+            self._table_dev = DeviceArray.from_numpy(host)
+            self._table_key = raw
+        return self._table_dev.ptr, n, max_n
+
+    def _sync_grads(self) -> float:
+        """Data-parallel exchange: one SUM all-reduce of the gradient arena; returns the 1/world scale."""
+        world = distributed.world_size()
+        if world == 1:
+            return 1.0
+        if self._arena is None:
+            raise RuntimeError("data-parallel step needs cuda parameters (gradient arena missing)")
+        self._gather_grads_into_arena()
+        distributed.all_reduce_sum(self._arena)
+        return 1.0 / world
+
+
+class SGD(Optimizer):
+    """optimizers.py:95-176"""
+
+    def __init__(self, parameters: Optional[Iterable[Parameter]] = None, lr: float = 1e-3, momentum: float = 0.0,
+                 nesterov: bool = False, weight_decay: float = 0.0) -> None:
+        super().__init__(parameters, lr)
+        self.momentum, self.nesterov, self.weight_decay = momentum, nesterov, weight_decay
+
+    def step(self) -> None:
+        scale = self._sync_grads()
+        keys = ("v",) if self.momentum > 0.0 else ()
+        table, n, max_n = self._table(keys)
+        _lib.check(_lib.lib().cpt_sgd_step(table, n, max_n, float(self.lr), float(self.momentum), int(self.nesterov),
+                                           float(self.weight_decay), float(scale), stream_ptr()))
+        self.t += 1
+
+
+class Adam(Optimizer):
+    """optimizers.py:179-271"""
+
+    _decoupled = 0
+
+    def __init__(self, parameters: Optional[Iterable[Parameter]] = None, lr: float = 1e-3, beta1: float = 0.9,
+                 beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0) -> None:
+        super().__init__(parameters, lr)
+        self.beta1, self.beta2, self.eps, self.weight_decay = beta1, beta2, eps, weight_decay
+
+    def step(self) -> None:
+        scale = self._sync_grads()
+        m_div = 1.0 - self.beta1 ** self.t  # python double, like optimizers.py:243-244
+        v_div = 1.0 - self.beta2 ** self.t
+        table, n, max_n = self._table(("m", "v"))
+        _lib.check(_lib.lib().cpt_adam_step(table, n, max_n, float(self.lr), float(self.beta1), float(self.beta2),
+                                            float(self.eps), float(self.weight_decay), float(m_div), float(v_div),
+                                            float(scale), self._decoupled, stream_ptr()))
+        self.t += 1
+
+
+class AdamW(Adam):
+    """optimizers.py:274-362 (decoupled weight decay, default 1e-2)."""
+
+    _decoupled = 1
+
+    def __init__(self, parameters: Optional[Iterable[Parameter]] = None, lr: float = 1e-3, beta1: float = 0.9,
+                 beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 1e-2) -> None:
+        super().__init__(parameters, lr, beta1, beta2, eps, weight_decay)

@@ -1,0 +1,198 @@
+/*
+ * compyute_b200 — C ABI of the B200-native CNN-training hot path (libcompyute_b200.so).
+ *
+ * This is the drop-in boundary.  The reference (dakofler/Compyute v0.1.8) has no
+ * FFI layer: its operator interface is the Python `Function` protocol
+ * (compyute/nn/functional/functions.py:37-54) whose bodies call NumPy/CuPy through
+ * `Device.module` (compyute/backend.py:31,60).  Each entry point below replaces the array-library
+ * calls made by one reference `XxxFn.forward/backward`; the citation on each declaration is the
+ * reference code it stands in for.  `compyute_b200/_lib.py` binds them with ctypes; a maintainer
+ * of the reference would add the same stub.
+ *
+ * Conventions
+ *  - All tensor pointers are DEVICE pointers (e.g. CuPy `arr.data.ptr`, torch `t.data_ptr()`,
+ *    `__cuda_array_interface__['data'][0]`), fp32, C-contiguous, NCHW / OIHW, unless stated.
+ *  - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).  Every call
+ *    is asynchronous on `stream`; nothing allocates, synchronises or takes ownership.
+ *  - `ws` / `ws_bytes`: caller-owned scratch, size from the matching `*_workspace_size` call.
+ *  - `mode`: arithmetic of the contractions (CPT_MODE_*).  FP32 = exact fp32 FFMA (matches the
+ *    reference at 1e-5); TF32 / BF16 = tcgen05 tensor cores, fp32 accumulate (looser, stated
+ *    tolerances in tests/).
+ *  - Return value: 0 on success, a negative CPT_ERR_* otherwise; `cpt_last_error()` returns a
+ *    thread-local message.  Error mapping to the reference's exceptions is in INTEGRATION.md.
+ */
+#ifndef COMPYUTE_B200_H
+#define COMPYUTE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPT_OK 0
+#define CPT_ERR_INVALID (-1)     /* bad shape / argument          -> ShapeError / ValueError  */
+#define CPT_ERR_CUDA (-2)        /* CUDA runtime / driver failure -> CUDARuntimeError         */
+#define CPT_ERR_UNSUPPORTED (-3) /* configuration not implemented -> NotImplementedError      */
+#define CPT_ERR_WORKSPACE (-4)   /* ws_bytes too small            -> ValueError               */
+
+#define CPT_MODE_FP32 0
+#define CPT_MODE_TF32 1
+#define CPT_MODE_BF16 2
+
+#define CPT_OP_FPROP 0
+#define CPT_OP_DGRAD 1
+#define CPT_OP_WGRAD 2
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* cpt_last_error(void);
+int cpt_version(void);
+/* compyute/backend.py:69-86 (CUDA.properties / mem_info) */
+int cpt_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin,
+                    size_t* total_mem);
+
+/* ---- Conv2D: compyute/nn/functional/convolution_funcs.py:218-410 --------------------------- */
+typedef struct cpt_conv2d_desc {
+  int32_t B, Ci, H, W; /* input  (B, Ci, H, W)                                        */
+  int32_t Co, K;       /* filter (Co, Ci, K, K); square kernel like the reference      */
+  int32_t pad, stride, dil;
+} cpt_conv2d_desc;
+
+/* Output extent: Ho = (H + 2 pad - dil (K-1) - 1) / stride + 1 (shape_ops.py:297). */
+int cpt_conv2d_out_shape(const cpt_conv2d_desc* d, int* Ho, int* Wo);
+size_t cpt_conv2d_workspace_size(int op, const cpt_conv2d_desc* d, int mode);
+
+/* Conv2DFn.forward :222-241  (dilate f, pad x, window view, einsum 'biyxjk,oijk->boyx', + b).
+ * bias may be NULL.  y: (B, Co, Ho, Wo). */
+int cpt_conv2d_fprop(const cpt_conv2d_desc* d, const float* x, const float* w, const float* bias,
+                     float* y, int mode, void* ws, size_t ws_bytes, void* stream);
+/* RawConv2DFn.backward dx branch :390-403 + Pad2DFn.backward :351-355.  dx: (B, Ci, H, W). */
+int cpt_conv2d_dgrad(const cpt_conv2d_desc* d, const float* dy, const float* w, float* dx,
+                     int mode, void* ws, size_t ws_bytes, void* stream);
+/* RawConv2DFn.backward dW branch :405-408 + Dilation2DFn.backward :312-316 + db = dy.sum((0,2,3))
+ * :252.  db may be NULL.  dw: (Co, Ci, K, K), db: (Co,). */
+int cpt_conv2d_wgrad(const cpt_conv2d_desc* d, const float* x, const float* dy, float* dw,
+                     float* db, int mode, void* ws, size_t ws_bytes, void* stream);
+
+/* Tensor-core modes stage activations as channels-last (NHWC, C padded to a multiple of 8) in
+ * bf16 (BF16) or tf32-rounded fp32 (TF32) so that TMA im2col can feed tcgen05.  These expose the
+ * staging so a caller can keep x_cl from forward for wgrad (what Conv2DFn's cache does). */
+size_t cpt_channels_last_bytes(int B, int C, int H, int W, int mode);
+/* chan_sum (C floats, pre-zeroed) may be NULL; if given it accumulates the per-channel sum of
+ * src (fuses db = dy.sum((0,2,3)) into the staging pass). */
+int cpt_to_channels_last(const float* src, void* dst, int B, int C, int H, int W, int mode,
+                         float* chan_sum, void* stream);
+int cpt_conv2d_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w,
+                        const float* bias, float* y, int mode, void* ws, size_t ws_bytes,
+                        void* stream);
+int cpt_conv2d_dgrad_cl(const cpt_conv2d_desc* d, const void* dy_cl, const float* w, float* dx,
+                        int mode, void* ws, size_t ws_bytes, void* stream);
+int cpt_conv2d_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl, float* dw,
+                        int mode, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Linear: compyute/nn/functional/linear_funcs.py:11-35 ---------------------------------- */
+/* x: (N, In) (leading dims flattened), w: (Out, In), bias: (Out,) or NULL, y: (N, Out). */
+size_t cpt_linear_workspace_size(int op, int64_t N, int In, int Out, int mode);
+/* LinearFn.forward :15-23   y = x @ w.T (+ b) */
+int cpt_linear_fwd(const float* x, const float* w, const float* bias, float* y, int64_t N, int In,
+                   int Out, int mode, void* ws, size_t ws_bytes, void* stream);
+/* LinearFn.backward :31     dx = dy @ w */
+int cpt_linear_dgrad(const float* dy, const float* w, float* dx, int64_t N, int In, int Out,
+                     int mode, void* ws, size_t ws_bytes, void* stream);
+/* LinearFn.backward :32-33  dw = (dy.T @ x).sum(leading), db = dy.sum(leading); db may be NULL */
+int cpt_linear_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t N, int In,
+                     int Out, int mode, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Pooling: compyute/nn/functional/pooling_funcs.py -------------------------------------- */
+/* MaxPooling2DFn.forward :71-76 — stride = k, no padding, floor.  y: (B, C, H/k, W/k). */
+int cpt_maxpool2d_fwd(const float* x, float* y, int B, int C, int H, int W, int k, void* stream);
+/* MaxPooling2DFn.backward :79-82 — equality mask: every tied maximum receives dy; uncovered tail
+ * rows/cols get 0; non-selected positions are dy*0 (so -0.0 where dy < 0), bit-exact. */
+int cpt_maxpool2d_bwd(const float* x, const float* y, const float* dy, float* dx, int B, int C,
+                      int H, int W, int k, void* stream);
+/* AvgPooling2DFn :111-121 */
+int cpt_avgpool2d_fwd(const float* x, float* y, int B, int C, int H, int W, int k, void* stream);
+int cpt_avgpool2d_bwd(const float* dy, float* dx, int B, int C, int H, int W, int k, void* stream);
+
+/* ---- BatchNorm 1-D/2-D: compyute/nn/functional/normalization_funcs.py:10-177 ---------------- */
+/* x viewed as (N, C, HW): BatchNorm2D → (B, C, H*W); BatchNorm1D 2-D input → (B, C, 1), 3-D → (B, C, S).
+ * Training forward :139-147: batch mean / biased var for normalisation, running stats updated with
+ * the UNBIASED variance.  save_mean/save_rstd (C floats each) replace the reference's cached
+ * (std, x_norm): backward recomputes x_norm from x. */
+size_t cpt_bn_workspace_size(int N, int C, int HW);
+int cpt_bn_fwd_train(const float* x, const float* w, const float* b, const float* rmean,
+                     const float* rvar, float* y, float* rmean_out, float* rvar_out,
+                     float* save_mean, float* save_rstd, int N, int C, int HW, float m, float eps,
+                     void* ws, size_t ws_bytes, void* stream);
+/* Inference forward :148-152 (running stats). */
+int cpt_bn_fwd_eval(const float* x, const float* w, const float* b, const float* rmean,
+                    const float* rvar, float* y, float* save_mean, float* save_rstd, int N, int C,
+                    int HW, float eps, void* stream);
+/* backward :161-177: dx = w/(std n) (n dy − Σdy − x̂ Σ(dy x̂)), dw = Σ(dy x̂), db = Σdy. */
+int cpt_bn_bwd(const float* x, const float* dy, const float* w, const float* save_mean,
+               const float* save_rstd, float* dx, float* dw, float* db, int N, int C, int HW,
+               void* ws, size_t ws_bytes, void* stream);
+
+/* ---- activations / elementwise ------------------------------------------------------------- */
+/* ReLUFn.forward activation_funcs.py:26-29.  mask = bit-packed (y > 0), (n+7)/8 bytes; may be NULL. */
+int cpt_relu_fwd(const float* x, float* y, uint8_t* mask, int64_t n, void* stream);
+/* ReLUFn.backward :32-34   dx = dy * mask */
+int cpt_relu_bwd(const float* dy, const uint8_t* mask, float* dx, int64_t n, void* stream);
+/* a += b  (ResidualConnection containers.py:153-162; grad accumulation module.py:399-400) */
+int cpt_add_inplace(float* a, const float* b, int64_t n, void* stream);
+/* y = alpha * x (+ y if accumulate) */
+int cpt_axpby(float* y, const float* x, float alpha, int accumulate, int64_t n, void* stream);
+int cpt_fill(float* a, float value, int64_t n, void* stream);
+/* is_nan(x).any() without a host sync (module.py:332,366): ORs 1 into *flag when any NaN. */
+int cpt_isnan_flag(const float* x, int64_t n, int* flag, void* stream);
+/* out[0] = Σ x   (fp32 tree; used for loss/metric scalars) */
+int cpt_sum(const float* x, int64_t n, float* out, void* stream);
+
+/* ---- loss / regularisation (closing the train step on the device) ---------- */
+/* CrossEntropyLossFn.forward loss_funcs.py:57-64: probs = softmax(logits), loss = -mean log(p_t + eta).
+ * targets int32.  loss: 1 float (pre-zeroed by the call). */
+int cpt_softmax_ce_fwd(const float* logits, const int32_t* targets, float* probs, float* loss,
+                       int B, int NC, float eta, void* stream);
+/* backward :67-69: dlogits = (probs - onehot) / B */
+int cpt_softmax_ce_bwd(const float* probs, const int32_t* targets, float* dlogits, int B, int NC,
+                       void* stream);
+/* count of argmax(logits) == target → *correct (int, pre-zeroed by the call)  metric_funcs.py:10-25 */
+int cpt_accuracy_count(const float* logits, const int32_t* targets, int* correct, int B, int NC,
+                       void* stream);
+/* DropoutFn regularization_funcs.py:15-32; mask int8 Bernoulli(1-p) from a counter-based RNG. */
+int cpt_dropout_fwd(const float* x, float* y, int8_t* mask, int64_t n, float p, uint64_t seed,
+                    void* stream);
+int cpt_dropout_bwd(const float* dy, const int8_t* mask, float* dx, int64_t n, float p,
+                    void* stream);
+
+/* ---- optimizers: compyute/nn/optimizers.py --------------------------------------------------- */
+typedef struct cpt_param_entry {
+  float* p;       /* parameter, updated in place (optimizers.py:174,269) */
+  const float* g; /* gradient (already all-reduced SUM over ranks in DP mode) */
+  float* m;       /* Adam first moment / SGD velocity (may be NULL for plain SGD) */
+  float* v;       /* Adam second moment (NULL for SGD) */
+  int64_t n;      /* elements; 0 = skip (p.grad is None, optimizers.py:155,247) */
+} cpt_param_entry;
+
+/* Multi-tensor fused steps.  `table` is a DEVICE array of n_entries entries.  grad_scale
+ * multiplies every gradient first (1/world_size in data-parallel mode).
+ * Adam.step :241-271 (decoupled = 0), AdamW.step :335-362 (decoupled = 1).  m_div = 1 - beta1^t,
+ * v_div = 1 - beta2^t are computed by the caller in double like the reference (:243-244). */
+int cpt_adam_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, float m_div, float v_div,
+                  float grad_scale, int decoupled, void* stream);
+/* SGD.step :152-176 (momentum / nesterov / L2 weight decay). */
+int cpt_sgd_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr,
+                 float momentum, int nesterov, float weight_decay, float grad_scale,
+                 void* stream);
+
+/* ---- diagnostics ----------------------------------------------------------------------------- */
+/* Synchronises the device and returns (then clears) the tensor-core pipeline watchdog flag: 0 = healthy,
+ * non-zero = an mbarrier wait timed out inside a tcgen05 kernel (results invalid).  Test/debug helper. */
+int cpt_tc_check_status(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMPYUTE_B200_H */

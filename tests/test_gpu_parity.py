@@ -1,0 +1,381 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200 box): the CUDA path, called through the Python mirror of the
+reference API (which goes through the C ABI), against (a) golden vectors produced by the real reference and
+(b) the CPU oracle on seeded inputs.
+
+Tolerances: fp32 mode ``allclose(rtol=atol=1e-5)`` like the reference's own tests (tests/utils.py:54-60), db at 1e-4
+(convolutions_test.py:146); tf32 mode max-abs error <= 2e-3 * max|ref|; bf16 mode <= 1e-2 * max|ref| (fp32 accumulate,
+operands rounded to 10 / 7 mantissa bits); MaxPool y/dx bit-exact including ties, -0.0 and NaN."""
+import numpy as np
+import pytest
+
+from oracle import compyute_ref as R
+from tests.conftest import load_golden, manifest
+
+pytestmark = pytest.mark.gpu
+M = manifest()
+TOL = {"fp32": None, "tf32": 2e-3, "bf16": 1e-2}
+
+
+@pytest.fixture(scope="module")
+def cp():
+    import compyute_b200 as cp
+    from compyute_b200 import _lib
+    _lib.lib()
+    assert cp.gpu_available(), "no CUDA device"
+    return cp
+
+
+def close(a, ref, tol=1e-5):
+    a = a.to_numpy() if hasattr(a, "to_numpy") else a
+    return a.shape == ref.shape and np.allclose(a, ref, rtol=tol, atol=tol)
+
+
+def relerr(a, ref):
+    a = a.to_numpy() if hasattr(a, "to_numpy") else a
+    assert a.shape == ref.shape
+    return float(np.abs(a.astype(np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def check(a, ref, mode, tol32=1e-5):
+    if mode == "fp32":
+        assert close(a, ref, tol32), f"max abs err {np.abs((a.to_numpy() if hasattr(a, 'to_numpy') else a) - ref).max():.3e}"
+    else:
+        assert relerr(a, ref) <= TOL[mode], f"{mode}: rel err {relerr(a, ref):.3e}"
+
+
+def tc_ok():
+    from compyute_b200 import _lib
+    assert _lib.lib().cpt_tc_check_status() == 0, "tensor-core pipeline watchdog fired"
+
+
+# ------------------------------------------------------------------ Conv2D
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("case", M["conv2d"], ids=lambda c: f"conv{c['id']}")
+def test_conv2d_golden(cp, case, mode):
+    from compyute_b200.nn.functional import Conv2DFn, FunctionCache
+    g = load_golden("conv2d"); n = case["id"]
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    b = T(g[f"c{n}_b"]) if case["bias"] else None
+    with cp.compute_mode(mode):
+        c = FunctionCache()
+        y = Conv2DFn.forward(c, T(g[f"c{n}_x"]), T(g[f"c{n}_w"]), b, case["padding"], case["stride"], case["dilation"])
+        dx, dw, db = Conv2DFn.backward(c, T(g[f"c{n}_dy"]))
+    assert not c.cache
+    tc_ok()
+    check(y, g[f"c{n}_y"], mode); check(dx, g[f"c{n}_dx"], mode); check(dw, g[f"c{n}_dw"], mode)
+    assert (db is None) == (not case["bias"])
+    if db is not None:
+        check(db, g[f"c{n}_db"], mode, 1e-4)
+
+
+CONV_ORACLE = [  # (B, Ci, Co, H, K, pad, stride, dil, bias)
+    (4, 32, 64, 28, 3, 1, 1, 1, True), (2, 64, 64, 56, 3, 1, 1, 1, True), (3, 48, 80, 14, 3, 1, 1, 1, False),
+    (2, 16, 32, 16, 5, 2, 1, 1, True), (2, 64, 128, 16, 3, 1, 2, 1, True), (2, 64, 128, 16, 1, 0, 2, 1, False),
+    (2, 3, 64, 32, 7, 3, 2, 1, True), (2, 130, 70, 9, 3, 1, 1, 1, True), (1, 8, 8, 10, 3, 2, 1, 2, True),
+    (8, 1, 32, 28, 5, 0, 1, 1, True), (2, 256, 256, 8, 3, 1, 1, 1, True),
+]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("shape", CONV_ORACLE, ids=lambda s: "x".join(map(str, s[:8])))
+def test_conv2d_oracle(cp, shape, mode):
+    from compyute_b200.nn.functional import Conv2DFn, FunctionCache
+    B, Ci, Co, H, K, P, s, d, bias = shape
+    rng = np.random.RandomState(42)
+    x = rng.uniform(-0.1, 0.1, (B, Ci, H, H)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (Co, Ci, K, K)) * 0.1).astype(np.float32)
+    b = (rng.uniform(-1, 1, (Co,)) * 0.1).astype(np.float32) if bias else None
+    rc = []
+    y_ref = R.conv2d_forward(rc, x, w, b, P, s, d)
+    dy = rng.uniform(-0.1, 0.1, y_ref.shape).astype(np.float32)
+    dx_ref, dw_ref, db_ref = R.conv2d_backward(rc, dy)
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    with cp.compute_mode(mode):
+        c = FunctionCache()
+        y = Conv2DFn.forward(c, T(x), T(w), None if b is None else T(b), P, s, d)
+        dx, dw, db = Conv2DFn.backward(c, T(dy))
+    tc_ok()
+    check(y, y_ref, mode); check(dx, dx_ref, mode); check(dw, dw_ref, mode, 2e-5)
+    if bias:
+        check(db, db_ref, mode, 1e-4)
+
+
+def test_conv2d_errors(cp):
+    from compyute_b200.nn.functional import conv2d
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    with pytest.raises(cp.ShapeError):
+        conv2d(T(np.zeros((2, 3, 8), np.float32)), T(np.zeros((4, 3, 3, 3), np.float32)))
+    with pytest.raises(cp.ShapeError):
+        conv2d(T(np.zeros((2, 3, 8, 8), np.float32)), T(np.zeros((4, 2, 3, 3), np.float32)))
+    with pytest.raises(cp.DeviceError):
+        conv2d(cp.tensor(np.zeros((2, 3, 8, 8), np.float32)), cp.tensor(np.zeros((4, 3, 3, 3), np.float32)))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_conv2d_full_size_properties(cp, mode):
+    """BASELINE config 2 at full size (B=256, C=64, 56x56, 3x3 same): sampled outputs against fp64 dot products,
+    linearity in dy for the backward pass, and db == dy.sum by an independent reduction."""
+    from compyute_b200.nn.functional import Conv2DFn, FunctionCache
+    B, C, H, K = 256, 64, 56, 3
+    rng = np.random.RandomState(0)
+    x = rng.uniform(-0.1, 0.1, (B, C, H, H)).astype(np.float32)
+    w = rng.uniform(-0.04, 0.04, (C, C, K, K)).astype(np.float32)
+    b = rng.uniform(-0.04, 0.04, (C,)).astype(np.float32)
+    dy = rng.uniform(-0.1, 0.1, (B, C, H, H)).astype(np.float32)
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    tol = 1e-5 if mode == "fp32" else TOL[mode]
+    with cp.compute_mode(mode):
+        c = FunctionCache()
+        xt, wt, bt, dyt = T(x), T(w), T(b), T(dy)
+        y = Conv2DFn.forward(c, xt, wt, bt, 1, 1, 1)
+        dx, dw, db = Conv2DFn.backward(c, dyt)
+        c2 = FunctionCache()
+        Conv2DFn.forward(c2, xt, wt, bt, 1, 1, 1)
+        dx2, dw2, _ = Conv2DFn.backward(c2, T(2.0 * dy))
+    tc_ok()
+    yh, dxh, dwh = y.to_numpy(), dx.to_numpy(), dw.to_numpy()
+    xp = np.pad(x, ((0, 0), (0, 0), (1, 1), (1, 1))).astype(np.float64)
+    dyp = np.pad(dy, ((0, 0), (0, 0), (1, 1), (1, 1))).astype(np.float64)
+    wf = w.astype(np.float64)
+    scale_y, scale_dx = np.abs(yh).max(), np.abs(dxh).max()
+    for _ in range(200):
+        bi, o, p, q = rng.randint(B), rng.randint(C), rng.randint(H), rng.randint(H)
+        ref = (xp[bi, :, p:p + 3, q:q + 3] * wf[o]).sum() + b[o]
+        assert abs(yh[bi, o, p, q] - ref) <= tol * max(scale_y, 1.0) + (1e-5 if mode == "fp32" else 0) * abs(ref)
+        i = rng.randint(C)
+        ref = (dyp[bi, :, p:p + 3, q:q + 3] * wf[:, i, ::-1, ::-1]).sum()
+        assert abs(dxh[bi, i, p, q] - ref) <= tol * max(scale_dx, 1.0) + 1e-6
+    for _ in range(20):
+        o, i, j, k = rng.randint(C), rng.randint(C), rng.randint(K), rng.randint(K)
+        ref = (dy[:, o].astype(np.float64) * xp[:, i, j:j + H, k:k + H]).sum()
+        assert abs(dwh[o, i, j, k] - ref) <= (2e-5 if mode == "fp32" else tol) * max(np.abs(dwh).max(), abs(ref))
+    assert np.allclose(db.to_numpy(), dy.astype(np.float64).sum((0, 2, 3)), rtol=1e-4, atol=1e-3)
+    # linearity of the backward pass: bwd(2 dy) == 2 bwd(dy) exactly (power-of-two scaling commutes with rounding)
+    assert np.array_equal(dx2.to_numpy(), 2.0 * dxh) and np.allclose(dw2.to_numpy(), 2.0 * dwh, rtol=1e-6, atol=0)
+
+
+# ------------------------------------------------------------------ Linear
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("case", M["linear"], ids=lambda c: f"lin{c['id']}")
+def test_linear_golden(cp, case, mode):
+    from compyute_b200.nn.functional import FunctionCache, LinearFn
+    g = load_golden("linear"); n = case["id"]
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    with cp.compute_mode(mode):
+        c = FunctionCache()
+        y = LinearFn.forward(c, T(g[f"c{n}_x"]), T(g[f"c{n}_w"]), T(g[f"c{n}_b"]) if case["bias"] else None)
+        dx, dw, db = LinearFn.backward(c, T(g[f"c{n}_dy"]))
+    tc_ok()
+    check(y, g[f"c{n}_y"], mode); check(dx, g[f"c{n}_dx"], mode); check(dw, g[f"c{n}_dw"], mode)
+    if case["bias"]:
+        check(db, g[f"c{n}_db"], mode)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("shape", [(128, 576, 256, True), (300, 84, 10, True), (512, 1024, 768, False), (1000, 333, 130, True),
+                                   (4096, 512, 1000, True)], ids=str)
+def test_linear_oracle(cp, shape, mode):
+    from compyute_b200.nn.functional import FunctionCache, LinearFn
+    N, In, Out, bias = shape
+    rng = np.random.RandomState(1)
+    x = rng.uniform(-0.1, 0.1, (N, In)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (Out, In)) * 0.1).astype(np.float32)
+    b = (rng.uniform(-1, 1, (Out,)) * 0.1).astype(np.float32) if bias else None
+    dy = rng.uniform(-0.1, 0.1, (N, Out)).astype(np.float32)
+    rc = []
+    y_ref = R.linear_forward(rc, x, w, b)
+    dx_ref, dw_ref, db_ref = R.linear_backward(rc, dy)
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    with cp.compute_mode(mode):
+        c = FunctionCache()
+        y = LinearFn.forward(c, T(x), T(w), None if b is None else T(b))
+        dx, dw, db = LinearFn.backward(c, T(dy))
+    tc_ok()
+    check(y, y_ref, mode); check(dx, dx_ref, mode); check(dw, dw_ref, mode, 2e-5)
+    if bias:
+        check(db, db_ref, mode, 1e-4)
+
+
+# ------------------------------------------------------------------ Pooling
+@pytest.mark.parametrize("case", M["pool"], ids=lambda c: f"pool{c['id']}")
+def test_pool_golden(cp, case):
+    from compyute_b200.nn.functional import AvgPooling2DFn, FunctionCache, MaxPooling2DFn
+    g = load_golden("pool"); n = case["id"]
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    c = FunctionCache()
+    y = MaxPooling2DFn.forward(c, T(g[f"max{n}_x"]), case["k"])
+    dx = MaxPooling2DFn.backward(c, T(g[f"max{n}_dy"]))
+    assert np.array_equal(y.to_numpy(), g[f"max{n}_y"])
+    assert np.array_equal(dx.to_numpy(), g[f"max{n}_dx"])  # bit-exact tie mask
+    assert np.array_equal(np.signbit(dx.to_numpy()), np.signbit(g[f"max{n}_dx"]))  # incl. -0.0
+    y = AvgPooling2DFn.forward(c, T(g[f"avg{n}_x"]), case["k"])
+    dx = AvgPooling2DFn.backward(c, T(g[f"avg{n}_dy"]))
+    assert close(y, g[f"avg{n}_y"]) and np.array_equal(dx.to_numpy(), g[f"avg{n}_dx"])
+
+
+def test_maxpool_nan_and_large(cp):
+    from compyute_b200.nn.functional import FunctionCache, MaxPooling2DFn
+    g = load_golden("pool")
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    c = FunctionCache()
+    y = MaxPooling2DFn.forward(c, T(g["nan_x"]), 2)
+    dx = MaxPooling2DFn.backward(c, T(g["nan_dy"]))
+    assert np.array_equal(y.to_numpy(), g["nan_y"], equal_nan=True) and np.array_equal(dx.to_numpy(), g["nan_dx"])
+    rng = np.random.RandomState(3)
+    for shape, k in [((16, 32, 28, 28), 2), ((16, 32, 28, 28), 3), ((8, 64, 112, 112), 2), ((4, 8, 30, 30), 4), ((3, 5, 9, 7), 2)]:
+        x = np.round(rng.uniform(-2, 2, shape), 1).astype(np.float32)  # coarse grid -> plenty of ties
+        rc = []
+        y_ref = R.maxpool2d_forward(rc, x, k) if shape[2] == shape[3] else None
+        if y_ref is None:  # the reference is square-only (Appendix A.2): restate per-dim for the non-square superset
+            Ho, Wo = shape[2] // k, shape[3] // k
+            y_ref = x[:, :, :Ho * k, :Wo * k].reshape(shape[0], shape[1], Ho, k, Wo, k).max((3, 5))
+            dy = rng.uniform(-1, 1, y_ref.shape).astype(np.float32)
+            up = lambda a: np.pad(np.repeat(np.repeat(a, k, 2), k, 3), ((0, 0), (0, 0), (0, shape[2] - Ho * k), (0, shape[3] - Wo * k)))
+            dx_ref = up(dy) * (up(y_ref) == x)
+        else:
+            dy = rng.uniform(-1, 1, y_ref.shape).astype(np.float32)
+            dx_ref = R.maxpool2d_backward(rc, dy)
+        c = FunctionCache()
+        y = MaxPooling2DFn.forward(c, T(x), k)
+        dx = MaxPooling2DFn.backward(c, T(dy))
+        assert np.array_equal(y.to_numpy(), y_ref) and np.array_equal(dx.to_numpy(), dx_ref)
+        assert np.array_equal(np.signbit(dx.to_numpy()), np.signbit(dx_ref))
+
+
+# ------------------------------------------------------------------ BatchNorm / ReLU / CE / dropout
+@pytest.mark.parametrize("case", M["batchnorm"], ids=lambda c: f"bn{c['id']}")
+def test_batchnorm_golden(cp, case):
+    from compyute_b200.nn.functional import BatchNorm1DFn, BatchNorm2DFn, FunctionCache
+    g = load_golden("batchnorm"); n = case["id"]; k = lambda s: g[f"c{n}_{s}"]
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    Fn = BatchNorm2DFn if len(case["shape"]) == 4 else BatchNorm1DFn
+    c = FunctionCache()
+    y, rm, rv = Fn.forward(c, T(k("x")), T(k("rmean")), T(k("rvar")), T(k("w")), T(k("b")), case["m"], case["eps"], case["training"])
+    dx, dw, db = Fn.backward(c, T(k("dy")))
+    assert close(y, k("y")) and close(rm, k("rmean2")) and close(rv, k("rvar2"))
+    assert close(dx, k("dx")) and close(dw, k("dw")) and close(db, k("db"))
+
+
+@pytest.mark.parametrize("shape", [(8, 16, 32, 32), (16, 32, 64, 64), (32, 64, 56, 56), (128, 256), (64, 84), (16, 12, 50), (5, 3, 7, 9)], ids=str)
+def test_batchnorm_oracle(cp, shape):
+    from compyute_b200.nn.functional import BatchNorm1DFn, BatchNorm2DFn, FunctionCache
+    rng = np.random.RandomState(5)
+    C = shape[1]
+    x = (rng.normal(2.0, 1.5, shape)).astype(np.float32)  # |mean| > std: exercises the shifted-sum variance
+    w, b = rng.uniform(0.5, 1.5, C).astype(np.float32), rng.uniform(-0.5, 0.5, C).astype(np.float32)
+    rmean, rvar = rng.uniform(-0.2, 0.2, C).astype(np.float32), rng.uniform(0.5, 1.5, C).astype(np.float32)
+    dy = rng.uniform(-0.1, 0.1, shape).astype(np.float32)
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    Fn = BatchNorm2DFn if len(shape) == 4 else BatchNorm1DFn
+    for training in (True, False):
+        rc = []
+        y_ref, rm_ref, rv_ref = R.batchnorm_forward(rc, x, rmean, rvar, w, b, 0.1, 1e-5, training)
+        dx_ref, dw_ref, db_ref = R.batchnorm_backward(rc, dy)
+        c = FunctionCache()
+        y, rm, rv = Fn.forward(c, T(x), T(rmean), T(rvar), T(w), T(b), 0.1, 1e-5, training)
+        dx, dw, db = Fn.backward(c, T(dy))
+        assert close(y, y_ref, 2e-5) and close(rm, rm_ref) and close(rv, rv_ref)
+        assert close(dx, dx_ref, 2e-5) and close(dw, dw_ref, 1e-4) and close(db, db_ref, 1e-4)
+
+
+def test_relu_dropout_ce(cp):
+    from compyute_b200.nn.functional import CrossEntropyLossFn, DropoutFn, FunctionCache, ReLUFn, accuracy_score
+    g = load_golden("misc")
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    c = FunctionCache()
+    y = ReLUFn.forward(c, T(g["relu_x"]))
+    dx = ReLUFn.backward(c, T(g["relu_dy"]))
+    assert np.array_equal(y.to_numpy(), g["relu_y"]) and np.array_equal(dx.to_numpy(), g["relu_dx"])
+    rng = np.random.RandomState(0)
+    for n in (1, 7, 8, 1000, 12345):  # vector body + tail
+        x = rng.normal(0, 1, (n,)).astype(np.float32); dy = rng.normal(0, 1, (n,)).astype(np.float32)
+        y = ReLUFn.forward(c, T(x)); dx = ReLUFn.backward(c, T(dy))
+        assert np.array_equal(y.to_numpy(), np.maximum(x, 0)) and np.array_equal(dx.to_numpy(), dy * (x > 0))
+    for n in range(2):
+        loss = CrossEntropyLossFn.forward(c, T(g[f"ce{n}_logits"]), T(g[f"ce{n}_targets"]), 1e-8)
+        d = CrossEntropyLossFn.backward(c)
+        assert abs(loss.item() - float(g[f"ce{n}_loss"])) <= 1e-5 * max(1.0, abs(float(g[f"ce{n}_loss"])))
+        assert close(d, g[f"ce{n}_dlogits"])
+        acc = accuracy_score(T(g[f"ce{n}_logits"]), T(g[f"ce{n}_targets"]))
+        assert acc == float((g[f"ce{n}_logits"].argmax(-1) == g[f"ce{n}_targets"]).mean())
+    # dropout: statistical contract + exact backward/forward consistency with the mask it drew
+    x = np.ones((64, 1024), np.float32)
+    y = DropoutFn.forward(c, T(x), 0.25, True).to_numpy()
+    kept = (y != 0).mean()
+    assert abs(kept - 0.75) < 0.01 and np.allclose(y[y != 0], 1 / 0.75)
+    dx = DropoutFn.backward(c, T(2 * x)).to_numpy()
+    assert np.array_equal(dx != 0, y != 0) and np.allclose(dx[dx != 0], 2 / 0.75)
+    assert DropoutFn.forward(c, T(x), 0.25, False).to_numpy().sum() == x.sum()
+    DropoutFn.backward(c, T(x))
+
+
+# ------------------------------------------------------------------ optimizers / model-level trace
+@pytest.mark.parametrize("case", M["optim"], ids=lambda c: f"opt{c['id']}_{c['name']}")
+def test_optim_golden(cp, case):
+    from compyute_b200 import nn
+    g = load_golden("optim"); n = case["id"]
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    params = [nn.Parameter(T(g[f"c{n}_init_{j}"])) for j in range(2)]
+    O = {"sgd": nn.optimizers.SGD, "adam": nn.optimizers.Adam, "adamw": nn.optimizers.AdamW}[case["name"]]
+    o = O(params, **case["kw"])
+    for step in range(5):
+        for j, p in enumerate(params):
+            p.grad = T(g[f"c{n}_g{step}_{j}"])
+        o.step()
+        for j, p in enumerate(params):
+            assert close(p, g[f"c{n}_p{step}_{j}"], 1e-5 if case["name"] != "sgd" else 1e-4), (step, j)
+    assert o.t == 6
+
+
+def build_trace_model(cp, nn):
+    return nn.Sequential(nn.Conv2D(2, 4, 3, padding="same"), nn.BatchNorm2D(4), nn.ReLU(), nn.MaxPooling2D(2),
+                         nn.Conv2D(4, 6, 3, padding="valid", bias=False), nn.ReLU(), nn.Flatten(), nn.Linear(6 * 2 * 2, 5))
+
+
+def test_train_trace_golden(cp):
+    """Two Adam steps of a small CNN through the module API reproduce the reference's losses, logits and final
+    state dict (same keys, same order)."""
+    from compyute_b200 import nn
+    g = load_golden("train_trace")
+    with cp.use_device(cp.cuda):
+        model = build_trace_model(cp, nn)
+    keys = list(model.get_state_dict().keys())
+    assert keys == M["train_trace"][0]["keys"]
+    sd = model.get_state_dict()
+    for k in keys:
+        sd[k].data = cp.tensor(g[f"init_{k}"], device=cp.cuda).data
+    model.training()
+    loss_fn = nn.CrossEntropyLoss(); opt = nn.optimizers.Adam(model.get_parameters(), lr=1e-2)
+    x, t = cp.tensor(g["x"], device=cp.cuda), cp.tensor(g["t"], device=cp.cuda)
+    for step in range(2):
+        y = model(x); loss = loss_fn(y, t)
+        opt.reset_grads(); model.backward(loss_fn.backward()); opt.step()
+        assert close(y, g[f"logits{step}"], 2e-5)
+        assert abs(loss.item() - float(g[f"loss{step}"])) < 1e-5
+    for k, v in model.get_state_dict().items():
+        assert close(v, g[f"final_{k}"], 5e-5), k
+    assert all(not m.fcache.cache for m in model.get_modules())
+
+
+def test_residual_and_inference(cp):
+    from compyute_b200 import nn
+    np.random.seed(0)
+    with cp.use_device(cp.cuda):
+        block = nn.ResidualConnection(nn.Conv2D(4, 4, 3, padding="same"), nn.BatchNorm2D(4), nn.ReLU(),
+                                      nn.Conv2D(4, 4, 3, padding="same"))
+        proj = nn.ResidualConnection(nn.Conv2D(4, 8, 3, padding=1, stride=2), residual_proj=nn.Conv2D(4, 8, 1, stride=2))
+    rng = np.random.RandomState(0)
+    x = rng.normal(0, 1, (2, 4, 8, 8)).astype(np.float32)
+    for m in (block, proj):
+        m.training()
+        y = m(cp.tensor(x, device=cp.cuda))
+        dx = m.backward(cp.tensor(np.ones(y.shape, np.float32), device=cp.cuda))
+        assert dx.shape == x.shape and np.isfinite(dx.to_numpy()).all()
+        m.inference()
+        m(cp.tensor(x, device=cp.cuda))
+        with pytest.raises(AttributeError):
+            m.backward(cp.tensor(np.ones(y.shape, np.float32), device=cp.cuda))
+    # residual identity: y = f(x) + x
+    block.inference()
+    fx = block.residual_block(cp.tensor(x, device=cp.cuda)).to_numpy()
+    assert np.allclose(block(cp.tensor(x, device=cp.cuda)).to_numpy(), fx + x, atol=1e-6)

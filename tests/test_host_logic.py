@@ -1,0 +1,151 @@
+"""CPU-only tests: the C ABI exports what include/*.h declares, host-side protocol logic (cache, module registry,
+state dict, optimizer bookkeeping), and the no-fallback guarantees.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import compyute_b200 as cp
+from compyute_b200 import _lib, nn
+from compyute_b200.nn.functional import FunctionCache, PseudoCache, conv2d, no_caching, relu
+
+
+def test_abi_symbols_match_header():
+    protos = _lib.parse_header()
+    assert len(protos) >= 40
+    dll = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(dll, name), f"{name} declared in include/compyute_b200.h but not exported"
+    # every extern "C" cpt_* symbol of the library is declared in the header (no undocumented entry points)
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (cpt_\w+)", out))
+    assert exported == set(protos), exported ^ set(protos)
+    lib = _lib.lib()
+    assert lib.cpt_version() == 100 and lib.cpt_last_error() is not None
+
+
+def test_abi_argument_validation_without_gpu():
+    """Argument errors are reported before any CUDA work, so they are testable on a CPU box."""
+    lib = _lib.lib()
+    d = _lib.ConvDesc(2, 3, 8, 8, 4, 3, 1, 1, 1)
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    assert lib.cpt_conv2d_out_shape(ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo)) == 0 and (ho.value, wo.value) == (8, 8)
+    d2 = _lib.ConvDesc(2, 3, 8, 8, 4, 3, 0, 2, 2)
+    lib.cpt_conv2d_out_shape(ctypes.byref(d2), ctypes.byref(ho), ctypes.byref(wo))
+    assert (ho.value, wo.value) == (2, 2)  # (8 - 2*2 - 1)//2 + 1
+    bad = _lib.ConvDesc(2, 3, 2, 2, 4, 5, 0, 1, 1)
+    assert lib.cpt_conv2d_out_shape(ctypes.byref(bad), ctypes.byref(ho), ctypes.byref(wo)) == _lib.ERR_INVALID
+    assert b"larger than padded input" in lib.cpt_last_error()
+    assert lib.cpt_maxpool2d_fwd(None, None, 1, 1, 2, 2, 3, None) == _lib.ERR_INVALID
+    assert lib.cpt_conv2d_workspace_size(_lib.OP_WGRAD, ctypes.byref(d), _lib.MODE_FP32) > 0
+    assert lib.cpt_channels_last_bytes(2, 3, 8, 8, _lib.MODE_BF16) >= 2 * 8 * 8 * 8 * 2
+    with pytest.raises(cp.ShapeError):
+        _lib.check(_lib.ERR_INVALID)
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.ERR_UNSUPPORTED)
+
+
+def test_no_cpu_fallback():
+    x = cp.tensor(np.zeros((2, 3, 8, 8), np.float32))
+    w = cp.tensor(np.zeros((4, 3, 3, 3), np.float32))
+    assert x.device == cp.cpu
+    with pytest.raises(cp.DeviceError):
+        conv2d(x, w)
+    with pytest.raises(cp.DeviceError):
+        relu(x)
+    # nothing in the product package imports the oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dp, _, files in os.walk(os.path.join(root, "compyute_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+\.*oracle", src, re.M), f"{f} imports the oracle"
+
+
+def test_function_cache_protocol():
+    c = FunctionCache()
+    c.push(1, 2); c.push("a")
+    assert c.pop() == ("a",) and c.pop() == (1, 2)
+    with no_caching():
+        c.push(3)
+    assert not c.cache
+    p = PseudoCache(); p.push(1)
+    assert not p.cache
+
+
+def test_module_registry_state_dict_and_modes():
+    np.random.seed(0)
+    m = nn.Sequential(nn.Conv2D(1, 2, 3, padding="same"), nn.BatchNorm2D(2), nn.ReLU(), nn.MaxPooling2D(2), nn.Flatten(),
+                      nn.Linear(8, 3, bias=False))
+    keys = list(m.get_state_dict().keys())
+    assert keys == ["layers.0.w", "layers.0.b", "layers.1.w", "layers.1.b", "layers.1.rmean", "layers.1.rvar", "layers.5.w"]
+    assert len(list(m.get_parameters())) == 5 and len(list(m.get_buffers())) == 2 and m.n_modules == 6
+    conv = m.layers[0]
+    assert conv.padding == 1 and conv.w.shape == (2, 1, 3, 3) and abs(conv.w.to_numpy()).max() <= 1 / 3
+    assert nn.Conv2D(1, 1, 4, padding="same", dilation=2).padding == (4 * 2 - 1) // 2
+    # default init is the reference's: first draw of U(-k, k) from numpy's legacy stream
+    np.random.seed(0); w0 = np.random.uniform(-1 / 3, 1 / 3, (2, 1, 3, 3)).astype(np.float32)
+    assert np.array_equal(conv.w.to_numpy(), w0)
+    bn = m.layers[1]
+    assert np.array_equal(bn.w.to_numpy(), np.ones(2)) and np.array_equal(bn.rvar.to_numpy(), np.ones(2))
+    m.inference()
+    assert all(isinstance(x.fcache, PseudoCache) and not x.is_training for x in m.get_modules())
+    with pytest.raises(AttributeError):
+        m.backward(cp.tensor(np.zeros((1, 3), np.float32)))
+    m.training()
+    assert all(type(x.fcache) is FunctionCache for x in m.get_modules())
+    # load_state_dict: ordered, key-checked, rebinding .data
+    m2 = nn.Sequential(nn.Conv2D(1, 2, 3, padding="same"), nn.BatchNorm2D(2), nn.ReLU(), nn.MaxPooling2D(2), nn.Flatten(),
+                       nn.Linear(8, 3, bias=False))
+    m2.load_state_dict(m.get_state_dict())
+    assert m2.layers[0].w.data is m.layers[0].w.data
+    with pytest.raises(ValueError):
+        nn.Sequential(nn.BatchNorm2D(2)).load_state_dict(m.get_state_dict())
+    with pytest.raises(nn.EmptyContainerError):
+        nn.Sequential()
+    m.trainable = False
+    p = m.layers[5].w
+    m.layers[5].update_parameter_grad(p, cp.tensor(np.ones(p.shape, np.float32)))
+    assert p.grad is None
+    m.trainable = True
+    g = cp.tensor(np.ones(p.shape, np.float32))
+    m.layers[5].update_parameter_grad(p, g)
+    assert p.grad is g  # first grad stored by reference
+    m.layers[5].update_parameter_grad(p, cp.tensor(np.ones(p.shape, np.float32)))
+    assert p.grad is g and np.array_equal(g.to_numpy(), 2 * np.ones(p.shape))  # later ones accumulate in place
+    m.clean()
+    assert p.grad is None
+    with pytest.raises(TypeError):
+        nn.Parameter(cp.tensor(np.zeros(3, np.int32)))
+
+
+def test_optimizer_bookkeeping():
+    p = nn.Parameter(cp.tensor(np.ones((2, 2), np.float32)))
+    q = nn.Parameter(cp.tensor(np.ones(3, np.float32)))
+    o = nn.optimizers.Adam([p, q, p], lr=0.5)
+    assert len(o._parameters) == 2 and o.t == 1 and o._state == {0: {}, 1: {}}
+    sd = o.get_state_dict()
+    assert set(sd) == {"state", "vars"} and sd["vars"]["lr"] == 0.5 and sd["vars"]["beta1"] == 0.9 and "t" in sd["vars"]
+    o2 = nn.optimizers.Adam([p, q]); o2.load_state_dict({"state": {0: {}, 1: {}}, "vars": {"lr": 0.25, "t": 7}})
+    assert o2.lr == 0.25 and o2.t == 7
+    p.grad = cp.tensor(np.ones((2, 2), np.float32)); o.reset_grads()
+    assert p.grad is None
+    p.grad = cp.tensor(np.ones((2, 2), np.float32))
+    with pytest.raises(TypeError):  # host parameters: no CPU fallback
+        o.step()
+    assert nn.optimizers.AdamW([p]).weight_decay == 1e-2 and nn.optimizers.SGD([p]).momentum == 0.0
+
+
+def test_compute_mode_context():
+    assert cp.get_compute_mode() == _lib.MODE_FP32
+    with cp.compute_mode("bf16"):
+        assert cp.get_compute_mode() == _lib.MODE_BF16
+        with cp.compute_mode("tf32"):
+            assert cp.get_compute_mode() == _lib.MODE_TF32
+    assert cp.get_compute_mode() == _lib.MODE_FP32
+    with cp.use_device(cp.cuda):
+        assert cp.select_device(None) == cp.cuda
+    assert cp.select_device(None) == cp.cpu
