@@ -1,0 +1,360 @@
+"""bench.py — headline benchmark of the Compyute CNN-training hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode bf16|tf32|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], the one the "Conv2D fwd+bwd TFLOP/s" half of the metric is quoted on):
+``Conv2D(C, C, 3, padding="same")`` for C in {64, 128, 256, 512}, x = (256, C, 56, 56) fp32 NCHW.  One *step* =
+forward + backward (dX, dW, db) of all four layers on one batch + the optimizer step (SGD; in data-parallel runs the
+gradient arena is all-reduced first).  ``value`` = algorithmic FLOPs of the step (6·B·Co·Ci·Ho·Wo·K² per layer,
+SURVEY §8d) ÷ device time, summed over ranks (weak scaling: every rank has its own batch of 256).
+
+Prints ONE JSON line (rank 0).  See the task contract for the keys; extra keys: ``images_per_s``, ``per_layer``,
+``modes`` (the other compute modes measured after the timed region), ``tolerance``.
+
+``--impl reference`` times the CPU oracle port (oracle/compyute_ref.py: the reference's as_strided+einsum algorithm,
+NumPy) on a bounded sample of the same workload — the reference itself is pure Python and cannot travel to the GPU
+box, so kind = "port".
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SWEEP = (64, 128, 256, 512)
+BATCH, HW, KS = 256, 56, 3
+TOL = {"fp32": "allclose rtol=atol=1e-5 vs the NumPy reference (db 1e-4)", "tf32": "max-abs err <= 2e-3*max|ref|",
+       "bf16": "max-abs err <= 1e-2*max|ref|"}
+
+
+def layer_flops(C: int, B: int) -> float:
+    return 6.0 * B * C * C * HW * HW * KS * KS
+
+
+def peaks() -> dict:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "hbm_gbs": p["hbm_gbs"], "source": "MEASURED_PEAKS.json (measured)"}
+    except Exception:
+        return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU oracle arm
+def cpu_conv_sample(budget_s: float, reps: int = 1):
+    """Times the oracle port (reference algorithm, NumPy) on a bounded sample of the sweep.  Returns
+    (tflops, sample description, seconds per rep)."""
+    from oracle import compyute_ref as R
+    # the einsum path runs at ~0.5 GFLOP/s whatever the shape: size the sample to the budget
+    cands = [((64, 2), (128, 1)), ((64, 2),), ((64, 1),)]
+    est = lambda s: sum(layer_flops(C, b) for C, b in s) / 0.45e9
+    sample = next((s for s in cands if est(s) <= budget_s), cands[-1])
+    rng = np.random.RandomState(0)
+    data = []
+    for C, b in sample:
+        k = 1.0 / np.sqrt(C * KS * KS)
+        data.append((rng.normal(0, 1, (b, C, HW, HW)).astype(np.float32), rng.uniform(-k, k, (C, C, KS, KS)).astype(np.float32),
+                     rng.uniform(-k, k, (C,)).astype(np.float32), rng.uniform(-0.1, 0.1, (b, C, HW, HW)).astype(np.float32)))
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for x, w, b, dy in data:
+            cache = []
+            R.conv2d_forward(cache, x, w, b, 1, 1, 1)
+            R.conv2d_backward(cache, dy)
+        times.append(time.perf_counter() - t0)
+    fl = sum(layer_flops(C, b) for C, b in sample)
+    desc = "Conv2D 3x3 same 56x56 fwd+bwd, " + " + ".join(f"C={C} at B={b}" for C, b in sample) + " (oracle port: as_strided + numpy.einsum, single-threaded like the reference)"
+    return fl / min(times) / 1e12, desc, times
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = max(5.0, 150.0 / (args.steps + args.warmup))
+    tf, desc, _ = cpu_conv_sample(budget, 1)  # warm-up + sizing
+    vals = []
+    t_all = time.perf_counter()
+    for _ in range(args.warmup - 1 if args.warmup > 1 else 0):
+        cpu_conv_sample(budget, 1)
+    for _ in range(args.steps):
+        v, desc, _ = cpu_conv_sample(budget, 1)
+        vals.append(v)
+    value = float(np.median(vals))
+    sample_flops = None
+    line = {"impl": "reference", "metric": "conv2d_fwd_bwd_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t_all) / max(1, args.steps + max(0, args.warmup - 1)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, "n/a (CPU)"),
+            "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": 1, "host_cores": os.cpu_count(), "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, mode: str) -> dict:
+    return {"workload": "BASELINE configs[1]: single Conv2D layer fwd+bwd sweep, C_in=C_out in {64,128,256,512}, 3x3 same, 56x56, "
+                        "batch 256 per GPU, fp32 NCHW in/out, + SGD step (DP: gradient-arena all-reduce)",
+            "batch_per_gpu": BATCH, "channels": list(SWEEP), "compute_mode": mode, "tolerance": TOL.get(mode, "n/a"),
+            "l2_policy": "inputs larger than L2 (x, dy >= 205 MB per layer vs 126 MB L2)", "parallelism": f"dp{args.gpus}"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args) -> None:
+    import torch
+
+    import compyute_b200 as cp
+    from compyute_b200 import _lib, distributed, nn
+
+    L = _lib.lib()  # no fallback: raises if the CUDA library is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        distributed.init("nccl")
+    dev = cp.cuda
+    rng = np.random.RandomState(1234 + rank)
+
+    def make_layers(mode):
+        np.random.seed(0)  # identical weights on every rank
+        with cp.use_device(dev):
+            layers = [nn.Conv2D(C, C, KS, padding="same") for C in SWEEP]
+        for l in layers:
+            l.training()
+        opt = nn.optimizers.SGD([p for l in layers for p in l.get_parameters()], lr=1e-3)
+        return layers, opt
+
+    # device-resident inputs (value) and pinned host copies (e2e)
+    xs = [torch.randn(BATCH, C, HW, HW, device="cuda", generator=torch.Generator("cuda").manual_seed(10 + rank)) for C in SWEEP]
+    dys = [torch.empty(BATCH, C, HW, HW, device="cuda").uniform_(-0.1, 0.1) for C in SWEEP]
+    from compyute_b200.tensors import DeviceArray, Tensor
+    wrap = lambda t: Tensor(DeviceArray(t, tuple(t.shape), np.float32))
+    x_t, dy_t = [wrap(t) for t in xs], [wrap(t) for t in dys]
+
+    probe = {"ev": [], "C": 512}
+    orig_fprop = L.cpt_conv2d_fprop_cl
+
+    def fprop_probe(d, *a):  # CUDA events on the launching stream around the dominant kernel's C-ABI call
+        dd = d._obj if hasattr(d, "_obj") else d
+        if probe.get("on") and dd.Ci == probe["C"]:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = orig_fprop(d, *a); e1.record()
+            probe["ev"].append((e0, e1))
+            return r
+        return orig_fprop(d, *a)
+
+    def step(layers, opt):
+        opt.reset_grads()
+        for l, x, dy in zip(layers, x_t, dy_t):
+            l(x)
+            l.backward(dy)
+        opt.step()
+
+    def timed(layers, opt, steps, warmup, with_probe=False):
+        for _ in range(warmup):
+            step(layers, opt)
+        torch.cuda.synchronize()
+        if world > 1:
+            distributed.barrier()
+        probe["on"] = with_probe
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = L.cpt_launch_count()
+        e0.record()
+        for _ in range(steps):
+            step(layers, opt)
+        e1.record()
+        torch.cuda.synchronize()
+        probe["on"] = False
+        if world > 1:
+            distributed.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, L.cpt_launch_count() - n0
+
+    step_flops = sum(layer_flops(C, BATCH) for C in SWEEP)
+    pk = peaks()
+    sampler = ClockSampler(local)
+    results = {}
+    with cp.compute_mode(args.mode):
+        L.cpt_conv2d_fprop_cl = fprop_probe if args.mode != "fp32" else orig_fprop
+        layers, opt = make_layers(args.mode)
+        if rank == 0:
+            sampler.start()
+        ms, launches = timed(layers, opt, args.steps, args.warmup, with_probe=True)
+        clocks = sampler.stop() if rank == 0 else {}
+        L.cpt_conv2d_fprop_cl = orig_fprop
+        status = L.cpt_tc_check_status()
+        # per-layer device times (separate short pass, for the report)
+        per_layer = {}
+        for l, x, dy, C in zip(layers, x_t, dy_t, SWEEP):
+            def one():
+                l(x); l.backward(dy)
+            for _ in range(2):
+                one()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                one()
+            e1.record(); torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) / 3
+            per_layer[f"C{C}"] = {"ms_fwd_bwd": round(t, 4), "tflops": round(layer_flops(C, BATCH) / t / 1e9, 1)}
+
+        # ---- end to end through the public API with HOST buffers (pinned): H2D of x, w, b, dy; D2H of y, dx, dw, db
+        e2e = None
+        if rank == 0 or world > 1:
+            e2e_steps = max(1, min(args.steps, 2))
+            Cmax = max(SWEEP)
+            pin = lambda *s: torch.empty(*s, dtype=torch.float32).pin_memory()
+            hx, hdy, hy, hdx = (pin(BATCH * Cmax * HW * HW) for _ in range(4))
+            hx.normal_(); hdy.uniform_(-0.1, 0.1)
+            hw, hb, hdw, hdb = pin(Cmax * Cmax * KS * KS), pin(Cmax), pin(Cmax * Cmax * KS * KS), pin(Cmax)
+            hw.uniform_(-0.01, 0.01); hb.uniform_(-0.01, 0.01)
+            h2d = d2h = 0
+
+            def e2e_step(count=False):
+                nonlocal h2d, d2h
+                from compyute_b200.nn.functional import Conv2DFn, FunctionCache
+                for C in SWEEP:
+                    n, nw = BATCH * C * HW * HW, C * C * KS * KS
+                    dx_ = torch.empty(BATCH, C, HW, HW, device="cuda"); dx_.copy_(hx[:n].view(BATCH, C, HW, HW), non_blocking=True)
+                    dg_ = torch.empty(BATCH, C, HW, HW, device="cuda"); dg_.copy_(hdy[:n].view(BATCH, C, HW, HW), non_blocking=True)
+                    dw_ = torch.empty(C, C, KS, KS, device="cuda"); dw_.copy_(hw[:nw].view(C, C, KS, KS), non_blocking=True)
+                    db_ = torch.empty(C, device="cuda"); db_.copy_(hb[:C], non_blocking=True)
+                    c = FunctionCache()
+                    y = Conv2DFn.forward(c, wrap(dx_), wrap(dw_), wrap(db_), 1, 1, 1)
+                    gx, gw, gb = Conv2DFn.backward(c, wrap(dg_))
+                    hy[:n].copy_(y.data._buf.view(-1), non_blocking=True)
+                    hdx[:n].copy_(gx.data._buf.view(-1), non_blocking=True)
+                    hdw[:nw].copy_(gw.data._buf.view(-1), non_blocking=True)
+                    hdb[:C].copy_(gb.data._buf.view(-1), non_blocking=True)
+                    if count:
+                        h2d += 4 * (2 * n + nw + C); d2h += 4 * (2 * n + nw + C)
+                torch.cuda.synchronize()
+
+            e2e_step()
+            if world > 1:
+                distributed.barrier()
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                e2e_step(count=(i == 0))
+            dt = (time.perf_counter() - t0) / e2e_steps
+            if world > 1:
+                t = torch.tensor([dt], device="cuda")
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                dt = float(t.item())
+            e2e = {"value": round(world * step_flops / dt / 1e12, 3), "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "steps": e2e_steps, "note": "Conv2DFn.forward/backward per layer with pinned host buffers: H2D x,w,b,dy and D2H y,dx,dw,db inside the timed region"}
+            del hx, hdy, hy, hdx
+
+    # ---- other compute modes (outside the headline timed region; same step, fewer iterations)
+    modes = {}
+    if rank == 0 and world == 1 and not args.no_extra_modes:
+        for m, (k, w) in {"bf16": (3, 2), "tf32": (3, 2), "fp32": (1, 1)}.items():
+            if m == args.mode:
+                continue
+            with cp.compute_mode(m):
+                lay, op = make_layers(m)
+                mms, _ = timed(lay, op, k, w)
+            modes[m] = {"tflops": round(step_flops / mms / 1e9, 1), "ms_per_step": round(mms, 3), "tolerance": TOL[m]}
+
+    if rank != 0:
+        return
+    # dominant kernel: tc_kernel<bf16, OP_CONV, BN=256> for the C=512 fprop (same kernel runs dgrad)
+    roof = None
+    if probe["ev"]:
+        kms = float(np.mean([a.elapsed_time(b) for a, b in probe["ev"]]))
+        fl = layer_flops(512, BATCH) / 3.0
+        ach = fl / kms / 1e9
+        roof = {"bound": "tensor", "kernel": "tc_kernel<BF16,K-major,K-major,BN=256,OP_CONV> (C=512 fprop; includes the <1% weight re-layout launch)",
+                "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": round(ach / pk["bf16_tflops"], 4),
+                "frac_of_sustained": round(ach / pk["bf16_tflops_sustained"], 4) if pk.get("bf16_tflops_sustained") else None,
+                "peak_source": pk["source"] + " (burst cuBLAS bf16)", "ms_per_launch": round(kms, 4), "launches_timed": len(probe["ev"]),
+                "flops_per_launch": fl, "traffic": None}
+    cpu_tf, cpu_desc, cpu_times = cpu_conv_sample(12.0, 1)
+    value = world * step_flops / ms / 1e9
+    line = {"metric": "conv2d_fwd_bwd_tflops", "value": round(value, 2), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.mode], "data": "synthetic",
+            "config": workload_config(args, args.mode), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": {"value": round(cpu_tf, 7), "unit": "TFLOP/s", "cores": 1, "host_cores": os.cpu_count(),
+                                                "kind": "port", "sample": cpu_desc, "seconds": round(cpu_times[0], 2)},
+            "images_per_s": round(world * BATCH * len(SWEEP) / (ms / 1e3), 1), "frac_of_bf16_peak": round(value / world / pk["bf16_tflops"], 4),
+            "per_layer": per_layer, "modes": modes, "tc_watchdog": int(status)}
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("COMPYUTE_B200_MODE", "bf16"), choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--no-extra-modes", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

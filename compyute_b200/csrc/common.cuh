@@ -17,6 +17,9 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // number of SMs of the current device (cached)
 int sm_count();
 
+// kernels launched by this library since load (what bench.py reports as gpu_launches)
+void count_launch();
+
 #define CPT_REQUIRE(cond, code, ...)   \
   do {                                 \
     if (!(cond)) {                     \
@@ -33,6 +36,7 @@ int sm_count();
 
 #define CPT_LAUNCH_CHECK(name)                                       \
   do {                                                               \
+    ::cpt::count_launch();                                           \
     cudaError_t _e = cudaGetLastError();                             \
     if (_e != cudaSuccess) return ::cpt::cuda_fail(_e, name);        \
   } while (0)

@@ -21,6 +21,9 @@ int cuda_fail(cudaError_t e, const char* what) {
   return CPT_ERR_CUDA;
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 int sm_count() {
   static int cached[16] = {0};
   int dev = 0;
@@ -166,6 +169,7 @@ extern "C" {
 
 const char* cpt_last_error(void) { return g_err; }
 int cpt_version(void) { return 100; }
+uint64_t cpt_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int cpt_device_info(int device, int* sm, int* major, int* minor, size_t* smem_optin, size_t* total_mem) {
   cudaDeviceProp p;

@@ -152,6 +152,7 @@ inline cudaError_t sg_launch(const P& p, int splits, cudaStream_t st) {
   if (k_per_split < SG_BK) k_per_split = SG_BK;
   dim3 grid((p.M + SG_BM - 1) / SG_BM, (p.N + SG_BN - 1) / SG_BN, splits);
   simt_gemm_kernel<P><<<grid, SG_THREADS, 0, st>>>(p, k_per_split);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -40,8 +40,13 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // 2-D tiled map over a row-major [rows][cols] matrix with `pitch` elements per row; box = (box_cols, box_rows)
+// mn_major: the tile feeds an MN-major UMMA operand; for 32-bit elements that needs the 32-byte-atom 128B swizzle
+static inline CUtensorMapSwizzle swizzle_of(int mode, bool mn_major) {
+  return (mn_major && mode != CPT_MODE_BF16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+}
+
 static int make_map_2d(CUtensorMap* m, const void* base, int mode, uint64_t cols, uint64_t rows, uint64_t pitch, int box_cols,
-                       int box_rows) {
+                       int box_rows, bool mn_major = false) {
   if (int e = load_driver()) return e;
   const int es = esize(mode);
   CPT_REQUIRE(((uintptr_t)base & 15) == 0 && (pitch * es) % 16 == 0, CPT_ERR_UNSUPPORTED,
@@ -53,7 +58,7 @@ static int make_map_2d(CUtensorMap* m, const void* base, int mode, uint64_t cols
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode_tiled(m, mode == CPT_MODE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                               const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              swizzle_of(mode, mn_major), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CPT_REQUIRE(r == CUDA_SUCCESS, CPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) cols=%llu rows=%llu pitch=%llu box=%dx%d", (int)r,
               (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch, box_cols, box_rows);
   return CPT_OK;
@@ -63,7 +68,7 @@ static int make_map_2d(CUtensorMap* m, const void* base, int mode, uint64_t cols
 // Bounding box of the *base pixel* in input coordinates: [lower, extent - 1 + upper] per spatial dim, walked with
 // `stride`; the filter-tap offset is added per load (PTX {off_w, off_h}).  Out-of-bounds reads are zero-filled.
 static int make_map_im2col(CUtensorMap* m, const void* base, int mode, int Cp, int W, int H, int N, int lower, int upper_w,
-                           int upper_h, int stride, int channels_per_pixel, int pixels_per_column) {
+                           int upper_h, int stride, int channels_per_pixel, int pixels_per_column, bool mn_major = false) {
   if (int e = load_driver()) return e;
   const int es = esize(mode);
   CPT_REQUIRE(((uintptr_t)base & 15) == 0 && ((size_t)Cp * es) % 16 == 0, CPT_ERR_UNSUPPORTED, "im2col TMA alignment");
@@ -77,7 +82,7 @@ static int make_map_im2col(CUtensorMap* m, const void* base, int mode, int Cp, i
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = g_encode_im2col(m, mode == CPT_MODE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                                const_cast<void*>(base), dims, strides, lo, hi, (cuuint32_t)channels_per_pixel,
-                               (cuuint32_t)pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               (cuuint32_t)pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(mode, mn_major),
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CPT_REQUIRE(r == CUDA_SUCCESS, CPT_ERR_CUDA,
               "cuTensorMapEncodeIm2col failed (%d) C=%d W=%d H=%d N=%d lo=%d hi=%d,%d stride=%d cpp=%d ppc=%d", (int)r, Cp, W, H, N,
@@ -351,10 +356,10 @@ int conv_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl,
   TcParams p{};
   const int upper = g.P - (g.K - 1) * g.D;
   // A: x_cl through im2col, lanes = input channels (MN-major), reduction = output pixels
-  if (int e = make_map_im2col(&p.tmA, x_cl, mode, round_up(g.Ci, 8), g.W, g.H, g.B, -g.P, upper, upper, g.S, kc, bk)) return e;
+  if (int e = make_map_im2col(&p.tmA, x_cl, mode, round_up(g.Ci, 8), g.W, g.H, g.B, -g.P, upper, upper, g.S, kc, bk, true)) return e;
   // B: dy_cl as [pixels][Cop], columns = output channels (MN-major)
   const int Cop = round_up(g.Co, 8);
-  if (int e = make_map_2d(&p.tmB, dy_cl, mode, Cop, (uint64_t)pixels, Cop, kc, bk)) return e;
+  if (int e = make_map_2d(&p.tmB, dy_cl, mode, Cop, (uint64_t)pixels, Cop, kc, bk, true)) return e;
   p.out = reinterpret_cast<float*>(ws);
   p.bias = nullptr;
   p.bias_mode = BIAS_NONE;
@@ -501,7 +506,7 @@ int linear_dgrad(const float* dy, const float* w, float* dx, int64_t N, int In, 
   const int kc = kc_of(mode), BN = pick_bn(N);
   TcParams p{};
   // dx[n][i]: lanes = i.  A(m=i, k=o) = w[o][i]: MN-major over the [Out][In] matrix; B = dy [N][Out] K-major
-  if (int e = make_map_2d(&p.tmA, wa, mode, In, Out, wpitch, kc, kc)) return e;
+  if (int e = make_map_2d(&p.tmA, wa, mode, In, Out, wpitch, kc, kc, true)) return e;
   if (int e = make_map_2d(&p.tmB, ga, mode, Out, (uint64_t)N, gpitch, kc, BN)) return e;
   p.out = dx; p.bias = nullptr; p.bias_mode = BIAS_NONE;
   if (int e = get_status_ptr(&p.status)) return e;
@@ -539,8 +544,8 @@ int linear_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t 
   const size_t part_bytes = align_up((size_t)(splits > 1 ? splits : 0) * Out * In * sizeof(float), 1024);
   TcParams p{};
   // dw[o][i]: lanes = i.  A(m=i, k=n) = x[n][i] MN-major; B(col=o, k=n) = dy[n][o] MN-major
-  if (int e = make_map_2d(&p.tmA, xa, mode, In, (uint64_t)N, xpitch, kc, bk)) return e;
-  if (int e = make_map_2d(&p.tmB, ga, mode, Out, (uint64_t)N, gpitch, kc, bk)) return e;
+  if (int e = make_map_2d(&p.tmA, xa, mode, In, (uint64_t)N, xpitch, kc, bk, true)) return e;
+  if (int e = make_map_2d(&p.tmB, ga, mode, Out, (uint64_t)N, gpitch, kc, bk, true)) return e;
   p.out = splits > 1 ? partial : dw; p.bias = nullptr; p.bias_mode = BIAS_NONE;
   if (int e = get_status_ptr(&p.status)) return e;
   p.M = In; p.N = Out;

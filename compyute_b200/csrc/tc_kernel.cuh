@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
   constexpr uint32_t IDESC = make_idesc(BF16, A_MN, B_MN, 128, BN);
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   constexpr uint32_t CHUNK_BYTES = E::BK * 128;  // one MN-major chunk: BK k-rows x 128 B
+  constexpr uint32_t MN_SBO = BF16 ? 1024u : 512u;
+  constexpr uint32_t MN_LAYOUT = BF16 ? 2u : 1u;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -190,9 +192,10 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
           // K-major: advance 32 B inside the 128-B swizzle row; MN-major: advance UMMA_K k-rows (x128 B)
-          const uint64_t da = A_MN ? make_smem_desc(sa + s * (E::UMMA_K * 128), CHUNK_BYTES, 1024)
+          // MN-major tf32 uses the 32-byte-atom swizzle: k-groups of 4 rows (512 B) instead of 8 rows (1024 B)
+          const uint64_t da = A_MN ? make_smem_desc(sa + s * (E::UMMA_K * 128), CHUNK_BYTES, MN_SBO, MN_LAYOUT)
                                    : make_smem_desc(sa + s * 32, 16, 1024);
-          const uint64_t db = B_MN ? make_smem_desc(sb + s * (E::UMMA_K * 128), CHUNK_BYTES, 1024)
+          const uint64_t db = B_MN ? make_smem_desc(sb + s * (E::UMMA_K * 128), CHUNK_BYTES, MN_SBO, MN_LAYOUT)
                                    : make_smem_desc(sb + s * 32, 16, 1024);
           umma<BF16>(d_tmem, da, db, IDESC, (uint32_t)((i | s) != 0));
         }

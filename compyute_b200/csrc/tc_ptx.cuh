@@ -121,10 +121,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor, SWIZZLE_128B (PTX ISA "tcgen05 matrix descriptor"):
-//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type
+//   layout 2 = SWIZZLE_128B (16-byte atoms, 8-row period); layout 1 = SWIZZLE_128B_BASE32B (32-byte atoms, 4-row
+//   period) — the only swizzled layout the hardware accepts for MN-major 32-bit (tf32) operands.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 // Instruction descriptor (kind::f16 / kind::tf32, fp32 accumulate):
 //   [4,6) D fmt (1 = f32) | [7,10) A fmt | [10,13) B fmt (1 = bf16, 2 = tf32) | 15 A MN-major | 16 B MN-major |

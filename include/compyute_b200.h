@@ -191,6 +191,8 @@ int cpt_sgd_step(const cpt_param_entry* table, int n_entries, int64_t max_n, flo
 /* Synchronises the device and returns (then clears) the tensor-core pipeline watchdog flag: 0 = healthy,
  * non-zero = an mbarrier wait timed out inside a tcgen05 kernel (results invalid).  Test/debug helper. */
 int cpt_tc_check_status(void);
+/* Number of kernels this library has launched since it was loaded (bench.py's gpu_launches). */
+uint64_t cpt_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -214,8 +214,9 @@ def main() -> None:
     from compyute.nn import (BatchNorm2D, Conv2D, CrossEntropyLoss, Flatten, Linear, MaxPooling2D, ReLU, Sequential)
     from compyute.nn.optimizers import Adam
     cp.random.set_seed(3)
-    model = Sequential(Conv2D(2, 4, 3, padding="same"), BatchNorm2D(4), ReLU(), MaxPooling2D(2),
-                       Conv2D(4, 6, 3, padding="valid", bias=False), ReLU(), Flatten(), Linear(6 * 2 * 2, 5))
+    # (no conv bias in front of BatchNorm: its gradient is exactly-zero-plus-rounding-noise, which Adam amplifies to +-lr)
+    model = Sequential(Conv2D(2, 4, 3, padding="same", bias=False), BatchNorm2D(4), ReLU(), MaxPooling2D(2),
+                       Conv2D(4, 6, 3, padding="valid"), ReLU(), Flatten(), Linear(6 * 2 * 2, 5))
     cp.random.set_seed(None)
     model.training()
     tr = {f"init_{k}": v.to_numpy().copy() for k, v in model.get_state_dict().items()}

@@ -328,8 +328,8 @@ def test_optim_golden(cp, case):
 
 
 def build_trace_model(cp, nn):
-    return nn.Sequential(nn.Conv2D(2, 4, 3, padding="same"), nn.BatchNorm2D(4), nn.ReLU(), nn.MaxPooling2D(2),
-                         nn.Conv2D(4, 6, 3, padding="valid", bias=False), nn.ReLU(), nn.Flatten(), nn.Linear(6 * 2 * 2, 5))
+    return nn.Sequential(nn.Conv2D(2, 4, 3, padding="same", bias=False), nn.BatchNorm2D(4), nn.ReLU(), nn.MaxPooling2D(2),
+                         nn.Conv2D(4, 6, 3, padding="valid"), nn.ReLU(), nn.Flatten(), nn.Linear(6 * 2 * 2, 5))
 
 
 def test_train_trace_golden(cp):
