@@ -102,39 +102,94 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// NCHW fp32 -> NHWC (C padded to Cp) bf16 / tf32-rounded fp32.  Tile = 64 channels x 32 pixels through smem:
-// reads are 128 B per channel row, writes 128 B (bf16) / 256 B (fp32) per pixel.  8 B/elem (bf16: 6 B/elem).
+// NCHW fp32 -> NHWC (C padded to Cp) bf16 / tf32-rounded fp32 — HBM-bound staging pass (6 B/elem bf16, 8 B/elem tf32).
+// Tile = 64 channels x 128 pixels through shared memory, every access conflict-free and 128-byte coalesced:
+//   load : lanes run along pixels (each warp reads 4 x 128 B of one channel row; 32 independent loads per thread)
+//   store: lanes run along channels (each warp writes the 128 B / 2 x 128 B of one pixel)
+// BF16 packs channel pairs into 32-bit words before the transpose, so the smem tile is [32 pairs][129] words and
+// both phases hit 32 distinct banks.  chan_sum (optional) fuses db = dy.sum((0,2,3)): warp-shuffle tree + one atomic
+// per (block, channel).
+constexpr int CL_PX = 128, CL_CH = 64;
+
 template <bool BF16>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW,
                                                            int Cp, float* __restrict__ chan_sum) {
-  __shared__ float tile[64][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 64, b = blockIdx.z;
+  __shared__ uint32_t tile[BF16 ? 32 : 64][CL_PX + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * CL_PX, c0 = blockIdx.y * CL_CH, b = blockIdx.z;
   const float* s = src + (int64_t)b * C * HW;
+  if (BF16) {
+    float v0[4][4], v1[4][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = ty + 8 * i, c = c0 + r, px = p0 + tx;
-    float v = 0.f;
-    if (c < C && px < HW) v = s[(int64_t)c * HW + px];
-    tile[r][tx] = v;
-    if (chan_sum) {
-      const float t = warp_sum(v);
-      if (tx == 0 && c < C) atomicAdd(chan_sum + c, t);
+    for (int ci = 0; ci < 4; ++ci) {
+      const int c = c0 + 2 * (warp + 8 * ci);
+#pragma unroll
+      for (int pi = 0; pi < 4; ++pi) {
+        const int px = p0 + lane + 32 * pi;
+        const bool okp = px < HW;
+        v0[ci][pi] = (okp && c < C) ? s[(int64_t)c * HW + px] : 0.f;
+        v1[ci][pi] = (okp && c + 1 < C) ? s[(int64_t)(c + 1) * HW + px] : 0.f;
+      }
     }
-  }
-  __syncthreads();
-  const int ch = c0 + 2 * tx;
-  if (ch < Cp) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pp = ty + 8 * i, px = p0 + pp;
-      if (px < HW) {
-        const float v0 = tile[2 * tx][pp], v1 = tile[2 * tx + 1][pp];
-        const int64_t o = ((int64_t)b * HW + px) * Cp + ch;
-        if (BF16) {
-          *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(dst) + o) = __floats2bfloat162_rn(v0, v1);
-        } else {
-          *reinterpret_cast<float2*>(reinterpret_cast<float*>(dst) + o) = make_float2(round_tf32(v0), round_tf32(v1));
+    for (int ci = 0; ci < 4; ++ci) {
+      const int cp = warp + 8 * ci;
+#pragma unroll
+      for (int pi = 0; pi < 4; ++pi) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v0[ci][pi], v1[ci][pi]);
+        tile[cp][lane + 32 * pi] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      if (chan_sum) {
+        const float s0 = warp_sum((v0[ci][0] + v0[ci][1]) + (v0[ci][2] + v0[ci][3]));
+        const float s1 = warp_sum((v1[ci][0] + v1[ci][1]) + (v1[ci][2] + v1[ci][3]));
+        const int c = c0 + 2 * cp;
+        if (lane == 0) {
+          if (c < C) atomicAdd(chan_sum + c, s0);
+          if (c + 1 < C) atomicAdd(chan_sum + c + 1, s1);
+        }
+      }
+    }
+    __syncthreads();
+    const int c = c0 + 2 * lane;  // this lane's channel pair
+    if (c < Cp) {
+      uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int pp = warp + 8 * i, px = p0 + pp;
+        if (px < HW) d[(((int64_t)b * HW + px) * Cp + c) >> 1] = tile[lane][pp];
+      }
+    }
+  } else {
+    float v[8][4];
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) {
+      const int c = c0 + warp + 8 * ci;
+#pragma unroll
+      for (int pi = 0; pi < 4; ++pi) {
+        const int px = p0 + lane + 32 * pi;
+        v[ci][pi] = (px < HW && c < C) ? s[(int64_t)c * HW + px] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) {
+      const int cl = warp + 8 * ci;
+#pragma unroll
+      for (int pi = 0; pi < 4; ++pi) tile[cl][lane + 32 * pi] = __float_as_uint(round_tf32(v[ci][pi]));
+      if (chan_sum) {
+        const float s0 = warp_sum((v[ci][0] + v[ci][1]) + (v[ci][2] + v[ci][3]));
+        if (lane == 0 && c0 + cl < C) atomicAdd(chan_sum + c0 + cl, s0);
+      }
+    }
+    __syncthreads();
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + lane + 32 * h;
+      if (c < Cp) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int pp = warp + 8 * i, px = p0 + pp;
+          if (px < HW) d[((int64_t)b * HW + px) * Cp + c] = tile[lane + 32 * h][pp];
         }
       }
     }
@@ -268,7 +323,7 @@ static int wgrad_splits(const G& g, int mode) {
 
 int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, int mode, float* chan_sum, cudaStream_t st) {
   const int Cp = round_up(C, 8), HW = H * W;
-  dim3 grid((HW + 31) / 32, (Cp + 63) / 64, B);
+  dim3 grid((HW + CL_PX - 1) / CL_PX, (Cp + CL_CH - 1) / CL_CH, B);
   CPT_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CPT_ERR_UNSUPPORTED, "to_channels_last: grid too large");
   if (mode == CPT_MODE_BF16) nchw_to_nhwc_kernel<true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum);
   else nchw_to_nhwc_kernel<false><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum);

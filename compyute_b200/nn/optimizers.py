@@ -41,6 +41,7 @@ class Optimizer:
         self._arena: Optional[DeviceArray] = None
         self._table_dev: Optional[DeviceArray] = None
         self._table_key: Optional[bytes] = None
+        self._data_parallel = True  # all-reduce gradients in step() whenever a process group with world > 1 exists
         if parameters is not None:
             self.set_parameters(parameters)
 
@@ -58,7 +59,7 @@ class Optimizer:
         self._build_arena()
 
     def get_state_dict(self) -> dict[str, dict[Any, Any]]:
-        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key"}
+        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel"}
         return {"state": self._state, "vars": {k: v for k, v in vars(self).items() if k not in skip}}
 
     def load_state_dict(self, state_dict: dict[str, dict[Any, Any]]) -> None:
@@ -134,7 +135,7 @@ class Optimizer:
 
     def _sync_grads(self) -> float:
         """Data-parallel exchange: one SUM all-reduce of the gradient arena; returns the 1/world scale."""
-        world = distributed.world_size()
+        world = distributed.world_size() if self._data_parallel else 1
         if world == 1:
             return 1.0
         if self._arena is None:
