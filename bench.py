@@ -326,7 +326,10 @@ def run_ours(args) -> None:
                 "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": round(ach / pk["bf16_tflops"], 4),
                 "frac_of_sustained": round(ach / pk["bf16_tflops_sustained"], 4) if pk.get("bf16_tflops_sustained") else None,
                 "peak_source": pk["source"] + " (burst cuBLAS bf16)", "ms_per_launch": round(kms, 4), "launches_timed": len(probe["ev"]),
-                "flops_per_launch": fl, "traffic": None}
+                "flops_per_launch": fl,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture
+                # (profiles/r01_conv512_ncu_summary.md); algorithmic bytes = 2.47e9 (x_cl bf16 + y fp32 + filters)
+                "traffic": 3.254e9, "algorithmic_bytes": 2.47e9}
     cpu_tf, cpu_desc, cpu_times = cpu_conv_sample(12.0, 1)
     value = world * step_flops / ms / 1e9
     line = {"metric": "conv2d_fwd_bwd_tflops", "value": round(value, 2), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,

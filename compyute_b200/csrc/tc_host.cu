@@ -116,82 +116,88 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
                                                            int Cp, float* __restrict__ chan_sum) {
   __shared__ uint32_t tile[BF16 ? 32 : 64][CL_PX + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int p0 = blockIdx.x * CL_PX, c0 = blockIdx.y * CL_CH, b = blockIdx.z;
+  const int c0 = blockIdx.y * CL_CH, b = blockIdx.z;
+  const int n_tiles = (HW + CL_PX - 1) / CL_PX;
   const float* s = src + (int64_t)b * C * HW;
-  if (BF16) {
-    float v0[4][4], v1[4][4];
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+  float acc[8];  // per-thread channel partial sums, reduced once per block (not once per tile)
 #pragma unroll
-    for (int ci = 0; ci < 4; ++ci) {
-      const int c = c0 + 2 * (warp + 8 * ci);
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int p0 = t * CL_PX;
+    if (BF16) {
+      float v0[4][4], v1[4][4];
 #pragma unroll
-      for (int pi = 0; pi < 4; ++pi) {
-        const int px = p0 + lane + 32 * pi;
-        const bool okp = px < HW;
-        v0[ci][pi] = (okp && c < C) ? s[(int64_t)c * HW + px] : 0.f;
-        v1[ci][pi] = (okp && c + 1 < C) ? s[(int64_t)(c + 1) * HW + px] : 0.f;
-      }
-    }
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = c0 + 2 * (warp + 8 * ci);
 #pragma unroll
-    for (int ci = 0; ci < 4; ++ci) {
-      const int cp = warp + 8 * ci;
-#pragma unroll
-      for (int pi = 0; pi < 4; ++pi) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(v0[ci][pi], v1[ci][pi]);
-        tile[cp][lane + 32 * pi] = *reinterpret_cast<uint32_t*>(&h);
-      }
-      if (chan_sum) {
-        const float s0 = warp_sum((v0[ci][0] + v0[ci][1]) + (v0[ci][2] + v0[ci][3]));
-        const float s1 = warp_sum((v1[ci][0] + v1[ci][1]) + (v1[ci][2] + v1[ci][3]));
-        const int c = c0 + 2 * cp;
-        if (lane == 0) {
-          if (c < C) atomicAdd(chan_sum + c, s0);
-          if (c + 1 < C) atomicAdd(chan_sum + c + 1, s1);
+        for (int pi = 0; pi < 4; ++pi) {
+          const int px = p0 + lane + 32 * pi;
+          const bool okp = px < HW;
+          v0[ci][pi] = (okp && c < C) ? s[(int64_t)c * HW + px] : 0.f;
+          v1[ci][pi] = (okp && c + 1 < C) ? s[(int64_t)(c + 1) * HW + px] : 0.f;
         }
       }
-    }
-    __syncthreads();
-    const int c = c0 + 2 * lane;  // this lane's channel pair
-    if (c < Cp) {
-      uint32_t* d = reinterpret_cast<uint32_t*>(dst);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int pp = warp + 8 * i, px = p0 + pp;
-        if (px < HW) d[(((int64_t)b * HW + px) * Cp + c) >> 1] = tile[lane][pp];
+      for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll
+        for (int pi = 0; pi < 4; ++pi) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v0[ci][pi], v1[ci][pi]);
+          tile[warp + 8 * ci][lane + 32 * pi] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        acc[2 * ci] += (v0[ci][0] + v0[ci][1]) + (v0[ci][2] + v0[ci][3]);
+        acc[2 * ci + 1] += (v1[ci][0] + v1[ci][1]) + (v1[ci][2] + v1[ci][3]);
       }
-    }
-  } else {
-    float v[8][4];
-#pragma unroll
-    for (int ci = 0; ci < 8; ++ci) {
-      const int c = c0 + warp + 8 * ci;
-#pragma unroll
-      for (int pi = 0; pi < 4; ++pi) {
-        const int px = p0 + lane + 32 * pi;
-        v[ci][pi] = (px < HW && c < C) ? s[(int64_t)c * HW + px] : 0.f;
-      }
-    }
-#pragma unroll
-    for (int ci = 0; ci < 8; ++ci) {
-      const int cl = warp + 8 * ci;
-#pragma unroll
-      for (int pi = 0; pi < 4; ++pi) tile[cl][lane + 32 * pi] = __float_as_uint(round_tf32(v[ci][pi]));
-      if (chan_sum) {
-        const float s0 = warp_sum((v[ci][0] + v[ci][1]) + (v[ci][2] + v[ci][3]));
-        if (lane == 0 && c0 + cl < C) atomicAdd(chan_sum + c0 + cl, s0);
-      }
-    }
-    __syncthreads();
-    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int c = c0 + lane + 32 * h;
+      __syncthreads();
+      const int c = c0 + 2 * lane;  // this lane's channel pair
       if (c < Cp) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int pp = warp + 8 * i, px = p0 + pp;
-          if (px < HW) d[((int64_t)b * HW + px) * Cp + c] = tile[lane + 32 * h][pp];
+          if (px < HW) d[(((int64_t)b * HW + px) * Cp + c) >> 1] = tile[lane][pp];
         }
       }
+    } else {
+      float v[8][4];
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) {
+        const int c = c0 + warp + 8 * ci;
+#pragma unroll
+        for (int pi = 0; pi < 4; ++pi) {
+          const int px = p0 + lane + 32 * pi;
+          v[ci][pi] = (px < HW && c < C) ? s[(int64_t)c * HW + px] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) {
+#pragma unroll
+        for (int pi = 0; pi < 4; ++pi) tile[warp + 8 * ci][lane + 32 * pi] = __float_as_uint(round_tf32(v[ci][pi]));
+        acc[ci] += (v[ci][0] + v[ci][1]) + (v[ci][2] + v[ci][3]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = c0 + lane + 32 * h;
+        if (c < Cp) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int pp = warp + 8 * i, px = p0 + pp;
+            if (px < HW) d[((int64_t)b * HW + px) * Cp + c] = tile[lane + 32 * h][pp];
+          }
+        }
+      }
+    }
+    __syncthreads();  // tile is reused by the next pixel tile
+  }
+
+  if (chan_sum) {  // warp-shuffle tree, then one atomic per (block, channel)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = warp_sum(acc[i]);
+      // BF16: acc[2ci], acc[2ci+1] <-> channels c0 + 2(warp + 8ci) + {0,1};  TF32: acc[ci] <-> channel c0 + warp + 8ci
+      const int c = BF16 ? c0 + 2 * (warp + 8 * (i >> 1)) + (i & 1) : c0 + warp + 8 * i;
+      if (lane == 0 && c < C) atomicAdd(chan_sum + c, t);
     }
   }
 }
@@ -323,7 +329,13 @@ static int wgrad_splits(const G& g, int mode) {
 
 int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, int mode, float* chan_sum, cudaStream_t st) {
   const int Cp = round_up(C, 8), HW = H * W;
-  dim3 grid((HW + CL_PX - 1) / CL_PX, (Cp + CL_CH - 1) / CL_CH, B);
+  // each block walks several pixel tiles of its (image, 64-channel group) so the per-channel partial sums are reduced
+  // once per block; keep >= ~16 blocks per SM overall (several waves)
+  const int n_tiles = (HW + CL_PX - 1) / CL_PX, groups = (Cp + CL_CH - 1) / CL_CH;
+  int gx = (int)((16LL * sm_count() + (int64_t)groups * B - 1) / ((int64_t)groups * B));
+  if (gx < 1) gx = 1;
+  if (gx > n_tiles) gx = n_tiles;
+  dim3 grid(gx, groups, B);
   CPT_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CPT_ERR_UNSUPPORTED, "to_channels_last: grid too large");
   if (mode == CPT_MODE_BF16) nchw_to_nhwc_kernel<true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum);
   else nchw_to_nhwc_kernel<false><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum);
