@@ -254,29 +254,61 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 // ------------------------------------------------------------------ kernel launch
 __device__ int g_tc_status = 0;
 
-template <bool BF16, bool A_MN, bool B_MN, int BN, int OP>
+template <bool BF16, bool A_MN, bool B_MN, int BN, int OP, bool CTA2>
 static int launch_inst(const TcParams& p, cudaStream_t st) {
-  using S = StageCfg<BN>;
+  using S = StageCfg<BN, CTA2>;
   static bool configured = false;
-  auto kern = tc_kernel<BF16, A_MN, B_MN, BN, OP>;
+  auto kern = tc_kernel<BF16, A_MN, B_MN, BN, OP, CTA2>;
   if (!configured) {
     CPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
     configured = true;
   }
-  const int total = p.m_tiles * p.n_tiles * p.z_tiles;
-  int grid = total < sm_count() ? total : sm_count();
-  if (grid < 1) return CPT_OK;
-  kern<<<grid, 256, S::SMEM_BYTES, st>>>(p);
+  const int total = p.m_tiles * p.n_tiles * p.z_tiles;  // tiles (1-CTA) or tile pairs (2-CTA)
+  const int ncta = CTA2 ? 2 : 1;
+  int groups = sm_count() / ncta;
+  if (total < groups) groups = total;
+  if (groups < 1) return CPT_OK;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(groups * ncta);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = S::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ncta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CTA2 ? 1 : 0;
+  CPT_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   CPT_LAUNCH_CHECK("tc_kernel");
   return CPT_OK;
 }
 
+// 2-CTA (cta_group::2) is used when the tile grid is large enough to keep all SM pairs busy; CPT_TC_2CTA=0/1 overrides.
+// The drivers ask this BEFORE building the B tensor map (its box covers BN/2 columns per CTA in 2-CTA mode).
+static bool want_2cta(int BN, int64_t m_tiles128) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("CPT_TC_2CTA");
+    forced = e ? atoi(e) : -1;
+  }
+  if (BN < 128 || m_tiles128 < 2) return false;
+  if (forced >= 0) return forced != 0;
+  return true;  // measured: C=512 fprop 2.85 -> 2.65 ms, never slower for BN >= 128
+}
+
 template <bool A_MN, bool B_MN, int OP>
-static int launch_bn(const TcParams& p, int mode, int BN, cudaStream_t st) {
+static int launch_bn(TcParams p, int mode, int BN, bool use2, cudaStream_t st) {
   const bool bf = mode == CPT_MODE_BF16;
-  if (BN == 256) return bf ? launch_inst<true, A_MN, B_MN, 256, OP>(p, st) : launch_inst<false, A_MN, B_MN, 256, OP>(p, st);
-  if (BN == 128) return bf ? launch_inst<true, A_MN, B_MN, 128, OP>(p, st) : launch_inst<false, A_MN, B_MN, 128, OP>(p, st);
-  return bf ? launch_inst<true, A_MN, B_MN, 64, OP>(p, st) : launch_inst<false, A_MN, B_MN, 64, OP>(p, st);
+  if (use2) {
+    p.m_tiles = (p.m_tiles + 1) / 2;  // 256-row tiles
+    if (BN == 256) return bf ? launch_inst<true, A_MN, B_MN, 256, OP, true>(p, st) : launch_inst<false, A_MN, B_MN, 256, OP, true>(p, st);
+    return bf ? launch_inst<true, A_MN, B_MN, 128, OP, true>(p, st) : launch_inst<false, A_MN, B_MN, 128, OP, true>(p, st);
+  }
+  if (BN == 256) return bf ? launch_inst<true, A_MN, B_MN, 256, OP, false>(p, st) : launch_inst<false, A_MN, B_MN, 256, OP, false>(p, st);
+  if (BN == 128) return bf ? launch_inst<true, A_MN, B_MN, 128, OP, false>(p, st) : launch_inst<false, A_MN, B_MN, 128, OP, false>(p, st);
+  return bf ? launch_inst<true, A_MN, B_MN, 64, OP, false>(p, st) : launch_inst<false, A_MN, B_MN, 64, OP, false>(p, st);
 }
 
 static int pick_bn(int64_t n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
@@ -351,12 +383,13 @@ static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Wi
   TcParams p{};
   const int upper = pad - (K - 1) * dil;  // CUTLASS detail.hpp compute_upper_corner_whd (fprop)
   if (int e = make_map_im2col(&p.tmA, act_cl, mode, Cp, Win, Hin, B, -pad, upper, upper, stride, kc, 128)) return e;
-  if (int e = make_map_2d(&p.tmB, wmat, mode, (uint64_t)T * Ck, Ncols, (uint64_t)T * Ck, kc, BN)) return e;
+  const int64_t M = (int64_t)B * Hout * Wout;
+  const bool use2 = want_2cta(BN, (M + 127) / 128);
+  if (int e = make_map_2d(&p.tmB, wmat, mode, (uint64_t)T * Ck, Ncols, (uint64_t)T * Ck, kc, use2 ? BN / 2 : BN)) return e;
   p.out = out;
   p.bias = bias;
   p.bias_mode = bias ? BIAS_COL : BIAS_NONE;
   if (int e = get_status_ptr(&p.status)) return e;
-  const int64_t M = (int64_t)B * Hout * Wout;
   p.M = (int)M;
   p.N = Ncols;
   p.m_tiles = (int)((M + 127) / 128);
@@ -376,7 +409,7 @@ static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Wi
   p.Kw = K;
   p.taps = T;
   p.wk_cols = Ck;
-  return launch_bn<false, false, OP_CONV>(p, mode, BN, st);
+  return launch_bn<false, false, OP_CONV>(p, mode, BN, use2, st);
 }
 
 int conv_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w, const float* bias, float* y, int mode, void* ws,
@@ -449,7 +482,7 @@ int conv_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl,
   p.dil = g.D;
   p.Kw = g.K;
   p.taps = g.T;
-  if (int e = launch_bn<true, true, OP_WGRAD>(p, mode, BN, st)) return e;
+  if (int e = launch_bn<true, true, OP_WGRAD>(p, mode, BN, want_2cta(BN, (g.Ci + 127) / 128), st)) return e;
   const int64_t n = (int64_t)g.Co * g.Ci * g.T;
   wgrad_reduce_kernel<<<ew_grid(n, 256), 256, 0, st>>>(reinterpret_cast<float*>(ws), dw, g.Co, g.Ci, g.T, splits);
   CPT_LAUNCH_CHECK("wgrad_reduce");
@@ -546,14 +579,15 @@ int linear_fwd(const float* x, const float* w, const float* bias, float* y, int6
   TcParams p{};
   // y[n][o]: lanes = o.  A = w [Out][In] K-major, B = x [N][In] K-major
   if (int e = make_map_2d(&p.tmA, wa, mode, In, Out, pitch, kc, 128)) return e;
-  if (int e = make_map_2d(&p.tmB, xa, mode, In, (uint64_t)N, pitch, kc, BN)) return e;
+  const bool use2 = want_2cta(BN, (Out + 127) / 128);
+  if (int e = make_map_2d(&p.tmB, xa, mode, In, (uint64_t)N, pitch, kc, use2 ? BN / 2 : BN)) return e;
   p.out = y; p.bias = bias; p.bias_mode = bias ? BIAS_LANE : BIAS_NONE;
   if (int e = get_status_ptr(&p.status)) return e;
   p.M = Out; p.N = (int)N;
   p.m_tiles = (Out + 127) / 128; p.n_tiles = (int)((N + BN - 1) / BN); p.z_tiles = 1;
   p.k_iters_total = (In + kc - 1) / kc; p.k_iters_per_split = p.k_iters_total;
   p.col_stride = Out; p.taps = 1;
-  return launch_bn<false, false, OP_GEMM>(p, mode, BN, st);
+  return launch_bn<false, false, OP_GEMM>(p, mode, BN, use2, st);
 }
 
 int linear_dgrad(const float* dy, const float* w, float* dx, int64_t N, int In, int Out, int mode, void* ws, size_t ws_bytes,
@@ -574,14 +608,15 @@ int linear_dgrad(const float* dy, const float* w, float* dx, int64_t N, int In, 
   TcParams p{};
   // dx[n][i]: lanes = i.  A(m=i, k=o) = w[o][i]: MN-major over the [Out][In] matrix; B = dy [N][Out] K-major
   if (int e = make_map_2d(&p.tmA, wa, mode, In, Out, wpitch, kc, kc, true)) return e;
-  if (int e = make_map_2d(&p.tmB, ga, mode, Out, (uint64_t)N, gpitch, kc, BN)) return e;
+  const bool use2 = want_2cta(BN, (In + 127) / 128);
+  if (int e = make_map_2d(&p.tmB, ga, mode, Out, (uint64_t)N, gpitch, kc, use2 ? BN / 2 : BN)) return e;
   p.out = dx; p.bias = nullptr; p.bias_mode = BIAS_NONE;
   if (int e = get_status_ptr(&p.status)) return e;
   p.M = In; p.N = (int)N;
   p.m_tiles = (In + 127) / 128; p.n_tiles = (int)((N + BN - 1) / BN); p.z_tiles = 1;
   p.k_iters_total = (Out + kc - 1) / kc; p.k_iters_per_split = p.k_iters_total;
   p.col_stride = In; p.taps = 1;
-  return launch_bn<true, false, OP_GEMM>(p, mode, BN, st);
+  return launch_bn<true, false, OP_GEMM>(p, mode, BN, use2, st);
 }
 
 int linear_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t N, int In, int Out, int mode, void* ws,
@@ -619,7 +654,7 @@ int linear_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t 
   p.m_tiles = (In + 127) / 128; p.n_tiles = (Out + BN - 1) / BN; p.z_tiles = splits;
   p.k_iters_total = k_iters; p.k_iters_per_split = kps;
   p.col_stride = In; p.split_stride = (long long)Out * In; p.taps = 1;
-  if (int e = launch_bn<true, true, OP_GEMM>(p, mode, BN, st)) return e;
+  if (int e = launch_bn<true, true, OP_GEMM>(p, mode, BN, want_2cta(BN, (In + 127) / 128), st)) return e;
   if (splits > 1) {
     launch_reduce_splits(partial, dw, (int64_t)Out * In, splits, st);
     CPT_LAUNCH_CHECK("linear_wgrad reduce");

@@ -1,9 +1,15 @@
 // Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM convolution kernel for sm_100a.
 //
 //   warp 0 (1 lane)  TMA producer: tiled 2-D or im2col 4-D loads into a ring of 128B-swizzled smem stages
-//   warp 1 (1 lane)  MMA issuer:   tcgen05.mma (M=128, N=BN, fp32 accumulate in TMEM), tcgen05.commit
+//   warp 1 (1 lane)  MMA issuer:   tcgen05.mma (fp32 accumulate in TMEM), tcgen05.commit
 //   warp 2           TMEM allocator (2 x BN columns: double-buffered accumulator)
 //   warps 4-7        epilogue: tcgen05.ld -> registers -> (bias) -> global, overlapped with the next tile
+//
+// CTA2 = false: one CTA per SM computes a 128 x BN tile (cta_group::1, UMMA M=128).
+// CTA2 = true : a cluster of two CTAs (an SM pair) computes a 256 x BN tile with cta_group::2 (UMMA M=256): each
+//   CTA stages its own 128 rows of A and HALF of B (BN/2 columns); the leader CTA issues the MMAs, which read both
+//   CTAs' shared memory and write both CTAs' TMEM.  Per SM this halves the B bytes written by TMA and read by the
+//   tensor core, which is what bounds the 1-CTA kernel.
 //
 // The GEMM "M" (TMEM lane) dimension is always mapped onto the output's CONTIGUOUS dimension (pixels for
 // NCHW conv outputs, the feature dimension for row-major Linear outputs, Ci for wgrad partials) so that the
@@ -25,7 +31,7 @@ struct alignas(64) TcParams {
   int* status;      // device int: set non-zero on a pipeline timeout
   int bias_mode;
   int M, N;         // valid extents of the lane / column dimensions
-  int m_tiles, n_tiles, z_tiles;  // z = split (GEMM), 1 (CONV), tap * split (WGRAD)
+  int m_tiles, n_tiles, z_tiles;  // m_tiles counts 128-row (1-CTA) or 256-row (2-CTA) tiles; z = split / tap*split
   int k_iters_total;              // k iterations of the whole reduction (GEMM / WGRAD) or per tile (CONV)
   int k_iters_per_split;
   // epilogue addressing: dst = out + z_off + lane_off(m) + col * col_stride
@@ -45,21 +51,23 @@ struct Elem {
   static constexpr int BK = KC;               // reduction elements per stage (also k-rows of an MN-major stage)
 };
 
-template <int BN>
+template <int BN, bool CTA2>
 struct StageCfg {
   static constexpr int A_BYTES = 128 * 128;   // 128 lanes x 128 B (K-major) == (128/KC chunks) x BK rows x 128 B
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int BN_CTA = CTA2 ? BN / 2 : BN;  // B columns staged by one CTA
+  static constexpr int B_BYTES = BN_CTA * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <bool BF16, bool A_MN, bool B_MN, int BN, int OP>
+template <bool BF16, bool A_MN, bool B_MN, int BN, int OP, bool CTA2>
 __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcParams p) {
   using E = Elem<BF16>;
-  using S = StageCfg<BN>;
+  using S = StageCfg<BN, CTA2>;
   constexpr int STAGES = S::STAGES;
-  constexpr uint32_t IDESC = make_idesc(BF16, A_MN, B_MN, 128, BN);
+  constexpr int NCTA = CTA2 ? 2 : 1;
+  constexpr uint32_t IDESC = make_idesc(BF16, A_MN, B_MN, 128 * NCTA, BN);
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   constexpr uint32_t CHUNK_BYTES = E::BK * 128;  // one MN-major chunk: BK k-rows x 128 B
   constexpr uint32_t MN_SBO = BF16 ? 1024u : 512u;
@@ -77,6 +85,8 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
   auto b_smem = [&](int s) { return smem_base + s * S::STAGE_BYTES + S::A_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta_rank = CTA2 ? (int)cluster_ctarank() : 0;  // 0 = leader (issues the MMAs)
+  const int group = blockIdx.x / NCTA, n_groups = gridDim.x / NCTA;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA);
@@ -84,21 +94,22 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), NCTA);   // one arrive(+expect_tx) per CTA's producer (on the leader's barrier)
+      mbar_init(empty_bar(s), 1);     // tcgen05.commit (multicast to both CTAs in 2-CTA mode)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), 4 * NCTA);  // one arrive per epilogue warp of every CTA of the group
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc<CTA2>(tmem_slot, TMEM_COLS);
+    tmem_relinquish<CTA2>();
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync();  // peer's barriers initialised and TMEM allocated before any cross-CTA traffic
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -113,13 +124,14 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
   };
 
   if (warp == 0 && lane == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer (every CTA) ===========================
     int stage = 0;
     uint32_t phase = 0;
     bool ok = true;
-    for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+    for (int t = group; t < total_tiles && ok; t += n_groups) {
       const int m_tile = t % p.m_tiles, r = t / p.m_tiles, n_tile = r % p.n_tiles, z = r / p.n_tiles;
-      const int m0 = m_tile * 128, n0 = n_tile * BN;
+      const int m0 = m_tile * (128 * NCTA) + cta_rank * 128;   // this CTA's 128 rows of A
+      const int n0 = n_tile * BN + cta_rank * S::BN_CTA;       // this CTA's columns of B
       const int iters = tile_k_iters(z);
       int cw = 0, ch = 0, cn = 0, tap = 0, k_begin = 0;
       if (OP == OP_CONV) {
@@ -135,14 +147,17 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
       }
       for (int i = 0; i < iters; ++i) {
         if (!mbar_wait(empty_bar(stage), phase ^ 1)) { atomicExch(p.status, 1); ok = false; break; }
-        mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
-        const uint32_t fb = full_bar(stage), sa = a_smem(stage), sb = b_smem(stage);
+        // the full barrier lives in the leader CTA; TMA of both CTAs completes on it
+        const uint32_t fb = CTA2 ? mapa_cluster(full_bar(stage), 0) : full_bar(stage);
+        if (CTA2 && cta_rank != 0) mbar_arrive_expect_tx_cluster(fb, S::STAGE_BYTES);
+        else mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
+        const uint32_t sa = a_smem(stage), sb = b_smem(stage);
         if (OP == OP_CONV) {
           // A: 128 output pixels x KC channels of filter tap (j, kk); B: weights [Co][tap][C] rows n0.., K-major
           const int tp = i / p.cchunks, cc = i - tp * p.cchunks;
           const int j = tp / p.Kw, kk = tp - j * p.Kw;
-          tma_load_im2col_4d(&p.tmA, fb, sa, cc * E::KC, cw, ch, cn, (uint16_t)(kk * p.dil), (uint16_t)(j * p.dil));
-          tma_load_2d(&p.tmB, fb, sb, tp * p.wk_cols + cc * E::KC, n0);
+          tma_load_im2col_4d<CTA2>(&p.tmA, fb, sa, cc * E::KC, cw, ch, cn, (uint16_t)(kk * p.dil), (uint16_t)(j * p.dil));
+          tma_load_2d<CTA2>(&p.tmB, fb, sb, tp * p.wk_cols + cc * E::KC, n0);
         } else if (OP == OP_WGRAD) {
           // reduction over output pixels: chunk of BK pixels starting at flattened pixel k0
           const int k0 = (k_begin + i) * E::BK;
@@ -150,36 +165,37 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
           const int j = tap / p.Kw, kk = tap - j * p.Kw;
 #pragma unroll
           for (int c = 0; c < 128 / E::KC; ++c)
-            tma_load_im2col_4d(&p.tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, qx * p.conv_stride - p.pad,
-                               py * p.conv_stride - p.pad, b, (uint16_t)(kk * p.dil), (uint16_t)(j * p.dil));
+            tma_load_im2col_4d<CTA2>(&p.tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, qx * p.conv_stride - p.pad,
+                                     py * p.conv_stride - p.pad, b, (uint16_t)(kk * p.dil), (uint16_t)(j * p.dil));
 #pragma unroll
-          for (int c = 0; c < BN / E::KC; ++c) tma_load_2d(&p.tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, k0);
+          for (int c = 0; c < S::BN_CTA / E::KC; ++c)
+            tma_load_2d<CTA2>(&p.tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, k0);
         } else {
           const int kidx = k_begin + i;
           if (A_MN) {
 #pragma unroll
             for (int c = 0; c < 128 / E::KC; ++c)
-              tma_load_2d(&p.tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, kidx * E::BK);
+              tma_load_2d<CTA2>(&p.tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, kidx * E::BK);
           } else {
-            tma_load_2d(&p.tmA, fb, sa, kidx * E::KC, m0);
+            tma_load_2d<CTA2>(&p.tmA, fb, sa, kidx * E::KC, m0);
           }
           if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / E::KC; ++c)
-              tma_load_2d(&p.tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, kidx * E::BK);
+            for (int c = 0; c < S::BN_CTA / E::KC; ++c)
+              tma_load_2d<CTA2>(&p.tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, kidx * E::BK);
           } else {
-            tma_load_2d(&p.tmB, fb, sb, kidx * E::KC, n0);
+            tma_load_2d<CTA2>(&p.tmB, fb, sb, kidx * E::KC, n0);
           }
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // =========================== MMA issuer ===========================
+  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+    // =========================== MMA issuer (leader CTA only) ===========================
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     bool ok = true;
-    for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+    for (int t = group; t < total_tiles && ok; t += n_groups) {
       const int z = (t / p.m_tiles) / p.n_tiles;
       const int iters = tile_k_iters(z);
       if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1)) { atomicExch(p.status, 2); break; }
@@ -197,22 +213,22 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
                                    : make_smem_desc(sa + s * 32, 16, 1024);
           const uint64_t db = B_MN ? make_smem_desc(sb + s * (E::UMMA_K * 128), CHUNK_BYTES, MN_SBO, MN_LAYOUT)
                                    : make_smem_desc(sb + s * 32, 16, 1024);
-          umma<BF16>(d_tmem, da, db, IDESC, (uint32_t)((i | s) != 0));
+          umma<BF16, CTA2>(d_tmem, da, db, IDESC, (uint32_t)((i | s) != 0));
         }
-        umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+        umma_commit<CTA2>(empty_bar(stage));  // frees the smem stage (in both CTAs) once these MMAs have read it
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull_bar(acc));      // accumulator complete -> epilogue
+      umma_commit<CTA2>(tfull_bar(acc));      // accumulator complete -> epilogue warps of both CTAs
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // =========================== epilogue ===========================
+    // =========================== epilogue (every CTA: its own 128 TMEM lanes) ===========================
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = group; t < total_tiles; t += n_groups) {
       const int m_tile = t % p.m_tiles, r = t / p.m_tiles, n_tile = r % p.n_tiles, z = r / p.n_tiles;
-      const int m = m_tile * 128 + ew * 32 + lane, n0 = n_tile * BN;
+      const int m = m_tile * (128 * NCTA) + cta_rank * 128 + ew * 32 + lane, n0 = n_tile * BN;
       const int iters = tile_k_iters(z);
       long long z_off = 0;
       if (OP == OP_WGRAD) z_off = (long long)(z / p.taps) * p.split_stride + (long long)(z % p.taps) * p.tap_stride;
@@ -253,16 +269,20 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {  // the MMA issuer (leader CTA) waits for all epilogue warps of the group
+        if (CTA2 && cta_rank != 0) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync();  // the peer may still be reading this CTA's smem / signalling its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc<CTA2>(tmem_base, TMEM_COLS);
   }
 }
 
