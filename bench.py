@@ -343,6 +343,153 @@ def run_ours(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ model workloads
+MODEL_WORKLOADS = {
+    # name: (spec factory, input shape per sample, classes, batch per GPU, BASELINE config text)
+    "mnist": ("mnist_cnn", (1, 28, 28), 10, 128, "BASELINE configs[0]: example_cnn_mnist CNN, synthetic 1x28x28, batch 128/GPU, Adam, CE"),
+    "vgg": ("vgg", (3, 32, 32), 10, 1024, "BASELINE configs[2]: VGG-style Conv2D+BatchNorm2D+MaxPool2D CNN, synthetic 3x32x32, batch 1024/GPU, Adam, CE"),
+    "resnet18": ("resnet18", (3, 224, 224), 1000, 256, "BASELINE configs[3]: ResNet-18-shaped Sequential CNN, synthetic 3x224x224, batch 256/GPU, Adam, CE"),
+    "mlp": ("mlp", (4096,), 4096, 8192, "BASELINE configs[4]: MLP 8 x Linear(4096,4096), batch 8192/GPU, Adam, CE"),
+}
+
+
+def run_model(args) -> None:
+    """Train-step throughput (images/s) of one of the model configs through the public module API."""
+    import torch
+
+    import bench_workloads as W
+    import compyute_b200 as cp
+    from compyute_b200 import _lib, distributed, nn
+    from compyute_b200.tensors import DeviceArray, Tensor
+
+    L = _lib.lib()
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        distributed.init("nccl")
+    factory, xshape, classes, B, desc = MODEL_WORKLOADS[args.workload]
+    B = args.batch or B
+    spec = getattr(W, factory)()
+    hw = xshape[-1] if len(xshape) == 3 else 1
+    flops_img = W.train_flops_per_image(spec, hw)
+    np.random.seed(0)
+    with cp.use_device(cp.cuda), cp.compute_mode(args.mode):
+        model = W.build(spec)
+    model.training()
+    opt = nn.optimizers.Adam(model.get_parameters(), lr=1e-3)
+    loss_fn = nn.CrossEntropyLoss()
+    g = torch.Generator("cuda").manual_seed(100 + rank)
+    wrapf = lambda t: Tensor(DeviceArray(t, tuple(t.shape), np.float32))
+    wrapi = lambda t: Tensor(DeviceArray(t, tuple(t.shape), np.int32))
+    hx = torch.randn(B, *xshape).pin_memory()
+    ht = torch.randint(0, classes, (B,), dtype=torch.int32).pin_memory()
+    dx, dt = hx.cuda(), ht.cuda()
+    hloss = torch.zeros(1).pin_memory()
+
+    def step(x, t):
+        loss = loss_fn(model(x), t)
+        opt.reset_grads()
+        model.backward(loss_fn.backward())
+        opt.step()
+        return loss
+
+    def step_resident():
+        return step(wrapf(dx), wrapi(dt))
+
+    def step_e2e():  # H2D of the batch from pinned memory + D2H of the loss, every step
+        x = torch.empty_like(dx); x.copy_(hx, non_blocking=True)
+        t = torch.empty_like(dt); t.copy_(ht, non_blocking=True)
+        loss = step(wrapf(x), wrapi(t))
+        hloss.copy_(loss.data._buf.view(1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, device_timed=True):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            distributed.barrier()
+        n0 = L.cpt_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter(); e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            distributed.barrier()
+        ms = e0.elapsed_time(e1) if device_timed else wall
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda"); torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX); ms = float(tt.item())
+        return ms / steps, L.cpt_launch_count() - n0
+
+    sampler = ClockSampler(local)
+    with cp.compute_mode(args.mode):
+        if rank == 0:
+            sampler.start()
+        ms, launches = timed(step_resident, args.steps, args.warmup)
+        clocks = sampler.stop() if rank == 0 else {}
+        e2e_ms, _ = timed(step_e2e, max(2, args.steps // 2), 2, device_timed=False)
+    status = L.cpt_tc_check_status()
+    if rank != 0:
+        return
+    pk = peaks()
+    ips = world * B / (ms / 1e3)
+    tfl = ips * flops_img / 1e12
+    # CPU oracle port on a bounded sample: a few images through the same spec (fwd + bwd + Adam)
+    from oracle.model_ref import RefModel
+    nb = {"mnist": 16, "vgg": 2, "resnet18": 1, "mlp": 64}[args.workload]
+    if args.workload == "resnet18":  # a full 224x224 ResNet-18 image costs ~5 h on the einsum path: time the stem stage only
+        cpu_spec = spec[:4]
+        cpu_note = "stem only (Conv7x7/s2+BN+ReLU+MaxPool), 1 image; the full model is ~10.9 GFLOP/image at ~1 GFLOP/s"
+    else:
+        cpu_spec, cpu_note = spec, f"{nb} images, fwd + bwd"
+    cpu_val = None
+    try:
+        rs = np.random.RandomState(0)
+        def rand_params(sp):
+            ps, bs = [], []
+            for s_ in sp:
+                if s_[0] == "conv":
+                    ps.append(rs.normal(0, 0.05, (s_[2], s_[1], s_[3], s_[3])).astype(np.float32))
+                    if s_[6]: ps.append(np.zeros(s_[2], np.float32))
+                elif s_[0] == "linear":
+                    ps.append(rs.normal(0, 0.02, (s_[2], s_[1])).astype(np.float32))
+                    if s_[3]: ps.append(np.zeros(s_[2], np.float32))
+                elif s_[0] in ("bn2d", "bn1d"):
+                    ps += [np.ones(s_[1], np.float32), np.zeros(s_[1], np.float32)]; bs += [np.zeros(s_[1], np.float32), np.ones(s_[1], np.float32)]
+                elif s_[0] == "residual":
+                    for sub in (s_[1], s_[2] or []):
+                        p2, b2 = rand_params(sub); ps += p2; bs += b2
+            return ps, bs
+        ps, bs = rand_params(cpu_spec)
+        ref = RefModel(cpu_spec, ps, bs)
+        xs = rs.normal(0, 1, (nb, *xshape)).astype(np.float32)
+        t0 = time.perf_counter()
+        y = ref.forward(xs, True)
+        ref.backward(np.ones_like(y) / y.size)
+        cpu_s = time.perf_counter() - t0
+        cpu_val = nb / cpu_s
+        if args.workload == "resnet18":
+            cpu_val = cpu_val * (W.train_flops_per_image(cpu_spec, hw) / flops_img)  # images/s scaled by the FLOP share of the timed stage
+            cpu_note += " — value = measured stem images/s x (stem FLOPs / model FLOPs), i.e. an optimistic bound for the CPU"
+    except Exception as e:  # pragma: no cover
+        cpu_note = f"cpu sample failed: {e}"
+    line = {"metric": "cnn_train_images_per_s" if args.workload != "mlp" else "mlp_train_samples_per_s", "value": round(ips, 1), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.mode], "data": "synthetic",
+            "config": {"workload": desc, "batch_per_gpu": B, "compute_mode": args.mode, "tolerance": TOL[args.mode], "parallelism": f"dp{world}",
+                       "l2_policy": "activations of one step exceed L2" if B * int(np.prod(xshape)) * 4 > 126e6 else "L2 flushed implicitly: per-step activation traffic exceeds L2"},
+            "clocks": clocks, "e2e": {"value": round(world * B / (e2e_ms / 1e3), 1), "unit": "images/s", "h2d_bytes_per_step": int(hx.numel() * 4 + ht.numel() * 4),
+                                      "d2h_bytes_per_step": 4, "note": "module API; batch H2D from pinned memory and loss D2H every step; wall clock incl. host dispatch"},
+            "gpu_launches": int(launches), "roofline": {"bound": "tensor", "achieved": round(tfl / world, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                                                        "frac": round(tfl / world / pk["bf16_tflops"], 4), "traffic": None,
+                                                        "note": f"whole step: {flops_img / 1e9:.3f} GFLOP/image algorithmic (3 x contraction FLOPs)"},
+            "cpu_baseline": {"value": None if cpu_val is None else round(cpu_val, 4), "unit": "images/s", "cores": 1, "host_cores": os.cpu_count(), "kind": "port", "sample": cpu_note},
+            "tflops": round(tfl, 2), "tc_watchdog": int(status)}
+    print(json.dumps(line), flush=True)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -351,10 +498,14 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("COMPYUTE_B200_MODE", "bf16"), choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--no-extra-modes", action="store_true")
+    ap.add_argument("--workload", default="conv2d_sweep", choices=["conv2d_sweep", "mnist", "vgg", "resnet18", "mlp"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of a model workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "conv2d_sweep":
+        run_model(args)
     else:
         run_ours(args)
 

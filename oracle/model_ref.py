@@ -1,0 +1,156 @@
+"""CPU oracle, model level: interprets a bench_workloads spec with the function-level oracle (oracle/compyute_ref.py),
+reproducing what the reference's Sequential / ResidualConnection / BatchNorm modules + CrossEntropyLoss + Adam do
+(compyute/nn/modules/containers.py:35-45, 153-162; normalizations.py:150-171; module.py:392-400; trainer.py:118-135).
+
+TEST INFRASTRUCTURE ONLY (see compyute_ref.py).  Parameters are kept in the flat order of ``Module.get_parameters()``
+(own parameters, then children depth-first: residual block before projection), so they can be exchanged with a
+compyute_b200 model one-to-one."""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import compyute_ref as R
+
+
+class _Layer:
+    def __init__(self, spec, rng_params):
+        self.spec = spec
+        self.kind = spec[0]
+        self.params: list[np.ndarray] = []   # trainable, in the module's registration order (w, b)
+        self.buffers: list[np.ndarray] = []  # rmean, rvar
+        self.grads: list = []
+        self.cache: list = []
+        self.block = self.proj = None
+        if self.kind == "residual":
+            self.block = [_Layer(s, rng_params) for s in spec[1]]
+            self.proj = [_Layer(s, rng_params) for s in spec[2]] if spec[2] else None
+
+    def leaves(self):
+        if self.kind == "residual":
+            for l in self.block:
+                yield from l.leaves()
+            if self.proj:
+                for l in self.proj:
+                    yield from l.leaves()
+        else:
+            yield self
+
+    def forward(self, x, training):
+        k, s, c = self.kind, self.spec, self.cache
+        if k == "conv":
+            return R.conv2d_forward(c, x, self.params[0], self.params[1] if s[6] else None, s[4], s[5], 1)
+        if k == "linear":
+            return R.linear_forward(c, x, self.params[0], self.params[1] if s[3] else None)
+        if k in ("bn2d", "bn1d"):
+            y, rm, rv = R.batchnorm_forward(c, x, self.buffers[0], self.buffers[1], self.params[0], self.params[1], 0.1, 1e-5, training)
+            self.buffers = [rm, rv]
+            return y
+        if k == "relu":
+            return R.relu_forward(c, x)
+        if k == "maxpool":
+            return R.maxpool2d_forward(c, x, s[1])
+        if k == "avgpool":
+            return R.avgpool2d_forward(c, x, s[1])
+        if k == "dropout":
+            return R.dropout_forward(c, x, s[1], training)
+        if k == "flatten":
+            c.append(x.shape)
+            return x.reshape(x.shape[0], -1)
+        if k == "residual":
+            y = x
+            for l in self.block:
+                y = l.forward(y, training)
+            r = x
+            if self.proj:
+                for l in self.proj:
+                    r = l.forward(r, training)
+            return y + r
+        raise ValueError(k)
+
+    def backward(self, dy):
+        k, s, c = self.kind, self.spec, self.cache
+        if k == "conv":
+            dx, dw, db = R.conv2d_backward(c, dy)
+            self.grads = [dw] + ([db] if s[6] else [])
+            return dx
+        if k == "linear":
+            dx, dw, db = R.linear_backward(c, dy)
+            self.grads = [dw] + ([db] if s[3] else [])
+            return dx
+        if k in ("bn2d", "bn1d"):
+            dx, dw, db = R.batchnorm_backward(c, dy)
+            self.grads = [dw, db]
+            return dx
+        if k == "relu":
+            return R.relu_backward(c, dy)
+        if k == "maxpool":
+            return R.maxpool2d_backward(c, dy)
+        if k == "avgpool":
+            return R.avgpool2d_backward(c, dy)
+        if k == "dropout":
+            return R.dropout_backward(c, dy)
+        if k == "flatten":
+            return dy.reshape(c.pop())
+        if k == "residual":
+            dx = dy
+            for l in reversed(self.block):
+                dx = l.backward(dx)
+            r = dy
+            if self.proj:
+                for l in reversed(self.proj):
+                    r = l.backward(r)
+            return dx + r
+        raise ValueError(k)
+
+
+class RefModel:
+    """Sequential model over a spec.  ``params`` / ``buffers``: flat lists in get_parameters() / get_buffers() order."""
+
+    def __init__(self, spec, params, buffers):
+        self.layers = [_Layer(s, None) for s in spec]
+        pi, bi = iter(params), iter(buffers)
+        for l in self.leaves():
+            s = l.spec
+            if l.kind == "conv":
+                l.params = [next(pi)] + ([next(pi)] if s[6] else [])
+            elif l.kind == "linear":
+                l.params = [next(pi)] + ([next(pi)] if s[3] else [])
+            elif l.kind in ("bn2d", "bn1d"):
+                l.params = [next(pi), next(pi)]
+                l.buffers = [next(bi), next(bi)]
+
+    def leaves(self):
+        for l in self.layers:
+            yield from l.leaves()
+
+    def parameters(self):
+        return [p for l in self.leaves() for p in l.params]
+
+    def buffers(self):
+        return [b for l in self.leaves() for b in l.buffers]
+
+    def gradients(self):
+        return [g for l in self.leaves() if l.params for g in l.grads]
+
+    def forward(self, x, training=True):
+        for l in self.layers:
+            x = l.forward(x, training)
+        return x
+
+    def backward(self, dy):
+        for l in reversed(self.layers):
+            dy = l.backward(dy)
+        return dy
+
+    def train_steps(self, x, t, steps, lr=1e-3):
+        """README.md:170-183 loop with CrossEntropyLoss + Adam; returns the loss trace."""
+        opt = R.Adam(lr=lr)
+        losses = []
+        for _ in range(steps):
+            lc = []
+            logits = self.forward(x, True)
+            losses.append(float(R.cross_entropy_forward(lc, logits, t)))
+            self.backward(R.cross_entropy_backward(lc))
+            opt.step(self.parameters(), self.gradients())
+        return losses

@@ -1,0 +1,87 @@
+"""Model-level GPU parity (``-m gpu``): reduced-size instances of BASELINE.json's configs 1, 3, 4, 5 trained for a few
+Adam steps through the compyute_b200 module API, against the oracle's model interpreter (same spec, same initial
+parameters, same batch).  fp32 mode.  Tolerance: losses 1e-4 relative, parameters allclose(2e-4): per-op agreement is
+1e-5 (test_gpu_parity.py); a 20-60-op deep fp32 network compounds that, and Adam turns relative gradient error into
+absolute parameter error of the same order times lr."""
+import numpy as np
+import pytest
+
+import bench_workloads as W
+from oracle.model_ref import RefModel
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "c1_mnist_cnn": (W.mnist_cnn(drop=0.0), (8, 1, 28, 28), 10),
+    "c3_vgg_w8": (W.vgg(width=8, hw=32, hidden=32), (6, 3, 32, 32), 10),
+    "c4_resnet18_w8": (W.resnet18(width=8, hw=64, classes=16), (4, 3, 64, 64), 16),
+    "c5_mlp_w64": (W.mlp(width=64, depth=8), (16, 64), 64),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES), ids=list(CASES))
+def test_config_train_steps(name):
+    import compyute_b200 as cp
+    from compyute_b200 import nn
+    spec, xshape, classes = CASES[name]
+    np.random.seed(11)
+    with cp.use_device(cp.cuda):
+        model = W.build(spec)
+    model.training()
+    params0 = [p.to_numpy().copy() for p in model.get_parameters()]
+    bufs0 = [b.to_numpy().copy() for b in model.get_buffers()]
+    rng = np.random.RandomState(5)
+    x = rng.normal(0, 1, xshape).astype(np.float32)
+    t = rng.randint(0, classes, (xshape[0],))
+    ref = RefModel(spec, [p.copy() for p in params0], [b.copy() for b in bufs0])
+    ref_losses = ref.train_steps(x, t, 3, lr=1e-3)
+
+    opt = nn.optimizers.Adam(model.get_parameters(), lr=1e-3)
+    loss_fn = nn.CrossEntropyLoss()
+    xt, tt = cp.tensor(x, device=cp.cuda), cp.tensor(t.astype(np.int32), device=cp.cuda)
+    losses = []
+    for _ in range(3):
+        loss = loss_fn(model(xt), tt)
+        opt.reset_grads()
+        model.backward(loss_fn.backward())
+        opt.step()
+        losses.append(loss.item())
+    assert np.allclose(losses, ref_losses, rtol=1e-4, atol=1e-5), (losses, ref_losses)
+    for i, (p, r) in enumerate(zip(model.get_parameters(), ref.parameters())):
+        assert p.shape == r.shape
+        assert np.allclose(p.to_numpy(), r, rtol=2e-4, atol=2e-4), f"param {i} max err {np.abs(p.to_numpy() - r).max():.3e}"
+    for b, r in zip(model.get_buffers(), ref.buffers()):
+        assert np.allclose(b.to_numpy(), r, rtol=1e-4, atol=1e-5)
+    assert all(not m.fcache.cache for m in model.get_modules())
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_vgg_tensor_core_modes_track_fp32(mode):
+    """Same VGG-style model in a tensor-core mode: the first-step loss matches fp32 within the mode's tolerance and
+    training still decreases the loss."""
+    import compyute_b200 as cp
+    from compyute_b200 import nn
+    spec = W.vgg(width=16, hw=32, hidden=64)
+    rng = np.random.RandomState(2)
+    x = rng.normal(0, 1, (32, 3, 32, 32)).astype(np.float32)
+    t = rng.randint(0, 10, (32,)).astype(np.int32)
+
+    def run(m):
+        np.random.seed(3)
+        with cp.use_device(cp.cuda):
+            model = W.build(spec)
+        model.training()
+        opt = nn.optimizers.Adam(model.get_parameters(), lr=2e-3)
+        loss_fn = nn.CrossEntropyLoss()
+        xt, tt = cp.tensor(x, device=cp.cuda), cp.tensor(t, device=cp.cuda)
+        out = []
+        with cp.compute_mode(m):
+            for _ in range(8):
+                loss = loss_fn(model(xt), tt)
+                opt.reset_grads(); model.backward(loss_fn.backward()); opt.step()
+                out.append(loss.item())
+        return out
+
+    ref, got = run("fp32"), run(mode)
+    assert abs(got[0] - ref[0]) <= {"tf32": 2e-3, "bf16": 1e-2}[mode] * max(1.0, abs(ref[0]))
+    assert got[-1] < got[0] and np.isfinite(got).all()
