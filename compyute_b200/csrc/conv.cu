@@ -72,59 +72,170 @@ struct ConvFpropP {
   }
 };
 
-// ---- dgrad: M = B*H*W (input pixels), N = Ci, K = Co*K*K
+// ---- dgrad, decomposed by stride residue class (rh, rw): the input pixels h = rh + S*hs, w = rw + S*ws form a sub-grid
+// on which dgrad is a dense stride-1 correlation over only the taps with (h + P - j*D) % S == 0 — no multiplications by
+// the zeros of the stride-dilated dy (RawConv2DFn.backward :391 materialises them).  S = 1 has one class = all taps.
+//   M = B*Hs*Ws (sub-grid pixels), N = Ci, K = Co * ntaps
 struct ConvDgradP {
   const float* dy; const float* w; float* dx;
-  ConvGeom g; int M, N, K, KK, HW, vec;
+  ConvGeom g; int M, N, K, KK, Hs, Ws, rh, rw, ntaps, vec;
+  unsigned char tj[64], tk[64];  // taps of this class
   static constexpr bool A_MN_CONTIG = true, B_MN_CONTIG = false, OUT_M_CONTIG = true;
   struct RowA { const float* base; int u, v; };
   struct ColB { const float* base; };
   __device__ RowA rowA(int m) const {
     RowA r;
     if (m >= M) { r.base = nullptr; r.u = r.v = 0; return r; }
-    const int b = m / HW, rem = m - b * HW, h = rem / g.W, ww = rem - h * g.W;
+    const int hw = Hs * Ws, b = m / hw, rem = m - b * hw, hs = rem / Ws, ws = rem - hs * Ws;
     r.base = dy + (int64_t)b * g.Co * g.Ho * g.Wo;
-    r.u = h + g.P;
-    r.v = ww + g.P;
+    r.u = rh + g.S * hs + g.P;
+    r.v = rw + g.S * ws + g.P;
     return r;
   }
   __device__ float loadA(const RowA& r, int k) const {
     if (!r.base) return 0.f;
-    const int co = k / KK, t = k - co * KK, j = t / g.K, kk = t - j * g.K;
-    const int nu = r.u - j * g.D, nv = r.v - kk * g.D;
+    const int co = k / ntaps, t = k - co * ntaps;
+    const int nu = r.u - (int)tj[t] * g.D, nv = r.v - (int)tk[t] * g.D;
     if (nu < 0 || nv < 0) return 0.f;
-    int p = nu, q = nv;
-    if (g.S > 1) {
-      p = nu / g.S; q = nv / g.S;
-      if (p * g.S != nu || q * g.S != nv) return 0.f;  // rows/cols the stride skipped (zeros of the dilated dy)
-    }
+    const int p = nu / g.S, q = nv / g.S;  // exact: the class guarantees divisibility
     if (p >= g.Ho || q >= g.Wo) return 0.f;
     return __ldg(r.base + ((int64_t)co * g.Ho + p) * g.Wo + q);
   }
   __device__ ColB colB(int n) const { return ColB{n < N ? w + (int64_t)n * KK : nullptr}; }
   __device__ float loadB(const ColB& c, int k) const {
     if (!c.base) return 0.f;
-    const int co = k / KK, t = k - co * KK;
-    return __ldg(c.base + (int64_t)co * N * KK + t);  // w[co][ci][j][kk]
+    const int co = k / ntaps, t = k - co * ntaps;
+    return __ldg(c.base + (int64_t)co * N * KK + (int)tj[t] * g.K + (int)tk[t]);  // w[co][ci][j][kk]
   }
   __device__ void store4(int, int m, int n, const float v[4]) const {
     if (n >= N || m >= M) return;
-    const int b = m / HW, rem = m - b * HW;
-    float* dst = dx + ((int64_t)b * N + n) * HW + rem;
-    if (vec && (HW & 3) == 0 && m + 3 < M) {
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
+    if (g.S == 1 && vec && ((g.H * g.W) & 3) == 0 && m + 3 < M) {  // dense case: 4 consecutive pixels of one image
+      const int HW = g.H * g.W, b = m / HW, rem = m - b * HW;
+      *reinterpret_cast<float4*>(dx + ((int64_t)b * N + n) * HW + rem) = make_float4(v[0], v[1], v[2], v[3]);
+      return;
+    }
+    const int hw = Hs * Ws;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int mm = m + i;
-        if (mm < M) {
-          const int b2 = mm / HW, r2 = mm - b2 * HW;
-          dx[((int64_t)b2 * N + n) * HW + r2] = v[i];
-        }
+    for (int i = 0; i < 4; ++i) {
+      const int mm = m + i;
+      if (mm < M) {
+        const int b = mm / hw, rem = mm - b * hw, hs = rem / Ws, ws = rem - hs * Ws;
+        dx[(((int64_t)b * N + n) * g.H + rh + g.S * hs) * g.W + rw + g.S * ws] = v[i];
       }
     }
   }
 };
+
+// ---- dgrad for tiny Ci (e.g. the 3-channel stem): a GEMM formulation would waste a 128-wide N tile on <= 8 columns.
+// One thread per input pixel of one residue class, CI accumulators in registers, filter in shared memory as
+// [co][tap][ci]; lanes run along ws so dy reads are coalesced and the tap set is warp-uniform.
+template <int CI>
+__global__ void __launch_bounds__(256) dgrad_small_ci_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                             float* __restrict__ dx, ConvGeom g, int Hs, int Ws, int rh, int rw,
+                                                             int ntaps, const unsigned char* __restrict__ taps /*[2][64] in gmem*/) {
+  extern __shared__ float wsm[];  // [Co][ntaps][CI]
+  __shared__ int s_tj[64], s_tk[64];
+  for (int i = threadIdx.x; i < ntaps; i += blockDim.x) { s_tj[i] = taps[i]; s_tk[i] = taps[64 + i]; }
+  __syncthreads();
+  const int KK = g.K * g.K;
+  for (int i = threadIdx.x; i < g.Co * ntaps * CI; i += blockDim.x) {
+    const int ci = i % CI, t = (i / CI) % ntaps, co = i / (CI * ntaps);
+    wsm[i] = ci < g.Ci ? w[((int64_t)co * g.Ci + ci) * KK + s_tj[t] * g.K + s_tk[t]] : 0.f;
+  }
+  __syncthreads();
+  const int64_t total = (int64_t)g.B * Hs * Ws;
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (int64_t)gridDim.x * blockDim.x) {
+    const int ws = (int)(m % Ws);
+    const int64_t r = m / Ws;
+    const int hs = (int)(r % Hs), b = (int)(r / Hs);
+    const int u = rh + g.S * hs + g.P, v = rw + g.S * ws + g.P;
+    float acc[CI];
+#pragma unroll
+    for (int c = 0; c < CI; ++c) acc[c] = 0.f;
+    const float* src = dy + (int64_t)b * g.Co * g.Ho * g.Wo;
+    for (int t = 0; t < ntaps; ++t) {
+      const int nu = u - s_tj[t] * g.D, nv = v - s_tk[t] * g.D;
+      if (nu < 0 || nv < 0) continue;
+      const int p = nu / g.S, q = nv / g.S;
+      if (p >= g.Ho || q >= g.Wo) continue;
+      const float* sp = src + (int64_t)p * g.Wo + q;
+      const float* wp = wsm + t * CI;
+#pragma unroll 4
+      for (int co = 0; co < g.Co; ++co) {
+        const float d = __ldg(sp + (int64_t)co * g.Ho * g.Wo);
+#pragma unroll
+        for (int c = 0; c < CI; ++c) acc[c] = fmaf(d, wp[(co * ntaps) * CI + c], acc[c]);
+      }
+    }
+    const int h = rh + g.S * hs, wv = rw + g.S * ws;
+#pragma unroll
+    for (int c = 0; c < CI; ++c)
+      if (c < g.Ci) dx[(((int64_t)b * g.Ci + c) * g.H + h) * g.W + wv] = acc[c];
+  }
+}
+
+// taps (j, kk) contributing to residue class (rh, rw); returns the count
+static int class_taps(const ConvGeom& g, int rh, int rw, unsigned char* tj, unsigned char* tk) {
+  int n = 0;
+  for (int j = 0; j < g.K; ++j) {
+    if (((rh + g.P - j * g.D) % g.S + g.S) % g.S != 0) continue;
+    for (int kk = 0; kk < g.K; ++kk) {
+      if (((rw + g.P - kk * g.D) % g.S + g.S) % g.S != 0) continue;
+      if (n < 64) { tj[n] = (unsigned char)j; tk[n] = (unsigned char)kk; }
+      ++n;
+    }
+  }
+  return n;
+}
+
+// exact-fp32 dgrad driver (all strides): one launch per non-empty residue class
+static int dgrad_fp32(const ConvGeom& g, const float* dy, const float* w, float* dx, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int classes = g.S * g.S;
+  bool any_empty = false;
+  for (int c = 0; c < classes && !any_empty; ++c) {
+    unsigned char a[64], b2[64];
+    const int rh = c / g.S, rw = c % g.S;
+    if (rh < g.H && rw < g.W && class_taps(g, rh, rw, a, b2) == 0) any_empty = true;
+  }
+  if (any_empty)  // input pixels no output window touches (e.g. 1x1 stride 2) get dx = 0
+    CPT_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)g.B * g.Ci * g.H * g.W, st));
+  for (int c = 0; c < classes; ++c) {
+    const int rh = c / g.S, rw = c % g.S;
+    if (rh >= g.H || rw >= g.W) continue;
+    ConvDgradP p;
+    p.ntaps = class_taps(g, rh, rw, p.tj, p.tk);
+    if (p.ntaps == 0) continue;
+    CPT_REQUIRE(p.ntaps <= 64, CPT_ERR_UNSUPPORTED, "conv2d_dgrad: more than 64 taps per stride class (K=%d)", g.K);
+    const int Hs = (g.H - rh + g.S - 1) / g.S, Ws = (g.W - rw + g.S - 1) / g.S;
+    const size_t wbytes = (size_t)g.Co * p.ntaps * (g.Ci <= 4 ? 4 : 8) * sizeof(float);
+    if (g.Ci <= 8 && wbytes <= 96 * 1024 && ws && ws_bytes >= 128) {
+      // tap table through the workspace (tiny, stream-ordered)
+      unsigned char host[128];
+      for (int i = 0; i < 64; ++i) { host[i] = p.tj[i]; host[64 + i] = p.tk[i]; }
+      unsigned char* dtaps = reinterpret_cast<unsigned char*>(ws) + (size_t)c * 128;
+      CPT_REQUIRE(ws_bytes >= (size_t)classes * 128, CPT_ERR_WORKSPACE, "conv2d_dgrad: workspace too small");
+      CPT_CUDA(cudaMemcpyAsync(dtaps, host, 128, cudaMemcpyHostToDevice, st));
+      const int64_t total = (int64_t)g.B * Hs * Ws;
+      const int grid = ew_grid(total, 256);
+      if (g.Ci <= 4) {
+        static bool cfg4 = false;
+        if (!cfg4) { CPT_CUDA(cudaFuncSetAttribute(dgrad_small_ci_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); cfg4 = true; }
+        dgrad_small_ci_kernel<4><<<grid, 256, wbytes, st>>>(dy, w, dx, g, Hs, Ws, rh, rw, p.ntaps, dtaps);
+      } else {
+        static bool cfg8 = false;
+        if (!cfg8) { CPT_CUDA(cudaFuncSetAttribute(dgrad_small_ci_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); cfg8 = true; }
+        dgrad_small_ci_kernel<8><<<grid, 256, wbytes, st>>>(dy, w, dx, g, Hs, Ws, rh, rw, p.ntaps, dtaps);
+      }
+      CPT_LAUNCH_CHECK("dgrad_small_ci");
+      continue;
+    }
+    p.dy = dy; p.w = w; p.dx = dx; p.g = g; p.vec = aligned16(dx);
+    p.KK = g.K * g.K; p.Hs = Hs; p.Ws = Ws; p.rh = rh; p.rw = rw;
+    p.M = g.B * Hs * Ws; p.N = g.Ci; p.K = g.Co * p.ntaps;
+    CPT_CUDA(sg_launch(p, 1, st));
+  }
+  return CPT_OK;
+}
 
 // ---- wgrad: M = Co, N = Ci*K*K, K(reduction) = B*Ho*Wo; split-K partials [split][M][N]
 struct ConvWgradP {
@@ -266,6 +377,7 @@ size_t cpt_conv2d_workspace_size(int op, const cpt_conv2d_desc* d, int mode) {
     const int splits = sg_pick_splits(M, N, K);
     return align_up((size_t)(splits > 1 ? splits : 0) * M * N * sizeof(float), 256) + chan_sum_ws(g.Co) + 256;
   }
+  if (op == CPT_OP_DGRAD) return (size_t)g.S * g.S * 128 + 256;  // tap tables of the small-Ci kernel
   return 256;
 }
 
@@ -289,12 +401,7 @@ int cpt_conv2d_dgrad(const cpt_conv2d_desc* d, const float* dy, const float* w, 
   if (int e = make_geom(d, g, "conv2d_dgrad")) return e;
   CPT_REQUIRE(dy && w && dx, CPT_ERR_INVALID, "conv2d_dgrad: null tensor");
   if (mode != CPT_MODE_FP32) return tc::conv_dgrad(d, dy, w, dx, mode, ws, ws_bytes, as_stream(stream));
-  ConvDgradP p;
-  p.dy = dy; p.w = w; p.dx = dx; p.g = g; p.vec = aligned16(dx);
-  p.KK = g.K * g.K; p.HW = g.H * g.W;
-  p.M = g.B * p.HW; p.N = g.Ci; p.K = g.Co * p.KK;
-  CPT_CUDA(sg_launch(p, 1, as_stream(stream)));
-  return CPT_OK;
+  return dgrad_fp32(g, dy, w, dx, ws, ws_bytes, as_stream(stream));
 }
 
 int cpt_conv2d_wgrad(const cpt_conv2d_desc* d, const float* x, const float* dy, float* dw, float* db, int mode,

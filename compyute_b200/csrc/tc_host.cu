@@ -67,17 +67,19 @@ static int make_map_2d(CUtensorMap* m, const void* base, int mode, uint64_t cols
 // im2col map over a channels-last activation tensor (N, H, W, C) [C innermost, Cp channels per pixel].
 // Bounding box of the *base pixel* in input coordinates: [lower, extent - 1 + upper] per spatial dim, walked with
 // `stride`; the filter-tap offset is added per load (PTX {off_w, off_h}).  Out-of-bounds reads are zero-filled.
-static int make_map_im2col(CUtensorMap* m, const void* base, int mode, int Cp, int W, int H, int N, int lower, int upper_w,
-                           int upper_h, int stride, int channels_per_pixel, int pixels_per_column, bool mn_major = false) {
+static int make_map_im2col(CUtensorMap* m, const void* base, int mode, int Cp, int W, int H, int N, int lower_w, int lower_h,
+                           int upper_w, int upper_h, int stride, int channels_per_pixel, int pixels_per_column,
+                           bool mn_major = false) {
   if (int e = load_driver()) return e;
   const int es = esize(mode);
   CPT_REQUIRE(((uintptr_t)base & 15) == 0 && ((size_t)Cp * es) % 16 == 0, CPT_ERR_UNSUPPORTED, "im2col TMA alignment");
-  CPT_REQUIRE(lower >= -128 && lower <= 127 && upper_w >= -128 && upper_w <= 127 && upper_h >= -128 && upper_h <= 127,
+  CPT_REQUIRE(lower_w >= -128 && lower_w <= 127 && lower_h >= -128 && lower_h <= 127 && upper_w >= -128 && upper_w <= 127 &&
+                  upper_h >= -128 && upper_h <= 127,
               CPT_ERR_UNSUPPORTED, "im2col corner out of the 8-bit range");
   CPT_REQUIRE(stride >= 1 && stride <= 8, CPT_ERR_UNSUPPORTED, "im2col traversal stride %d unsupported", stride);
   cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)Cp * es, (cuuint64_t)W * Cp * es, (cuuint64_t)H * W * Cp * es};
-  int lo[2] = {lower, lower};
+  int lo[2] = {lower_w, lower_h};
   int hi[2] = {upper_w, upper_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = g_encode_im2col(m, mode == CPT_MODE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
@@ -85,8 +87,8 @@ static int make_map_im2col(CUtensorMap* m, const void* base, int mode, int Cp, i
                                (cuuint32_t)pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(mode, mn_major),
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CPT_REQUIRE(r == CUDA_SUCCESS, CPT_ERR_CUDA,
-              "cuTensorMapEncodeIm2col failed (%d) C=%d W=%d H=%d N=%d lo=%d hi=%d,%d stride=%d cpp=%d ppc=%d", (int)r, Cp, W, H, N,
-              lower, upper_w, upper_h, stride, channels_per_pixel, pixels_per_column);
+              "cuTensorMapEncodeIm2col failed (%d) C=%d W=%d H=%d N=%d lo=%d,%d hi=%d,%d stride=%d cpp=%d ppc=%d", (int)r, Cp, W, H, N,
+              lower_w, lower_h, upper_w, upper_h, stride, channels_per_pixel, pixels_per_column);
   // Known driver issue (also worked around by CUTLASS, copy_traits_sm90_im2col.hpp): for tensors < 128 KiB the
   // encoder sets a descriptor bit that makes small im2col loads fault; clear it.
   int drv = 0;
@@ -215,15 +217,17 @@ __global__ void w_fprop_kernel(const float* __restrict__ w, void* __restrict__ d
     else reinterpret_cast<float*>(dst)[i] = round_tf32(v);
   }
 }
-// dgrad weight matrix [Ci][T][Cok] with both spatial axes flipped: w'[ci][t][co] = w[co][ci][T-1-t]
+// dgrad weight matrix [Ci][nt][Cok] for the taps of one stride class: w'[ci][t][co] = w[co][ci][tap_idx[t]]
+struct TapIdx { unsigned char idx[64]; };
 template <bool BF16>
-__global__ void w_dgrad_kernel(const float* __restrict__ w, void* __restrict__ dst, int Co, int Ci, int T, int Cok) {
-  const int64_t n = (int64_t)Ci * T * Cok;
+__global__ void w_dgrad_kernel(const float* __restrict__ w, void* __restrict__ dst, int Co, int Ci, int T, int nt, int Cok,
+                               const TapIdx taps) {
+  const int64_t n = (int64_t)Ci * nt * Cok;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int co = (int)(i % Cok);
     const int64_t r = i / Cok;
-    const int tap = (int)(r % T), ci = (int)(r / T);
-    const float v = co < Co ? w[((int64_t)co * Ci + ci) * T + (T - 1 - tap)] : 0.f;
+    const int tap = (int)(r % nt), ci = (int)(r / nt);
+    const float v = co < Co ? w[((int64_t)co * Ci + ci) * T + taps.idx[tap]] : 0.f;
     if (BF16) reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
     else reinterpret_cast<float*>(dst)[i] = round_tf32(v);
   }
@@ -350,7 +354,7 @@ static size_t cl_bytes(int B, int C, int H, int W, int mode) {
 static size_t wmat_bytes(int rows, int T, int C, int mode) {
   return align_up((size_t)rows * T * round_up(C, kc_of(mode)) * esize(mode), 1024);
 }
-static bool dgrad_tc_ok(const G& g) { return g.S == 1 && (g.K - 1) * g.D - g.P >= 0 && (g.K - 1) * g.D - g.P <= 127; }
+static bool dgrad_tc_ok(const G& g);
 
 static int wgrad_splits(const G& g, int mode) {
   const int bk = kc_of(mode);
@@ -375,16 +379,26 @@ int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, in
   return CPT_OK;
 }
 
-// fprop-form implicit GEMM: out[b, n, p, q] = Σ_{tap, c} act_cl[b, p*s - P + j*d, q*s - P + kk*d, c] * wmat[n][tap][c]
-static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Win, const void* wmat, int Ncols, int K, int pad,
-                            int stride, int dil, int Hout, int Wout, const float* bias, float* out, int mode, cudaStream_t st) {
-  const int kc = kc_of(mode), Cp = round_up(Cact, 8), Ck = round_up(Cact, kc), T = K * K;
+// Geometry of one implicit-GEMM launch over a channels-last activation tensor.
+struct ConvPlan {
+  int ntaps;
+  unsigned short off_w[64], off_h[64];  // im2col offsets per tap (>= 0, relative to the lower corner)
+  int lower_w, lower_h, upper_w, upper_h, trav;  // bounding box of the base pixel, traversal stride
+  int sub_H, sub_W;                     // grid of base pixels == GEMM lanes per image
+  int out_H, out_W, out_s, out_r0, out_c0;  // where lane (r, c) lands in the NCHW output plane
+};
+
+// out[b, n, out_r0 + out_s*r, out_c0 + out_s*c] = Σ_{t, ch} act_cl[b, lower_h + r*trav + off_h[t], lower_w + c*trav + off_w[t], ch]
+//                                                          * wmat[n][t][ch]     (+ bias[n])
+static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Win, const void* wmat, int Ncols, const ConvPlan& pl,
+                            const float* bias, float* out, int mode, cudaStream_t st) {
+  const int kc = kc_of(mode), Cp = round_up(Cact, 8), Ck = round_up(Cact, kc), T = pl.ntaps;
   const int BN = pick_bn(Ncols);
   TcParams p{};
-  const int upper = pad - (K - 1) * dil;  // CUTLASS detail.hpp compute_upper_corner_whd (fprop)
-  if (int e = make_map_im2col(&p.tmA, act_cl, mode, Cp, Win, Hin, B, -pad, upper, upper, stride, kc, 128)) return e;
-  const int64_t M = (int64_t)B * Hout * Wout;
+  const int64_t M = (int64_t)B * pl.sub_H * pl.sub_W;
+  CPT_REQUIRE(M < (1LL << 31), CPT_ERR_UNSUPPORTED, "conv: pixel count exceeds int32");
   const bool use2 = want_2cta(BN, (M + 127) / 128);
+  if (int e = make_map_im2col(&p.tmA, act_cl, mode, Cp, Win, Hin, B, pl.lower_w, pl.lower_h, pl.upper_w, pl.upper_h, pl.trav, kc, 128)) return e;
   if (int e = make_map_2d(&p.tmB, wmat, mode, (uint64_t)T * Ck, Ncols, (uint64_t)T * Ck, kc, use2 ? BN / 2 : BN)) return e;
   p.out = out;
   p.bias = bias;
@@ -398,23 +412,28 @@ static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Wi
   p.cchunks = Ck / kc;
   p.k_iters_total = T * p.cchunks;
   p.k_iters_per_split = p.k_iters_total;
-  p.col_stride = (long long)Hout * Wout;
+  p.col_stride = (long long)pl.out_H * pl.out_W;
   p.lane_is_pixel = 1;
-  p.px_per_img = Hout * Wout;
-  p.img_stride = (long long)Ncols * Hout * Wout;
-  p.Wo = Wout;
-  p.conv_stride = stride;
-  p.pad = pad;
-  p.dil = dil;
-  p.Kw = K;
+  p.px_per_img = pl.sub_H * pl.sub_W;
+  p.img_stride = (long long)Ncols * pl.out_H * pl.out_W;
+  p.out_W = pl.out_W; p.out_s = pl.out_s; p.out_r0 = pl.out_r0; p.out_c0 = pl.out_c0;
+  p.Wo = pl.sub_W;
+  p.trav = pl.trav; p.lower_w = pl.lower_w; p.lower_h = pl.lower_h;
   p.taps = T;
   p.wk_cols = Ck;
+  for (int t = 0; t < T; ++t) { p.tap_w[t] = pl.off_w[t]; p.tap_h[t] = pl.off_h[t]; }
   return launch_bn<false, false, OP_CONV>(p, mode, BN, use2, st);
+}
+
+static bool fprop_tc_ok(const G& g) {
+  const int upper = g.P - (g.K - 1) * g.D;
+  return g.T <= 64 && g.P <= 128 && upper >= -128 && upper <= 127 && (g.K - 1) * g.D <= 255 && g.S <= 8;
 }
 
 int conv_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w, const float* bias, float* y, int mode, void* ws,
                   size_t ws_bytes, cudaStream_t st) {
   const G g = geom(d);
+  CPT_REQUIRE(fprop_tc_ok(g), CPT_ERR_UNSUPPORTED, "conv2d_fprop_cl: kernel %d / padding %d / dilation %d outside the TMA im2col limits", g.K, g.P, g.D);
   const size_t need = wmat_bytes(g.Co, g.T, g.Ci, mode);
   CPT_REQUIRE(ws && ws_bytes >= need, CPT_ERR_WORKSPACE, "conv2d_fprop_cl: workspace too small (%zu < %zu)", ws_bytes, need);
   const int Ck = round_up(g.Ci, kc_of(mode));
@@ -422,23 +441,111 @@ int conv_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w, co
   if (mode == CPT_MODE_BF16) w_fprop_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Ck);
   else w_fprop_kernel<false><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Ck);
   CPT_LAUNCH_CHECK("w_fprop");
-  return conv_im2col_gemm(x_cl, g.B, g.Ci, g.H, g.W, ws, g.Co, g.K, g.P, g.S, g.D, g.Ho, g.Wo, bias, y, mode, st);
+  ConvPlan pl{};
+  pl.ntaps = g.T;
+  for (int j = 0; j < g.K; ++j)
+    for (int kk = 0; kk < g.K; ++kk) { pl.off_h[j * g.K + kk] = (unsigned short)(j * g.D); pl.off_w[j * g.K + kk] = (unsigned short)(kk * g.D); }
+  pl.lower_w = pl.lower_h = -g.P;
+  // upper corner = P - (K-1) D (same rule as CUTLASS detail.hpp compute_upper_corner_whd, fprop): base pixels run from
+  // -P to extent-1+upper in steps of S, i.e. exactly Wo (Ho) positions per row (column)
+  pl.upper_w = pl.upper_h = g.P - (g.K - 1) * g.D;
+  pl.trav = g.S;
+  pl.sub_H = g.Ho; pl.sub_W = g.Wo;
+  pl.out_H = g.Ho; pl.out_W = g.Wo; pl.out_s = 1; pl.out_r0 = pl.out_c0 = 0;
+  return conv_im2col_gemm(x_cl, g.B, g.Ci, g.H, g.W, ws, g.Co, pl, bias, y, mode, st);
+}
+
+// taps (j, kk) of stride class (rh, rw) — same rule as the exact path (conv.cu class_taps)
+static int tc_class_taps(const G& g, int rh, int rw, int* tj, int* tk) {
+  int n = 0;
+  for (int j = 0; j < g.K; ++j) {
+    if (((rh + g.P - j * g.D) % g.S + g.S) % g.S != 0) continue;
+    for (int kk = 0; kk < g.K; ++kk) {
+      if (((rw + g.P - kk * g.D) % g.S + g.S) % g.S != 0) continue;
+      if (n < 64) { tj[n] = j; tk[n] = kk; }
+      ++n;
+    }
+  }
+  return n;
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// Plans dgrad for one stride class; returns false if it cannot run on the im2col path.
+static bool dgrad_class_plan(const G& g, int rh, int rw, ConvPlan& pl, TapIdx& ti) {
+  int tj[64], tk[64];
+  const int nt = tc_class_taps(g, rh, rw, tj, tk);
+  if (nt > 64) return false;
+  pl = ConvPlan{};
+  pl.ntaps = nt;
+  pl.sub_H = (g.H - rh + g.S - 1) / g.S;
+  pl.sub_W = (g.W - rw + g.S - 1) / g.S;
+  pl.out_H = g.H; pl.out_W = g.W; pl.out_s = g.S; pl.out_r0 = rh; pl.out_c0 = rw;
+  pl.trav = 1;
+  if (nt == 0) return true;
+  // dy row read by tap j for sub-grid row hs: p = hs + (rh + P - j*D) / S  (exact division inside a class)
+  int lo_h = 1 << 30, lo_w = 1 << 30, hi_h = -(1 << 30), hi_w = -(1 << 30);
+  for (int t = 0; t < nt; ++t) {
+    const int oh = floordiv(rh + g.P - tj[t] * g.D, g.S), ow = floordiv(rw + g.P - tk[t] * g.D, g.S);
+    lo_h = oh < lo_h ? oh : lo_h; hi_h = oh > hi_h ? oh : hi_h;
+    lo_w = ow < lo_w ? ow : lo_w; hi_w = ow > hi_w ? ow : hi_w;
+  }
+  for (int t = 0; t < nt; ++t) {
+    pl.off_h[t] = (unsigned short)(floordiv(rh + g.P - tj[t] * g.D, g.S) - lo_h);
+    pl.off_w[t] = (unsigned short)(floordiv(rw + g.P - tk[t] * g.D, g.S) - lo_w);
+    ti.idx[t] = (unsigned char)(tj[t] * g.K + tk[t]);
+  }
+  pl.lower_h = lo_h; pl.lower_w = lo_w;
+  // base pixels lower .. lower + sub - 1 over a (Ho, Wo) tensor: upper = lower + sub - extent
+  pl.upper_h = lo_h + pl.sub_H - g.Ho;
+  pl.upper_w = lo_w + pl.sub_W - g.Wo;
+  auto in8 = [](int v) { return v >= -128 && v <= 127; };
+  return in8(pl.lower_h) && in8(pl.lower_w) && in8(pl.upper_h) && in8(pl.upper_w) && hi_h - lo_h <= 255 && hi_w - lo_w <= 255;
+}
+
+static bool dgrad_tc_ok(const G& g) {
+  if (g.S > 8) return false;
+  for (int c = 0; c < g.S * g.S; ++c) {
+    const int rh = c / g.S, rw = c % g.S;
+    if (rh >= g.H || rw >= g.W) continue;
+    ConvPlan pl; TapIdx ti;
+    if (!dgrad_class_plan(g, rh, rw, pl, ti)) return false;
+  }
+  return true;
 }
 
 int conv_dgrad_cl(const cpt_conv2d_desc* d, const void* dy_cl, const float* w, float* dx, int mode, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
   const G g = geom(d);
-  CPT_REQUIRE(dgrad_tc_ok(g), CPT_ERR_UNSUPPORTED, "conv2d_dgrad_cl: stride %d / padding %d not supported on the tensor-core path",
-              g.S, g.P);
-  const size_t need = wmat_bytes(g.Ci, g.T, g.Co, mode);
-  CPT_REQUIRE(ws && ws_bytes >= need, CPT_ERR_WORKSPACE, "conv2d_dgrad_cl: workspace too small (%zu < %zu)", ws_bytes, need);
+  CPT_REQUIRE(dgrad_tc_ok(g), CPT_ERR_UNSUPPORTED, "conv2d_dgrad_cl: geometry (K=%d, stride=%d, pad=%d, dil=%d) outside the TMA im2col limits",
+              g.K, g.S, g.P, g.D);
   const int Cok = round_up(g.Co, kc_of(mode));
-  const int64_t n = (int64_t)g.Ci * g.T * Cok;
-  if (mode == CPT_MODE_BF16) w_dgrad_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Cok);
-  else w_dgrad_kernel<false><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Cok);
-  CPT_LAUNCH_CHECK("w_dgrad");
-  // dx = full correlation of dy with the flipped filter: an fprop over dy with padding (K-1)d - P, stride 1
-  return conv_im2col_gemm(dy_cl, g.B, g.Co, g.Ho, g.Wo, ws, g.Ci, g.K, (g.K - 1) * g.D - g.P, 1, g.D, g.H, g.W, nullptr, dx, mode, st);
+  const size_t per_class = align_up((size_t)g.Ci * g.T * Cok * esize(mode), 1024);
+  const size_t need = per_class * g.S * g.S;
+  CPT_REQUIRE(ws && ws_bytes >= need, CPT_ERR_WORKSPACE, "conv2d_dgrad_cl: workspace too small (%zu < %zu)", ws_bytes, need);
+  bool any_empty = false;
+  for (int c = 0; c < g.S * g.S; ++c) {
+    const int rh = c / g.S, rw = c % g.S;
+    if (rh >= g.H || rw >= g.W) continue;
+    ConvPlan pl; TapIdx ti;
+    dgrad_class_plan(g, rh, rw, pl, ti);
+    if (pl.ntaps == 0) any_empty = true;
+  }
+  if (any_empty) CPT_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)g.B * g.Ci * g.H * g.W, st));
+  for (int c = 0; c < g.S * g.S; ++c) {
+    const int rh = c / g.S, rw = c % g.S;
+    if (rh >= g.H || rw >= g.W) continue;
+    ConvPlan pl; TapIdx ti{};
+    dgrad_class_plan(g, rh, rw, pl, ti);
+    if (pl.ntaps == 0) continue;
+    void* wm = reinterpret_cast<char*>(ws) + per_class * c;
+    const int64_t n = (int64_t)g.Ci * pl.ntaps * Cok;
+    if (mode == CPT_MODE_BF16) w_dgrad_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w, wm, g.Co, g.Ci, g.T, pl.ntaps, Cok, ti);
+    else w_dgrad_kernel<false><<<ew_grid(n, 256), 256, 0, st>>>(w, wm, g.Co, g.Ci, g.T, pl.ntaps, Cok, ti);
+    CPT_LAUNCH_CHECK("w_dgrad");
+    if (int e = conv_im2col_gemm(dy_cl, g.B, g.Co, g.Ho, g.Wo, wm, g.Ci, pl, nullptr, dx, mode, st)) return e;
+  }
+  return CPT_OK;
 }
 
 int conv_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl, float* dw, int mode, void* ws, size_t ws_bytes,
@@ -454,9 +561,9 @@ int conv_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl,
   CPT_REQUIRE(ws && ws_bytes >= need, CPT_ERR_WORKSPACE, "conv2d_wgrad_cl: workspace too small (%zu < %zu)", ws_bytes, need);
   const int BN = pick_bn(g.Co);
   TcParams p{};
-  const int upper = g.P - (g.K - 1) * g.D;
+  const int upper_w = g.P - (g.K - 1) * g.D, upper_h = upper_w;
   // A: x_cl through im2col, lanes = input channels (MN-major), reduction = output pixels
-  if (int e = make_map_im2col(&p.tmA, x_cl, mode, round_up(g.Ci, 8), g.W, g.H, g.B, -g.P, upper, upper, g.S, kc, bk, true)) return e;
+  if (int e = make_map_im2col(&p.tmA, x_cl, mode, round_up(g.Ci, 8), g.W, g.H, g.B, -g.P, -g.P, upper_w, upper_h, g.S, kc, bk, true)) return e;
   // B: dy_cl as [pixels][Cop], columns = output channels (MN-major)
   const int Cop = round_up(g.Co, 8);
   if (int e = make_map_2d(&p.tmB, dy_cl, mode, Cop, (uint64_t)pixels, Cop, kc, bk, true)) return e;
@@ -482,6 +589,7 @@ int conv_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl,
   p.dil = g.D;
   p.Kw = g.K;
   p.taps = g.T;
+  p.out_s = 1;
   if (int e = launch_bn<true, true, OP_WGRAD>(p, mode, BN, want_2cta(BN, (g.Ci + 127) / 128), st)) return e;
   const int64_t n = (int64_t)g.Co * g.Ci * g.T;
   wgrad_reduce_kernel<<<ew_grid(n, 256), 256, 0, st>>>(reinterpret_cast<float*>(ws), dw, g.Co, g.Ci, g.T, splits);
@@ -493,8 +601,8 @@ size_t conv_workspace_size(int op, const cpt_conv2d_desc* d, int mode) {
   const G g = geom(d);
   if (op == CPT_OP_FPROP) return cl_bytes(g.B, g.Ci, g.H, g.W, mode) + wmat_bytes(g.Co, g.T, g.Ci, mode) + 1024;
   if (op == CPT_OP_DGRAD) {
-    if (!dgrad_tc_ok(g)) return 1024;
-    return cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode) + wmat_bytes(g.Ci, g.T, g.Co, mode) + 1024;
+    if (!dgrad_tc_ok(g)) return 8192;  // exact path: tap tables of the stride classes
+    return cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode) + (size_t)g.S * g.S * wmat_bytes(g.Ci, g.T, g.Co, mode) + 1024;
   }
   const size_t part = align_up((size_t)wgrad_splits(g, mode) * g.Co * g.T * g.Ci * sizeof(float), 1024);
   return cl_bytes(g.B, g.Ci, g.H, g.W, mode) + cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode) + part + 1024;
@@ -698,6 +806,10 @@ int cpt_conv2d_dgrad_cl(const cpt_conv2d_desc* d, const void* dy_cl, const float
                         size_t ws_bytes, void* stream) {
   if (int e = check_tc(d, mode, "conv2d_dgrad_cl")) return e;
   return tc::conv_dgrad_cl(d, dy_cl, w, dx, mode, ws, ws_bytes, as_stream(stream));
+}
+int cpt_conv2d_dgrad_cl_supported(const cpt_conv2d_desc* d, int mode) {
+  if (check_tc(d, mode, "conv2d_dgrad_cl_supported")) return 0;
+  return tc::dgrad_tc_ok(tc::geom(d)) ? 1 : 0;
 }
 int cpt_conv2d_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl, float* dw, int mode, void* ws,
                         size_t ws_bytes, void* stream) {

@@ -36,11 +36,16 @@ struct alignas(64) TcParams {
   int k_iters_per_split;
   // epilogue addressing: dst = out + z_off + lane_off(m) + col * col_stride
   long long col_stride, split_stride, tap_stride;
-  int lane_is_pixel;              // 1: m -> (image b, pixel pq): lane_off = b * img_stride + pq
-  int px_per_img;                 // Ho*Wo (CONV lanes, WGRAD reduction)
+  int lane_is_pixel;              // 1: lane m -> (image b, sub-grid row r, col c): lane_off = b*img_stride + (out_r0 + out_s*r)*out_W + out_c0 + out_s*c
+  int px_per_img;                 // pixels per image of the lane / reduction grid (CONV lanes: sub_H*sub_W, WGRAD: Ho*Wo)
   long long img_stride;
-  // convolution geometry (im2col coordinates)
-  int Wo, conv_stride, pad, dil, Kw, taps, cchunks, wk_cols;  // wk_cols: weight-matrix columns per tap (padded C)
+  int out_W, out_s, out_r0, out_c0;  // output scatter of CONV lanes (dense fprop/dgrad: out_W = Wo, out_s = 1, r0 = c0 = 0)
+  // convolution geometry (im2col coordinates): base pixel of grid position (r, c) = (lower_h + r*trav, lower_w + c*trav)
+  int Wo;                          // width of the lane / reduction pixel grid
+  int trav, lower_w, lower_h;      // traversal stride and lower corner of the im2col bounding box
+  int conv_stride, pad, dil, Kw;   // WGRAD: conv geometry for the tap of this tile
+  int taps, cchunks, wk_cols;      // wk_cols: weight-matrix columns per tap (padded C)
+  unsigned short tap_w[64], tap_h[64];  // CONV: im2col offsets of tap t (fprop: kk*dil, j*dil; dgrad: class offsets)
 };
 
 template <bool BF16>
@@ -136,8 +141,8 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
       int cw = 0, ch = 0, cn = 0, tap = 0, k_begin = 0;
       if (OP == OP_CONV) {
         const int b = m0 / p.px_per_img, rem = m0 - b * p.px_per_img, py = rem / p.Wo, qx = rem - py * p.Wo;
-        cw = qx * p.conv_stride - p.pad;
-        ch = py * p.conv_stride - p.pad;
+        cw = qx * p.trav + p.lower_w;
+        ch = py * p.trav + p.lower_h;
         cn = b;
       } else if (OP == OP_WGRAD) {
         tap = z % p.taps;
@@ -155,8 +160,7 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
         if (OP == OP_CONV) {
           // A: 128 output pixels x KC channels of filter tap (j, kk); B: weights [Co][tap][C] rows n0.., K-major
           const int tp = i / p.cchunks, cc = i - tp * p.cchunks;
-          const int j = tp / p.Kw, kk = tp - j * p.Kw;
-          tma_load_im2col_4d<CTA2>(&p.tmA, fb, sa, cc * E::KC, cw, ch, cn, (uint16_t)(kk * p.dil), (uint16_t)(j * p.dil));
+          tma_load_im2col_4d<CTA2>(&p.tmA, fb, sa, cc * E::KC, cw, ch, cn, p.tap_w[tp], p.tap_h[tp]);
           tma_load_2d<CTA2>(&p.tmB, fb, sb, tp * p.wk_cols + cc * E::KC, n0);
         } else if (OP == OP_WGRAD) {
           // reduction over output pixels: chunk of BK pixels starting at flattened pixel k0
@@ -235,8 +239,8 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
       else if (OP == OP_GEMM) z_off = (long long)z * p.split_stride;
       long long lane_off = m;
       if (p.lane_is_pixel) {
-        const int b = m / p.px_per_img;
-        lane_off = (long long)b * p.img_stride + (m - b * p.px_per_img);
+        const int b = m / p.px_per_img, rem = m - b * p.px_per_img, r = rem / p.Wo, c = rem - r * p.Wo;
+        lane_off = (long long)b * p.img_stride + (long long)(p.out_r0 + p.out_s * r) * p.out_W + p.out_c0 + p.out_s * c;
       }
       const bool m_ok = m < p.M;
       const float lane_bias = (p.bias_mode == BIAS_LANE && m_ok) ? __ldg(p.bias + m) : 0.f;

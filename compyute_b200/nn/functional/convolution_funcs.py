@@ -50,6 +50,8 @@ class Conv2DFn(Function):
         d = _desc(x.shape, f.shape, padding, stride, dilation)
         ho, wo = _out_hw(d)
         mode = get_compute_mode()
+        if mode != _lib.MODE_FP32 and (d.K * d.K > 64 or (d.K - 1) * d.dil > 255 or d.pad > 127 or d.stride > 8):
+            mode = _lib.MODE_FP32  # outside the TMA im2col limits (8-bit corners, 64 taps): exact path for this layer
         y = DeviceArray.empty((d.B, d.Co, ho, wo), np.float32)
         st = stream_ptr()
         x_cl = None
@@ -81,7 +83,7 @@ class Conv2DFn(Function):
             db = db_out.reshape((d.Co,)) if db_out is not None else DeviceArray.empty((d.Co,), np.float32)
         dbp = db.ptr if db is not None else None
         ho, wo = dy.shape[2], dy.shape[3]
-        tc_dgrad = mode != _lib.MODE_FP32 and d.stride == 1 and 0 <= (d.K - 1) * d.dil - d.pad <= 127
+        tc_dgrad = mode != _lib.MODE_FP32 and bool(L.cpt_conv2d_dgrad_cl_supported(dref, mode))
         if mode == _lib.MODE_FP32:
             ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_DGRAD, dref, mode))
             _lib.check(L.cpt_conv2d_dgrad(dref, f32ptr(dy), f32ptr(f), dx.ptr, mode, ws, wsb, st))
@@ -96,7 +98,7 @@ class Conv2DFn(Function):
             if tc_dgrad:
                 ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_DGRAD, dref, mode))
                 _lib.check(L.cpt_conv2d_dgrad_cl(dref, dy_cl.ptr, f32ptr(f), dx.ptr, mode, ws, wsb, st))
-            else:  # strided dgrad has no tensor-core kernel yet: exact path
+            else:  # geometry outside the TMA im2col limits: exact path
                 ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_DGRAD, dref, _lib.MODE_FP32))
                 _lib.check(L.cpt_conv2d_dgrad(dref, f32ptr(dy), f32ptr(f), dx.ptr, _lib.MODE_FP32, ws, wsb, st))
             ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_WGRAD, dref, mode))

@@ -88,6 +88,9 @@ int cpt_conv2d_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float*
                         void* stream);
 int cpt_conv2d_dgrad_cl(const cpt_conv2d_desc* d, const void* dy_cl, const float* w, float* dx,
                         int mode, void* ws, size_t ws_bytes, void* stream);
+/* 1 if cpt_conv2d_dgrad_cl can run this geometry on the tensor-core path (stride classes within the TMA im2col
+ * limits), else 0: the caller then uses cpt_conv2d_dgrad with CPT_MODE_FP32 on the fp32 dy. */
+int cpt_conv2d_dgrad_cl_supported(const cpt_conv2d_desc* d, int mode);
 int cpt_conv2d_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl, float* dw,
                         int mode, void* ws, size_t ws_bytes, void* stream);
 

@@ -143,9 +143,9 @@ class RefModel:
             dy = l.backward(dy)
         return dy
 
-    def train_steps(self, x, t, steps, lr=1e-3):
-        """README.md:170-183 loop with CrossEntropyLoss + Adam; returns the loss trace."""
-        opt = R.Adam(lr=lr)
+    def train_steps(self, x, t, steps, lr=1e-3, optimizer="adam", **kw):
+        """README.md:170-183 loop with CrossEntropyLoss + Adam / SGD; returns the loss trace."""
+        opt = R.Adam(lr=lr, **kw) if optimizer == "adam" else R.SGD(lr=lr, **kw)
         losses = []
         for _ in range(steps):
             lc = []

@@ -1,8 +1,10 @@
 """Model-level GPU parity (``-m gpu``): reduced-size instances of BASELINE.json's configs 1, 3, 4, 5 trained for a few
-Adam steps through the compyute_b200 module API, against the oracle's model interpreter (same spec, same initial
-parameters, same batch).  fp32 mode.  Tolerance: losses 1e-4 relative, parameters allclose(2e-4): per-op agreement is
-1e-5 (test_gpu_parity.py); a 20-60-op deep fp32 network compounds that, and Adam turns relative gradient error into
-absolute parameter error of the same order times lr."""
+steps through the compyute_b200 module API, against the oracle's model interpreter (same spec, same initial parameters,
+same batch).  fp32 mode.  Checked: every parameter gradient of the first backward (error <= 2e-4 of the gradient's max
+magnitude: per-op agreement is 1e-5, test_gpu_parity.py, and a 20-60-op deep fp32 network compounds it), the loss trace
+(1e-4) and the parameters after 3 SGD-momentum steps.  SGD rather than Adam on purpose: several parameters of these models
+have an analytically ZERO gradient (a conv bias feeding a BatchNorm, possibly through an all-positive ReLU channel), which
+both implementations return as rounding noise of different sign, and Adam's g/sqrt(g^2) turns that noise into +-lr."""
 import numpy as np
 import pytest
 
@@ -34,22 +36,33 @@ def test_config_train_steps(name):
     x = rng.normal(0, 1, xshape).astype(np.float32)
     t = rng.randint(0, classes, (xshape[0],))
     ref = RefModel(spec, [p.copy() for p in params0], [b.copy() for b in bufs0])
-    ref_losses = ref.train_steps(x, t, 3, lr=1e-3)
+    # gradients of the first backward pass
+    from oracle import compyute_ref as R
+    gref = RefModel(spec, [p.copy() for p in params0], [b.copy() for b in bufs0])
+    lc = []
+    R.cross_entropy_forward(lc, gref.forward(x, True), t)
+    gref.backward(R.cross_entropy_backward(lc))
+    ref_losses = ref.train_steps(x, t, 3, lr=0.05, optimizer="sgd", momentum=0.9)
 
-    opt = nn.optimizers.Adam(model.get_parameters(), lr=1e-3)
+    opt = nn.optimizers.SGD(model.get_parameters(), lr=0.05, momentum=0.9)
     loss_fn = nn.CrossEntropyLoss()
     xt, tt = cp.tensor(x, device=cp.cuda), cp.tensor(t.astype(np.int32), device=cp.cuda)
     losses = []
-    for _ in range(3):
+    for step in range(3):
         loss = loss_fn(model(xt), tt)
         opt.reset_grads()
         model.backward(loss_fn.backward())
+        if step == 0:
+            for i, (p, g) in enumerate(zip(model.get_parameters(), gref.gradients())):
+                got = p.grad.to_numpy()
+                assert got.shape == g.shape
+                assert np.abs(got - g).max() <= 2e-4 * max(np.abs(g).max(), 1e-3), f"grad {i}: {np.abs(got - g).max():.3e} vs max {np.abs(g).max():.3e}"
         opt.step()
         losses.append(loss.item())
     assert np.allclose(losses, ref_losses, rtol=1e-4, atol=1e-5), (losses, ref_losses)
     for i, (p, r) in enumerate(zip(model.get_parameters(), ref.parameters())):
         assert p.shape == r.shape
-        assert np.allclose(p.to_numpy(), r, rtol=2e-4, atol=2e-4), f"param {i} max err {np.abs(p.to_numpy() - r).max():.3e}"
+        assert np.allclose(p.to_numpy(), r, rtol=5e-4, atol=5e-5), f"param {i} max err {np.abs(p.to_numpy() - r).max():.3e}"
     for b, r in zip(model.get_buffers(), ref.buffers()):
         assert np.allclose(b.to_numpy(), r, rtol=1e-4, atol=1e-5)
     assert all(not m.fcache.cache for m in model.get_modules())

@@ -110,4 +110,8 @@ if __name__ == "__main__":
         results.append(conv_case(mode, 2, 32, 32, 16, 3, 1, 2, 1))   # strided fprop / wgrad (dgrad -> exact path)
         results.append(conv_case(mode, 2, 16, 16, 12, 3, 2, 1, 2))   # dilation
         results.append(conv_case(mode, 2, 3, 8, 10, 3, 1, 1, 1))     # tiny channel count
+        results.append(conv_case(mode, 2, 64, 128, 16, 1, 0, 2, 1))  # 1x1 stride 2: empty stride classes (dx = 0 there)
+        results.append(conv_case(mode, 2, 3, 16, 30, 7, 3, 2, 1))    # ResNet stem shape: 7x7 / s2 / p3, Ci = 3
+        results.append(conv_case(mode, 2, 16, 24, 17, 3, 1, 3, 1))   # stride 3, odd extent
+        results.append(conv_case(mode, 1, 8, 8, 13, 3, 0, 2, 2))     # stride 2 + dilation 2
     print("SUMMARY", sum(bool(r) for r in results), "/", len(results), flush=True)
