@@ -37,59 +37,76 @@ int sm_count() {
 }
 
 // ------------------------------------------------------------------ ReLU (8 B/elem + 1/8 B mask)
+// Mask layout (private to this pair of kernels): elements are processed in chunks of 1024 by one warp; lane l handles the
+// float4s at (j*32 + l), j = 0..7, of the chunk and owns mask word chunk*32 + l (bit 4j+i = element i of its j-th float4),
+// so both the eight 128-bit loads per thread and the 128-byte mask store per warp are fully coalesced.  The tail
+// (< 1024 elements) uses plain bit order after the last full chunk.
 __global__ void __launch_bounds__(256) relu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                       uint8_t* __restrict__ mask, int64_t n8, int64_t n) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
-    const float4* xp = reinterpret_cast<const float4*>(x) + 2 * i;
-    float4 a = ld_stream(xp), b = ld_stream(xp + 1);
-    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    unsigned bits = 0;
+                                                       uint32_t* __restrict__ mask, int64_t n_chunks, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp0; c < n_chunks; c += nwarps) {
+    const float4* xp = reinterpret_cast<const float4*>(x) + c * 256 + lane;
+    float4* yp = reinterpret_cast<float4*>(y) + c * 256 + lane;
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ld_stream(xp + j * 32);
+    uint32_t bits = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v[j] = fmaxf(v[j], 0.f);  // numpy.maximum(x, 0): NaN propagates in numpy; fmaxf drops it -> fix below
-      bits |= (v[j] > 0.f ? 1u : 0u) << j;
-    }
-    // numpy.maximum propagates NaN; restore that behaviour
-    float w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (w[j] != w[j]) v[j] = w[j];
-    float4* yp = reinterpret_cast<float4*>(y) + 2 * i;
-    st_stream(yp, make_float4(v[0], v[1], v[2], v[3]));
-    st_stream(yp + 1, make_float4(v[4], v[5], v[6], v[7]));
-    if (mask) mask[i] = (uint8_t)bits;
-  }
-  // tail (< 8 elements): one thread
-  if (blockIdx.x == 0 && threadIdx.x == 0 && (n8 * 8 < n)) {
-    unsigned bits = 0;
-    for (int64_t i = n8 * 8; i < n; ++i) {
-      float xv = x[i];
-      float r = (xv != xv) ? xv : fmaxf(xv, 0.f);
-      y[i] = r;
-      bits |= (r > 0.f ? 1u : 0u) << (i - n8 * 8);
+      for (int i = 0; i < 4; ++i) {
+        const float r = (e[i] != e[i]) ? e[i] : fmaxf(e[i], 0.f);  // numpy.maximum propagates NaN
+        bits |= (r > 0.f ? 1u : 0u) << (4 * j + i);
+        e[i] = r;
+      }
+      st_stream(yp + j * 32, make_float4(e[0], e[1], e[2], e[3]));
     }
-    if (mask) mask[n8] = (uint8_t)bits;
+    if (mask) mask[c * 32 + lane] = bits;
+  }
+  // tail: one warp, plain bit order
+  if (warp0 == 0) {
+    const int64_t t0 = n_chunks * 1024;
+    for (int64_t base = t0; base < n; base += 32) {
+      const int64_t i = base + lane;
+      float r = 0.f;
+      if (i < n) {
+        const float xv = x[i];
+        r = (xv != xv) ? xv : fmaxf(xv, 0.f);
+        y[i] = r;
+      }
+      const uint32_t b = __ballot_sync(0xffffffffu, i < n && r > 0.f);
+      if (mask && lane == 0) mask[n_chunks * 32 + (base - t0) / 32] = b;
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ mask,
-                                                       float* __restrict__ dx, int64_t n8, int64_t n) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
-    const float4* gp = reinterpret_cast<const float4*>(dy) + 2 * i;
-    float4 a = ld_stream(gp), b = ld_stream(gp + 1);
-    unsigned bits = mask[i];
-    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ dy, const uint32_t* __restrict__ mask,
+                                                       float* __restrict__ dx, int64_t n_chunks, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp0; c < n_chunks; c += nwarps) {
+    const float4* gp = reinterpret_cast<const float4*>(dy) + c * 256 + lane;
+    float4* xp = reinterpret_cast<float4*>(dx) + c * 256 + lane;
+    float4 v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = v[j] * (float)((bits >> j) & 1u);  // dy * mask (keeps -0.0 / NaN like numpy)
-    float4* xp = reinterpret_cast<float4*>(dx) + 2 * i;
-    st_stream(xp, make_float4(v[0], v[1], v[2], v[3]));
-    st_stream(xp + 1, make_float4(v[4], v[5], v[6], v[7]));
+    for (int j = 0; j < 8; ++j) v[j] = ld_stream(gp + j * 32);
+    const uint32_t bits = mask[c * 32 + lane];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // dy * mask (keeps -0.0 / NaN like numpy's float * bool)
+      st_stream(xp + j * 32, make_float4(v[j].x * (float)((bits >> (4 * j)) & 1u), v[j].y * (float)((bits >> (4 * j + 1)) & 1u),
+                                         v[j].z * (float)((bits >> (4 * j + 2)) & 1u), v[j].w * (float)((bits >> (4 * j + 3)) & 1u)));
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && (n8 * 8 < n)) {
-    unsigned bits = mask[n8];
-    for (int64_t i = n8 * 8; i < n; ++i) dx[i] = dy[i] * (float)((bits >> (i - n8 * 8)) & 1u);
+  if (warp0 == 0) {
+    const int64_t t0 = n_chunks * 1024;
+    for (int64_t base = t0; base < n; base += 32) {
+      const int64_t i = base + lane;
+      const uint32_t b = mask[n_chunks * 32 + (base - t0) / 32];
+      if (i < n) dx[i] = dy[i] * (float)((b >> lane) & 1u);
+    }
   }
 }
 
@@ -185,9 +202,11 @@ int cpt_device_info(int device, int* sm, int* major, int* minor, size_t* smem_op
 int cpt_relu_fwd(const float* x, float* y, uint8_t* mask, int64_t n, void* stream) {
   CPT_REQUIRE(n >= 0 && x && y, CPT_ERR_INVALID, "relu_fwd: bad arguments");
   if (n == 0) return CPT_OK;
-  CPT_REQUIRE(aligned16(x) && aligned16(y), CPT_ERR_INVALID, "relu_fwd: pointers must be 16-byte aligned");
-  int64_t n8 = n / 8;
-  relu_fwd_kernel<<<ew_grid(n8 > 0 ? n8 : 1, 256), 256, 0, as_stream(stream)>>>(x, y, mask, n8, n);
+  CPT_REQUIRE(aligned16(x) && aligned16(y) && (!mask || (reinterpret_cast<uintptr_t>(mask) & 3) == 0), CPT_ERR_INVALID,
+              "relu_fwd: x, y must be 16-byte aligned and mask 4-byte aligned");
+  const int64_t n_chunks = n / 1024;
+  relu_fwd_kernel<<<ew_grid((n_chunks > 0 ? n_chunks : 1) * 32, 256), 256, 0, as_stream(stream)>>>(
+      x, y, reinterpret_cast<uint32_t*>(mask), n_chunks, n);
   CPT_LAUNCH_CHECK("relu_fwd");
   return CPT_OK;
 }
@@ -196,8 +215,9 @@ int cpt_relu_bwd(const float* dy, const uint8_t* mask, float* dx, int64_t n, voi
   CPT_REQUIRE(n >= 0 && dy && dx && mask, CPT_ERR_INVALID, "relu_bwd: bad arguments");
   if (n == 0) return CPT_OK;
   CPT_REQUIRE(aligned16(dy) && aligned16(dx), CPT_ERR_INVALID, "relu_bwd: pointers must be 16-byte aligned");
-  int64_t n8 = n / 8;
-  relu_bwd_kernel<<<ew_grid(n8 > 0 ? n8 : 1, 256), 256, 0, as_stream(stream)>>>(dy, mask, dx, n8, n);
+  const int64_t n_chunks = n / 1024;
+  relu_bwd_kernel<<<ew_grid((n_chunks > 0 ? n_chunks : 1) * 32, 256), 256, 0, as_stream(stream)>>>(
+      dy, reinterpret_cast<const uint32_t*>(mask), dx, n_chunks, n);
   CPT_LAUNCH_CHECK("relu_bwd");
   return CPT_OK;
 }

@@ -115,7 +115,7 @@ constexpr int CL_PX = 128, CL_CH = 64;
 
 template <bool BF16>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW,
-                                                           int Cp, float* __restrict__ chan_sum) {
+                                                           int Cp, float* __restrict__ chan_sum, float* __restrict__ partial) {
   __shared__ uint32_t tile[BF16 ? 32 : 64][CL_PX + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = blockIdx.y * CL_CH, b = blockIdx.z;
@@ -193,15 +193,33 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
     __syncthreads();  // tile is reused by the next pixel tile
   }
 
-  if (chan_sum) {  // warp-shuffle tree, then one atomic per (block, channel)
+  if (chan_sum || partial) {  // warp-shuffle tree, then one value per (block, channel)
+    const int64_t blk = (int64_t)blockIdx.z * gridDim.x + blockIdx.x;  // row of the partial matrix [B*gx][groups*64]
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float t = warp_sum(acc[i]);
       // BF16: acc[2ci], acc[2ci+1] <-> channels c0 + 2(warp + 8ci) + {0,1};  TF32: acc[ci] <-> channel c0 + warp + 8ci
       const int c = BF16 ? c0 + 2 * (warp + 8 * (i >> 1)) + (i & 1) : c0 + warp + 8 * i;
-      if (lane == 0 && c < C) atomicAdd(chan_sum + c, t);
+      if (lane == 0 && c < C) {
+        if (partial) partial[blk * ((int64_t)gridDim.y * CL_CH) + c] = t;  // deterministic: reduced in fixed order below
+        else atomicAdd(chan_sum + c, t);
+      }
     }
   }
+}
+
+// out[c] = Σ_rows partial[row][c] in fixed row order (one thread per channel, coalesced across channels)
+__global__ void chan_partial_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int C, int64_t rows, int pitch) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int64_t r = 0;
+  for (; r + 3 < rows; r += 4) {
+    s0 += partial[r * pitch + c]; s1 += partial[(r + 1) * pitch + c];
+    s2 += partial[(r + 2) * pitch + c]; s3 += partial[(r + 3) * pitch + c];
+  }
+  for (; r < rows; ++r) s0 += partial[r * pitch + c];
+  out[c] = (s0 + s1) + (s2 + s3);
 }
 
 // w (Co, Ci, K, K) fp32 -> fprop weight matrix [Co][T][Ck] (zero padded, Ck = round_up(Ci, KC))
@@ -327,6 +345,10 @@ static int pick_splits(int tiles, int k_iters, int min_iters) {
   const int sms = sm_count();
   int best = 1;
   double best_eff = 0.0;
+  {  // a split costs a partial write + a reduce pass: not worth it when one pass already fills >= 80 % of its waves
+    const int waves1 = (tiles + sms - 1) / sms;
+    if ((double)tiles / ((double)waves1 * sms) >= 0.8) return 1;
+  }
   for (int s = 1; s <= 64; ++s) {
     if (s > 1 && k_iters / s < min_iters) break;
     const int total = tiles * s;
@@ -363,19 +385,41 @@ static int wgrad_splits(const G& g, int mode) {
   return pick_splits(tiles, k_iters, 8);
 }
 
-int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, int mode, float* chan_sum, cudaStream_t st) {
+static void cl_grid(int B, int C, int H, int W, int& gx, int& groups) {
   const int Cp = round_up(C, 8), HW = H * W;
   // each block walks several pixel tiles of its (image, 64-channel group) so the per-channel partial sums are reduced
   // once per block; keep >= ~16 blocks per SM overall (several waves)
-  const int n_tiles = (HW + CL_PX - 1) / CL_PX, groups = (Cp + CL_CH - 1) / CL_CH;
-  int gx = (int)((16LL * sm_count() + (int64_t)groups * B - 1) / ((int64_t)groups * B));
+  const int n_tiles = (HW + CL_PX - 1) / CL_PX;
+  groups = (Cp + CL_CH - 1) / CL_CH;
+  gx = (int)((16LL * sm_count() + (int64_t)groups * B - 1) / ((int64_t)groups * B));
   if (gx < 1) gx = 1;
   if (gx > n_tiles) gx = n_tiles;
+}
+
+size_t to_channels_last_ws(int B, int C, int H, int W) {
+  int gx, groups;
+  cl_grid(B, C, H, W, gx, groups);
+  return align_up((size_t)B * gx * groups * CL_CH * sizeof(float), 256);
+}
+
+// chan_sum != NULL: per-channel sums of src.  With a workspace they are reduced deterministically (per-block partials +
+// fixed-order pass) and chan_sum is overwritten; without one they are atomically accumulated into chan_sum (pre-zeroed).
+int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, int mode, float* chan_sum, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  const int Cp = round_up(C, 8), HW = H * W;
+  int gx, groups;
+  cl_grid(B, C, H, W, gx, groups);
   dim3 grid(gx, groups, B);
   CPT_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CPT_ERR_UNSUPPORTED, "to_channels_last: grid too large");
-  if (mode == CPT_MODE_BF16) nchw_to_nhwc_kernel<true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum);
-  else nchw_to_nhwc_kernel<false><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum);
+  float* partial = nullptr;
+  if (chan_sum && ws && ws_bytes >= to_channels_last_ws(B, C, H, W)) partial = reinterpret_cast<float*>(ws);
+  if (mode == CPT_MODE_BF16) nchw_to_nhwc_kernel<true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial);
+  else nchw_to_nhwc_kernel<false><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial);
   CPT_LAUNCH_CHECK("nchw_to_nhwc");
+  if (partial) {
+    chan_partial_reduce_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, chan_sum, C, (int64_t)B * gx, groups * CL_CH);
+    CPT_LAUNCH_CHECK("chan_partial_reduce");
+  }
   return CPT_OK;
 }
 
@@ -604,7 +648,9 @@ size_t conv_workspace_size(int op, const cpt_conv2d_desc* d, int mode) {
     if (!dgrad_tc_ok(g)) return 8192;  // exact path: tap tables of the stride classes
     return cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode) + (size_t)g.S * g.S * wmat_bytes(g.Ci, g.T, g.Co, mode) + 1024;
   }
-  const size_t part = align_up((size_t)wgrad_splits(g, mode) * g.Co * g.T * g.Ci * sizeof(float), 1024);
+  size_t part = align_up((size_t)wgrad_splits(g, mode) * g.Co * g.T * g.Ci * sizeof(float), 1024);
+  const size_t csum = to_channels_last_ws(g.B, g.Co, g.Ho, g.Wo);
+  if (part < csum) part = csum;
   return cl_bytes(g.B, g.Ci, g.H, g.W, mode) + cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode) + part + 1024;
 }
 
@@ -613,7 +659,7 @@ int conv_fprop(const cpt_conv2d_desc* d, const float* x, const float* w, const f
   const G g = geom(d);
   CPT_REQUIRE(ws && ws_bytes >= conv_workspace_size(CPT_OP_FPROP, d, mode), CPT_ERR_WORKSPACE, "conv2d_fprop: workspace too small");
   const size_t xb = cl_bytes(g.B, g.Ci, g.H, g.W, mode);
-  if (int e = to_channels_last(x, ws, g.B, g.Ci, g.H, g.W, mode, nullptr, st)) return e;
+  if (int e = to_channels_last(x, ws, g.B, g.Ci, g.H, g.W, mode, nullptr, nullptr, 0, st)) return e;
   return conv_fprop_cl(d, ws, w, bias, y, mode, reinterpret_cast<char*>(ws) + xb, ws_bytes - xb, st);
 }
 
@@ -624,7 +670,7 @@ int conv_dgrad(const cpt_conv2d_desc* d, const float* dy, const float* w, float*
     return cpt_conv2d_dgrad(d, dy, w, dx, CPT_MODE_FP32, ws, ws_bytes, st);
   CPT_REQUIRE(ws && ws_bytes >= conv_workspace_size(CPT_OP_DGRAD, d, mode), CPT_ERR_WORKSPACE, "conv2d_dgrad: workspace too small");
   const size_t yb = cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode);
-  if (int e = to_channels_last(dy, ws, g.B, g.Co, g.Ho, g.Wo, mode, nullptr, st)) return e;
+  if (int e = to_channels_last(dy, ws, g.B, g.Co, g.Ho, g.Wo, mode, nullptr, nullptr, 0, st)) return e;
   return conv_dgrad_cl(d, ws, w, dx, mode, reinterpret_cast<char*>(ws) + yb, ws_bytes - yb, st);
 }
 
@@ -634,9 +680,9 @@ int conv_wgrad(const cpt_conv2d_desc* d, const float* x, const float* dy, float*
   CPT_REQUIRE(ws && ws_bytes >= conv_workspace_size(CPT_OP_WGRAD, d, mode), CPT_ERR_WORKSPACE, "conv2d_wgrad: workspace too small");
   char* base = reinterpret_cast<char*>(ws);
   const size_t xb = cl_bytes(g.B, g.Ci, g.H, g.W, mode), yb = cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode);
-  if (int e = to_channels_last(x, base, g.B, g.Ci, g.H, g.W, mode, nullptr, st)) return e;
-  if (db) CPT_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * g.Co, st));
-  if (int e = to_channels_last(dy, base + xb, g.B, g.Co, g.Ho, g.Wo, mode, db, st)) return e;  // db fused into the staging pass
+  if (int e = to_channels_last(x, base, g.B, g.Ci, g.H, g.W, mode, nullptr, nullptr, 0, st)) return e;
+  // db fused into the staging pass of dy (deterministic partials in the part of ws that wgrad uses afterwards)
+  if (int e = to_channels_last(dy, base + xb, g.B, g.Co, g.Ho, g.Wo, mode, db, base + xb + yb, ws_bytes - xb - yb, st)) return e;
   return conv_wgrad_cl(d, base, base + xb, dw, mode, base + xb + yb, ws_bytes - xb - yb, st);
 }
 
@@ -669,20 +715,30 @@ size_t linear_workspace_size(int op, int64_t N, int In, int Out, int mode) {
   return s;
 }
 
+int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, int64_t N, int In, int Out, int mode, cudaStream_t st);
+int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In, int Out, int mode, cudaStream_t st);
+int linear_wgrad_lp(const void* xa, const void* ga, float* dw, int64_t N, int In, int Out, int mode, void* ws, size_t ws_bytes,
+                    cudaStream_t st);
+
 int linear_fwd(const float* x, const float* w, const float* bias, float* y, int64_t N, int In, int Out, int mode, void* ws,
                size_t ws_bytes, cudaStream_t st) {
   const void* xa = x;
   const void* wa = w;
-  int pitch = In;
   if (mode == CPT_MODE_BF16) {
     CPT_REQUIRE(ws && ws_bytes >= linear_workspace_size(CPT_OP_FPROP, N, In, Out, mode), CPT_ERR_WORKSPACE, "linear_fwd: workspace too small");
     char* base = reinterpret_cast<char*>(ws);
     if (int e = cast_to_bf16(x, base, N, In, st)) return e;
     if (int e = cast_to_bf16(w, base + cast_bytes(N, In), Out, In, st)) return e;
-    xa = base; wa = base + cast_bytes(N, In); pitch = round_up(In, 8);
+    xa = base; wa = base + cast_bytes(N, In);
   } else if (!tf32_direct_ok(x, w, In, 4)) {
     return cpt_linear_fwd(x, w, bias, y, N, In, Out, CPT_MODE_FP32, ws, ws_bytes, st);
   }
+  return linear_fwd_lp(xa, wa, bias, y, N, In, Out, mode, st);
+}
+
+// operands already in the mode's element type: bf16 with row pitch round_up(C, 8), or fp32 (tf32) with pitch C
+int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, int64_t N, int In, int Out, int mode, cudaStream_t st) {
+  const int pitch = mode == CPT_MODE_BF16 ? round_up(In, 8) : In;
   const int kc = kc_of(mode), BN = pick_bn(N);
   TcParams p{};
   // y[n][o]: lanes = o.  A = w [Out][In] K-major, B = x [N][In] K-major
@@ -702,16 +758,20 @@ int linear_dgrad(const float* dy, const float* w, float* dx, int64_t N, int In, 
                  cudaStream_t st) {
   const void* ga = dy;
   const void* wa = w;
-  int gpitch = Out, wpitch = In;
   if (mode == CPT_MODE_BF16) {
     CPT_REQUIRE(ws && ws_bytes >= linear_workspace_size(CPT_OP_DGRAD, N, In, Out, mode), CPT_ERR_WORKSPACE, "linear_dgrad: workspace too small");
     char* base = reinterpret_cast<char*>(ws);
     if (int e = cast_to_bf16(dy, base, N, Out, st)) return e;
     if (int e = cast_to_bf16(w, base + cast_bytes(N, Out), Out, In, st)) return e;
-    ga = base; wa = base + cast_bytes(N, Out); gpitch = round_up(Out, 8); wpitch = round_up(In, 8);
+    ga = base; wa = base + cast_bytes(N, Out);
   } else if (!tf32_direct_ok(dy, w, In, Out)) {
     return cpt_linear_dgrad(dy, w, dx, N, In, Out, CPT_MODE_FP32, ws, ws_bytes, st);
   }
+  return linear_dgrad_lp(ga, wa, dx, N, In, Out, mode, st);
+}
+
+int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In, int Out, int mode, cudaStream_t st) {
+  const int gpitch = mode == CPT_MODE_BF16 ? round_up(Out, 8) : Out, wpitch = mode == CPT_MODE_BF16 ? round_up(In, 8) : In;
   const int kc = kc_of(mode), BN = pick_bn(N);
   TcParams p{};
   // dx[n][i]: lanes = i.  A(m=i, k=o) = w[o][i]: MN-major over the [Out][In] matrix; B = dy [N][Out] K-major
@@ -733,16 +793,29 @@ int linear_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t 
   char* base = reinterpret_cast<char*>(ws);
   const void* xa = x;
   const void* ga = dy;
-  int xpitch = In, gpitch = Out;
   size_t off = 0;
   if (mode == CPT_MODE_BF16) {
     if (int e = cast_to_bf16(x, base, N, In, st)) return e;
     if (int e = cast_to_bf16(dy, base + cast_bytes(N, In), N, Out, st)) return e;
-    xa = base; ga = base + cast_bytes(N, In); xpitch = round_up(In, 8); gpitch = round_up(Out, 8);
+    xa = base; ga = base + cast_bytes(N, In);
     off = cast_bytes(N, In) + cast_bytes(N, Out);
   } else if (!tf32_direct_ok(x, dy, In, Out)) {
     return cpt_linear_wgrad(x, dy, dw, db, N, In, Out, CPT_MODE_FP32, ws, ws_bytes, st);
   }
+  if (int e = linear_wgrad_lp(xa, ga, dw, N, In, Out, mode, base + off, ws_bytes - off, st)) return e;
+  if (db) {
+    const size_t part = align_up((size_t)16 * Out * In * sizeof(float), 1024);
+    return channel_sum(dy, db, (int)N, Out, 1, base + off + part, st);
+  }
+  return CPT_OK;
+}
+
+// ws: split-K partials (up to 16 x Out x In floats)
+int linear_wgrad_lp(const void* xa, const void* ga, float* dw, int64_t N, int In, int Out, int mode, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
+  char* base = reinterpret_cast<char*>(ws);
+  const size_t off = 0;
+  const int xpitch = mode == CPT_MODE_BF16 ? round_up(In, 8) : In, gpitch = mode == CPT_MODE_BF16 ? round_up(Out, 8) : Out;
   const int kc = kc_of(mode), bk = kc, BN = pick_bn(Out);
   const int k_iters = (int)((N + bk - 1) / bk);
   const int tiles = ((In + 127) / 128) * ((Out + BN - 1) / BN);
@@ -751,7 +824,8 @@ int linear_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t 
   const int kps = (k_iters + splits_req - 1) / splits_req;
   const int splits = (k_iters + kps - 1) / kps;
   float* partial = reinterpret_cast<float*>(base + off);
-  const size_t part_bytes = align_up((size_t)(splits > 1 ? splits : 0) * Out * In * sizeof(float), 1024);
+  CPT_REQUIRE(splits == 1 || (ws && ws_bytes >= (size_t)splits * Out * In * sizeof(float)), CPT_ERR_WORKSPACE,
+              "linear_wgrad: workspace too small for %d split-K partials", splits);
   TcParams p{};
   // dw[o][i]: lanes = i.  A(m=i, k=n) = x[n][i] MN-major; B(col=o, k=n) = dy[n][o] MN-major
   if (int e = make_map_2d(&p.tmA, xa, mode, In, (uint64_t)N, xpitch, kc, bk, true)) return e;
@@ -767,7 +841,6 @@ int linear_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t 
     launch_reduce_splits(partial, dw, (int64_t)Out * In, splits, st);
     CPT_LAUNCH_CHECK("linear_wgrad reduce");
   }
-  if (db) return channel_sum(dy, db, (int)N, Out, 1, base + off + part_bytes, st);
   return CPT_OK;
 }
 
@@ -783,10 +856,16 @@ size_t cpt_channels_last_bytes(int B, int C, int H, int W, int mode) {
   return tc::cl_bytes(B, C, H, W, mode);
 }
 
-int cpt_to_channels_last(const float* src, void* dst, int B, int C, int H, int W, int mode, float* chan_sum, void* stream) {
+size_t cpt_to_channels_last_workspace_size(int B, int C, int H, int W) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  return tc::to_channels_last_ws(B, C, H, W);
+}
+
+int cpt_to_channels_last(const float* src, void* dst, int B, int C, int H, int W, int mode, float* chan_sum, void* ws,
+                         size_t ws_bytes, void* stream) {
   CPT_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, CPT_ERR_INVALID, "to_channels_last: bad arguments");
   CPT_REQUIRE(mode == CPT_MODE_TF32 || mode == CPT_MODE_BF16, CPT_ERR_INVALID, "to_channels_last: mode must be TF32 or BF16");
-  return tc::to_channels_last(src, dst, B, C, H, W, mode, chan_sum, as_stream(stream));
+  return tc::to_channels_last(src, dst, B, C, H, W, mode, chan_sum, ws, ws_bytes, as_stream(stream));
 }
 
 static int check_tc(const cpt_conv2d_desc* d, int mode, const char* who) {
@@ -815,6 +894,36 @@ int cpt_conv2d_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* 
                         size_t ws_bytes, void* stream) {
   if (int e = check_tc(d, mode, "conv2d_wgrad_cl")) return e;
   return tc::conv_wgrad_cl(d, x_cl, dy_cl, dw, mode, ws, ws_bytes, as_stream(stream));
+}
+
+size_t cpt_cast_bf16_bytes(int64_t rows, int cols) { return rows > 0 && cols > 0 ? tc::cast_bytes(rows, cols) : 0; }
+int cpt_cast_bf16(const float* src, void* dst, int64_t rows, int cols, void* stream) {
+  CPT_REQUIRE(src && dst && rows > 0 && cols > 0, CPT_ERR_INVALID, "cast_bf16: bad arguments");
+  return tc::cast_to_bf16(src, dst, rows, cols, as_stream(stream));
+}
+static int check_lp(int64_t N, int In, int Out, int mode, const char* who) {
+  CPT_REQUIRE(N > 0 && In > 0 && Out > 0 && N < (1LL << 31), CPT_ERR_INVALID, "%s: bad dimensions", who);
+  CPT_REQUIRE(mode == CPT_MODE_BF16, CPT_ERR_INVALID, "%s: pre-cast operands are bf16 (mode must be CPT_MODE_BF16)", who);
+  return CPT_OK;
+}
+int cpt_linear_fwd_bf16(const void* x_bf, const void* w_bf, const float* bias, float* y, int64_t N, int In, int Out, void* stream) {
+  if (int e = check_lp(N, In, Out, CPT_MODE_BF16, "linear_fwd_bf16")) return e;
+  return tc::linear_fwd_lp(x_bf, w_bf, bias, y, N, In, Out, CPT_MODE_BF16, as_stream(stream));
+}
+int cpt_linear_dgrad_bf16(const void* dy_bf, const void* w_bf, float* dx, int64_t N, int In, int Out, void* stream) {
+  if (int e = check_lp(N, In, Out, CPT_MODE_BF16, "linear_dgrad_bf16")) return e;
+  return tc::linear_dgrad_lp(dy_bf, w_bf, dx, N, In, Out, CPT_MODE_BF16, as_stream(stream));
+}
+int cpt_linear_wgrad_bf16(const void* x_bf, const void* dy_bf, float* dw, int64_t N, int In, int Out, void* ws, size_t ws_bytes,
+                          void* stream) {
+  if (int e = check_lp(N, In, Out, CPT_MODE_BF16, "linear_wgrad_bf16")) return e;
+  return tc::linear_wgrad_lp(x_bf, dy_bf, dw, N, In, Out, CPT_MODE_BF16, ws, ws_bytes, as_stream(stream));
+}
+/* db = dy.sum(leading) on its own (linear_funcs.py:33): out[c] = sum_n x[n][c][hw] */
+int cpt_channel_sum(const float* x, float* out, int N, int C, int HW, void* ws, size_t ws_bytes, void* stream) {
+  CPT_REQUIRE(x && out && N > 0 && C > 0 && HW > 0, CPT_ERR_INVALID, "channel_sum: bad arguments");
+  CPT_REQUIRE(ws && ws_bytes >= (size_t)C * 64 * sizeof(float), CPT_ERR_WORKSPACE, "channel_sum: workspace too small");
+  return channel_sum(x, out, N, C, HW, ws, as_stream(stream));
 }
 
 // Debug/test helper: synchronises the device and returns the pipeline-timeout flag of the tensor-core kernels

@@ -20,7 +20,7 @@ class ReLUFn(Function):
         n = x.size
         y = DeviceArray.empty(x.shape, np.float32)
         want_mask = get_caching_enabled() and not isinstance(cache, PseudoCache)
-        mask = DeviceArray.empty(((n + 7) // 8,), np.uint8) if want_mask else None
+        mask = DeviceArray.empty(((n + 31) // 32 * 4,), np.uint8) if want_mask else None
         _lib.check(_lib.lib().cpt_relu_fwd(f32ptr(x), y.ptr, mask.ptr if mask is not None else None, n, stream_ptr()))
         cache.push(mask)
         return Tensor(y)

@@ -61,7 +61,7 @@ class Conv2DFn(Function):
         else:
             # stage x once as channels-last; kept in the cache so wgrad does not convert it again
             x_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Ci, d.H, d.W, mode),), np.uint8)
-            _lib.check(L.cpt_to_channels_last(f32ptr(x), x_cl.ptr, d.B, d.Ci, d.H, d.W, mode, None, st))
+            _lib.check(L.cpt_to_channels_last(f32ptr(x), x_cl.ptr, d.B, d.Ci, d.H, d.W, mode, None, None, 0, st))
             ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_FPROP, ctypes.byref(d), mode))
             _lib.check(L.cpt_conv2d_fprop_cl(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, mode, ws, wsb, st))
         cache.push(x, f, b is not None, d, mode, x_cl)
@@ -92,9 +92,8 @@ class Conv2DFn(Function):
         else:
             # dy staged once (db fused into the staging pass), shared by dgrad and wgrad
             dy_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Co, ho, wo, mode),), np.uint8)
-            if db is not None:
-                db.fill(0.0)
-            _lib.check(L.cpt_to_channels_last(f32ptr(dy), dy_cl.ptr, d.B, d.Co, ho, wo, mode, dbp, st))
+            ws, wsb = workspace(L.cpt_to_channels_last_workspace_size(d.B, d.Co, ho, wo))
+            _lib.check(L.cpt_to_channels_last(f32ptr(dy), dy_cl.ptr, d.B, d.Co, ho, wo, mode, dbp, ws, wsb, st))
             if tc_dgrad:
                 ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_DGRAD, dref, mode))
                 _lib.check(L.cpt_conv2d_dgrad_cl(dref, dy_cl.ptr, f32ptr(f), dx.ptr, mode, ws, wsb, st))

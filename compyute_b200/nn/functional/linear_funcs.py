@@ -28,15 +28,25 @@ class LinearFn(Function):
         mode = get_compute_mode()
         L = _lib.lib()
         y = DeviceArray.empty((*x.shape[:-1], out_f), np.float32)
-        ws, wsb = workspace(L.cpt_linear_workspace_size(_lib.OP_FPROP, n, in_f, out_f, mode))
-        _lib.check(L.cpt_linear_fwd(f32ptr(x), f32ptr(w), f32ptr(b), y.ptr, n, in_f, out_f, mode, ws, wsb, stream_ptr()))
-        cache.push(x, w, b is not None, mode)
+        st = stream_ptr()
+        x_bf = w_bf = None
+        if mode == _lib.MODE_BF16:
+            # operands staged once as bf16 and kept in the cache: x_bf16 is reused by wgrad, w_bf16 by dgrad
+            x_bf = DeviceArray.empty((L.cpt_cast_bf16_bytes(n, in_f),), np.uint8)
+            w_bf = DeviceArray.empty((L.cpt_cast_bf16_bytes(out_f, in_f),), np.uint8)
+            _lib.check(L.cpt_cast_bf16(f32ptr(x), x_bf.ptr, n, in_f, st))
+            _lib.check(L.cpt_cast_bf16(f32ptr(w), w_bf.ptr, out_f, in_f, st))
+            _lib.check(L.cpt_linear_fwd_bf16(x_bf.ptr, w_bf.ptr, f32ptr(b), y.ptr, n, in_f, out_f, st))
+        else:
+            ws, wsb = workspace(L.cpt_linear_workspace_size(_lib.OP_FPROP, n, in_f, out_f, mode))
+            _lib.check(L.cpt_linear_fwd(f32ptr(x), f32ptr(w), f32ptr(b), y.ptr, n, in_f, out_f, mode, ws, wsb, st))
+        cache.push(x, w, b is not None, mode, x_bf, w_bf)
         return Tensor(y)
 
     @staticmethod
     def backward(cache: FunctionCache, dy: Tensor, dw_out: Optional[DeviceArray] = None,
                  db_out: Optional[DeviceArray] = None) -> tuple[Tensor, Tensor, Optional[Tensor]]:
-        x, w, has_bias, mode = cache.pop()
+        x, w, has_bias, mode, x_bf, w_bf = cache.pop()
         require_cuda(dy)
         out_f, in_f = w.shape
         n = x.size // in_f
@@ -47,11 +57,20 @@ class LinearFn(Function):
         db = None
         if has_bias:
             db = db_out.reshape((out_f,)) if db_out is not None else DeviceArray.empty((out_f,), np.float32)
-        ws, wsb = workspace(L.cpt_linear_workspace_size(_lib.OP_DGRAD, n, in_f, out_f, mode))
-        _lib.check(L.cpt_linear_dgrad(f32ptr(dy), f32ptr(w), dx.ptr, n, in_f, out_f, mode, ws, wsb, st))
-        ws, wsb = workspace(L.cpt_linear_workspace_size(_lib.OP_WGRAD, n, in_f, out_f, mode))
-        _lib.check(L.cpt_linear_wgrad(f32ptr(x), f32ptr(dy), dw.ptr, db.ptr if db is not None else None, n, in_f, out_f, mode,
-                                      ws, wsb, st))
+        if mode == _lib.MODE_BF16:
+            dy_bf = DeviceArray.empty((L.cpt_cast_bf16_bytes(n, out_f),), np.uint8)
+            _lib.check(L.cpt_cast_bf16(f32ptr(dy), dy_bf.ptr, n, out_f, st))
+            _lib.check(L.cpt_linear_dgrad_bf16(dy_bf.ptr, w_bf.ptr, dx.ptr, n, in_f, out_f, st))
+            ws, wsb = workspace(L.cpt_linear_workspace_size(_lib.OP_WGRAD, n, in_f, out_f, mode))
+            _lib.check(L.cpt_linear_wgrad_bf16(x_bf.ptr, dy_bf.ptr, dw.ptr, n, in_f, out_f, ws, wsb, st))
+            if db is not None:
+                _lib.check(L.cpt_channel_sum(f32ptr(dy), db.ptr, n, out_f, 1, ws, wsb, st))
+        else:
+            ws, wsb = workspace(L.cpt_linear_workspace_size(_lib.OP_DGRAD, n, in_f, out_f, mode))
+            _lib.check(L.cpt_linear_dgrad(f32ptr(dy), f32ptr(w), dx.ptr, n, in_f, out_f, mode, ws, wsb, st))
+            ws, wsb = workspace(L.cpt_linear_workspace_size(_lib.OP_WGRAD, n, in_f, out_f, mode))
+            _lib.check(L.cpt_linear_wgrad(f32ptr(x), f32ptr(dy), dw.ptr, db.ptr if db is not None else None, n, in_f, out_f, mode,
+                                          ws, wsb, st))
         return Tensor(dx), Tensor(dw), (Tensor(db) if db is not None else None)
 
 

@@ -79,10 +79,13 @@ int cpt_conv2d_wgrad(const cpt_conv2d_desc* d, const float* x, const float* dy, 
  * bf16 (BF16) or tf32-rounded fp32 (TF32) so that TMA im2col can feed tcgen05.  These expose the
  * staging so a caller can keep x_cl from forward for wgrad (what Conv2DFn's cache does). */
 size_t cpt_channels_last_bytes(int B, int C, int H, int W, int mode);
-/* chan_sum (C floats, pre-zeroed) may be NULL; if given it accumulates the per-channel sum of
- * src (fuses db = dy.sum((0,2,3)) into the staging pass). */
+/* chan_sum (C floats) may be NULL; if given it receives the per-channel sum of src (fuses db = dy.sum((0,2,3)) into
+ * the staging pass).  With ws >= cpt_to_channels_last_workspace_size the sums are reduced deterministically (per-block
+ * partials + fixed-order pass) and chan_sum is overwritten; with ws = NULL they are atomically ADDED to chan_sum, which
+ * the caller must have zeroed. */
+size_t cpt_to_channels_last_workspace_size(int B, int C, int H, int W);
 int cpt_to_channels_last(const float* src, void* dst, int B, int C, int H, int W, int mode,
-                         float* chan_sum, void* stream);
+                         float* chan_sum, void* ws, size_t ws_bytes, void* stream);
 int cpt_conv2d_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w,
                         const float* bias, float* y, int mode, void* ws, size_t ws_bytes,
                         void* stream);
@@ -106,6 +109,21 @@ int cpt_linear_dgrad(const float* dy, const float* w, float* dx, int64_t N, int 
 /* LinearFn.backward :32-33  dw = (dy.T @ x).sum(leading), db = dy.sum(leading); db may be NULL */
 int cpt_linear_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t N, int In,
                      int Out, int mode, void* ws, size_t ws_bytes, void* stream);
+
+/* bf16 tensor-core mode with operands staged once by the caller (what LinearFn's cache does: x_bf16 made in forward is
+ * reused by wgrad, dy_bf16 is shared by dgrad and wgrad, w_bf16 by forward and dgrad).  Staged layout: row-major bf16,
+ * row pitch = cols rounded up to 8 elements, zero padded (cpt_cast_bf16). */
+size_t cpt_cast_bf16_bytes(int64_t rows, int cols);
+int cpt_cast_bf16(const float* src, void* dst, int64_t rows, int cols, void* stream);
+int cpt_linear_fwd_bf16(const void* x_bf, const void* w_bf, const float* bias, float* y, int64_t N, int In,
+                        int Out, void* stream);
+int cpt_linear_dgrad_bf16(const void* dy_bf, const void* w_bf, float* dx, int64_t N, int In, int Out,
+                          void* stream);
+/* ws: room for up to 16 split-K partials (16 * Out * In floats), see cpt_linear_workspace_size(CPT_OP_WGRAD, ...) */
+int cpt_linear_wgrad_bf16(const void* x_bf, const void* dy_bf, float* dw, int64_t N, int In, int Out, void* ws,
+                          size_t ws_bytes, void* stream);
+/* out[c] = sum over n, hw of x[n][c][hw] (db of Linear: HW = 1; of Conv2D: HW = Ho*Wo).  ws: C * 64 floats. */
+int cpt_channel_sum(const float* x, float* out, int N, int C, int HW, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Pooling: compyute/nn/functional/pooling_funcs.py -------------------------------------- */
 /* MaxPooling2DFn.forward :71-76 — stride = k, no padding, floor.  y: (B, C, H/k, W/k). */
@@ -138,7 +156,8 @@ int cpt_bn_bwd(const float* x, const float* dy, const float* w, const float* sav
                void* ws, size_t ws_bytes, void* stream);
 
 /* ---- activations / elementwise ------------------------------------------------------------- */
-/* ReLUFn.forward activation_funcs.py:26-29.  mask = bit-packed (y > 0), (n+7)/8 bytes; may be NULL. */
+/* ReLUFn.forward activation_funcs.py:26-29.  mask = bit-packed (y > 0), 4 * ((n + 31) / 32) bytes, 4-byte aligned, in a
+ * layout private to cpt_relu_fwd / cpt_relu_bwd; may be NULL. */
 int cpt_relu_fwd(const float* x, float* y, uint8_t* mask, int64_t n, void* stream);
 /* ReLUFn.backward :32-34   dx = dy * mask */
 int cpt_relu_bwd(const float* dy, const uint8_t* mask, float* dx, int64_t n, void* stream);
