@@ -11,5 +11,6 @@ Hand-written CUDA for sm_100a (compyute_b200/csrc) behind a C ABI (include/compy
 from . import distributed, nn
 from .backend import *
 from .tensors import DeviceArray, ShapeError, Tensor, tensor
+from .utils import load, save
 
 __version__ = "0.1.0"

@@ -53,6 +53,32 @@ __global__ void __launch_bounds__(256) adam_kernel(const cpt_param_entry* __rest
   }
 }
 
+// NAdam.step optimizers.py:437-475: m_hat = mu_next * m / m_div + (1 - mu) * g / g_div, v_hat = v / v_div
+__global__ void __launch_bounds__(256) nadam_kernel(const cpt_param_entry* __restrict__ table, float lr, float beta1, float beta2,
+                                                    float eps, float wd, float mu, float mu_next, float m_div, float g_div,
+                                                    float v_div, float grad_scale) {
+  const cpt_param_entry e = table[blockIdx.y];
+  const int64_t n = e.n;
+  if (n == 0) return;
+  float* __restrict__ p = e.p;
+  const float* __restrict__ g = e.g;
+  float* __restrict__ m = e.m;
+  float* __restrict__ v = e.v;
+  const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2, omu = 1.0f - mu;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float pv = p[i], gv = g[i] * grad_scale;
+    if (wd != 0.0f) gv = gv + wd * pv;
+    const float mv = beta1 * m[i] + omb1 * gv;
+    const float vv = beta2 * v[i] + omb2 * (gv * gv);
+    m[i] = mv;
+    v[i] = vv;
+    const float mh = mu_next * mv / m_div + omu * gv / g_div;
+    const float vh = vv / v_div;
+    p[i] = pv - lr * mh / (sqrtf(vh) + eps);
+  }
+}
+
 __global__ void __launch_bounds__(256) sgd_kernel(const cpt_param_entry* __restrict__ table, float lr, float momentum,
                                                   int nesterov, float wd, float grad_scale) {
   const cpt_param_entry e = table[blockIdx.y];
@@ -97,6 +123,17 @@ int cpt_adam_step(const cpt_param_entry* table, int n_entries, int64_t max_n, fl
   adam_kernel<<<mt_grid(n_entries, max_n), 256, 0, as_stream(stream)>>>(table, lr, beta1, beta2, eps, weight_decay, m_div,
                                                                       v_div, grad_scale, decoupled);
   CPT_LAUNCH_CHECK("adam_step");
+  return CPT_OK;
+}
+
+int cpt_nadam_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, float mu, float mu_next, float m_div, float g_div, float v_div, float grad_scale,
+                   void* stream) {
+  CPT_REQUIRE(table && n_entries >= 0 && n_entries <= 65535, CPT_ERR_INVALID, "nadam_step: bad table");
+  if (n_entries == 0) return CPT_OK;
+  nadam_kernel<<<mt_grid(n_entries, max_n), 256, 0, as_stream(stream)>>>(table, lr, beta1, beta2, eps, weight_decay, mu, mu_next,
+                                                                       m_div, g_div, v_div, grad_scale);
+  CPT_LAUNCH_CHECK("nadam_step");
   return CPT_OK;
 }
 

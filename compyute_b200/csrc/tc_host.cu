@@ -208,18 +208,30 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
-// out[c] = Σ_rows partial[row][c] in fixed row order (one thread per channel, coalesced across channels)
-__global__ void chan_partial_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int C, int64_t rows, int pitch) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int64_t r = 0;
-  for (; r + 3 < rows; r += 4) {
-    s0 += partial[r * pitch + c]; s1 += partial[(r + 1) * pitch + c];
-    s2 += partial[(r + 2) * pitch + c]; s3 += partial[(r + 3) * pitch + c];
+// out[c] = Σ_rows partial[row][c]: block per 32 channels, 32 warps split the rows (lanes = channels: 128 B coalesced),
+// then the 32 warp partials are added in fixed order -> deterministic
+__global__ void __launch_bounds__(1024) chan_partial_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int C,
+                                                                  int64_t rows, int pitch) {
+  __shared__ float sm[32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    int64_t r = warp;
+    for (; r + 32 < rows; r += 64) {
+      s0 += partial[r * pitch + c];
+      s1 += partial[(r + 32) * pitch + c];
+    }
+    if (r < rows) s0 += partial[r * pitch + c];
   }
-  for (; r < rows; ++r) s0 += partial[r * pitch + c];
-  out[c] = (s0 + s1) + (s2 + s3);
+  sm[warp][lane] = s0 + s1;
+  __syncthreads();
+  if (warp == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) t += sm[w][lane];
+    out[c] = t;
+  }
 }
 
 // w (Co, Ci, K, K) fp32 -> fprop weight matrix [Co][T][Ck] (zero padded, Ck = round_up(Ci, KC))
@@ -417,7 +429,7 @@ int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, in
   else nchw_to_nhwc_kernel<false><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial);
   CPT_LAUNCH_CHECK("nchw_to_nhwc");
   if (partial) {
-    chan_partial_reduce_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, chan_sum, C, (int64_t)B * gx, groups * CL_CH);
+    chan_partial_reduce_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partial, chan_sum, C, (int64_t)B * gx, groups * CL_CH);
     CPT_LAUNCH_CHECK("chan_partial_reduce");
   }
   return CPT_OK;

@@ -25,7 +25,7 @@ from .. import _lib, distributed
 from ..tensors import DeviceArray, Tensor, stream_ptr
 from .parameter import Parameter
 
-__all__ = ["Optimizer", "SGD", "Adam", "AdamW"]
+__all__ = ["Optimizer", "SGD", "Adam", "AdamW", "NAdam"]
 
 
 class Optimizer:
@@ -191,3 +191,28 @@ class AdamW(Adam):
     def __init__(self, parameters: Optional[Iterable[Parameter]] = None, lr: float = 1e-3, beta1: float = 0.9,
                  beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 1e-2) -> None:
         super().__init__(parameters, lr, beta1, beta2, eps, weight_decay)
+
+
+class NAdam(Optimizer):
+    """optimizers.py:365-475 (Nesterov-accelerated Adam with the momentum-decay schedule)."""
+
+    def __init__(self, parameters: Optional[Iterable[Parameter]] = None, lr: float = 2e-3, beta1: float = 0.9,
+                 beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0, momentum_decay: float = 4e-3) -> None:
+        super().__init__(parameters, lr)
+        self.beta1, self.beta2, self.eps, self.weight_decay = beta1, beta2, eps, weight_decay
+        self.momentum_decay = momentum_decay
+        self._mu_prod = 1.0
+
+    def step(self) -> None:
+        scale = self._sync_grads()
+        mu = self.beta1 * (1.0 - 0.5 * 0.96 ** (self.t * self.momentum_decay))  # python doubles, like :438-447
+        mu_next = self.beta1 * (1.0 - 0.5 * 0.96 ** ((self.t + 1) * self.momentum_decay))
+        self._mu_prod *= mu
+        m_div = 1.0 - self._mu_prod * mu_next
+        g_div = 1.0 - self._mu_prod
+        v_div = 1.0 - self.beta2 ** self.t
+        table, n, max_n = self._table(("m", "v"))
+        _lib.check(_lib.lib().cpt_nadam_step(table, n, max_n, float(self.lr), float(self.beta1), float(self.beta2), float(self.eps),
+                                             float(self.weight_decay), float(mu), float(mu_next), float(m_div), float(g_div),
+                                             float(v_div), float(scale), stream_ptr()))
+        self.t += 1

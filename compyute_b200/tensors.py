@@ -173,6 +173,11 @@ class DeviceArray:
     def __repr__(self) -> str:
         return f"DeviceArray(shape={self.shape}, dtype={self.dtype}, ptr=0x{self.ptr:x})"
 
+    def __reduce__(self):
+        """Pickling goes through a host copy (``cp.save(model.get_state_dict())`` keeps working, utils.py:44-73);
+        unpickling uploads to this process's CUDA device, like unpickling a CuPy array does."""
+        return (DeviceArray.from_numpy, (self.numpy(),))
+
 
 # -- per-process scratch: one growable buffer, safe because every op of the path is ordered on one stream
 _ws: Optional[DeviceArray] = None

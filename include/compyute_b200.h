@@ -204,6 +204,11 @@ typedef struct cpt_param_entry {
 int cpt_adam_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, float m_div, float v_div,
                   float grad_scale, int decoupled, void* stream);
+/* NAdam.step :437-475.  mu, mu_next, m_div = 1 - mu_prod*mu_next, g_div = 1 - mu_prod, v_div = 1 - beta2^t are computed
+ * by the caller in double like the reference (:438-447). */
+int cpt_nadam_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float mu, float mu_next, float m_div,
+                   float g_div, float v_div, float grad_scale, void* stream);
 /* SGD.step :152-176 (momentum / nesterov / L2 weight decay). */
 int cpt_sgd_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr,
                  float momentum, int nesterov, float weight_decay, float grad_scale,

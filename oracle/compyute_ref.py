@@ -349,6 +349,38 @@ class Adam:
         self.t += 1
 
 
+class NAdam:
+    """``NAdam.step`` (optimizers.py:437-475)."""
+
+    def __init__(self, lr=2e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, momentum_decay=4e-3):
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        self.weight_decay, self.momentum_decay = weight_decay, momentum_decay
+        self.t, self.mu_prod = 1, 1.0
+        self.state: dict[int, dict[str, np.ndarray]] = {}
+
+    def step(self, params, grads):
+        mu = self.beta1 * (1.0 - 0.5 * 0.96 ** (self.t * self.momentum_decay))
+        mu_next = self.beta1 * (1.0 - 0.5 * 0.96 ** ((self.t + 1) * self.momentum_decay))
+        self.mu_prod *= mu
+        m_div = 1.0 - self.mu_prod * mu_next
+        g_div = 1.0 - self.mu_prod
+        v_div = 1.0 - self.beta2**self.t
+        for i, (p, g) in enumerate(zip(params, grads)):
+            if g is None:
+                continue
+            st = self.state.setdefault(i, {})
+            if self.weight_decay != 0.0:
+                g = g + self.weight_decay * p
+            m = self.beta1 * st.get("m", 0.0) + (1.0 - self.beta1) * g
+            st["m"] = m.copy()
+            v = self.beta2 * st.get("v", 0.0) + (1.0 - self.beta2) * g**2
+            st["v"] = v.copy()
+            m = mu_next * m / m_div + (1.0 - mu) * g / g_div
+            v = v / v_div
+            p -= (self.lr * m / (np.sqrt(v) + self.eps)).astype(p.dtype)
+        self.t += 1
+
+
 # --------------------------------------------------------------------------------------
 # Direct-form equations (SURVEY Appendix D) -- an independent second statement, small cases only
 # --------------------------------------------------------------------------------------

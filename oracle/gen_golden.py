@@ -191,11 +191,13 @@ def main() -> None:
     ocases = [("sgd", dict(lr=0.1)), ("sgd", dict(lr=0.1, momentum=0.9)),
               ("sgd", dict(lr=0.1, momentum=0.9, nesterov=True, weight_decay=0.1)),
               ("adam", dict(lr=1e-2)), ("adam", dict(lr=1e-2, weight_decay=0.1, beta1=0.8, beta2=0.99)),
-              ("adamw", dict(lr=1e-2, weight_decay=0.1))]
+              ("adamw", dict(lr=1e-2, weight_decay=0.1)), ("nadam", dict(lr=1e-2)),
+              ("nadam", dict(lr=1e-2, weight_decay=0.05, momentum_decay=1e-2))]
     for n, (name, kw) in enumerate(ocases):
         p0 = [rnd((4, 6), -1, 1), rnd((5,), -1, 1, seed=48)]
         params = [Parameter(T(a.copy())) for a in p0]
-        O = {"sgd": cp.nn.optimizers.SGD, "adam": cp.nn.optimizers.Adam, "adamw": cp.nn.optimizers.AdamW}[name]
+        O = {"sgd": cp.nn.optimizers.SGD, "adam": cp.nn.optimizers.Adam, "adamw": cp.nn.optimizers.AdamW,
+             "nadam": cp.nn.optimizers.NAdam}[name]
         o = O(params, **kw)
         for step in range(5):
             for j, p in enumerate(params):

@@ -316,7 +316,7 @@ def test_optim_golden(cp, case):
     g = load_golden("optim"); n = case["id"]
     T = lambda a: cp.tensor(a, device=cp.cuda)
     params = [nn.Parameter(T(g[f"c{n}_init_{j}"])) for j in range(2)]
-    O = {"sgd": nn.optimizers.SGD, "adam": nn.optimizers.Adam, "adamw": nn.optimizers.AdamW}[case["name"]]
+    O = {"sgd": nn.optimizers.SGD, "adam": nn.optimizers.Adam, "adamw": nn.optimizers.AdamW, "nadam": nn.optimizers.NAdam}[case["name"]]
     o = O(params, **case["kw"])
     for step in range(5):
         for j, p in enumerate(params):
@@ -379,3 +379,41 @@ def test_residual_and_inference(cp):
     block.inference()
     fx = block.residual_block(cp.tensor(x, device=cp.cuda)).to_numpy()
     assert np.allclose(block(cp.tensor(x, device=cp.cuda)).to_numpy(), fx + x, atol=1e-6)
+
+
+def test_dataloader_and_checkpoint_on_device(cp, tmp_path):
+    """Dataloader uploads batches through pinned double-buffered staging (values identical to host slicing), and a
+    model/optimizer checkpoint of device state round-trips through cp.save / cp.load (README.md:197-213)."""
+    from compyute_b200 import nn
+    from compyute_b200.nn.utils import Dataloader
+    rng = np.random.RandomState(0)
+    X = rng.normal(0, 1, (37, 3, 8, 8)).astype(np.float32); Y = rng.randint(0, 10, (37,)).astype(np.int64)
+    dl = Dataloader((cp.tensor(X), cp.tensor(Y)), batch_size=8, device=cp.cuda, shuffle_data=False)
+    seen = 0
+    for xb, yb in dl():
+        assert xb.device == cp.cuda and yb.data.dtype == np.int32
+        n = xb.shape[0]
+        assert np.array_equal(xb.to_numpy(), X[seen:seen + n]) and np.array_equal(yb.to_numpy(), Y[seen:seen + n])
+        seen += n
+    assert seen == 37 and len(dl) == 5
+    np.random.seed(1)
+    with cp.use_device(cp.cuda):
+        model = nn.Sequential(nn.Conv2D(3, 4, 3, padding="same"), nn.BatchNorm2D(4), nn.ReLU(), nn.Flatten(), nn.Linear(4 * 64, 10))
+    model.training()
+    opt = nn.optimizers.Adam(model.get_parameters(), lr=1e-2)
+    loss_fn = nn.CrossEntropyLoss()
+    for xb, yb in dl():
+        loss_fn(model(xb), yb); opt.reset_grads(); model.backward(loss_fn.backward()); opt.step()
+    f = tmp_path / "ckpt.cp"
+    cp.save({"model": model.get_state_dict(), "optim": opt.get_state_dict()}, str(f))
+    back = cp.load(str(f))
+    for (k, a), (k2, b) in zip(model.get_state_dict().items(), back["model"].items()):
+        assert k == k2 and b.device == cp.cuda and np.array_equal(a.to_numpy(), b.to_numpy())
+    assert back["optim"]["vars"]["t"] == opt.t and np.array_equal(back["optim"]["state"][0]["m"].to_numpy(), opt._state[0]["m"].to_numpy())
+    np.random.seed(1)
+    with cp.use_device(cp.cuda):
+        model2 = nn.Sequential(nn.Conv2D(3, 4, 3, padding="same"), nn.BatchNorm2D(4), nn.ReLU(), nn.Flatten(), nn.Linear(4 * 64, 10))
+    model2.load_state_dict(back["model"])
+    model.inference(); model2.inference()
+    xb = cp.tensor(X[:8], device=cp.cuda)
+    assert np.array_equal(model(xb).to_numpy(), model2(xb).to_numpy())

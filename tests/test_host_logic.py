@@ -149,3 +149,38 @@ def test_compute_mode_context():
     with cp.use_device(cp.cuda):
         assert cp.select_device(None) == cp.cuda
     assert cp.select_device(None) == cp.cpu
+
+
+def test_dataloader_host_side():
+    """Reference semantics of Dataloader (dataloaders.py:18-69): length, last partial batch, shuffling from numpy's
+    legacy stream, and contiguous DP shards."""
+    from compyute_b200.nn.utils import Dataloader
+    x = cp.tensor(np.arange(10 * 3, dtype=np.float32).reshape(10, 3)); y = cp.tensor(np.arange(10, dtype=np.int64))
+    dl = Dataloader((x, y), batch_size=4, shuffle_data=False)
+    assert len(dl) == 3
+    got = list(dl())
+    assert [b[0].shape[0] for b in got] == [4, 4, 2] and got[2][1].to_numpy().tolist() == [8, 9]
+    assert len(Dataloader((x, y), batch_size=4, drop_remaining=True)) == 2 and len(Dataloader((x, y), batch_size=64)) == 1
+    np.random.seed(3); order = np.random.permutation(10)
+    np.random.seed(3); first = next(iter(Dataloader((x, y), batch_size=5)()))
+    assert first[1].to_numpy().tolist() == order[:5].tolist()
+    assert got[0][1].dtype == np.int32  # labels are narrowed for the device kernels
+
+
+def test_lr_scheduler_interplay_and_state_dict_roundtrip(tmp_path):
+    """`lr` / `t` stay live python attributes (Appendix A.17) and optimizer/module state pickles through cp.save/load."""
+    p = nn.Parameter(cp.tensor(np.ones((2, 2), np.float32)))
+    o = nn.optimizers.NAdam([p], lr=0.1)
+    for epoch in range(3):  # what compyute.nn.utils.lr_schedulers.ExponentialLrScheduler does: optimizer.lr *= decay
+        o.lr *= 0.5
+    assert abs(o.lr - 0.0125) < 1e-12
+    sd = o.get_state_dict()
+    assert sd["vars"]["lr"] == o.lr and "_mu_prod" in sd["vars"] and "momentum_decay" in sd["vars"]
+    m = nn.Sequential(nn.Linear(3, 2), nn.ReLU())
+    f = tmp_path / "state.cp"
+    cp.save({"model": m.get_state_dict(), "optim": sd}, str(f))
+    back = cp.load(str(f))
+    assert list(back["model"].keys()) == ["layers.0.w", "layers.0.b"]
+    assert np.array_equal(back["model"]["layers.0.w"].to_numpy(), m.layers[0].w.to_numpy())
+    m2 = nn.Sequential(nn.Linear(3, 2), nn.ReLU()); m2.load_state_dict(back["model"])
+    assert np.array_equal(m2.layers[0].w.to_numpy(), m.layers[0].w.to_numpy())
