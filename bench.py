@@ -442,6 +442,20 @@ def run_model(args) -> None:
             tt = torch.tensor([ms], device="cuda"); torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX); ms = float(tt.item())
         return ms / steps, L.cpt_launch_count() - n0
 
+    graphed = None
+    if args.graph and world == 1:
+        # CUDA-graph replay of the whole step (fwd + loss + bwd + fused Adam): static input tensors, one launch per step
+        xs_t, ts_t = wrapf(dx), wrapi(dt)
+        with cp.compute_mode(args.mode):
+            graphed = cp.graph.CapturedStep(lambda: step(xs_t, ts_t), optimizers=[opt], warmup=3)
+        step_resident = graphed  # noqa: F811
+
+        def step_e2e():  # noqa: F811
+            dx.copy_(hx, non_blocking=True); dt.copy_(ht, non_blocking=True)
+            loss = graphed()
+            hloss.copy_(loss.data._buf.view(1), non_blocking=True)
+            torch.cuda.synchronize()
+
     sampler = ClockSampler(local)
     with cp.compute_mode(args.mode):
         if rank == 0:
@@ -497,7 +511,7 @@ def run_model(args) -> None:
     line = {"metric": "cnn_train_images_per_s" if args.workload != "mlp" else "mlp_train_samples_per_s", "value": round(ips, 1), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.mode], "data": "synthetic",
-            "config": {"workload": desc, "batch_per_gpu": B, "compute_mode": args.mode, "tolerance": TOL[args.mode], "parallelism": f"dp{world}",
+            "config": {"workload": desc, "batch_per_gpu": B, "compute_mode": args.mode, "cuda_graph": bool(graphed), "tolerance": TOL[args.mode], "parallelism": f"dp{world}",
                        "l2_policy": "activations of one step exceed L2" if B * int(np.prod(xshape)) * 4 > 126e6 else "L2 flushed implicitly: per-step activation traffic exceeds L2"},
             "clocks": clocks, "e2e": {"value": round(world * B / (e2e_ms / 1e3), 1), "unit": "images/s", "h2d_bytes_per_step": int(hx.numel() * 4 + ht.numel() * 4),
                                       "d2h_bytes_per_step": 4, "note": "module API; batch H2D from pinned memory and loss D2H every step; wall clock incl. host dispatch"},
@@ -519,6 +533,7 @@ def main() -> None:
     ap.add_argument("--no-extra-modes", action="store_true")
     ap.add_argument("--workload", default="conv2d_sweep", choices=["conv2d_sweep", "mnist", "vgg", "resnet18", "mlp"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of a model workload")
+    ap.add_argument("--graph", action="store_true", help="model workloads: replay the train step as one CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

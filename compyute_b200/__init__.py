@@ -8,7 +8,7 @@
 Hand-written CUDA for sm_100a (compyute_b200/csrc) behind a C ABI (include/compyute_b200.h); no CPU fallback.
 """
 
-from . import distributed, nn
+from . import distributed, graph, nn
 from .backend import *
 from .tensors import DeviceArray, ShapeError, Tensor, tensor
 from .utils import load, save

@@ -129,13 +129,15 @@ struct ConvDgradP {
 // ---- dgrad for tiny Ci (e.g. the 3-channel stem): a GEMM formulation would waste a 128-wide N tile on <= 8 columns.
 // One thread per input pixel of one residue class, CI accumulators in registers, filter in shared memory as
 // [co][tap][ci]; lanes run along ws so dy reads are coalesced and the tap set is warp-uniform.
+struct SmallTaps { unsigned char tj[64], tk[64]; };  // passed by value: nothing to upload, CUDA-graph safe
+
 template <int CI>
 __global__ void __launch_bounds__(256) dgrad_small_ci_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                              float* __restrict__ dx, ConvGeom g, int Hs, int Ws, int rh, int rw,
-                                                             int ntaps, const unsigned char* __restrict__ taps /*[2][64] in gmem*/) {
+                                                             int ntaps, const SmallTaps taps) {
   extern __shared__ float wsm[];  // [Co][ntaps][CI]
   __shared__ int s_tj[64], s_tk[64];
-  for (int i = threadIdx.x; i < ntaps; i += blockDim.x) { s_tj[i] = taps[i]; s_tk[i] = taps[64 + i]; }
+  for (int i = threadIdx.x; i < ntaps; i += blockDim.x) { s_tj[i] = taps.tj[i]; s_tk[i] = taps.tk[i]; }
   __syncthreads();
   const int KK = g.K * g.K;
   for (int i = threadIdx.x; i < g.Co * ntaps * CI; i += blockDim.x) {
@@ -189,7 +191,7 @@ static int class_taps(const ConvGeom& g, int rh, int rw, unsigned char* tj, unsi
 }
 
 // exact-fp32 dgrad driver (all strides): one launch per non-empty residue class
-static int dgrad_fp32(const ConvGeom& g, const float* dy, const float* w, float* dx, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int dgrad_fp32(const ConvGeom& g, const float* dy, const float* w, float* dx, void* /*ws*/, size_t /*ws_bytes*/, cudaStream_t st) {
   const int classes = g.S * g.S;
   bool any_empty = false;
   for (int c = 0; c < classes && !any_empty; ++c) {
@@ -208,13 +210,9 @@ static int dgrad_fp32(const ConvGeom& g, const float* dy, const float* w, float*
     CPT_REQUIRE(p.ntaps <= 64, CPT_ERR_UNSUPPORTED, "conv2d_dgrad: more than 64 taps per stride class (K=%d)", g.K);
     const int Hs = (g.H - rh + g.S - 1) / g.S, Ws = (g.W - rw + g.S - 1) / g.S;
     const size_t wbytes = (size_t)g.Co * p.ntaps * (g.Ci <= 4 ? 4 : 8) * sizeof(float);
-    if (g.Ci <= 8 && wbytes <= 96 * 1024 && ws && ws_bytes >= 128) {
-      // tap table through the workspace (tiny, stream-ordered)
-      unsigned char host[128];
-      for (int i = 0; i < 64; ++i) { host[i] = p.tj[i]; host[64 + i] = p.tk[i]; }
-      unsigned char* dtaps = reinterpret_cast<unsigned char*>(ws) + (size_t)c * 128;
-      CPT_REQUIRE(ws_bytes >= (size_t)classes * 128, CPT_ERR_WORKSPACE, "conv2d_dgrad: workspace too small");
-      CPT_CUDA(cudaMemcpyAsync(dtaps, host, 128, cudaMemcpyHostToDevice, st));
+    if (g.Ci <= 8 && wbytes <= 96 * 1024) {
+      SmallTaps dtaps;
+      for (int i = 0; i < 64; ++i) { dtaps.tj[i] = p.tj[i]; dtaps.tk[i] = p.tk[i]; }
       const int64_t total = (int64_t)g.B * Hs * Ws;
       const int grid = ew_grid(total, 256);
       if (g.Ci <= 4) {

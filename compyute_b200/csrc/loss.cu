@@ -75,7 +75,9 @@ __device__ __forceinline__ float u01(uint64_t seed, uint64_t idx) {
 }
 
 __global__ void __launch_bounds__(256) dropout_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                          int8_t* __restrict__ mask, int64_t n, float keep, uint64_t seed) {
+                                                          int8_t* __restrict__ mask, int64_t n, float keep, uint64_t seed,
+                                                          const uint64_t* __restrict__ live_seed) {
+  if (live_seed) seed ^= *live_seed * 0xD6E8FEB86659FD93ull;  // per-replay stream when the launch is inside a CUDA graph
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int8_t mk = u01(seed, (uint64_t)i) < keep ? 1 : 0;  // bernoulli(1-p): random() < p_keep (random.py:264)
@@ -125,10 +127,11 @@ int cpt_accuracy_count(const float* logits, const int32_t* targets, int* correct
   return CPT_OK;
 }
 
-int cpt_dropout_fwd(const float* x, float* y, int8_t* mask, int64_t n, float p, uint64_t seed, void* stream) {
+int cpt_dropout_fwd(const float* x, float* y, int8_t* mask, int64_t n, float p, uint64_t seed, const uint64_t* live_seed,
+                    void* stream) {
   CPT_REQUIRE(n >= 0 && x && y && mask && p >= 0.f && p < 1.f, CPT_ERR_INVALID, "dropout_fwd: bad arguments");
   if (n == 0) return CPT_OK;
-  dropout_fwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, y, mask, n, 1.0f - p, seed);
+  dropout_fwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, y, mask, n, 1.0f - p, seed, live_seed);
   CPT_LAUNCH_CHECK("dropout_fwd");
   return CPT_OK;
 }

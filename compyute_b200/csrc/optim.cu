@@ -8,7 +8,8 @@ namespace cpt {
 
 __global__ void __launch_bounds__(256) adam_kernel(const cpt_param_entry* __restrict__ table, float lr, float beta1,
                                                    float beta2, float eps, float wd, float m_div, float v_div,
-                                                   float grad_scale, int decoupled) {
+                                                   float grad_scale, int decoupled, const float* __restrict__ live) {
+  if (live) { lr = live[0]; m_div = live[1]; v_div = live[2]; }  // per-step scalars from device memory (CUDA-graph replay)
   const cpt_param_entry e = table[blockIdx.y];
   const int64_t n = e.n;
   if (n == 0) return;
@@ -56,7 +57,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const cpt_param_entry* __rest
 // NAdam.step optimizers.py:437-475: m_hat = mu_next * m / m_div + (1 - mu) * g / g_div, v_hat = v / v_div
 __global__ void __launch_bounds__(256) nadam_kernel(const cpt_param_entry* __restrict__ table, float lr, float beta1, float beta2,
                                                     float eps, float wd, float mu, float mu_next, float m_div, float g_div,
-                                                    float v_div, float grad_scale) {
+                                                    float v_div, float grad_scale, const float* __restrict__ live) {
+  if (live) { lr = live[0]; m_div = live[1]; v_div = live[2]; mu = live[3]; mu_next = live[4]; g_div = live[5]; }
   const cpt_param_entry e = table[blockIdx.y];
   const int64_t n = e.n;
   if (n == 0) return;
@@ -80,7 +82,8 @@ __global__ void __launch_bounds__(256) nadam_kernel(const cpt_param_entry* __res
 }
 
 __global__ void __launch_bounds__(256) sgd_kernel(const cpt_param_entry* __restrict__ table, float lr, float momentum,
-                                                  int nesterov, float wd, float grad_scale) {
+                                                  int nesterov, float wd, float grad_scale, const float* __restrict__ live) {
+  if (live) lr = live[0];
   const cpt_param_entry e = table[blockIdx.y];
   const int64_t n = e.n;
   if (n == 0) return;
@@ -117,32 +120,32 @@ extern "C" {
 
 int cpt_adam_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, float m_div, float v_div, float grad_scale, int decoupled,
-                  void* stream) {
+                  const float* live_scalars, void* stream) {
   CPT_REQUIRE(table && n_entries >= 0 && n_entries <= 65535, CPT_ERR_INVALID, "adam_step: bad table");
   if (n_entries == 0) return CPT_OK;
   adam_kernel<<<mt_grid(n_entries, max_n), 256, 0, as_stream(stream)>>>(table, lr, beta1, beta2, eps, weight_decay, m_div,
-                                                                      v_div, grad_scale, decoupled);
+                                                                      v_div, grad_scale, decoupled, live_scalars);
   CPT_LAUNCH_CHECK("adam_step");
   return CPT_OK;
 }
 
 int cpt_nadam_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, float mu, float mu_next, float m_div, float g_div, float v_div, float grad_scale,
-                   void* stream) {
+                   const float* live_scalars, void* stream) {
   CPT_REQUIRE(table && n_entries >= 0 && n_entries <= 65535, CPT_ERR_INVALID, "nadam_step: bad table");
   if (n_entries == 0) return CPT_OK;
   nadam_kernel<<<mt_grid(n_entries, max_n), 256, 0, as_stream(stream)>>>(table, lr, beta1, beta2, eps, weight_decay, mu, mu_next,
-                                                                       m_div, g_div, v_div, grad_scale);
+                                                                       m_div, g_div, v_div, grad_scale, live_scalars);
   CPT_LAUNCH_CHECK("nadam_step");
   return CPT_OK;
 }
 
 int cpt_sgd_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr, float momentum, int nesterov,
-                 float weight_decay, float grad_scale, void* stream) {
+                 float weight_decay, float grad_scale, const float* live_scalars, void* stream) {
   CPT_REQUIRE(table && n_entries >= 0 && n_entries <= 65535, CPT_ERR_INVALID, "sgd_step: bad table");
   if (n_entries == 0) return CPT_OK;
   sgd_kernel<<<mt_grid(n_entries, max_n), 256, 0, as_stream(stream)>>>(table, lr, momentum, nesterov, weight_decay,
-                                                                     grad_scale);
+                                                                     grad_scale, live_scalars);
   CPT_LAUNCH_CHECK("sgd_step");
   return CPT_OK;
 }

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ... import _lib
+from ... import _lib, graph
 from ...tensors import DeviceArray, ShapeError, Tensor, f32ptr, require_cuda, stream_ptr, workspace
 from .functions import Function, FunctionCache, PseudoCache
 
@@ -19,8 +19,11 @@ def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW):
     save_mean = DeviceArray.empty((C,), np.float32)
     save_rstd = DeviceArray.empty((C,), np.float32)
     if training:
-        new_rmean = DeviceArray.empty((C,), np.float32)
-        new_rvar = DeviceArray.empty((C,), np.float32)
+        if graph.is_capturing():  # running stats must chain across replays: update the existing buffers in place
+            new_rmean, new_rvar = rmean.data, rvar.data
+        else:
+            new_rmean = DeviceArray.empty((C,), np.float32)
+            new_rvar = DeviceArray.empty((C,), np.float32)
         ws, wsb = workspace(L.cpt_bn_workspace_size(N, C, HW))
         _lib.check(L.cpt_bn_fwd_train(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, new_rmean.ptr,
                                       new_rvar.ptr, save_mean.ptr, save_rstd.ptr, N, C, HW, float(m), float(eps), ws, wsb, st))

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ... import _lib
+from ... import _lib, graph
 from ...tensors import DeviceArray, Tensor, f32ptr, require_cuda, stream_ptr
 from .functions import Function, FunctionCache, PseudoCache
 
@@ -31,7 +31,8 @@ class DropoutFn(Function):
         mask = DeviceArray.empty(x.shape, np.int8)
         _seed[1] += 1
         seed = (_seed[0] * 0x9E3779B1 + _seed[1] * 0x85EBCA77) & 0xFFFFFFFFFFFFFFFF
-        _lib.check(_lib.lib().cpt_dropout_fwd(f32ptr(x), y.ptr, mask.ptr, x.size, float(p), seed, stream_ptr()))
+        live = graph.replay_counter().ptr if graph.is_capturing() else None
+        _lib.check(_lib.lib().cpt_dropout_fwd(f32ptr(x), y.ptr, mask.ptr, x.size, float(p), seed, live, stream_ptr()))
         cache.push(True, p, mask)
         return Tensor(y)
 

@@ -21,7 +21,7 @@ from typing import Any, Iterable, Optional
 
 import numpy as np
 
-from .. import _lib, distributed
+from .. import _lib, distributed, graph
 from ..tensors import DeviceArray, Tensor, stream_ptr
 from .parameter import Parameter
 
@@ -42,6 +42,7 @@ class Optimizer:
         self._table_dev: Optional[DeviceArray] = None
         self._table_key: Optional[bytes] = None
         self._data_parallel = True  # all-reduce gradients in step() whenever a process group with world > 1 exists
+        self._live = None           # (device float[8], pinned host float[8]): per-step scalars for CUDA-graph replays
         if parameters is not None:
             self.set_parameters(parameters)
 
@@ -59,7 +60,7 @@ class Optimizer:
         self._build_arena()
 
     def get_state_dict(self) -> dict[str, dict[Any, Any]]:
-        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel"}
+        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel", "_live"}
         return {"state": self._state, "vars": {k: v for k, v in vars(self).items() if k not in skip}}
 
     def load_state_dict(self, state_dict: dict[str, dict[Any, Any]]) -> None:
@@ -74,7 +75,40 @@ class Optimizer:
             p.grad = None
 
     def step(self) -> None:
+        """Updates the parameters (one fused launch).  Inside a CUDA-graph capture the per-step scalars are read from device
+        memory and ``t`` is advanced by ``upload_live_scalars`` at replay time instead."""
+        scale = self._sync_grads()
+        if graph.is_capturing():
+            self._launch(self._peek_scalars(), self._live_buffers()[0].ptr, scale)
+            return
+        self._launch(self._step_scalars(), None, scale)
+        self.t += 1
+
+    def _step_scalars(self) -> list[float]:
+        """Per-step scalars [lr, ...] for the current ``t``; may advance internal products (NAdam)."""
         raise NotImplementedError
+
+    def _peek_scalars(self) -> list[float]:
+        """Like ``_step_scalars`` but without side effects (placeholder values baked into a captured launch)."""
+        return [float(self.lr)] + [1.0] * 5
+
+    def _launch(self, sc: list[float], live, scale: float) -> None:
+        raise NotImplementedError
+
+    def _live_buffers(self):
+        if self._live is None:
+            import torch
+            self._live = (DeviceArray.zeros((8,), np.float32), torch.zeros(8, dtype=torch.float32).pin_memory())
+        return self._live
+
+    def upload_live_scalars(self) -> None:
+        """Called before each replay of a captured step: scalars of step ``t`` -> device buffer, then ``t += 1``."""
+        dev, host = self._live_buffers()
+        sc = self._step_scalars()
+        for i, v in enumerate(sc):
+            host[i] = v
+        dev._buf.copy_(host, non_blocking=True)
+        self.t += 1
 
     # ---- arena / pointer table -----------------------------------------------------------------
     def _build_arena(self) -> None:
@@ -153,13 +187,14 @@ class SGD(Optimizer):
         super().__init__(parameters, lr)
         self.momentum, self.nesterov, self.weight_decay = momentum, nesterov, weight_decay
 
-    def step(self) -> None:
-        scale = self._sync_grads()
+    def _step_scalars(self) -> list[float]:
+        return [float(self.lr)]
+
+    def _launch(self, sc, live, scale) -> None:
         keys = ("v",) if self.momentum > 0.0 else ()
         table, n, max_n = self._table(keys)
-        _lib.check(_lib.lib().cpt_sgd_step(table, n, max_n, float(self.lr), float(self.momentum), int(self.nesterov),
-                                           float(self.weight_decay), float(scale), stream_ptr()))
-        self.t += 1
+        _lib.check(_lib.lib().cpt_sgd_step(table, n, max_n, sc[0], float(self.momentum), int(self.nesterov),
+                                           float(self.weight_decay), float(scale), live, stream_ptr()))
 
 
 class Adam(Optimizer):
@@ -172,15 +207,15 @@ class Adam(Optimizer):
         super().__init__(parameters, lr)
         self.beta1, self.beta2, self.eps, self.weight_decay = beta1, beta2, eps, weight_decay
 
-    def step(self) -> None:
-        scale = self._sync_grads()
-        m_div = 1.0 - self.beta1 ** self.t  # python double, like optimizers.py:243-244
-        v_div = 1.0 - self.beta2 ** self.t
+    def _step_scalars(self) -> list[float]:
+        # python doubles, like optimizers.py:243-244
+        return [float(self.lr), 1.0 - self.beta1 ** self.t, 1.0 - self.beta2 ** self.t]
+
+    def _launch(self, sc, live, scale) -> None:
         table, n, max_n = self._table(("m", "v"))
-        _lib.check(_lib.lib().cpt_adam_step(table, n, max_n, float(self.lr), float(self.beta1), float(self.beta2),
-                                            float(self.eps), float(self.weight_decay), float(m_div), float(v_div),
-                                            float(scale), self._decoupled, stream_ptr()))
-        self.t += 1
+        _lib.check(_lib.lib().cpt_adam_step(table, n, max_n, sc[0], float(self.beta1), float(self.beta2), float(self.eps),
+                                            float(self.weight_decay), sc[1], sc[2], float(scale), self._decoupled, live,
+                                            stream_ptr()))
 
 
 class AdamW(Adam):
@@ -203,16 +238,17 @@ class NAdam(Optimizer):
         self.momentum_decay = momentum_decay
         self._mu_prod = 1.0
 
-    def step(self) -> None:
-        scale = self._sync_grads()
+    def _step_scalars(self) -> list[float]:
         mu = self.beta1 * (1.0 - 0.5 * 0.96 ** (self.t * self.momentum_decay))  # python doubles, like :438-447
         mu_next = self.beta1 * (1.0 - 0.5 * 0.96 ** ((self.t + 1) * self.momentum_decay))
         self._mu_prod *= mu
         m_div = 1.0 - self._mu_prod * mu_next
         g_div = 1.0 - self._mu_prod
         v_div = 1.0 - self.beta2 ** self.t
+        return [float(self.lr), m_div, v_div, mu, mu_next, g_div]  # order of the kernel's live-scalar layout
+
+    def _launch(self, sc, live, scale) -> None:
         table, n, max_n = self._table(("m", "v"))
-        _lib.check(_lib.lib().cpt_nadam_step(table, n, max_n, float(self.lr), float(self.beta1), float(self.beta2), float(self.eps),
-                                             float(self.weight_decay), float(mu), float(mu_next), float(m_div), float(g_div),
-                                             float(v_div), float(scale), stream_ptr()))
-        self.t += 1
+        _lib.check(_lib.lib().cpt_nadam_step(table, n, max_n, sc[0], float(self.beta1), float(self.beta2), float(self.eps),
+                                             float(self.weight_decay), sc[3], sc[4], sc[1], sc[5], sc[2], float(scale), live,
+                                             stream_ptr()))

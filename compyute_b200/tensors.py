@@ -41,7 +41,7 @@ def stream_ptr() -> int:
 
 
 _NP2TORCH = {"float32": "float32", "int32": "int32", "int64": "int64", "int8": "int8", "uint8": "uint8", "bool": "bool",
-             "float64": "float64", "bfloat16": "bfloat16"}
+             "float64": "float64", "bfloat16": "bfloat16", "uint64": "uint64"}
 
 
 class DeviceArray:
@@ -126,6 +126,20 @@ class DeviceArray:
         if other.size != self.size or other.dtype != self.dtype:
             raise ShapeError(f"copy_from: {other.shape}/{other.dtype} into {self.shape}/{self.dtype}")
         self._buf.view(-1).copy_(other._buf.view(-1))
+
+    def upload(self, a) -> None:
+        """In-place H2D copy into this buffer (keeps the address: used to feed CUDA-graph-captured steps)."""
+        torch = _t()
+        if isinstance(a, DeviceArray):
+            return self.copy_from(a)
+        if hasattr(a, "to_numpy"):
+            a = a.data if isinstance(a.data, DeviceArray) else a.to_numpy()
+            if isinstance(a, DeviceArray):
+                return self.copy_from(a)
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        if a.size != self.size:
+            raise ShapeError(f"upload: {a.shape} into {self.shape}")
+        self._buf.view(-1).copy_(torch.from_numpy(a).view(-1), non_blocking=True)
 
     def numpy(self) -> np.ndarray:
         return self._buf.detach().cpu().numpy().reshape(self.shape)  # cudaMemcpy D2H (synchronising)

@@ -182,9 +182,10 @@ int cpt_softmax_ce_bwd(const float* probs, const int32_t* targets, float* dlogit
 /* count of argmax(logits) == target → *correct (int, pre-zeroed by the call)  metric_funcs.py:10-25 */
 int cpt_accuracy_count(const float* logits, const int32_t* targets, int* correct, int B, int NC,
                        void* stream);
-/* DropoutFn regularization_funcs.py:15-32; mask int8 Bernoulli(1-p) from a counter-based RNG. */
+/* DropoutFn regularization_funcs.py:15-32; mask int8 Bernoulli(1-p) from a counter-based RNG.  live_seed (device, may be
+ * NULL) is mixed into the seed at run time so that a CUDA-graph replay draws a fresh mask. */
 int cpt_dropout_fwd(const float* x, float* y, int8_t* mask, int64_t n, float p, uint64_t seed,
-                    void* stream);
+                    const uint64_t* live_seed, void* stream);
 int cpt_dropout_bwd(const float* dy, const int8_t* mask, float* dx, int64_t n, float p,
                     void* stream);
 
@@ -200,19 +201,22 @@ typedef struct cpt_param_entry {
 /* Multi-tensor fused steps.  `table` is a DEVICE array of n_entries entries.  grad_scale
  * multiplies every gradient first (1/world_size in data-parallel mode).
  * Adam.step :241-271 (decoupled = 0), AdamW.step :335-362 (decoupled = 1).  m_div = 1 - beta1^t,
- * v_div = 1 - beta2^t are computed by the caller in double like the reference (:243-244). */
+ * v_div = 1 - beta2^t are computed by the caller in double like the reference (:243-244).
+ * live_scalars (device, may be NULL): when given, the per-step scalars are read from device memory instead of the
+ * by-value arguments — {lr, m_div, v_div} for Adam/AdamW, {lr, m_div, v_div, mu, mu_next, g_div} for NAdam, {lr} for SGD —
+ * so a CUDA graph that captured the step keeps following LR schedulers and bias correction. */
 int cpt_adam_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, float m_div, float v_div,
-                  float grad_scale, int decoupled, void* stream);
+                  float grad_scale, int decoupled, const float* live_scalars, void* stream);
 /* NAdam.step :437-475.  mu, mu_next, m_div = 1 - mu_prod*mu_next, g_div = 1 - mu_prod, v_div = 1 - beta2^t are computed
  * by the caller in double like the reference (:438-447). */
 int cpt_nadam_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, float mu, float mu_next, float m_div,
-                   float g_div, float v_div, float grad_scale, void* stream);
+                   float g_div, float v_div, float grad_scale, const float* live_scalars, void* stream);
 /* SGD.step :152-176 (momentum / nesterov / L2 weight decay). */
 int cpt_sgd_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr,
                  float momentum, int nesterov, float weight_decay, float grad_scale,
-                 void* stream);
+                 const float* live_scalars, void* stream);
 
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 /* Synchronises the device and returns (then clears) the tensor-core pipeline watchdog flag: 0 = healthy,

@@ -98,3 +98,62 @@ def test_vgg_tensor_core_modes_track_fp32(mode):
     ref, got = run("fp32"), run(mode)
     assert abs(got[0] - ref[0]) <= {"tf32": 2e-3, "bf16": 1e-2}[mode] * max(1.0, abs(ref[0]))
     assert got[-1] < got[0] and np.isfinite(got).all()
+
+
+def test_cuda_graph_captured_step_matches_eager():
+    """A train step captured into a CUDA graph (cp.graph.CapturedStep) replays to exactly the eager results: same losses,
+    bit-identical parameters, BatchNorm running stats and Adam state after 6 steps, with lr changed between replays."""
+    import compyute_b200 as cp
+    from compyute_b200 import nn
+    spec = W.mnist_cnn(drop=0.0)
+    rng = np.random.RandomState(9)
+    xs = [rng.normal(0, 1, (32, 1, 28, 28)).astype(np.float32) for _ in range(6)]
+    ts = [rng.randint(0, 10, (32,)).astype(np.int32) for _ in range(6)]
+
+    def make():
+        np.random.seed(21)
+        with cp.use_device(cp.cuda):
+            m = W.build(spec)
+        m.training()
+        return m, nn.optimizers.Adam(m.get_parameters(), lr=1e-3), nn.CrossEntropyLoss()
+
+    def lr_at(i):
+        return 1e-3 * (0.5 if i >= 5 else 1.0)
+
+    # eager
+    m1, o1, l1 = make()
+    eager = []
+    for i in range(6):
+        o1.lr = lr_at(i)
+        loss = l1(m1(cp.tensor(xs[i], device=cp.cuda)), cp.tensor(ts[i], device=cp.cuda))
+        o1.reset_grads(); m1.backward(l1.backward()); o1.step()
+        eager.append(loss.item())
+    # captured: 3 eager warm-up steps inside CapturedStep (on batches 0..2), then replays for batches 3..5
+    m2, o2, l2 = make()
+    xs_t, ts_t = cp.tensor(xs[0], device=cp.cuda), cp.tensor(ts[0], device=cp.cuda)
+    feed = iter(range(6))
+
+    def step():
+        loss = l2(m2(xs_t), ts_t)
+        o2.reset_grads(); m2.backward(l2.backward()); o2.step()
+        return loss
+
+    class Feeder:  # warm-up calls inside CapturedStep consume batches 0, 1, 2
+        n = 0
+    def step_with_feed():
+        i = Feeder.n
+        if not cp.graph.is_capturing():
+            xs_t.data.upload(xs[i]); ts_t.data.upload(ts[i]); o2.lr = lr_at(i); Feeder.n += 1
+        return step()
+
+    captured = cp.graph.CapturedStep(step_with_feed, optimizers=[o2], warmup=3)
+    got = []
+    for i in range(3, 6):
+        xs_t.data.upload(xs[i]); ts_t.data.upload(ts[i]); o2.lr = lr_at(i)
+        got.append(captured().item())
+    assert np.allclose(got, eager[3:], rtol=0, atol=0), (got, eager[3:])
+    assert o2.t == o1.t == 7
+    for a, b in zip(m1.get_state_dict().values(), m2.get_state_dict().values()):
+        assert np.array_equal(a.to_numpy(), b.to_numpy())
+    for i in o1._state:
+        assert np.array_equal(o1._state[i]["v"].to_numpy(), o2._state[i]["v"].to_numpy())
