@@ -104,6 +104,12 @@ __global__ void __launch_bounds__(256) sgd_kernel(const cpt_param_entry* __restr
   }
 }
 
+struct Live8 { float v[8]; };
+__global__ void set_live_kernel(float* __restrict__ dst, Live8 vals, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = vals.v[threadIdx.x];
+}
+__global__ void set_u64_kernel(unsigned long long* __restrict__ dst, unsigned long long v) { *dst = v; }
+
 static dim3 mt_grid(int n_entries, int64_t max_n) {
   int64_t gx = (max_n + 256 * 4 - 1) / (256 * 4);
   const int64_t cap = (int64_t)sm_count() * 4;
@@ -137,6 +143,22 @@ int cpt_nadam_step(const cpt_param_entry* table, int n_entries, int64_t max_n, f
   nadam_kernel<<<mt_grid(n_entries, max_n), 256, 0, as_stream(stream)>>>(table, lr, beta1, beta2, eps, weight_decay, mu, mu_next,
                                                                        m_div, g_div, v_div, grad_scale, live_scalars);
   CPT_LAUNCH_CHECK("nadam_step");
+  return CPT_OK;
+}
+
+int cpt_set_live_scalars(float* dst, const float* host_values, int n, void* stream) {
+  CPT_REQUIRE(dst && host_values && n >= 1 && n <= 8, CPT_ERR_INVALID, "set_live_scalars: bad arguments");
+  Live8 v{};
+  for (int i = 0; i < n; ++i) v.v[i] = host_values[i];  // copied into the launch parameters: no host-buffer lifetime issue
+  set_live_kernel<<<1, 32, 0, as_stream(stream)>>>(dst, v, n);
+  CPT_LAUNCH_CHECK("set_live_scalars");
+  return CPT_OK;
+}
+
+int cpt_set_u64(uint64_t* dst, uint64_t value, void* stream) {
+  CPT_REQUIRE(dst, CPT_ERR_INVALID, "set_u64: null pointer");
+  set_u64_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)value);
+  CPT_LAUNCH_CHECK("set_u64");
   return CPT_OK;
 }
 

@@ -45,8 +45,9 @@ class CapturedStep:
         self._torch = torch
         self.optimizers = list(optimizers)
         self._count = 0
-        self._host_counter = torch.zeros(1, dtype=torch.int64).pin_memory()
         replay_counter()
+        for o in self.optimizers:
+            o._live_buffer()  # created before the capture: an allocation + memset inside it would be replayed every time
         for _ in range(max(1, warmup)):  # eager: first-use initialisation, allocator warm-up, optimizer state creation
             fn()
         torch.cuda.synchronize()
@@ -59,10 +60,10 @@ class CapturedStep:
             _capturing = False
 
     def __call__(self):
-        torch = self._torch
+        from . import _lib
+        from .tensors import stream_ptr
         self._count += 1
-        self._host_counter[0] = self._count
-        replay_counter()._buf.view(torch.int64).copy_(self._host_counter, non_blocking=True)
+        _lib.check(_lib.lib().cpt_set_u64(replay_counter().ptr, self._count, stream_ptr()))
         for o in self.optimizers:
             o.upload_live_scalars()  # scalars of step t -> device, then t += 1 (what step() does in eager mode)
         self.graph.replay()

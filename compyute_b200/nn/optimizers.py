@@ -42,7 +42,7 @@ class Optimizer:
         self._table_dev: Optional[DeviceArray] = None
         self._table_key: Optional[bytes] = None
         self._data_parallel = True  # all-reduce gradients in step() whenever a process group with world > 1 exists
-        self._live = None           # (device float[8], pinned host float[8]): per-step scalars for CUDA-graph replays
+        self._live = None           # device float[8]: per-step scalars read by the update kernel in CUDA-graph replays
         if parameters is not None:
             self.set_parameters(parameters)
 
@@ -79,7 +79,7 @@ class Optimizer:
         memory and ``t`` is advanced by ``upload_live_scalars`` at replay time instead."""
         scale = self._sync_grads()
         if graph.is_capturing():
-            self._launch(self._peek_scalars(), self._live_buffers()[0].ptr, scale)
+            self._launch(self._peek_scalars(), self._live_buffer().ptr, scale)
             return
         self._launch(self._step_scalars(), None, scale)
         self.t += 1
@@ -95,19 +95,20 @@ class Optimizer:
     def _launch(self, sc: list[float], live, scale: float) -> None:
         raise NotImplementedError
 
-    def _live_buffers(self):
+    def _live_buffer(self) -> DeviceArray:
+        """Must exist BEFORE a capture starts (an allocation + memset inside the capture would be replayed every time)."""
         if self._live is None:
-            import torch
-            self._live = (DeviceArray.zeros((8,), np.float32), torch.zeros(8, dtype=torch.float32).pin_memory())
+            if graph.is_capturing():
+                raise RuntimeError("optimizer live-scalar buffer must be created before capture (use cp.graph.CapturedStep)")
+            self._live = DeviceArray.zeros((8,), np.float32)
         return self._live
 
     def upload_live_scalars(self) -> None:
         """Called before each replay of a captured step: scalars of step ``t`` -> device buffer, then ``t += 1``."""
-        dev, host = self._live_buffers()
+        import ctypes
         sc = self._step_scalars()
-        for i, v in enumerate(sc):
-            host[i] = v
-        dev._buf.copy_(host, non_blocking=True)
+        vals = (ctypes.c_float * len(sc))(*sc)
+        _lib.check(_lib.lib().cpt_set_live_scalars(self._live_buffer().ptr, vals, len(sc), stream_ptr()))
         self.t += 1
 
     # ---- arena / pointer table -----------------------------------------------------------------

@@ -213,6 +213,10 @@ int cpt_adam_step(const cpt_param_entry* table, int n_entries, int64_t max_n, fl
 int cpt_nadam_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, float mu, float mu_next, float m_div,
                    float g_div, float v_div, float grad_scale, const float* live_scalars, void* stream);
+/* Writes n <= 8 host floats / one uint64 into device memory with a 1-block kernel (values travel in the launch
+ * parameters): how the live scalars / Dropout replay counter are refreshed before a CUDA-graph replay. */
+int cpt_set_live_scalars(float* dst, const float* host_values, int n, void* stream);
+int cpt_set_u64(uint64_t* dst, uint64_t value, void* stream);
 /* SGD.step :152-176 (momentum / nesterov / L2 weight decay). */
 int cpt_sgd_step(const cpt_param_entry* table, int n_entries, int64_t max_n, float lr,
                  float momentum, int nesterov, float weight_decay, float grad_scale,
