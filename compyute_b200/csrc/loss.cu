@@ -5,9 +5,9 @@
 
 namespace cpt {
 
-// one warp per row (NC up to a few thousand); probs = exp(x - max) / Σ; loss += -log(p_t + eta) / B
+// one warp per row (NC up to a few thousand); probs = exp(x - max) / Σ; row_loss[row] = -log(p_t + eta)
 __global__ void __launch_bounds__(256) softmax_ce_fwd_kernel(const float* __restrict__ logits, const int32_t* __restrict__ targets,
-                                                             float* __restrict__ probs, float* __restrict__ loss, int B,
+                                                             float* __restrict__ probs, float* __restrict__ row_loss, int B,
                                                              int NC, float eta) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -29,8 +29,17 @@ __global__ void __launch_bounds__(256) softmax_ce_fwd_kernel(const float* __rest
   if (lane == 0) {
     const int t = targets[row];
     const float pt = (t >= 0 && t < NC) ? p[t] : 0.f;
-    atomicAdd(loss, -logf(pt + eta) / (float)B);
+    row_loss[row] = -logf(pt + eta);
   }
+}
+
+// loss = mean(row_loss): one block, fixed summation order -> run-to-run (and graph-replay) deterministic
+__global__ void __launch_bounds__(1024) ce_loss_mean_kernel(const float* __restrict__ row_loss, float* __restrict__ loss, int B) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) s += row_loss[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) *loss = s / (float)B;
 }
 
 __global__ void __launch_bounds__(256) softmax_ce_bwd_kernel(const float* __restrict__ probs, const int32_t* __restrict__ targets,
@@ -99,13 +108,14 @@ using namespace cpt;
 
 extern "C" {
 
-int cpt_softmax_ce_fwd(const float* logits, const int32_t* targets, float* probs, float* loss, int B, int NC, float eta,
-                       void* stream) {
-  CPT_REQUIRE(B > 0 && NC > 0 && logits && targets && probs && loss, CPT_ERR_INVALID, "softmax_ce_fwd: bad arguments");
+int cpt_softmax_ce_fwd(const float* logits, const int32_t* targets, float* probs, float* loss, float* row_loss, int B, int NC,
+                       float eta, void* stream) {
+  CPT_REQUIRE(B > 0 && NC > 0 && logits && targets && probs && loss && row_loss, CPT_ERR_INVALID, "softmax_ce_fwd: bad arguments");
   cudaStream_t st = as_stream(stream);
-  CPT_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
-  softmax_ce_fwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(logits, targets, probs, loss, B, NC, eta);
+  softmax_ce_fwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(logits, targets, probs, row_loss, B, NC, eta);
   CPT_LAUNCH_CHECK("softmax_ce_fwd");
+  ce_loss_mean_kernel<<<1, 1024, 0, st>>>(row_loss, loss, B);
+  CPT_LAUNCH_CHECK("ce_loss_mean");
   return CPT_OK;
 }
 

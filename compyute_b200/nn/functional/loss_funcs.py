@@ -33,7 +33,9 @@ class CrossEntropyLossFn(Function):
         t32 = _targets_i32(targets)
         probs = DeviceArray.empty((B, NC), np.float32)
         loss = DeviceArray.empty((1,), np.float32)
-        _lib.check(_lib.lib().cpt_softmax_ce_fwd(f32ptr(logits), t32.ptr, probs.ptr, loss.ptr, B, NC, float(eta), stream_ptr()))
+        rows = DeviceArray.empty((B,), np.float32)
+        _lib.check(_lib.lib().cpt_softmax_ce_fwd(f32ptr(logits), t32.ptr, probs.ptr, loss.ptr, rows.ptr, B, NC, float(eta),
+                                                 stream_ptr()))
         cache.push(t32, probs)
         return Tensor(loss.reshape(()))
 

@@ -173,9 +173,9 @@ int cpt_sum(const float* x, int64_t n, float* out, void* stream);
 
 /* ---- loss / regularisation (closing the train step on the device) ---------- */
 /* CrossEntropyLossFn.forward loss_funcs.py:57-64: probs = softmax(logits), loss = -mean log(p_t + eta).
- * targets int32.  loss: 1 float (pre-zeroed by the call). */
+ * targets int32.  loss: 1 float; row_loss: B floats of scratch (per-sample losses, reduced in a fixed order). */
 int cpt_softmax_ce_fwd(const float* logits, const int32_t* targets, float* probs, float* loss,
-                       int B, int NC, float eta, void* stream);
+                       float* row_loss, int B, int NC, float eta, void* stream);
 /* backward :67-69: dlogits = (probs - onehot) / B */
 int cpt_softmax_ce_bwd(const float* probs, const int32_t* targets, float* dlogits, int B, int NC,
                        void* stream);

@@ -151,7 +151,7 @@ def test_cuda_graph_captured_step_matches_eager():
     for i in range(3, 6):
         xs_t.data.upload(xs[i]); ts_t.data.upload(ts[i]); o2.lr = lr_at(i)
         got.append(captured().item())
-    assert np.allclose(got, eager[3:], rtol=0, atol=0), (got, eager[3:])
+    assert got == eager[3:], (got, eager[3:])  # every kernel on the path reduces in a fixed order: bit-identical
     assert o2.t == o1.t == 7
     for a, b in zip(m1.get_state_dict().values(), m2.get_state_dict().values()):
         assert np.array_equal(a.to_numpy(), b.to_numpy())
