@@ -141,7 +141,7 @@ def run_reference(args) -> None:
             "config": workload_config(args, "n/a (CPU)"),
             "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": 1, "host_cores": os.cpu_count(), "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, mode: str) -> dict:
@@ -362,7 +362,7 @@ def run_ours(args) -> None:
                                                 "kind": "port", "sample": cpu_desc, "seconds": round(cpu_times[0], 2)},
             "images_per_s": round(world * BATCH * len(SWEEP) / (ms / 1e3), 1), "frac_of_bf16_peak": round(value / world / pk["bf16_tflops"], 4),
             "per_layer": per_layer, "modes": modes, "tc_watchdog": int(status)}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ model workloads
@@ -523,10 +523,30 @@ def run_model(args) -> None:
                                                         "note": f"whole step: {flops_img / 1e9:.3f} GFLOP/image algorithmic (3 x contraction FLOPs)"},
             "cpu_baseline": {"value": None if cpu_val is None else round(cpu_val, 4), "unit": "images/s", "cores": 1, "host_cores": os.cpu_count(), "kind": "port", "sample": cpu_note},
             "tflops": round(tfl, 2), "tc_watchdog": int(status)}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _protect_stdout() -> None:
+    """Everything that writes to fd 1 while the benchmark runs (NCCL prints its version banner there) is sent to stderr;
+    the ONE JSON line is written to the original stdout by ``emit``."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.__stdout__
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main() -> None:
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
