@@ -730,7 +730,7 @@ size_t linear_workspace_size(int op, int64_t N, int In, int Out, int mode) {
 int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, int64_t N, int In, int Out, int mode, cudaStream_t st);
 int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In, int Out, int mode, cudaStream_t st);
 int linear_wgrad_lp(const void* xa, const void* ga, float* dw, int64_t N, int In, int Out, int mode, void* ws, size_t ws_bytes,
-                    cudaStream_t st);
+                    cudaStream_t st, int max_splits = 16);
 
 int linear_fwd(const float* x, const float* w, const float* bias, float* y, int64_t N, int In, int Out, int mode, void* ws,
                size_t ws_bytes, cudaStream_t st) {
@@ -824,7 +824,7 @@ int linear_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t 
 
 // ws: split-K partials (up to 16 x Out x In floats)
 int linear_wgrad_lp(const void* xa, const void* ga, float* dw, int64_t N, int In, int Out, int mode, void* ws, size_t ws_bytes,
-                    cudaStream_t st) {
+                    cudaStream_t st, int max_splits) {
   char* base = reinterpret_cast<char*>(ws);
   const size_t off = 0;
   const int xpitch = mode == CPT_MODE_BF16 ? round_up(In, 8) : In, gpitch = mode == CPT_MODE_BF16 ? round_up(Out, 8) : Out;
@@ -832,7 +832,7 @@ int linear_wgrad_lp(const void* xa, const void* ga, float* dw, int64_t N, int In
   const int k_iters = (int)((N + bk - 1) / bk);
   const int tiles = ((In + 127) / 128) * ((Out + BN - 1) / BN);
   int splits_req = pick_splits(tiles, k_iters, 8);
-  if (splits_req > 16) splits_req = 16;
+  if (splits_req > max_splits) splits_req = max_splits;
   const int kps = (k_iters + splits_req - 1) / splits_req;
   const int splits = (k_iters + kps - 1) / kps;
   float* partial = reinterpret_cast<float*>(base + off);
@@ -853,6 +853,208 @@ int linear_wgrad_lp(const void* xa, const void* ga, float* dw, int64_t N, int In
     launch_reduce_splits(partial, dw, (int64_t)Out * In, splits, st);
     CPT_LAUNCH_CHECK("linear_wgrad reduce");
   }
+  return CPT_OK;
+}
+
+// ------------------------------------------------------------------ packed-K convolution (first layers: tiny Ci)
+// The im2col TMA path spends one 64-channel k-iteration per filter tap, so a layer with Ci = 3 (ResNet stem 7x7: 49 taps,
+// VGG conv1) or Ci = 1 (MNIST conv1) wastes > 90 % of every tile's bytes and MMAs, and re-reads the activations once per
+// tap through L2.  For those layers the patches are written out ONCE as an explicit bf16 matrix
+//     col[(b, ho, wo)][k],  k = c*T + j*K + kk  (the OIHW order of one filter row),  row pitch Kp = round_up(Ci*T, 8)
+// and the three passes become plain GEMMs over it with K = Ci*T packed densely:
+//     fprop  y[b][co][px]   = col[px][:] . w[co][:] + bias      (lanes = pixels -> NCHW stores)
+//     wgrad  dw[co][k]      = Σ_px dy_cl[px][co] col[px][k]      (== Linear wgrad, split-K)
+//     dgrad  dcol[b][k][px] = dy_cl[px][:] . w[:][k]             (lanes = pixels), then a gather (col2im) into dx
+struct PackGeom {
+  int Kdim, Kp, Wpad;
+  int64_t px;
+  size_t smem;
+};
+static PackGeom pack_geom(const G& g) {
+  PackGeom q{};
+  q.Kdim = g.Ci * g.T;
+  q.Kp = round_up(q.Kdim, 8);
+  q.Wpad = (g.Wo - 1) * g.S + (g.K - 1) * g.D + 1;
+  q.px = (int64_t)g.B * g.Ho * g.Wo;
+  q.smem = (size_t)g.Ci * g.K * q.Wpad * sizeof(float) + (size_t)q.Kp * sizeof(int);
+  return q;
+}
+static bool packed_ok(const G& g, int mode) {
+  if (mode != CPT_MODE_BF16 || g.Ho < 1 || g.Wo < 1) return false;
+  const PackGeom q = pack_geom(g);
+  // worth it when the tap-per-k-iteration path would run mostly empty; limits: one input-row patch in shared memory,
+  // int32 pixel index, grid.y
+  return g.Ci <= 16 && q.Kdim <= 1024 && q.smem <= 160 * 1024 && q.px < (1LL << 31) && g.B <= 65535 &&
+         (int64_t)g.B * q.Kdim * g.Ho * g.Wo < (1LL << 40);
+}
+
+// One block per (image, output row): the Ci*K input rows that row needs are loaded once (coalesced, zero-filled outside the
+// image) into a patch [Ci*K][Wpad]; the Wo x Kp output elements are then written as contiguous bf16 pairs.
+__global__ void __launch_bounds__(256) im2col_pack_kernel(const float* __restrict__ x, uint32_t* __restrict__ col, int Ci, int H,
+                                                          int W, int K, int P, int S, int D, int Ho, int Wo, int Kdim, int Kp,
+                                                          int Wpad) {
+  extern __shared__ float patch[];
+  int* lut = reinterpret_cast<int*>(patch + (size_t)Ci * K * Wpad);
+  const int ho = blockIdx.x, b = blockIdx.y, T = K * K;
+  const float* xb = x + (int64_t)b * Ci * H * W;
+  for (int idx = threadIdx.x; idx < Ci * K * Wpad; idx += blockDim.x) {
+    const int r = idx / Wpad, wp = idx - r * Wpad, c = r / K, j = r - c * K;
+    const int h = ho * S - P + j * D, w = wp - P;
+    patch[idx] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(xb + ((int64_t)c * H + h) * W + w) : 0.f;
+  }
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    const int c = k / T, t = k - c * T, j = t / K, kk = t - j * K;
+    lut[k] = k < Kdim ? (c * K + j) * Wpad + kk * D : -1;
+  }
+  __syncthreads();
+  const int pairs = Kp >> 1;
+  uint32_t* dst = col + ((int64_t)b * Ho + ho) * Wo * pairs;
+  for (int idx = threadIdx.x; idx < Wo * pairs; idx += blockDim.x) {
+    const int wo = idx / pairs, k = (idx - wo * pairs) << 1;
+    const int l0 = lut[k], l1 = lut[k + 1];
+    const float v0 = l0 >= 0 ? patch[l0 + wo * S] : 0.f, v1 = l1 >= 0 ? patch[l1 + wo * S] : 0.f;
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+    dst[idx] = *reinterpret_cast<uint32_t*>(&h2);
+  }
+}
+
+// wT[k][co] = w[co][k] as bf16, row pitch Cop (zero padded): the K-major B operand of the dgrad GEMM
+__global__ void w_packT_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Co, int Kdim, int Cop) {
+  const int64_t n = (int64_t)Kdim * Cop;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cop), k = (int)(i / Cop);
+    dst[i] = __float2bfloat16_rn(co < Co ? w[(int64_t)co * Kdim + k] : 0.f);
+  }
+}
+
+// dx[b][c][h][w] = Σ_{j, kk : (h + P - j D) = S ho, (w + P - kk D) = S wo} dcol[b][c*T + j*K + kk][ho][wo]   (fixed order)
+// consecutive threads walk w: lanes of equal parity read consecutive wo of one dcol row
+__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int64_t total, int Ci,
+                                                     int H, int W, int K, int P, int S, int D, int Ho, int Wo) {
+  const int T = K * K;
+  const int64_t plane = (int64_t)Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    int64_t r = i / W;
+    const int h = (int)(r % H);
+    r /= H;
+    const int c = (int)(r % Ci);
+    const int64_t b = r / Ci;
+    const float* base = dcol + (b * Ci + c) * T * plane;
+    float acc = 0.f;
+    for (int j = 0; j < K; ++j) {
+      const int hh = h + P - j * D;
+      if (hh < 0) break;
+      const int ho = hh / S;
+      if (ho * S != hh || ho >= Ho) continue;
+      for (int kk = 0; kk < K; ++kk) {
+        const int ww = w + P - kk * D;
+        if (ww < 0) break;
+        const int wo = ww / S;
+        if (wo * S != ww || wo >= Wo) continue;
+        acc += __ldg(base + (int64_t)(j * K + kk) * plane + (int64_t)ho * Wo + wo);
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
+size_t conv_packed_bytes(const cpt_conv2d_desc* d, int mode) {
+  const G g = geom(d);
+  if (!packed_ok(g, mode)) return 0;
+  const PackGeom q = pack_geom(g);
+  return align_up((size_t)q.px * q.Kp * 2, 1024);
+}
+
+size_t conv_packed_workspace_size(int op, const cpt_conv2d_desc* d) {
+  const G g = geom(d);
+  const PackGeom q = pack_geom(g);
+  if (op == CPT_OP_FPROP) return cast_bytes(g.Co, q.Kdim) + 1024;
+  if (op == CPT_OP_DGRAD)
+    return align_up((size_t)q.Kdim * round_up(g.Co, 8) * 2, 1024) + align_up((size_t)g.B * q.Kdim * g.Ho * g.Wo * sizeof(float), 1024) + 1024;
+  return align_up((size_t)64 * g.Co * q.Kdim * sizeof(float), 1024) + 1024;
+}
+
+int conv_im2col_pack(const cpt_conv2d_desc* d, const float* x, void* col, cudaStream_t st) {
+  const G g = geom(d);
+  CPT_REQUIRE(packed_ok(g, CPT_MODE_BF16), CPT_ERR_UNSUPPORTED, "conv2d_im2col_pack: geometry not covered by the packed-K path");
+  const PackGeom q = pack_geom(g);
+  static size_t configured = 0;
+  if (q.smem > 48 * 1024 && q.smem > configured) {
+    CPT_CUDA(cudaFuncSetAttribute(im2col_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = 160 * 1024;
+  }
+  im2col_pack_kernel<<<dim3(g.Ho, g.B), 256, q.smem, st>>>(x, reinterpret_cast<uint32_t*>(col), g.Ci, g.H, g.W, g.K, g.P, g.S, g.D,
+                                                           g.Ho, g.Wo, q.Kdim, q.Kp, q.Wpad);
+  CPT_LAUNCH_CHECK("im2col_pack");
+  return CPT_OK;
+}
+
+int conv_fprop_packed(const cpt_conv2d_desc* d, const void* col, const float* w, const float* bias, float* y, void* ws,
+                      size_t ws_bytes, cudaStream_t st) {
+  const G g = geom(d);
+  const int mode = CPT_MODE_BF16;
+  CPT_REQUIRE(packed_ok(g, mode), CPT_ERR_UNSUPPORTED, "conv2d_fprop_packed: geometry not covered by the packed-K path");
+  CPT_REQUIRE(ws && ws_bytes >= conv_packed_workspace_size(CPT_OP_FPROP, d), CPT_ERR_WORKSPACE, "conv2d_fprop_packed: workspace too small");
+  const PackGeom q = pack_geom(g);
+  if (int e = cast_to_bf16(w, ws, g.Co, q.Kdim, st)) return e;  // [Co][Kp]: OIHW rows are already in k order
+  const int kc = kc_of(mode), BN = pick_bn(g.Co);
+  TcParams p{};
+  const bool use2 = want_2cta(BN, (q.px + 127) / 128);
+  if (int e = make_map_2d(&p.tmA, col, mode, q.Kdim, (uint64_t)q.px, q.Kp, kc, 128)) return e;
+  if (int e = make_map_2d(&p.tmB, ws, mode, q.Kdim, g.Co, q.Kp, kc, use2 ? BN / 2 : BN)) return e;
+  p.out = y; p.bias = bias; p.bias_mode = bias ? BIAS_COL : BIAS_NONE;
+  if (int e = get_status_ptr(&p.status)) return e;
+  p.M = (int)q.px; p.N = g.Co;
+  p.m_tiles = (int)((q.px + 127) / 128); p.n_tiles = (g.Co + BN - 1) / BN; p.z_tiles = 1;
+  p.k_iters_total = (q.Kdim + kc - 1) / kc; p.k_iters_per_split = p.k_iters_total;
+  p.col_stride = (long long)g.Ho * g.Wo;
+  p.lane_is_pixel = 1; p.px_per_img = g.Ho * g.Wo; p.img_stride = (long long)g.Co * g.Ho * g.Wo;
+  p.out_W = g.Wo; p.out_s = 1; p.Wo = g.Wo; p.taps = 1;
+  return launch_bn<false, false, OP_GEMM>(p, mode, BN, use2, st);
+}
+
+int conv_wgrad_packed(const cpt_conv2d_desc* d, const void* col, const void* dy_cl, float* dw, void* ws, size_t ws_bytes,
+                      cudaStream_t st) {
+  const G g = geom(d);
+  CPT_REQUIRE(packed_ok(g, CPT_MODE_BF16), CPT_ERR_UNSUPPORTED, "conv2d_wgrad_packed: geometry not covered by the packed-K path");
+  CPT_REQUIRE(ws && ws_bytes >= conv_packed_workspace_size(CPT_OP_WGRAD, d), CPT_ERR_WORKSPACE, "conv2d_wgrad_packed: workspace too small");
+  const PackGeom q = pack_geom(g);
+  // dw[co][k] = Σ_px dy_cl[px][co] * col[px][k]: the Linear weight gradient with x = col, In = Ci*T, Out = Co
+  return linear_wgrad_lp(col, dy_cl, dw, q.px, q.Kdim, g.Co, CPT_MODE_BF16, ws, ws_bytes, st, 64);
+}
+
+int conv_dgrad_packed(const cpt_conv2d_desc* d, const void* dy_cl, const float* w, float* dx, void* ws, size_t ws_bytes,
+                      cudaStream_t st) {
+  const G g = geom(d);
+  const int mode = CPT_MODE_BF16;
+  CPT_REQUIRE(packed_ok(g, mode), CPT_ERR_UNSUPPORTED, "conv2d_dgrad_packed: geometry not covered by the packed-K path");
+  CPT_REQUIRE(ws && ws_bytes >= conv_packed_workspace_size(CPT_OP_DGRAD, d), CPT_ERR_WORKSPACE, "conv2d_dgrad_packed: workspace too small");
+  const PackGeom q = pack_geom(g);
+  const int Cop = round_up(g.Co, 8), kc = kc_of(mode);
+  char* base = reinterpret_cast<char*>(ws);
+  __nv_bfloat16* wT = reinterpret_cast<__nv_bfloat16*>(base);
+  float* dcol = reinterpret_cast<float*>(base + align_up((size_t)q.Kdim * Cop * 2, 1024));
+  w_packT_kernel<<<ew_grid((int64_t)q.Kdim * Cop, 256), 256, 0, st>>>(w, wT, g.Co, q.Kdim, Cop);
+  CPT_LAUNCH_CHECK("w_packT");
+  const int BN = pick_bn(q.Kdim);
+  TcParams p{};
+  const bool use2 = want_2cta(BN, (q.px + 127) / 128);
+  // dcol[b][k][ho][wo]: lanes = pixels (A = dy_cl [px][Cop], K-major), columns = k (B = wT [Kdim][Cop], K-major)
+  if (int e = make_map_2d(&p.tmA, dy_cl, mode, g.Co, (uint64_t)q.px, Cop, kc, 128)) return e;
+  if (int e = make_map_2d(&p.tmB, wT, mode, g.Co, q.Kdim, Cop, kc, use2 ? BN / 2 : BN)) return e;
+  p.out = dcol; p.bias = nullptr; p.bias_mode = BIAS_NONE;
+  if (int e = get_status_ptr(&p.status)) return e;
+  p.M = (int)q.px; p.N = q.Kdim;
+  p.m_tiles = (int)((q.px + 127) / 128); p.n_tiles = (q.Kdim + BN - 1) / BN; p.z_tiles = 1;
+  p.k_iters_total = (g.Co + kc - 1) / kc; p.k_iters_per_split = p.k_iters_total;
+  p.col_stride = (long long)g.Ho * g.Wo;
+  p.lane_is_pixel = 1; p.px_per_img = g.Ho * g.Wo; p.img_stride = (long long)q.Kdim * g.Ho * g.Wo;
+  p.out_W = g.Wo; p.out_s = 1; p.Wo = g.Wo; p.taps = 1;
+  if (int e = launch_bn<false, false, OP_GEMM>(p, mode, BN, use2, st)) return e;
+  const int64_t total = (int64_t)g.B * g.Ci * g.H * g.W;
+  col2im_kernel<<<ew_grid(total, 256), 256, 0, st>>>(dcol, dx, total, g.Ci, g.H, g.W, g.K, g.P, g.S, g.D, g.Ho, g.Wo);
+  CPT_LAUNCH_CHECK("col2im");
   return CPT_OK;
 }
 
@@ -906,6 +1108,36 @@ int cpt_conv2d_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* 
                         size_t ws_bytes, void* stream) {
   if (int e = check_tc(d, mode, "conv2d_wgrad_cl")) return e;
   return tc::conv_wgrad_cl(d, x_cl, dy_cl, dw, mode, ws, ws_bytes, as_stream(stream));
+}
+
+/* packed-K path for first layers (tiny Ci): see include/compyute_b200.h */
+size_t cpt_conv2d_packed_bytes(const cpt_conv2d_desc* d, int mode) {
+  if (check_tc(d, mode, "conv2d_packed_bytes")) return 0;
+  return tc::conv_packed_bytes(d, mode);
+}
+size_t cpt_conv2d_packed_workspace_size(int op, const cpt_conv2d_desc* d) {
+  if (check_tc(d, CPT_MODE_BF16, "conv2d_packed_workspace_size")) return 0;
+  return tc::conv_packed_workspace_size(op, d);
+}
+int cpt_conv2d_im2col_pack(const cpt_conv2d_desc* d, const float* x, void* col, void* stream) {
+  if (int e = check_tc(d, CPT_MODE_BF16, "conv2d_im2col_pack")) return e;
+  CPT_REQUIRE(x && col, CPT_ERR_INVALID, "conv2d_im2col_pack: null pointer");
+  return tc::conv_im2col_pack(d, x, col, as_stream(stream));
+}
+int cpt_conv2d_fprop_packed(const cpt_conv2d_desc* d, const void* col, const float* w, const float* bias, float* y, void* ws,
+                            size_t ws_bytes, void* stream) {
+  if (int e = check_tc(d, CPT_MODE_BF16, "conv2d_fprop_packed")) return e;
+  return tc::conv_fprop_packed(d, col, w, bias, y, ws, ws_bytes, as_stream(stream));
+}
+int cpt_conv2d_dgrad_packed(const cpt_conv2d_desc* d, const void* dy_cl, const float* w, float* dx, void* ws, size_t ws_bytes,
+                            void* stream) {
+  if (int e = check_tc(d, CPT_MODE_BF16, "conv2d_dgrad_packed")) return e;
+  return tc::conv_dgrad_packed(d, dy_cl, w, dx, ws, ws_bytes, as_stream(stream));
+}
+int cpt_conv2d_wgrad_packed(const cpt_conv2d_desc* d, const void* col, const void* dy_cl, float* dw, void* ws, size_t ws_bytes,
+                            void* stream) {
+  if (int e = check_tc(d, CPT_MODE_BF16, "conv2d_wgrad_packed")) return e;
+  return tc::conv_wgrad_packed(d, col, dy_cl, dw, ws, ws_bytes, as_stream(stream));
 }
 
 size_t cpt_cast_bf16_bytes(int64_t rows, int cols) { return rows > 0 && cols > 0 ? tc::cast_bytes(rows, cols) : 0; }

@@ -247,35 +247,71 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
       bool ok = mbar_wait(tfull_bar(acc), acc_phase);
       if (!ok) { atomicExch(p.status, 4); break; }
       tc_fence_after();
-      float* dst = p.out + z_off + lane_off;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c * 32);
-        if (iters > 0) {
-          tmem_ld_32x32(taddr, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0u;
+      // Column n of this lane lives col_stride floats after column n-1: a running pointer, one 128-byte store per warp
+      // and column.  Chunks of 32 columns are double-buffered in registers: tcgen05.ld of chunk c+1 is in flight while
+      // chunk c is stored, and the accumulator stage is handed back to the MMA warp as soon as its last chunk is in
+      // registers (before that chunk's stores).
+      float* dst = p.out + z_off + lane_off + (long long)n0 * p.col_stride;
+      const long long cs = p.col_stride;
+      const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      constexpr int NCH = BN / 32;
+      static_assert(NCH % 2 == 0, "chunk pairs");
+      const bool col_bias = p.bias_mode == BIAS_COL;
+      uint32_t va[32], vb[32];
+      if (iters > 0) tmem_ld_32x32(tbase, va);
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {  // the MMA issuer (leader CTA) waits for all epilogue warps of the group
+          if (CTA2 && cta_rank != 0) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
+          else mbar_arrive(tempty_bar(acc));
         }
-        if (m_ok) {
+      };
+      auto store_chunk = [&](const uint32_t (&v)[32], int c) {
+        const int cbase = n0 + c * 32;
+        float* q = dst + (long long)(c * 32) * cs;
+        float bl = 0.f;  // this lane's column bias; column j's value is fetched with a shuffle (one LDG per chunk)
+        if (col_bias && cbase + lane < p.N) bl = __ldg(p.bias + cbase + lane);
+        if (cbase + 32 <= p.N) {
+          if (col_bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = n0 + c * 32 + j;
-            if (col < p.N) {
-              float val = __uint_as_float(v[j]) + lane_bias;
-              if (p.bias_mode == BIAS_COL) val += __ldg(p.bias + col);
-              dst[(long long)col * p.col_stride] = val;
+            for (int j = 0; j < 32; ++j) {
+              const float val = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j);
+              if (m_ok) *q = val;
+              q += cs;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (m_ok) *q = __uint_as_float(v[j]) + lane_bias;
+              q += cs;
             }
           }
+        } else {  // ragged last chunk of the N dimension
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float val = __uint_as_float(v[j]) + lane_bias + __shfl_sync(0xffffffffu, bl, j);
+            if (m_ok && cbase + j < p.N) *q = val;
+            q += cs;
+          }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {  // the MMA issuer (leader CTA) waits for all epilogue warps of the group
-        if (CTA2 && cta_rank != 0) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
-        else mbar_arrive(tempty_bar(acc));
+      };
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        if (iters > 0) {
+          tmem_ld_wait();                                   // chunk c in va
+          tmem_ld_32x32(tbase + (uint32_t)((c + 1) * 32), vb);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) va[j] = vb[j] = 0u;
+        }
+        store_chunk(va, c);
+        if (iters > 0) {
+          tmem_ld_wait();                                   // chunk c+1 in vb
+          if (c + 2 < NCH) tmem_ld_32x32(tbase + (uint32_t)((c + 2) * 32), va);
+        }
+        if (c + 2 >= NCH) release_acc();
+        store_chunk(vb, c + 1);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

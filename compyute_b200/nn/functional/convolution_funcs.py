@@ -20,6 +20,8 @@ from .functions import Function, FunctionCache, PseudoCache
 
 __all__ = ["conv2d", "Conv2DFn"]
 
+_MODE_PACKED = 100  # cache tag: bf16 layer that ran on the packed-K path (x_cl holds the patch matrix)
+
 
 def _desc(x_shape, f_shape, padding: int, stride: int, dilation: int) -> _lib.ConvDesc:
     B, Ci, H, W = x_shape
@@ -58,6 +60,13 @@ class Conv2DFn(Function):
         if mode == _lib.MODE_FP32:
             ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_FPROP, ctypes.byref(d), mode))
             _lib.check(L.cpt_conv2d_fprop(ctypes.byref(d), f32ptr(x), f32ptr(f), f32ptr(b), y.ptr, mode, ws, wsb, st))
+        elif L.cpt_conv2d_packed_bytes(ctypes.byref(d), mode):
+            # first layers (tiny Ci): explicit bf16 patch matrix with K = Ci*k*k packed densely, kept for wgrad
+            x_cl = DeviceArray.empty((L.cpt_conv2d_packed_bytes(ctypes.byref(d), mode),), np.uint8)
+            _lib.check(L.cpt_conv2d_im2col_pack(ctypes.byref(d), f32ptr(x), x_cl.ptr, st))
+            ws, wsb = workspace(L.cpt_conv2d_packed_workspace_size(_lib.OP_FPROP, ctypes.byref(d)))
+            _lib.check(L.cpt_conv2d_fprop_packed(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, ws, wsb, st))
+            mode = _MODE_PACKED
         else:
             # stage x once as channels-last; kept in the cache so wgrad does not convert it again
             x_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Ci, d.H, d.W, mode),), np.uint8)
@@ -83,6 +92,15 @@ class Conv2DFn(Function):
             db = db_out.reshape((d.Co,)) if db_out is not None else DeviceArray.empty((d.Co,), np.float32)
         dbp = db.ptr if db is not None else None
         ho, wo = dy.shape[2], dy.shape[3]
+        if mode == _MODE_PACKED:
+            dy_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Co, ho, wo, _lib.MODE_BF16),), np.uint8)
+            ws, wsb = workspace(L.cpt_to_channels_last_workspace_size(d.B, d.Co, ho, wo))
+            _lib.check(L.cpt_to_channels_last(f32ptr(dy), dy_cl.ptr, d.B, d.Co, ho, wo, _lib.MODE_BF16, dbp, ws, wsb, st))
+            ws, wsb = workspace(L.cpt_conv2d_packed_workspace_size(_lib.OP_DGRAD, dref))
+            _lib.check(L.cpt_conv2d_dgrad_packed(dref, dy_cl.ptr, f32ptr(f), dx.ptr, ws, wsb, st))
+            ws, wsb = workspace(L.cpt_conv2d_packed_workspace_size(_lib.OP_WGRAD, dref))
+            _lib.check(L.cpt_conv2d_wgrad_packed(dref, x_cl.ptr, dy_cl.ptr, df.ptr, ws, wsb, st))
+            return Tensor(dx), Tensor(df), (Tensor(db) if db is not None else None)
         tc_dgrad = mode != _lib.MODE_FP32 and bool(L.cpt_conv2d_dgrad_cl_supported(dref, mode))
         if mode == _lib.MODE_FP32:
             ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_DGRAD, dref, mode))

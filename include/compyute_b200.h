@@ -97,6 +97,26 @@ int cpt_conv2d_dgrad_cl_supported(const cpt_conv2d_desc* d, int mode);
 int cpt_conv2d_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl, float* dw,
                         int mode, void* ws, size_t ws_bytes, void* stream);
 
+/* Packed-K path for first layers (Ci <= 16: ResNet stem 3->64 7x7/s2, VGG / MNIST conv1), bf16 mode.  The reference
+ * evaluates these layers like any other (window view + einsum, convolution_funcs.py:357-408); the im2col-TMA path would
+ * spend one 64-channel k-iteration per tap on 1-3 real channels.  Here the patches are written once as an explicit bf16
+ * matrix col[(b, ho, wo)][c*K*K + j*K + kk] (row pitch round_up(Ci*K*K, 8)) and the three passes are dense GEMMs over it:
+ *   cpt_conv2d_packed_bytes          bytes of `col`, or 0 when the geometry / mode is not covered (use the *_cl path)
+ *   cpt_conv2d_im2col_pack           x (NCHW fp32) -> col                                   (kept for wgrad)
+ *   cpt_conv2d_fprop_packed          y = col . w^T + bias                                    :222-241
+ *   cpt_conv2d_dgrad_packed          dcol = dy_cl . w, dx = col2im(dcol) (fixed-order gather)  :390-403
+ *   cpt_conv2d_wgrad_packed          dw = dy_cl^T . col (split-K, fixed-order reduce)         :405-408
+ * dy_cl is the channels-last bf16 staging of dy made by cpt_to_channels_last (which also yields db). */
+size_t cpt_conv2d_packed_bytes(const cpt_conv2d_desc* d, int mode);
+size_t cpt_conv2d_packed_workspace_size(int op, const cpt_conv2d_desc* d);
+int cpt_conv2d_im2col_pack(const cpt_conv2d_desc* d, const float* x, void* col, void* stream);
+int cpt_conv2d_fprop_packed(const cpt_conv2d_desc* d, const void* col, const float* w,
+                            const float* bias, float* y, void* ws, size_t ws_bytes, void* stream);
+int cpt_conv2d_dgrad_packed(const cpt_conv2d_desc* d, const void* dy_cl, const float* w, float* dx,
+                            void* ws, size_t ws_bytes, void* stream);
+int cpt_conv2d_wgrad_packed(const cpt_conv2d_desc* d, const void* col, const void* dy_cl, float* dw,
+                            void* ws, size_t ws_bytes, void* stream);
+
 /* ---- Linear: compyute/nn/functional/linear_funcs.py:11-35 ---------------------------------- */
 /* x: (N, In) (leading dims flattened), w: (Out, In), bias: (Out,) or NULL, y: (N, Out). */
 size_t cpt_linear_workspace_size(int op, int64_t N, int In, int Out, int mode);

@@ -73,6 +73,9 @@ CONV_ORACLE = [  # (B, Ci, Co, H, K, pad, stride, dil, bias)
     (2, 16, 32, 16, 5, 2, 1, 1, True), (2, 64, 128, 16, 3, 1, 2, 1, True), (2, 64, 128, 16, 1, 0, 2, 1, False),
     (2, 3, 64, 32, 7, 3, 2, 1, True), (2, 130, 70, 9, 3, 1, 1, 1, True), (1, 8, 8, 10, 3, 2, 1, 2, True),
     (8, 1, 32, 28, 5, 0, 1, 1, True), (2, 256, 256, 8, 3, 1, 1, 1, True),
+    # first-layer shapes: bf16 mode runs them on the packed-K path (explicit patch matrix + dense GEMMs + col2im gather)
+    (2, 3, 16, 33, 3, 0, 2, 1, True), (3, 4, 24, 20, 3, 2, 2, 2, False), (2, 3, 64, 32, 3, 1, 1, 1, True),
+    (2, 16, 40, 12, 3, 1, 1, 1, True), (1, 3, 64, 224, 7, 3, 2, 1, False), (5, 2, 9, 11, 4, 1, 3, 1, True),
 ]
 
 
