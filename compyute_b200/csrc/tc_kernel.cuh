@@ -89,11 +89,14 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
   auto a_smem = [&](int s) { return smem_base + s * S::STAGE_BYTES; };
   auto b_smem = [&](int s) { return smem_base + s * S::STAGE_BYTES + S::A_BYTES; };
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cta_rank = CTA2 ? (int)cluster_ctarank() : 0;  // 0 = leader (issues the MMAs)
+  // warp index / CTA rank through a shuffle: the compiler then knows they are warp-uniform and keeps the role loops on
+  // the uniform datapath (UTMALDG / UTCHMMA operands live in uniform registers; a per-lane branch costs an
+  // ELECT + R2UR waterfall per instruction, which made the single-thread MMA loop the bottleneck: ~750 cycles / k-iteration)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int cta_rank = CTA2 ? __shfl_sync(0xffffffffu, (int)cluster_ctarank(), 0) : 0;  // 0 = leader (issues the MMAs)
   const int group = blockIdx.x / NCTA, n_groups = gridDim.x / NCTA;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
   }
@@ -128,8 +131,8 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
     return rem < p.k_iters_per_split ? rem : p.k_iters_per_split;
   };
 
-  if (warp == 0 && lane == 0) {
-    // =========================== TMA producer (every CTA) ===========================
+  if (warp == 0) {
+    // =========================== TMA producer (every CTA; whole warp loops, one elected lane issues) ===========
     int stage = 0;
     uint32_t phase = 0;
     bool ok = true;
@@ -151,7 +154,8 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
         k_begin = z * p.k_iters_per_split;
       }
       for (int i = 0; i < iters; ++i) {
-        if (!mbar_wait(empty_bar(stage), phase ^ 1)) { atomicExch(p.status, 1); ok = false; break; }
+        if (!__all_sync(0xffffffffu, mbar_wait(empty_bar(stage), phase ^ 1))) { atomicExch(p.status, 1); ok = false; break; }
+        if (elect_one_sync()) {
         // the full barrier lives in the leader CTA; TMA of both CTAs completes on it
         const uint32_t fb = CTA2 ? mapa_cluster(full_bar(stage), 0) : full_bar(stage);
         if (CTA2 && cta_rank != 0) mbar_arrive_expect_tx_cluster(fb, S::STAGE_BYTES);
@@ -191,23 +195,27 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
             tma_load_2d<CTA2>(&p.tmB, fb, sb, kidx * E::KC, n0);
           }
         }
+        }  // elected lane
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
-    // =========================== MMA issuer (leader CTA only) ===========================
+  } else if (warp == 1 && cta_rank == 0) {
+    // =========================== MMA issuer (leader CTA only; whole warp loops, one elected lane issues) =======
+    // tcgen05.commit tracks the MMAs of the issuing THREAD: elect.sync picks the same lane for the same member mask
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     bool ok = true;
     for (int t = group; t < total_tiles && ok; t += n_groups) {
       const int z = (t / p.m_tiles) / p.n_tiles;
       const int iters = tile_k_iters(z);
-      if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1)) { atomicExch(p.status, 2); break; }
+      if (!__all_sync(0xffffffffu, mbar_wait(tempty_bar(acc), acc_phase ^ 1))) { atomicExch(p.status, 2); break; }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       for (int i = 0; i < iters; ++i) {
-        if (!mbar_wait(full_bar(stage), phase)) { atomicExch(p.status, 3); ok = false; break; }
+        if (!__all_sync(0xffffffffu, mbar_wait(full_bar(stage), phase))) { atomicExch(p.status, 3); ok = false; break; }
         tc_fence_after();
+        if (elect_one_sync()) {
         const uint32_t sa = a_smem(stage), sb = b_smem(stage);
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -220,9 +228,12 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
           umma<BF16, CTA2>(d_tmem, da, db, IDESC, (uint32_t)((i | s) != 0));
         }
         umma_commit<CTA2>(empty_bar(stage));  // frees the smem stage (in both CTAs) once these MMAs have read it
+        }  // elected lane
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit<CTA2>(tfull_bar(acc));      // accumulator complete -> epilogue warps of both CTAs
+      if (elect_one_sync()) umma_commit<CTA2>(tfull_bar(acc));  // accumulator complete -> epilogue warps of both CTAs
+      __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
