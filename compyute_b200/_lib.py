@@ -46,6 +46,7 @@ def parse_header(path: str = HEADER) -> dict[str, tuple[object, list[object]]]:
     src = open(path).read()
     src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
     src = re.sub(r"//[^\n]*", " ", src)
+    src = re.sub(r"^[ \t]*#[^\n]*$", " ", src, flags=re.M)  # preprocessor lines
     protos = {}
     for ret, name, args in re.findall(r"([A-Za-z_][\w\s\*]*?)\b(cpt_\w+)\s*\(([^;{}]*?)\)\s*;", src):
         ret = ret.strip()

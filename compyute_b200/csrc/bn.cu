@@ -14,11 +14,20 @@ namespace cpt {
 
 constexpr int BN_THREADS = 256;
 
+// ReLU fused behind the affine output (Sequential peephole BatchNorm -> ReLU): the activation's mask is recomputed in
+// backward from the SAME expression the forward evaluates, y = fmaf(w, (x - mean) * rstd, b) > 0, so nothing is cached
+// for it and dy * mask keeps numpy's float * bool semantics (-0.0, NaN).
+__device__ __forceinline__ float relu_fwd_val(float v) { return (v != v) ? v : fmaxf(v, 0.f); }  // numpy.maximum keeps NaN
+__device__ __forceinline__ float relu_masked(float g, float x, float mu, float rs, float ww, float bb) {
+  return g * (fmaf(ww, (x - mu) * rs, bb) > 0.f ? 1.f : 0.f);
+}
+
 // partial sums for channel c = blockIdx.x, split s = blockIdx.y.  MODE 0: stats (a = x-K, b = (x-K)²);
-// MODE 1: backward (a = dy, b = dy * x̂).
+// MODE 1: backward (a = dy, b = dy * x̂); MODE 2: backward behind a fused ReLU (dy masked first).
 template <int MODE, int VEC>
 __global__ void __launch_bounds__(BN_THREADS) bn_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 const float* __restrict__ w, const float* __restrict__ b,
                                                                  float2* __restrict__ partial, int N, int C, int HW) {
   __shared__ float sh[32];
   const int c = blockIdx.x, S = gridDim.y, s = blockIdx.y;
@@ -26,9 +35,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_partial_kernel(const float* __r
   const int64_t items = (int64_t)N * HWv;
   const int64_t per = (items + S - 1) / S;
   const int64_t lo = per * s, hi = (lo + per < items) ? lo + per : items;
-  float k0, k1;
+  float k0, k1, ww = 0.f, bb = 0.f;
   if (MODE == 0) { k0 = __ldg(x + (int64_t)c * HW); k1 = 0.f; }
   else { k0 = __ldg(mean + c); k1 = __ldg(rstd + c); }
+  if (MODE == 2) { ww = __ldg(w + c); bb = __ldg(b + c); }
   float sa = 0.f, sb = 0.f;
   for (int64_t it = lo + threadIdx.x; it < hi; it += BN_THREADS) {
     const int64_t n = it / HWv;
@@ -38,13 +48,13 @@ __global__ void __launch_bounds__(BN_THREADS) bn_partial_kernel(const float* __r
     if (VEC == 4) {
       float4 v = ld_stream(reinterpret_cast<const float4*>(x + off));
       xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
-      if (MODE == 1) {
+      if (MODE >= 1) {
         float4 g = ld_stream(reinterpret_cast<const float4*>(dy + off));
         gv[0] = g.x; gv[1] = g.y; gv[2] = g.z; gv[3] = g.w;
       }
     } else {
       xv[0] = x[off];
-      if (MODE == 1) gv[0] = dy[off];
+      if (MODE >= 1) gv[0] = dy[off];
     }
 #pragma unroll
     for (int u = 0; u < VEC; ++u) {
@@ -53,8 +63,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_partial_kernel(const float* __r
         sa += d;
         sb = fmaf(d, d, sb);
       } else {
-        sa += gv[u];
-        sb = fmaf(gv[u], (xv[u] - k0) * k1, sb);
+        const float g = MODE == 2 ? relu_masked(gv[u], xv[u], k0, k1, ww, bb) : gv[u];
+        sa += g;
+        sb = fmaf(g, (xv[u] - k0) * k1, sb);
       }
     }
   }
@@ -67,15 +78,17 @@ __global__ void __launch_bounds__(BN_THREADS) bn_partial_kernel(const float* __r
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_partial_hw1_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             const float* __restrict__ w, const float* __restrict__ b,
                                                              float2* __restrict__ partial, int N, int C) {
   __shared__ float sa_s[8][33], sb_s[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx, S = gridDim.y, s = blockIdx.y;
   float sa = 0.f, sb = 0.f;
   if (c < C) {
-    float k0, k1;
+    float k0, k1, ww = 0.f, bb = 0.f;
     if (MODE == 0) { k0 = __ldg(x + c); k1 = 0.f; }
     else { k0 = __ldg(mean + c); k1 = __ldg(rstd + c); }
+    if (MODE == 2) { ww = __ldg(w + c); bb = __ldg(b + c); }
     for (int n = s * 8 + ty; n < N; n += S * 8) {
       const float xv = x[(int64_t)n * C + c];
       if (MODE == 0) {
@@ -83,7 +96,8 @@ __global__ void __launch_bounds__(256) bn_partial_hw1_kernel(const float* __rest
         sa += d;
         sb = fmaf(d, d, sb);
       } else {
-        const float g = dy[(int64_t)n * C + c];
+        float g = dy[(int64_t)n * C + c];
+        if (MODE == 2) g = relu_masked(g, xv, k0, k1, ww, bb);
         sa += g;
         sb = fmaf(g, (xv - k0) * k1, sb);
       }
@@ -133,8 +147,8 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const floa
   save_rstd[c] = 1.0f / sqrtf(rvar[c] + eps);
 }
 
-// y = w * ((x - mean) * rstd) + b
-template <int VEC>
+// y = w * ((x - mean) * rstd) + b   (RELU: followed by max(., 0))
+template <int VEC, bool RELU>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ b, const float* __restrict__ mean,
                                                        const float* __restrict__ rstd, float* __restrict__ y,
@@ -149,9 +163,11 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
       v.y = fmaf(ww, (v.y - mu) * rs, bb);
       v.z = fmaf(ww, (v.z - mu) * rs, bb);
       v.w = fmaf(ww, (v.w - mu) * rs, bb);
+      if (RELU) { v.x = relu_fwd_val(v.x); v.y = relu_fwd_val(v.y); v.z = relu_fwd_val(v.z); v.w = relu_fwd_val(v.w); }
       st_stream(reinterpret_cast<float4*>(y) + it, v);
     } else {
-      y[it] = fmaf(ww, (x[it] - mu) * rs, bb);
+      const float r = fmaf(ww, (x[it] - mu) * rs, bb);
+      y[it] = RELU ? relu_fwd_val(r) : r;
     }
   }
 }
@@ -177,9 +193,10 @@ __global__ void bn_bwd_finalize_kernel(const float2* __restrict__ partial, int S
   coef[3 * c + 2] = sb;
 }
 
-template <int VEC>
+template <int VEC, bool RELU>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ w, const float* __restrict__ b,
                                                            const float* __restrict__ coef, float* __restrict__ dx,
                                                            int64_t items, int C, int HWv, float count) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -187,9 +204,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     const int c = (int)((it / HWv) % C);
     const float mu = __ldg(mean + c), rs = __ldg(rstd + c);
     const float g = __ldg(coef + 3 * c), s1 = __ldg(coef + 3 * c + 1), s2 = __ldg(coef + 3 * c + 2);
+    float ww = 0.f, bb = 0.f;
+    if (RELU) { ww = __ldg(w + c); bb = __ldg(b + c); }
     if (VEC == 4) {
       const float4 xv = ld_stream(reinterpret_cast<const float4*>(x) + it);
-      const float4 gv = ld_stream(reinterpret_cast<const float4*>(dy) + it);
+      float4 gv = ld_stream(reinterpret_cast<const float4*>(dy) + it);
+      if (RELU) {
+        gv.x = relu_masked(gv.x, xv.x, mu, rs, ww, bb); gv.y = relu_masked(gv.y, xv.y, mu, rs, ww, bb);
+        gv.z = relu_masked(gv.z, xv.z, mu, rs, ww, bb); gv.w = relu_masked(gv.w, xv.w, mu, rs, ww, bb);
+      }
       float4 o;
       o.x = g * (count * gv.x - s1 - (xv.x - mu) * rs * s2);
       o.y = g * (count * gv.y - s1 - (xv.y - mu) * rs * s2);
@@ -197,7 +220,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
       o.w = g * (count * gv.w - s1 - (xv.w - mu) * rs * s2);
       st_stream(reinterpret_cast<float4*>(dx) + it, o);
     } else {
-      dx[it] = g * (count * dy[it] - s1 - (x[it] - mu) * rs * s2);
+      const float gd = RELU ? relu_masked(dy[it], x[it], mu, rs, ww, bb) : dy[it];
+      dx[it] = g * (count * gd - s1 - (x[it] - mu) * rs * s2);
     }
   }
 }
@@ -220,15 +244,33 @@ static int bn_check(const char* name, int N, int C, int HW) {
 }
 
 template <int MODE>
-static void launch_partial(const float* x, const float* dy, const float* mean, const float* rstd, float2* partial, int N,
-                           int C, int HW, int S, cudaStream_t st) {
+static void launch_partial(const float* x, const float* dy, const float* mean, const float* rstd, const float* w, const float* b,
+                           float2* partial, int N, int C, int HW, int S, cudaStream_t st) {
   if (HW == 1) {
     dim3 grid((C + 31) / 32, S);
-    bn_partial_hw1_kernel<MODE><<<grid, 256, 0, st>>>(x, dy, mean, rstd, partial, N, C);
+    bn_partial_hw1_kernel<MODE><<<grid, 256, 0, st>>>(x, dy, mean, rstd, w, b, partial, N, C);
   } else if (HW % 4 == 0 && aligned16(x) && (MODE == 0 || aligned16(dy))) {
-    bn_partial_kernel<MODE, 4><<<dim3(C, S), BN_THREADS, 0, st>>>(x, dy, mean, rstd, partial, N, C, HW);
+    bn_partial_kernel<MODE, 4><<<dim3(C, S), BN_THREADS, 0, st>>>(x, dy, mean, rstd, w, b, partial, N, C, HW);
   } else {
-    bn_partial_kernel<MODE, 1><<<dim3(C, S), BN_THREADS, 0, st>>>(x, dy, mean, rstd, partial, N, C, HW);
+    bn_partial_kernel<MODE, 1><<<dim3(C, S), BN_THREADS, 0, st>>>(x, dy, mean, rstd, w, b, partial, N, C, HW);
+  }
+}
+
+static int check_act(const char* name, int act) {
+  CPT_REQUIRE(act == CPT_ACT_NONE || act == CPT_ACT_RELU, CPT_ERR_INVALID, "%s: unknown activation %d", name, act);
+  return CPT_OK;
+}
+
+static void launch_apply(const float* x, const float* w, const float* b, const float* mean, const float* rstd, float* y, int N, int C,
+                         int HW, int act, cudaStream_t st) {
+  const int64_t total = (int64_t)N * C * HW;
+  const bool vec = HW % 4 == 0 && aligned16(x) && aligned16(y);
+  if (vec) {
+    if (act) bn_apply_kernel<4, true><<<ew_grid(total / 4, 256), 256, 0, st>>>(x, w, b, mean, rstd, y, total / 4, C, HW / 4);
+    else bn_apply_kernel<4, false><<<ew_grid(total / 4, 256), 256, 0, st>>>(x, w, b, mean, rstd, y, total / 4, C, HW / 4);
+  } else {
+    if (act) bn_apply_kernel<1, true><<<ew_grid(total, 256), 256, 0, st>>>(x, w, b, mean, rstd, y, total, C, HW);
+    else bn_apply_kernel<1, false><<<ew_grid(total, 256), 256, 0, st>>>(x, w, b, mean, rstd, y, total, C, HW);
   }
 }
 
@@ -244,68 +286,81 @@ size_t cpt_bn_workspace_size(int N, int C, int HW) {
   return (size_t)C * 64 * sizeof(float2) + (size_t)C * 3 * sizeof(float) + 256;
 }
 
-int cpt_bn_fwd_train(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,
-                     float* rmean_out, float* rvar_out, float* save_mean, float* save_rstd, int N, int C, int HW,
-                     float m, float eps, void* ws, size_t ws_bytes, void* stream) {
+int cpt_bn_act_fwd_train(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,
+                         float* rmean_out, float* rvar_out, float* save_mean, float* save_rstd, int N, int C, int HW,
+                         float m, float eps, int act, void* ws, size_t ws_bytes, void* stream) {
   if (int e = bn_check("bn_fwd_train", N, C, HW)) return e;
+  if (int e = check_act("bn_fwd_train", act)) return e;
   CPT_REQUIRE(ws && ws_bytes >= cpt_bn_workspace_size(N, C, HW), CPT_ERR_WORKSPACE, "bn_fwd_train: workspace too small");
   cudaStream_t st = as_stream(stream);
   const int S = (HW == 1) ? (int)((N / 8 / 64 > 0) ? ((N / 8 / 64 > 64) ? 64 : N / 8 / 64) : 1) : bn_splits(N, C, HW);
   float2* partial = reinterpret_cast<float2*>(ws);
-  launch_partial<0>(x, nullptr, nullptr, nullptr, partial, N, C, HW, S, st);
+  launch_partial<0>(x, nullptr, nullptr, nullptr, nullptr, nullptr, partial, N, C, HW, S, st);
   CPT_LAUNCH_CHECK("bn_stats");
   const float count = (float)((int64_t)N * HW);
   bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(x, partial, S, rmean, rvar, rmean_out, rvar_out, save_mean,
                                                           save_rstd, C, HW, count, m, eps);
   CPT_LAUNCH_CHECK("bn_fwd_finalize");
-  const int64_t total = (int64_t)N * C * HW;
-  if (HW % 4 == 0 && aligned16(x) && aligned16(y)) {
-    bn_apply_kernel<4><<<ew_grid(total / 4, 256), 256, 0, st>>>(x, w, b, save_mean, save_rstd, y, total / 4, C, HW / 4);
-  } else {
-    bn_apply_kernel<1><<<ew_grid(total, 256), 256, 0, st>>>(x, w, b, save_mean, save_rstd, y, total, C, HW);
-  }
+  launch_apply(x, w, b, save_mean, save_rstd, y, N, C, HW, act, st);
+  CPT_LAUNCH_CHECK("bn_apply");
+  return CPT_OK;
+}
+
+int cpt_bn_fwd_train(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,
+                     float* rmean_out, float* rvar_out, float* save_mean, float* save_rstd, int N, int C, int HW,
+                     float m, float eps, void* ws, size_t ws_bytes, void* stream) {
+  return cpt_bn_act_fwd_train(x, w, b, rmean, rvar, y, rmean_out, rvar_out, save_mean, save_rstd, N, C, HW, m, eps, CPT_ACT_NONE, ws,
+                              ws_bytes, stream);
+}
+
+int cpt_bn_act_fwd_eval(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,
+                        float* save_mean, float* save_rstd, int N, int C, int HW, float eps, int act, void* stream) {
+  if (int e = bn_check("bn_fwd_eval", N, C, HW)) return e;
+  if (int e = check_act("bn_fwd_eval", act)) return e;
+  cudaStream_t st = as_stream(stream);
+  bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(rmean, rvar, save_mean, save_rstd, C, eps);
+  CPT_LAUNCH_CHECK("bn_eval_stats");
+  launch_apply(x, w, b, save_mean, save_rstd, y, N, C, HW, act, st);
   CPT_LAUNCH_CHECK("bn_apply");
   return CPT_OK;
 }
 
 int cpt_bn_fwd_eval(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,
                     float* save_mean, float* save_rstd, int N, int C, int HW, float eps, void* stream) {
-  if (int e = bn_check("bn_fwd_eval", N, C, HW)) return e;
-  cudaStream_t st = as_stream(stream);
-  bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(rmean, rvar, save_mean, save_rstd, C, eps);
-  CPT_LAUNCH_CHECK("bn_eval_stats");
-  const int64_t total = (int64_t)N * C * HW;
-  if (HW % 4 == 0 && aligned16(x) && aligned16(y)) {
-    bn_apply_kernel<4><<<ew_grid(total / 4, 256), 256, 0, st>>>(x, w, b, save_mean, save_rstd, y, total / 4, C, HW / 4);
-  } else {
-    bn_apply_kernel<1><<<ew_grid(total, 256), 256, 0, st>>>(x, w, b, save_mean, save_rstd, y, total, C, HW);
-  }
-  CPT_LAUNCH_CHECK("bn_apply");
-  return CPT_OK;
+  return cpt_bn_act_fwd_eval(x, w, b, rmean, rvar, y, save_mean, save_rstd, N, C, HW, eps, CPT_ACT_NONE, stream);
 }
 
-int cpt_bn_bwd(const float* x, const float* dy, const float* w, const float* save_mean, const float* save_rstd,
-               float* dx, float* dw, float* db, int N, int C, int HW, void* ws, size_t ws_bytes, void* stream) {
+int cpt_bn_act_bwd(const float* x, const float* dy, const float* w, const float* b, const float* save_mean, const float* save_rstd,
+                   float* dx, float* dw, float* db, int N, int C, int HW, int act, void* ws, size_t ws_bytes, void* stream) {
   if (int e = bn_check("bn_bwd", N, C, HW)) return e;
+  if (int e = check_act("bn_bwd", act)) return e;
+  CPT_REQUIRE(act == CPT_ACT_NONE || b, CPT_ERR_INVALID, "bn_bwd: the fused ReLU mask needs the bias");
   CPT_REQUIRE(ws && ws_bytes >= cpt_bn_workspace_size(N, C, HW), CPT_ERR_WORKSPACE, "bn_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
   const int S = (HW == 1) ? (int)((N / 8 / 64 > 0) ? ((N / 8 / 64 > 64) ? 64 : N / 8 / 64) : 1) : bn_splits(N, C, HW);
   float2* partial = reinterpret_cast<float2*>(ws);
   float* coef = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + (size_t)C * 64 * sizeof(float2));
-  launch_partial<1>(x, dy, save_mean, save_rstd, partial, N, C, HW, S, st);
+  if (act) launch_partial<2>(x, dy, save_mean, save_rstd, w, b, partial, N, C, HW, S, st);
+  else launch_partial<1>(x, dy, save_mean, save_rstd, w, b, partial, N, C, HW, S, st);
   CPT_LAUNCH_CHECK("bn_bwd_partial");
   const float count = (float)((int64_t)N * HW);
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, S, w, save_rstd, dw, db, coef, C, count);
   CPT_LAUNCH_CHECK("bn_bwd_finalize");
   const int64_t total = (int64_t)N * C * HW;
   if (HW % 4 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx)) {
-    bn_bwd_apply_kernel<4><<<ew_grid(total / 4, 256), 256, 0, st>>>(x, dy, save_mean, save_rstd, coef, dx, total / 4, C,
-                                                                   HW / 4, count);
+    if (act) bn_bwd_apply_kernel<4, true><<<ew_grid(total / 4, 256), 256, 0, st>>>(x, dy, save_mean, save_rstd, w, b, coef, dx, total / 4, C, HW / 4, count);
+    else bn_bwd_apply_kernel<4, false><<<ew_grid(total / 4, 256), 256, 0, st>>>(x, dy, save_mean, save_rstd, w, b, coef, dx, total / 4, C, HW / 4, count);
   } else {
-    bn_bwd_apply_kernel<1><<<ew_grid(total, 256), 256, 0, st>>>(x, dy, save_mean, save_rstd, coef, dx, total, C, HW, count);
+    if (act) bn_bwd_apply_kernel<1, true><<<ew_grid(total, 256), 256, 0, st>>>(x, dy, save_mean, save_rstd, w, b, coef, dx, total, C, HW, count);
+    else bn_bwd_apply_kernel<1, false><<<ew_grid(total, 256), 256, 0, st>>>(x, dy, save_mean, save_rstd, w, b, coef, dx, total, C, HW, count);
   }
   CPT_LAUNCH_CHECK("bn_bwd_apply");
   return CPT_OK;
+}
+
+int cpt_bn_bwd(const float* x, const float* dy, const float* w, const float* save_mean, const float* save_rstd,
+               float* dx, float* dw, float* db, int N, int C, int HW, void* ws, size_t ws_bytes, void* stream) {
+  return cpt_bn_act_bwd(x, dy, w, nullptr, save_mean, save_rstd, dx, dw, db, N, C, HW, CPT_ACT_NONE, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

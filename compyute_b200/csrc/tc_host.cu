@@ -876,7 +876,7 @@ static PackGeom pack_geom(const G& g) {
   q.Kp = round_up(q.Kdim, 8);
   q.Wpad = (g.Wo - 1) * g.S + (g.K - 1) * g.D + 1;
   q.px = (int64_t)g.B * g.Ho * g.Wo;
-  q.smem = (size_t)g.Ci * g.K * q.Wpad * sizeof(float) + (size_t)q.Kp * sizeof(int);
+  q.smem = (size_t)g.Ci * g.K * q.Wpad * sizeof(float);
   return q;
 }
 static bool packed_ok(const G& g, int mode) {
@@ -884,37 +884,56 @@ static bool packed_ok(const G& g, int mode) {
   const PackGeom q = pack_geom(g);
   // worth it when the tap-per-k-iteration path would run mostly empty; limits: one input-row patch in shared memory,
   // int32 pixel index, grid.y
-  return g.Ci <= 16 && q.Kdim <= 1024 && q.smem <= 160 * 1024 && q.px < (1LL << 31) && g.B <= 65535 &&
+  return g.Ci <= 16 && q.Kdim <= 1024 && q.smem <= 160 * 1024 && q.px < (1LL << 31) && g.B <= 65535 && g.H <= 65535 &&
+         (int64_t)g.B * g.Ci <= 65535 &&
          (int64_t)g.B * q.Kdim * g.Ho * g.Wo < (1LL << 40);
 }
 
 // One block per (image, output row): the Ci*K input rows that row needs are loaded once (coalesced, zero-filled outside the
-// image) into a patch [Ci*K][Wpad]; the Wo x Kp output elements are then written as contiguous bf16 pairs.
+// image) into a patch [Ci*K][Wpad]; each warp then writes whole output rows (Kp bf16 = one contiguous run), every lane
+// owning fixed k-pairs whose patch offsets it looked up once — no integer division in either loop.
+template <int MAXQ>
 __global__ void __launch_bounds__(256) im2col_pack_kernel(const float* __restrict__ x, uint32_t* __restrict__ col, int Ci, int H,
                                                           int W, int K, int P, int S, int D, int Ho, int Wo, int Kdim, int Kp,
                                                           int Wpad) {
   extern __shared__ float patch[];
-  int* lut = reinterpret_cast<int*>(patch + (size_t)Ci * K * Wpad);
   const int ho = blockIdx.x, b = blockIdx.y, T = K * K;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const float* xb = x + (int64_t)b * Ci * H * W;
-  for (int idx = threadIdx.x; idx < Ci * K * Wpad; idx += blockDim.x) {
-    const int r = idx / Wpad, wp = idx - r * Wpad, c = r / K, j = r - c * K;
-    const int h = ho * S - P + j * D, w = wp - P;
-    patch[idx] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(xb + ((int64_t)c * H + h) * W + w) : 0.f;
+  for (int r = warp; r < Ci * K; r += nwarps) {
+    const int c = r / K, j = r - c * K, h = ho * S - P + j * D;
+    const bool row_ok = h >= 0 && h < H;
+    const float* src = xb + ((int64_t)c * H + (row_ok ? h : 0)) * W;
+    float* dst = patch + (size_t)r * Wpad;
+    for (int wp = lane; wp < Wpad; wp += 32) {
+      const int w = wp - P;
+      dst[wp] = (row_ok && w >= 0 && w < W) ? __ldg(src + w) : 0.f;
+    }
   }
-  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
-    const int c = k / T, t = k - c * T, j = t / K, kk = t - j * K;
-    lut[k] = k < Kdim ? (c * K + j) * Wpad + kk * D : -1;
+  // this lane's k-pairs: k = 2*(lane + 32 q), q < MAXQ = ceil(Kp / 64) rounded up to a power of two (Kp <= 1024 -> <= 16)
+  int l0[MAXQ], l1[MAXQ];
+  const int pairs = Kp >> 1;
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) {
+    const int k = 2 * (lane + 32 * q);
+    l0[q] = l1[q] = -1;
+    if (k < Kdim) { const int c = k / T, t = k - c * T, j = t / K, kk = t - j * K; l0[q] = (c * K + j) * Wpad + kk * D; }
+    if (k + 1 < Kdim) { const int c = (k + 1) / T, t = k + 1 - c * T, j = t / K, kk = t - j * K; l1[q] = (c * K + j) * Wpad + kk * D; }
   }
   __syncthreads();
-  const int pairs = Kp >> 1;
   uint32_t* dst = col + ((int64_t)b * Ho + ho) * Wo * pairs;
-  for (int idx = threadIdx.x; idx < Wo * pairs; idx += blockDim.x) {
-    const int wo = idx / pairs, k = (idx - wo * pairs) << 1;
-    const int l0 = lut[k], l1 = lut[k + 1];
-    const float v0 = l0 >= 0 ? patch[l0 + wo * S] : 0.f, v1 = l1 >= 0 ? patch[l1 + wo * S] : 0.f;
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-    dst[idx] = *reinterpret_cast<uint32_t*>(&h2);
+  for (int wo = warp; wo < Wo; wo += nwarps) {
+    const float* pw = patch + wo * S;
+    uint32_t* drow = dst + (int64_t)wo * pairs;
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) {
+      const int k2 = lane + 32 * q;
+      if (k2 < pairs) {
+        const float v0 = l0[q] >= 0 ? pw[l0[q]] : 0.f, v1 = l1[q] >= 0 ? pw[l1[q]] : 0.f;
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+        drow[k2] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+    }
   }
 }
 
@@ -928,35 +947,48 @@ __global__ void w_packT_kernel(const float* __restrict__ w, __nv_bfloat16* __res
 }
 
 // dx[b][c][h][w] = Σ_{j, kk : (h + P - j D) = S ho, (w + P - kk D) = S wo} dcol[b][c*T + j*K + kk][ho][wo]   (fixed order)
-// consecutive threads walk w: lanes of equal parity read consecutive wo of one dcol row
-__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int64_t total, int Ci,
-                                                     int H, int W, int K, int P, int S, int D, int Ho, int Wo) {
+// One thread per dx element, consecutive threads along w (lanes of equal parity read consecutive wo of one dcol row).
+// The loops run over the output positions (ho, wo) that can reach (h, w) — about (K/S)^2 of them — instead of over all
+// K^2 taps; DIL1 removes the divisibility test of the dilated case.
+template <bool DIL1>
+__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int Ci, int H, int W,
+                                                     int K, int P, int S, int D, int Ho, int Wo) {
   const int T = K * K;
   const int64_t plane = (int64_t)Ho * Wo;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int w = (int)(i % W);
-    int64_t r = i / W;
-    const int h = (int)(r % H);
-    r /= H;
-    const int c = (int)(r % Ci);
-    const int64_t b = r / Ci;
-    const float* base = dcol + (b * Ci + c) * T * plane;
-    float acc = 0.f;
-    for (int j = 0; j < K; ++j) {
-      const int hh = h + P - j * D;
-      if (hh < 0) break;
-      const int ho = hh / S;
-      if (ho * S != hh || ho >= Ho) continue;
-      for (int kk = 0; kk < K; ++kk) {
-        const int ww = w + P - kk * D;
-        if (ww < 0) break;
-        const int wo = ww / S;
-        if (wo * S != ww || wo >= Wo) continue;
-        acc += __ldg(base + (int64_t)(j * K + kk) * plane + (int64_t)ho * Wo + wo);
+  const int w = blockIdx.x * blockDim.x + threadIdx.x, h = blockIdx.y;
+  const int bc = blockIdx.z;  // b * Ci + c
+  if (w >= W) return;
+  const float* base = dcol + (int64_t)bc * T * plane;
+  const int span = (K - 1) * D;
+  // ho in [ceil((h + P - span) / S), floor((h + P) / S)] ∩ [0, Ho)
+  const int hp = h + P, wp = w + P;
+  int ho_lo = hp - span > 0 ? (hp - span + S - 1) / S : 0, ho_hi = hp / S;
+  int wo_lo = wp - span > 0 ? (wp - span + S - 1) / S : 0, wo_hi = wp / S;
+  if (ho_hi > Ho - 1) ho_hi = Ho - 1;
+  if (wo_hi > Wo - 1) wo_hi = Wo - 1;
+  float acc = 0.f;
+  // ascending j == descending ho: keeps the summation order of the tap loop.  The wo loop is walked four positions at a
+  // time with predicated loads so that several independent loads are in flight per thread (the kernel is latency-bound
+  // otherwise: ~16 dependent 4-byte loads per output).
+  for (int ho = ho_hi; ho >= ho_lo; --ho) {
+    const int hh = hp - ho * S;
+    int j = hh;
+    if (!DIL1) { j = hh / D; if (j * D != hh) continue; }
+    const float* rowp = base + (int64_t)(j * K) * plane + (int64_t)ho * Wo;
+    for (int wo0 = wo_hi; wo0 >= wo_lo; wo0 -= 4) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int wo = wo0 - u, ww = wp - wo * S;
+        int kk = ww;
+        bool ok = wo >= wo_lo;
+        if (!DIL1) { kk = ww / D; ok = ok && kk * D == ww; }
+        v[u] = ok ? __ldg(rowp + (int64_t)kk * plane + wo) : 0.f;
       }
+      acc += v[0]; acc += v[1]; acc += v[2]; acc += v[3];
     }
-    dx[i] = acc;
   }
+  dx[((int64_t)bc * H + h) * W + w] = acc;
 }
 
 size_t conv_packed_bytes(const cpt_conv2d_desc* d, int mode) {
@@ -979,13 +1011,20 @@ int conv_im2col_pack(const cpt_conv2d_desc* d, const float* x, void* col, cudaSt
   const G g = geom(d);
   CPT_REQUIRE(packed_ok(g, CPT_MODE_BF16), CPT_ERR_UNSUPPORTED, "conv2d_im2col_pack: geometry not covered by the packed-K path");
   const PackGeom q = pack_geom(g);
-  static size_t configured = 0;
-  if (q.smem > 48 * 1024 && q.smem > configured) {
-    CPT_CUDA(cudaFuncSetAttribute(im2col_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = 160 * 1024;
-  }
-  im2col_pack_kernel<<<dim3(g.Ho, g.B), 256, q.smem, st>>>(x, reinterpret_cast<uint32_t*>(col), g.Ci, g.H, g.W, g.K, g.P, g.S, g.D,
-                                                           g.Ho, g.Wo, q.Kdim, q.Kp, q.Wpad);
+  const int nq = (q.Kp / 2 + 31) / 32;
+  auto launch = [&](auto kern) -> int {
+    if (q.smem > 48 * 1024) CPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    kern<<<dim3(g.Ho, g.B), 256, q.smem, st>>>(x, reinterpret_cast<uint32_t*>(col), g.Ci, g.H, g.W, g.K, g.P, g.S, g.D, g.Ho, g.Wo,
+                                               q.Kdim, q.Kp, q.Wpad);
+    return CPT_OK;
+  };
+  int e;
+  if (nq <= 1) e = launch(im2col_pack_kernel<1>);
+  else if (nq <= 2) e = launch(im2col_pack_kernel<2>);
+  else if (nq <= 4) e = launch(im2col_pack_kernel<4>);
+  else if (nq <= 8) e = launch(im2col_pack_kernel<8>);
+  else e = launch(im2col_pack_kernel<16>);
+  if (e) return e;
   CPT_LAUNCH_CHECK("im2col_pack");
   return CPT_OK;
 }
@@ -1052,8 +1091,13 @@ int conv_dgrad_packed(const cpt_conv2d_desc* d, const void* dy_cl, const float* 
   p.lane_is_pixel = 1; p.px_per_img = g.Ho * g.Wo; p.img_stride = (long long)q.Kdim * g.Ho * g.Wo;
   p.out_W = g.Wo; p.out_s = 1; p.Wo = g.Wo; p.taps = 1;
   if (int e = launch_bn<false, false, OP_GEMM>(p, mode, BN, use2, st)) return e;
-  const int64_t total = (int64_t)g.B * g.Ci * g.H * g.W;
-  col2im_kernel<<<ew_grid(total, 256), 256, 0, st>>>(dcol, dx, total, g.Ci, g.H, g.W, g.K, g.P, g.S, g.D, g.Ho, g.Wo);
+  {
+    CPT_REQUIRE(g.H <= 65535 && (int64_t)g.B * g.Ci <= 65535, CPT_ERR_UNSUPPORTED, "conv2d_dgrad_packed: grid too large");
+    const int bx = g.W >= 256 ? 256 : (g.W >= 128 ? 128 : (g.W >= 64 ? 64 : 32));
+    dim3 grid((g.W + bx - 1) / bx, g.H, g.B * g.Ci);
+    if (g.D == 1) col2im_kernel<true><<<grid, bx, 0, st>>>(dcol, dx, g.Ci, g.H, g.W, g.K, g.P, g.S, g.D, g.Ho, g.Wo);
+    else col2im_kernel<false><<<grid, bx, 0, st>>>(dcol, dx, g.Ci, g.H, g.W, g.K, g.P, g.S, g.D, g.Ho, g.Wo);
+  }
   CPT_LAUNCH_CHECK("col2im");
   return CPT_OK;
 }

@@ -8,7 +8,11 @@ from ... import _lib
 from ...tensors import DeviceArray, Tensor, f32ptr, require_cuda, stream_ptr
 from .functions import Function, FunctionCache, PseudoCache, get_caching_enabled
 
-__all__ = ["relu", "ReLUFn"]
+__all__ = ["relu", "ReLUFn", "FUSED_INTO_PRODUCER"]
+
+# cache marker: this ReLU was evaluated inside its producer (Sequential peephole BatchNorm -> ReLU, see
+# normalization_funcs.BatchNormReLU2DFn); the producer's backward already applies dy * (y > 0)
+FUSED_INTO_PRODUCER = "fused-into-producer"
 
 
 class ReLUFn(Function):
@@ -28,6 +32,8 @@ class ReLUFn(Function):
     @staticmethod
     def backward(cache: FunctionCache, dy: Tensor) -> Tensor:
         (mask,) = cache.pop()
+        if mask is FUSED_INTO_PRODUCER:
+            return dy
         require_cuda(dy)
         dx = DeviceArray.empty(dy.shape, np.float32)
         _lib.check(_lib.lib().cpt_relu_bwd(f32ptr(dy), mask.ptr, dx.ptr, dy.size, stream_ptr()))

@@ -8,10 +8,13 @@ from ... import _lib, graph
 from ...tensors import DeviceArray, ShapeError, Tensor, f32ptr, require_cuda, stream_ptr, workspace
 from .functions import Function, FunctionCache, PseudoCache
 
-__all__ = ["batchnorm1d", "batchnorm2d", "BatchNorm1DFn", "BatchNorm2DFn"]
+__all__ = ["batchnorm1d", "batchnorm2d", "BatchNorm1DFn", "BatchNorm2DFn", "BatchNormReLU1DFn", "BatchNormReLU2DFn"]
 
 
-def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW):
+ACT_NONE, ACT_RELU = 0, 1  # CPT_ACT_*
+
+
+def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW, act=ACT_NONE):
     require_cuda(x, rmean, rvar, w, b)
     L = _lib.lib()
     st = stream_ptr()
@@ -25,27 +28,28 @@ def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW):
             new_rmean = DeviceArray.empty((C,), np.float32)
             new_rvar = DeviceArray.empty((C,), np.float32)
         ws, wsb = workspace(L.cpt_bn_workspace_size(N, C, HW))
-        _lib.check(L.cpt_bn_fwd_train(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, new_rmean.ptr,
-                                      new_rvar.ptr, save_mean.ptr, save_rstd.ptr, N, C, HW, float(m), float(eps), ws, wsb, st))
+        _lib.check(L.cpt_bn_act_fwd_train(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, new_rmean.ptr,
+                                          new_rvar.ptr, save_mean.ptr, save_rstd.ptr, N, C, HW, float(m), float(eps), act, ws, wsb, st))
         rmean, rvar = Tensor(new_rmean), Tensor(new_rvar)
     else:
-        _lib.check(L.cpt_bn_fwd_eval(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, save_mean.ptr,
-                                     save_rstd.ptr, N, C, HW, float(eps), st))
+        _lib.check(L.cpt_bn_act_fwd_eval(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, save_mean.ptr,
+                                         save_rstd.ptr, N, C, HW, float(eps), act, st))
     # the reference caches (w, dims, std, x_norm); x_norm is recomputed from (x, mean, rstd) in backward instead
-    cache.push(x, w, save_mean, save_rstd, (N, C, HW))
+    # with a fused ReLU the mask is recomputed from (x, mean, rstd, w, b) in backward: nothing extra is cached but b
+    cache.push(x, w, b if act else None, save_mean, save_rstd, (N, C, HW), act)
     return Tensor(y), rmean, rvar
 
 
 def _bn_backward(cache, dy, dw_out=None, db_out=None):
-    x, w, save_mean, save_rstd, (N, C, HW) = cache.pop()
+    x, w, b, save_mean, save_rstd, (N, C, HW), act = cache.pop()
     require_cuda(dy)
     L = _lib.lib()
     dx = DeviceArray.empty(x.shape, np.float32)
     dw = dw_out.reshape((C,)) if dw_out is not None else DeviceArray.empty((C,), np.float32)
     db = db_out.reshape((C,)) if db_out is not None else DeviceArray.empty((C,), np.float32)
     ws, wsb = workspace(L.cpt_bn_workspace_size(N, C, HW))
-    _lib.check(L.cpt_bn_bwd(f32ptr(x), f32ptr(dy), f32ptr(w), save_mean.ptr, save_rstd.ptr, dx.ptr, dw.ptr, db.ptr, N, C, HW,
-                            ws, wsb, stream_ptr()))
+    _lib.check(L.cpt_bn_act_bwd(f32ptr(x), f32ptr(dy), f32ptr(w), f32ptr(b), save_mean.ptr, save_rstd.ptr, dx.ptr, dw.ptr, db.ptr,
+                                N, C, HW, act, ws, wsb, stream_ptr()))
     return Tensor(dx), Tensor(dw), Tensor(db)
 
 
@@ -76,6 +80,41 @@ class BatchNorm1DFn(Function):
         N, C = x.shape[0], x.shape[1]
         HW = x.shape[2] if x.ndim == 3 else 1
         return _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW)
+
+    @staticmethod
+    def backward(cache: FunctionCache, dy: Tensor, dw_out=None, db_out=None) -> tuple[Tensor, Tensor, Tensor]:
+        return _bn_backward(cache, dy, dw_out, db_out)
+
+
+class BatchNormReLU2DFn(Function):
+    """``ReLUFn.forward(BatchNorm2DFn.forward(x))`` in one pass (no reference counterpart: this is what the Sequential
+    peephole BatchNorm2D -> ReLU calls).  Same signatures as BatchNorm2DFn; ``backward`` takes the gradient w.r.t. the
+    ReLU OUTPUT and folds ``dy * (y > 0)`` (activation_funcs.py:32-34) into both batch-norm backward passes."""
+
+    @staticmethod
+    def forward(cache: FunctionCache, x: Tensor, rmean: Tensor, rvar: Tensor, w: Tensor, b: Tensor, m: float, eps: float,
+                training: bool) -> tuple[Tensor, Tensor, Tensor]:
+        if x.ndim != 4:
+            raise ShapeError(f"Expected input to be 4D, got {x.ndim}D.")
+        B, C, H, W = x.shape
+        return _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, B, C, H * W, ACT_RELU)
+
+    @staticmethod
+    def backward(cache: FunctionCache, dy: Tensor, dw_out=None, db_out=None) -> tuple[Tensor, Tensor, Tensor]:
+        return _bn_backward(cache, dy, dw_out, db_out)
+
+
+class BatchNormReLU1DFn(Function):
+    """1-D counterpart of BatchNormReLU2DFn (statistics over (0,) / (0, 2))."""
+
+    @staticmethod
+    def forward(cache: FunctionCache, x: Tensor, rmean: Tensor, rvar: Tensor, w: Tensor, b: Tensor, m: float, eps: float,
+                training: bool) -> tuple[Tensor, Tensor, Tensor]:
+        if x.ndim not in {2, 3}:
+            raise ShapeError(f"Expected input to be 2D or 3D, got {x.ndim}D.")
+        N, C = x.shape[0], x.shape[1]
+        HW = x.shape[2] if x.ndim == 3 else 1
+        return _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW, ACT_RELU)
 
     @staticmethod
     def backward(cache: FunctionCache, dy: Tensor, dw_out=None, db_out=None) -> tuple[Tensor, Tensor, Tensor]:

@@ -4,10 +4,24 @@ from __future__ import annotations
 
 from typing import Optional
 
-from ...tensors import Tensor
-from .module import Module, ModuleList
+from ...tensors import DeviceArray, Tensor
+from ..functional.activation_funcs import FUSED_INTO_PRODUCER
+from .module import Module, ModuleList, get_debug_mode
 
-__all__ = ["Sequential", "ResidualConnection", "EmptyContainerError"]
+_fusion = True
+
+
+def set_fusion_enabled(enabled: bool) -> None:
+    """Peephole fusion inside ``Sequential`` (BatchNorm -> ReLU in one pass).  On by default; results are identical to the
+    unfused layers (the mask is recomputed from the forward's own expression), it only removes memory passes."""
+    global _fusion
+    _fusion = bool(enabled)
+
+
+def get_fusion_enabled() -> bool:
+    return _fusion
+
+__all__ = ["Sequential", "ResidualConnection", "EmptyContainerError", "set_fusion_enabled", "get_fusion_enabled"]
 
 
 class EmptyContainerError(Exception):
@@ -23,16 +37,33 @@ class Sequential(Module):
             raise EmptyContainerError()
         self.layers = ModuleList(modules)
 
+    def _fusable(self, i: int, x: Tensor) -> bool:
+        """layers[i] is a BatchNorm directly followed by a ReLU and nothing observes the tensor between them."""
+        from .layers import ReLU, _BatchNorm
+        if not _fusion or i + 1 >= len(self.layers) or get_debug_mode():
+            return False
+        a, b = self.layers[i], self.layers[i + 1]
+        return (isinstance(a, _BatchNorm) and type(b) is ReLU and not a.retain_values and not b.retain_values
+                and a.is_training == b.is_training and isinstance(x.data, DeviceArray))
+
     @Module.register_forward
     def forward(self, x: Tensor) -> Tensor:
-        for layer in self.layers:
-            x = layer(x)
+        i, n = 0, len(self.layers)
+        while i < n:
+            layer = self.layers[i]
+            if self._fusable(i, x):
+                x = layer.forward_relu(x)
+                self.layers[i + 1].fcache.push(FUSED_INTO_PRODUCER)  # its backward is folded into the BatchNorm's
+                i += 2
+            else:
+                x = layer(x)
+                i += 1
         return x
 
     @Module.register_backward
     def backward(self, dy: Tensor) -> Tensor:
         for layer in reversed(self.layers):
-            dy = layer.backward(dy)
+            dy = layer.backward(dy)  # a ReLU whose cache entry is FUSED_INTO_PRODUCER passes dy through
         return dy
 
 

@@ -22,7 +22,7 @@ from ...tensors import Tensor, tensor
 from ..functional.activation_funcs import ReLUFn
 from ..functional.convolution_funcs import Conv2DFn
 from ..functional.linear_funcs import LinearFn
-from ..functional.normalization_funcs import BatchNorm1DFn, BatchNorm2DFn
+from ..functional.normalization_funcs import BatchNorm1DFn, BatchNorm2DFn, BatchNormReLU1DFn, BatchNormReLU2DFn
 from ..functional.pooling_funcs import AvgPooling2DFn, MaxPooling2DFn
 from ..functional.regularization_funcs import DropoutFn
 from ..functional.shape_funcs import FlattenFn
@@ -119,6 +119,7 @@ class AvgPooling2D(Module):
 
 class _BatchNorm(Module):
     _fn = None
+    _fn_relu = None  # fused BatchNorm -> ReLU (Sequential peephole)
 
     def __init__(self, channels: int, eps: float = 1e-5, m: float = 0.1, label: Optional[str] = None) -> None:
         super().__init__(label)
@@ -130,8 +131,15 @@ class _BatchNorm(Module):
 
     @Module.register_forward
     def forward(self, x: Tensor) -> Tensor:
-        y, rmean, rvar = self._fn.forward(self.fcache, x, self.rmean, self.rvar, self.w, self.b, self.m, self.eps,
-                                          self._is_training)
+        return self._forward(self._fn, x)
+
+    def forward_relu(self, x: Tensor) -> Tensor:
+        """``relu(self(x))`` in one pass; ``backward`` then expects the gradient w.r.t. the ReLU output (the cache entry
+        records the fusion).  Called by ``Sequential`` for a BatchNorm directly followed by a ReLU."""
+        return self._forward(self._fn_relu, x)
+
+    def _forward(self, fn, x: Tensor) -> Tensor:
+        y, rmean, rvar = fn.forward(self.fcache, x, self.rmean, self.rvar, self.w, self.b, self.m, self.eps, self._is_training)
         self.rmean.data = rmean.data  # rebinding, like normalizations.py:163-164
         self.rvar.data = rvar.data
         return y
@@ -145,10 +153,12 @@ class _BatchNorm(Module):
 
 class BatchNorm1D(_BatchNorm):
     _fn = BatchNorm1DFn
+    _fn_relu = BatchNormReLU1DFn
 
 
 class BatchNorm2D(_BatchNorm):
     _fn = BatchNorm2DFn
+    _fn_relu = BatchNormReLU2DFn
 
 
 class ReLU(Module):

@@ -174,6 +174,22 @@ int cpt_bn_fwd_eval(const float* x, const float* w, const float* b, const float*
 int cpt_bn_bwd(const float* x, const float* dy, const float* w, const float* save_mean,
                const float* save_rstd, float* dx, float* dw, float* db, int N, int C, int HW,
                void* ws, size_t ws_bytes, void* stream);
+/* Fused variants for the Sequential peephole BatchNorm -> ReLU (normalizations.py:150-171 followed by activations.py:114-120):
+ * act = CPT_ACT_RELU applies y = max(bn(x), 0) in the same pass; backward recomputes the ReLU mask (y > 0) from
+ * (x, mean, rstd, w, b) with the forward's own expression, so no mask is stored and dy*mask is folded into both backward passes.
+ * act = CPT_ACT_NONE is identical to the plain entry points above. */
+#define CPT_ACT_NONE 0
+#define CPT_ACT_RELU 1
+int cpt_bn_act_fwd_train(const float* x, const float* w, const float* b, const float* rmean,
+                         const float* rvar, float* y, float* rmean_out, float* rvar_out,
+                         float* save_mean, float* save_rstd, int N, int C, int HW, float m, float eps,
+                         int act, void* ws, size_t ws_bytes, void* stream);
+int cpt_bn_act_fwd_eval(const float* x, const float* w, const float* b, const float* rmean,
+                        const float* rvar, float* y, float* save_mean, float* save_rstd, int N, int C,
+                        int HW, float eps, int act, void* stream);
+int cpt_bn_act_bwd(const float* x, const float* dy, const float* w, const float* b,
+                   const float* save_mean, const float* save_rstd, float* dx, float* dw, float* db,
+                   int N, int C, int HW, int act, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- activations / elementwise ------------------------------------------------------------- */
 /* ReLUFn.forward activation_funcs.py:26-29.  mask = bit-packed (y > 0), 4 * ((n + 31) / 32) bytes, 4-byte aligned, in a

@@ -384,6 +384,65 @@ def test_residual_and_inference(cp):
     assert np.allclose(block(cp.tensor(x, device=cp.cuda)).to_numpy(), fx + x, atol=1e-6)
 
 
+def test_bn_relu_peephole_is_bit_exact(cp):
+    """Sequential evaluates BatchNorm -> ReLU in one pass (cpt_bn_act_*): outputs, input gradient, parameter gradients and
+    running statistics must equal the unfused layers bit for bit (train and eval, 2-D and 1-D), and match the oracle."""
+    from compyute_b200 import nn
+    rng = np.random.RandomState(3)
+
+    def run(fused, x, dy, build, train=True):
+        nn.set_fusion_enabled(fused)
+        try:
+            np.random.seed(1)
+            with cp.use_device(cp.cuda):
+                model = build()
+            bn = model.layers[1]
+            bn.w.data = cp.tensor(rng_w, device=cp.cuda).data
+            bn.b.data = cp.tensor(rng_b, device=cp.cuda).data
+            model.training() if train else model.inference()
+            y = model(cp.tensor(x, device=cp.cuda))
+            out = [y.to_numpy(), bn.rmean.to_numpy(), bn.rvar.to_numpy()]
+            if train:
+                dx = model.backward(cp.tensor(dy, device=cp.cuda))
+                out += [dx.to_numpy()] + [p.grad.to_numpy() for p in model.get_parameters()]
+                assert all(not m.fcache.cache for m in model.get_modules())
+            return out
+        finally:
+            nn.set_fusion_enabled(True)
+
+    cases = [((6, 12, 10, 10), lambda: nn.Sequential(nn.Conv2D(12, 12, 1), nn.BatchNorm2D(12), nn.ReLU(), nn.Conv2D(12, 5, 3))),
+             ((5, 7, 9, 9), lambda: nn.Sequential(nn.Conv2D(7, 7, 1), nn.BatchNorm2D(7), nn.ReLU())),
+             ((64, 40), lambda: nn.Sequential(nn.Linear(40, 24), nn.BatchNorm1D(24), nn.ReLU(), nn.Linear(24, 3)))]
+    for shape, build in cases:
+        x = rng.normal(0, 1, shape).astype(np.float32)
+        np.random.seed(1)
+        with cp.use_device(cp.cuda):
+            probe = build()
+        C = probe.layers[1].channels
+        rng_w = rng.normal(1, 0.5, (C,)).astype(np.float32); rng_b = rng.normal(0, 0.5, (C,)).astype(np.float32)
+        probe.inference()
+        dy = rng.normal(0, 1, probe(cp.tensor(x, device=cp.cuda)).shape).astype(np.float32)
+        for train in (True, False):
+            a, b = run(True, x, dy, build, train), run(False, x, dy, build, train)
+            assert len(a) == len(b)
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v, equal_nan=True), (shape, train, np.abs(u - v).max())
+    # against the oracle: BN2D -> ReLU on its own
+    x = rng.normal(0, 2, (8, 6, 5, 5)).astype(np.float32); dy = rng.normal(0, 1, x.shape).astype(np.float32)
+    w = rng.normal(1, 0.5, (6,)).astype(np.float32); b = rng.normal(0, 0.5, (6,)).astype(np.float32)
+    rc = []
+    yr, _, _ = R.batchnorm_forward(rc, x, np.zeros(6, np.float32), np.ones(6, np.float32), w, b, 0.1, 1e-5, True)
+    rr = []
+    ar = R.relu_forward(rr, yr)
+    dxr, dwr, dbr = R.batchnorm_backward(rc, R.relu_backward(rr, dy))
+    from compyute_b200.nn.functional import BatchNormReLU2DFn, FunctionCache
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    c = FunctionCache()
+    y, _, _ = BatchNormReLU2DFn.forward(c, T(x), T(np.zeros(6, np.float32)), T(np.ones(6, np.float32)), T(w), T(b), 0.1, 1e-5, True)
+    dx, dw, db = BatchNormReLU2DFn.backward(c, T(dy))
+    assert close(y, ar) and close(dx, dxr, 2e-5) and close(dw, dwr, 2e-5) and close(db, dbr, 2e-5)
+
+
 def test_dataloader_and_checkpoint_on_device(cp, tmp_path):
     """Dataloader uploads batches through pinned double-buffered staging (values identical to host slicing), and a
     model/optimizer checkpoint of device state round-trips through cp.save / cp.load (README.md:197-213)."""
