@@ -399,6 +399,7 @@ def run_model(args) -> None:
         model = W.build(spec)
     model.training()
     opt = nn.optimizers.Adam(model.get_parameters(), lr=1e-3)
+    opt.overlap_grad_sync = world > 1 and not args.no_overlap  # bucketed all-reduces launched during backward
     loss_fn = nn.CrossEntropyLoss()
     g = torch.Generator("cuda").manual_seed(100 + rank)
     wrapf = lambda t: Tensor(DeviceArray(t, tuple(t.shape), np.float32))
@@ -515,6 +516,7 @@ def run_model(args) -> None:
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.mode], "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": B, "compute_mode": args.mode, "cuda_graph": bool(graphed), "tolerance": TOL[args.mode], "parallelism": f"dp{world}",
+                       "grad_sync": ("bucketed all-reduce overlapped with backward" if opt.overlap_grad_sync else "one all-reduce at step()") if world > 1 else "n/a",
                        "l2_policy": "activations of one step exceed L2" if B * int(np.prod(xshape)) * 4 > 126e6 else "L2 flushed implicitly: per-step activation traffic exceeds L2"},
             "clocks": clocks, "e2e": {"value": round(world * B / (e2e_ms / 1e3), 1), "unit": "images/s", "h2d_bytes_per_step": int(hx.numel() * 4 + ht.numel() * 4),
                                       "d2h_bytes_per_step": 4, "note": "module API; batch H2D from pinned memory and loss D2H every step; wall clock incl. host dispatch"},
@@ -557,6 +559,9 @@ def main() -> None:
     ap.add_argument("--workload", default="conv2d_sweep", choices=["conv2d_sweep", "mnist", "vgg", "resnet18", "mlp"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of a model workload")
     ap.add_argument("--graph", action="store_true", help="model workloads: replay the train step as one CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="data-parallel runs: one all-reduce of the whole gradient arena at step() instead of bucketed all-reduces "
+                         "launched during backward")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -640,6 +640,7 @@ int conv_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl,
   p.lane_is_pixel = 0;
   p.px_per_img = g.Ho * g.Wo;
   p.Wo = g.Wo;
+  p.Ho = g.Ho;
   p.conv_stride = g.S;
   p.pad = g.P;
   p.dil = g.D;

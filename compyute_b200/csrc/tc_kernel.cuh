@@ -41,7 +41,7 @@ struct alignas(64) TcParams {
   long long img_stride;
   int out_W, out_s, out_r0, out_c0;  // output scatter of CONV lanes (dense fprop/dgrad: out_W = Wo, out_s = 1, r0 = c0 = 0)
   // convolution geometry (im2col coordinates): base pixel of grid position (r, c) = (lower_h + r*trav, lower_w + c*trav)
-  int Wo;                          // width of the lane / reduction pixel grid
+  int Wo, Ho;                      // width (and, WGRAD, height) of the lane / reduction pixel grid
   int trav, lower_w, lower_h;      // traversal stride and lower corner of the im2col bounding box
   int conv_stride, pad, dil, Kw;   // WGRAD: conv geometry for the tap of this tile
   int taps, cchunks, wk_cols;      // wk_cols: weight-matrix columns per tap (padded C)
@@ -141,15 +141,24 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
       const int m0 = m_tile * (128 * NCTA) + cta_rank * 128;   // this CTA's 128 rows of A
       const int n0 = n_tile * BN + cta_rank * S::BN_CTA;       // this CTA's columns of B
       const int iters = tile_k_iters(z);
-      int cw = 0, ch = 0, cn = 0, tap = 0, k_begin = 0;
+      int cw = 0, ch = 0, cn = 0, k_begin = 0;
+      // per-k-iteration indices are advanced incrementally (no integer division inside the loop: the producer is one warp
+      // and its instruction count per k-iteration bounds the pipeline for small tiles)
+      int tp = 0, cc = 0;                          // CONV: filter tap / channel chunk of iteration i
+      int wb = 0, wpy = 0, wqx = 0, wj = 0, wkk = 0;  // WGRAD: (image, row, col) of the chunk's first pixel; tap (j, kk)
       if (OP == OP_CONV) {
         const int b = m0 / p.px_per_img, rem = m0 - b * p.px_per_img, py = rem / p.Wo, qx = rem - py * p.Wo;
         cw = qx * p.trav + p.lower_w;
         ch = py * p.trav + p.lower_h;
         cn = b;
       } else if (OP == OP_WGRAD) {
-        tap = z % p.taps;
+        const int tap = z % p.taps;
         k_begin = (z / p.taps) * p.k_iters_per_split;
+        wj = tap / p.Kw; wkk = tap - wj * p.Kw;
+        const int k0 = k_begin * E::BK;
+        wb = k0 / p.px_per_img;
+        const int rem = k0 - wb * p.px_per_img;
+        wpy = rem / p.Wo; wqx = rem - wpy * p.Wo;
       } else {
         k_begin = z * p.k_iters_per_split;
       }
@@ -163,18 +172,15 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
         const uint32_t sa = a_smem(stage), sb = b_smem(stage);
         if (OP == OP_CONV) {
           // A: 128 output pixels x KC channels of filter tap (j, kk); B: weights [Co][tap][C] rows n0.., K-major
-          const int tp = i / p.cchunks, cc = i - tp * p.cchunks;
           tma_load_im2col_4d<CTA2>(&p.tmA, fb, sa, cc * E::KC, cw, ch, cn, p.tap_w[tp], p.tap_h[tp]);
           tma_load_2d<CTA2>(&p.tmB, fb, sb, tp * p.wk_cols + cc * E::KC, n0);
         } else if (OP == OP_WGRAD) {
           // reduction over output pixels: chunk of BK pixels starting at flattened pixel k0
           const int k0 = (k_begin + i) * E::BK;
-          const int b = k0 / p.px_per_img, rem = k0 - b * p.px_per_img, py = rem / p.Wo, qx = rem - py * p.Wo;
-          const int j = tap / p.Kw, kk = tap - j * p.Kw;
 #pragma unroll
           for (int c = 0; c < 128 / E::KC; ++c)
-            tma_load_im2col_4d<CTA2>(&p.tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, qx * p.conv_stride - p.pad,
-                                     py * p.conv_stride - p.pad, b, (uint16_t)(kk * p.dil), (uint16_t)(j * p.dil));
+            tma_load_im2col_4d<CTA2>(&p.tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, wqx * p.conv_stride - p.pad,
+                                     wpy * p.conv_stride - p.pad, wb, (uint16_t)(wkk * p.dil), (uint16_t)(wj * p.dil));
 #pragma unroll
           for (int c = 0; c < S::BN_CTA / E::KC; ++c)
             tma_load_2d<CTA2>(&p.tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, k0);
@@ -197,6 +203,13 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
         }
         }  // elected lane
         __syncwarp();
+        if (OP == OP_CONV) {
+          if (++cc == p.cchunks) { cc = 0; ++tp; }
+        } else if (OP == OP_WGRAD) {  // advance the chunk's first pixel by BK
+          wqx += E::BK;
+          while (wqx >= p.Wo) { wqx -= p.Wo; ++wpy; }
+          while (wpy >= p.Ho) { wpy -= p.Ho; ++wb; }
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }

@@ -15,7 +15,7 @@ from typing import Iterable
 
 import numpy as np
 
-__all__ = ["init", "is_initialized", "rank", "world_size", "all_reduce_sum", "broadcast_parameters", "shard_batch",
+__all__ = ["init", "is_initialized", "rank", "world_size", "all_reduce_sum", "all_reduce_sum_async", "broadcast_parameters", "shard_batch",
            "shard_bounds", "barrier"]
 
 _dist = None
@@ -68,6 +68,13 @@ def all_reduce_sum(arr) -> None:
         return
     buf = getattr(arr, "_buf", arr)
     _d().all_reduce(buf, op=_d().ReduceOp.SUM)
+
+
+def all_reduce_sum_async(buf):
+    """Asynchronous SUM all-reduce of a torch tensor view: NCCL's stream first waits for the work already enqueued on
+    the current stream, then runs next to whatever is enqueued afterwards.  Returns the work handle (``.wait()`` makes
+    the current stream wait for it)."""
+    return _d().all_reduce(buf, op=_d().ReduceOp.SUM, async_op=True)
 
 
 def broadcast_parameters(tensors: Iterable, src: int = 0) -> None:

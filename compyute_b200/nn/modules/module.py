@@ -247,10 +247,14 @@ class Module:
     def update_parameter_grad(self, parameter: Optional[Parameter], grad: Optional[Tensor]) -> None:
         """First gradient is stored by reference, later ones accumulate with ``+=`` (module.py:392-400)."""
         if self.trainable and parameter is not None and grad is not None:
-            if parameter.grad is None:
+            first = parameter.grad is None
+            if first:
                 parameter.grad = grad
             else:
                 parameter.grad += grad
+            if getattr(parameter, "grad_slot", None) is not None:
+                from ..optimizers import notify_grad_written
+                notify_grad_written(parameter, first)  # overlapped data-parallel exchange (Optimizer.overlap_grad_sync)
 
     @staticmethod
     def grad_slot(parameter: Optional[Parameter]):

@@ -17,6 +17,7 @@ state layout ``{i: {"m": Tensor, "v": Tensor}}``.  What changes is *how* a step 
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Any, Iterable, Optional
 
 import numpy as np
@@ -25,7 +26,40 @@ from .. import _lib, distributed, graph
 from ..tensors import DeviceArray, Tensor, stream_ptr
 from .parameter import Parameter
 
-__all__ = ["Optimizer", "SGD", "Adam", "AdamW", "NAdam"]
+__all__ = ["Optimizer", "SGD", "Adam", "AdamW", "NAdam", "plan_grad_buckets"]
+
+
+_SLOT_OWNERS: dict[int, tuple[Any, int]] = {}  # arena slot pointer -> (weakref to its optimizer, parameter index)
+
+
+def notify_grad_written(parameter: Parameter, first: bool) -> None:
+    """Hook for ``Module.update_parameter_grad``: tells the owning optimizer that ``parameter``'s arena slot holds this
+    step's gradient (drives the overlapped data-parallel exchange; a no-op otherwise)."""
+    slot = getattr(parameter, "grad_slot", None)
+    if slot is None or parameter.grad is None or getattr(parameter.grad.data, "ptr", None) != slot.ptr:
+        return
+    owner = _SLOT_OWNERS.get(slot.ptr)
+    if owner is None:
+        return
+    opt = owner[0]()
+    if opt is not None and opt.overlap_grad_sync:
+        opt._on_grad_ready(owner[1], first)
+
+
+def plan_grad_buckets(offsets: list[int], sizes: list[int], bucket_elems: int) -> list[tuple[int, int, list[int]]]:
+    """Contiguous buckets over the gradient arena for the overlapped data-parallel exchange.  Backward produces gradients
+    from the LAST parameter to the first, so buckets are cut walking the arena from its end: returns
+    ``[(lo, hi, [param indices]), ...]`` in expected order of completion, each covering >= ``bucket_elems`` elements
+    (except possibly the last one, at the front of the arena); together they tile ``[0, arena size)`` exactly."""
+    buckets: list[tuple[int, int, list[int]]] = []
+    hi = (offsets[-1] + (sizes[-1] + 63) // 64 * 64) if offsets else 0
+    members: list[int] = []
+    for i in range(len(offsets) - 1, -1, -1):
+        members.append(i)
+        if hi - offsets[i] >= bucket_elems or i == 0:
+            buckets.append((offsets[i], hi, members))
+            hi, members = offsets[i], []
+    return buckets
 
 
 class Optimizer:
@@ -42,6 +76,15 @@ class Optimizer:
         self._table_dev: Optional[DeviceArray] = None
         self._table_key: Optional[bytes] = None
         self._data_parallel = True  # all-reduce gradients in step() whenever a process group with world > 1 exists
+        # overlapped exchange: buckets of the arena are all-reduced (async, NCCL's own stream) as soon as backward has
+        # produced every gradient in them, instead of one all-reduce at step(); opt-in, needs one gradient per parameter
+        # and step (no shared parameters)
+        self.overlap_grad_sync = False
+        self.bucket_bytes = 32 << 20
+        self._buckets = None
+        self._bucket_pending: list[int] = []
+        self._bucket_work: list[Any] = []
+        self._bucket_launched: list[bool] = []
         self._live = None           # device float[8]: per-step scalars read by the update kernel in CUDA-graph replays
         if parameters is not None:
             self.set_parameters(parameters)
@@ -60,7 +103,8 @@ class Optimizer:
         self._build_arena()
 
     def get_state_dict(self) -> dict[str, dict[Any, Any]]:
-        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel", "_live"}
+        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel", "_live", "overlap_grad_sync",
+                "bucket_bytes", "_buckets", "_bucket_pending", "_bucket_work", "_bucket_launched", "_offsets", "_bucket_of"}
         return {"state": self._state, "vars": {k: v for k, v in vars(self).items() if k not in skip}}
 
     def load_state_dict(self, state_dict: dict[str, dict[Any, Any]]) -> None:
@@ -73,6 +117,7 @@ class Optimizer:
         """``p.grad = None`` (optimizers.py:85-88); arena slots are simply overwritten by the next backward."""
         for p in self._parameters:
             p.grad = None
+        self._reset_buckets()
 
     def step(self) -> None:
         """Updates the parameters (one fused launch).  Inside a CUDA-graph capture the per-step scalars are read from device
@@ -123,9 +168,52 @@ class Optimizer:
             offs.append(total)
             total += (p.size + 63) // 64 * 64
         self._arena = DeviceArray.zeros((total,), np.float32)
+        self._offsets = offs
         flat = self._arena._buf
-        for p, o in zip(cuda_params, offs):
+        for i, (p, o) in enumerate(zip(cuda_params, offs)):
             p.grad_slot = DeviceArray(flat[o:o + p.size], p.shape, np.float32)
+            _SLOT_OWNERS[p.grad_slot.ptr] = (weakref.ref(self), i)  # looked up by Module.update_parameter_grad
+        self._buckets = None
+
+    # ---- overlapped data-parallel exchange -----------------------------------------------------
+    def _dp_world(self) -> int:
+        return distributed.world_size() if self._data_parallel else 1
+
+    def _reset_buckets(self) -> None:
+        if self._buckets is not None:
+            self._bucket_pending = [len(m) for _, _, m in self._buckets]
+            self._bucket_launched = [False] * len(self._buckets)
+            self._bucket_work = []
+
+    def _ensure_buckets(self) -> None:
+        if self._buckets is None:
+            self._buckets = plan_grad_buckets(self._offsets, [p.size for p in self._parameters], max(1, self.bucket_bytes // 4))
+            self._bucket_of = {}
+            for b, (_, _, members) in enumerate(self._buckets):
+                for i in members:
+                    self._bucket_of[i] = b
+            self._reset_buckets()
+
+    def _launch_bucket(self, b: int) -> None:
+        lo, hi, _ = self._buckets[b]
+        self._bucket_launched[b] = True
+        self._bucket_work.append(distributed.all_reduce_sum_async(self._arena._buf[lo:hi]))
+
+    def _on_grad_ready(self, i: int, first: bool) -> None:
+        """Called by ``Module.update_parameter_grad`` once parameter i's gradient has been written into its arena slot
+        (``first``) or accumulated into it again (shared parameter)."""
+        if not self.overlap_grad_sync or self._arena is None or self._dp_world() == 1 or graph.is_capturing():
+            return
+        self._ensure_buckets()
+        b = self._bucket_of[i]
+        if not first and not self._bucket_launched[b]:
+            return  # accumulated before the exchange: fine
+        if self._bucket_launched[b]:
+            raise RuntimeError("overlap_grad_sync: a parameter received a second gradient after its bucket was all-reduced "
+                               "(shared parameters need overlap_grad_sync = False)")
+        self._bucket_pending[b] -= 1
+        if self._bucket_pending[b] == 0:
+            self._launch_bucket(b)
 
     def _gather_grads_into_arena(self) -> None:
         """A gradient that was assigned by hand (not written into its slot by a layer) is copied into the arena so
@@ -176,7 +264,15 @@ class Optimizer:
         if self._arena is None:
             raise RuntimeError("data-parallel step needs cuda parameters (gradient arena missing)")
         self._gather_grads_into_arena()
-        distributed.all_reduce_sum(self._arena)
+        if self.overlap_grad_sync and self._buckets is not None and any(self._bucket_launched):
+            for b in range(len(self._buckets)):  # whatever backward did not complete (e.g. parameters without gradient)
+                if not self._bucket_launched[b]:
+                    self._launch_bucket(b)
+            for w in self._bucket_work:
+                w.wait()  # the compute stream waits for NCCL's stream; no host sync
+            self._reset_buckets()
+        else:
+            distributed.all_reduce_sum(self._arena)
         return 1.0 / world
 
 

@@ -184,3 +184,27 @@ def test_lr_scheduler_interplay_and_state_dict_roundtrip(tmp_path):
     assert np.array_equal(back["model"]["layers.0.w"].to_numpy(), m.layers[0].w.to_numpy())
     m2 = nn.Sequential(nn.Linear(3, 2), nn.ReLU()); m2.load_state_dict(back["model"])
     assert np.array_equal(m2.layers[0].w.to_numpy(), m.layers[0].w.to_numpy())
+
+
+def test_plan_grad_buckets_tiles_the_arena_from_the_end():
+    """Buckets of the overlapped data-parallel exchange: contiguous, disjoint, cover the arena, ordered from the last
+    parameter (whose gradient backward produces first) to the first, each >= the requested size except the front one."""
+    from compyute_b200.nn.optimizers import plan_grad_buckets
+    rng = np.random.RandomState(0)
+    for _ in range(20):
+        sizes = [int(v) for v in rng.randint(1, 5000, rng.randint(1, 12))]
+        offs, tot = [], 0
+        for s in sizes:
+            offs.append(tot)
+            tot += (s + 63) // 64 * 64
+        for be in (1, 700, 4096, 10 ** 7):
+            buckets = plan_grad_buckets(offs, sizes, be)
+            assert buckets[0][1] == tot and buckets[-1][0] == 0
+            seen = []
+            for k, (lo, hi, members) in enumerate(buckets):
+                assert lo < hi and members == sorted(members, reverse=True)
+                if k + 1 < len(buckets):
+                    assert buckets[k + 1][1] == lo and hi - lo >= be
+                assert lo == offs[members[-1]]
+                seen += members
+            assert seen == list(range(len(sizes) - 1, -1, -1))

@@ -29,6 +29,8 @@ def train(model, x, t, steps, dp):
     model.training()
     opt = nn.optimizers.Adam(model.get_parameters(), lr=1e-2)
     opt._data_parallel = dp
+    opt.overlap_grad_sync = dp and os.environ.get("DP_OVERLAP", "0") == "1"  # bucketed all-reduces during backward
+    opt.bucket_bytes = int(os.environ.get("DP_BUCKET_BYTES", 4096))           # tiny buckets: several of them even in this small model
     loss_fn = nn.CrossEntropyLoss()
     xt, tt = cp.tensor(x, device=cp.cuda), cp.tensor(t, device=cp.cuda)
     losses = []
