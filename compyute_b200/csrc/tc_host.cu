@@ -287,6 +287,9 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 
 // ------------------------------------------------------------------ kernel launch
 __device__ int g_tc_status = 0;
+// SMs left free by the persistent tensor-core kernels (cpt_tc_reserve_sms): room for a concurrent NCCL all-reduce in
+// data-parallel backward passes.  A persistent grid that owns every SM (and nearly every register) serialises with it.
+static int g_reserved_sms = 0;
 
 template <bool BF16, bool A_MN, bool B_MN, int BN, int OP, bool CTA2>
 static int launch_inst(const TcParams& p, cudaStream_t st) {
@@ -299,7 +302,8 @@ static int launch_inst(const TcParams& p, cudaStream_t st) {
   }
   const int total = p.m_tiles * p.n_tiles * p.z_tiles;  // tiles (1-CTA) or tile pairs (2-CTA)
   const int ncta = CTA2 ? 2 : 1;
-  int groups = sm_count() / ncta;
+  int groups = (sm_count() - g_reserved_sms) / ncta;
+  if (groups < 1) groups = 1;
   if (total < groups) groups = total;
   if (groups < 1) return CPT_OK;
   cudaLaunchConfig_t cfg{};
@@ -1213,6 +1217,12 @@ int cpt_channel_sum(const float* x, float* out, int N, int C, int HW, void* ws, 
   CPT_REQUIRE(x && out && N > 0 && C > 0 && HW > 0, CPT_ERR_INVALID, "channel_sum: bad arguments");
   CPT_REQUIRE(ws && ws_bytes >= (size_t)C * 64 * sizeof(float), CPT_ERR_WORKSPACE, "channel_sum: workspace too small");
   return channel_sum(x, out, N, C, HW, ws, as_stream(stream));
+}
+
+int cpt_tc_reserve_sms(int n) {
+  CPT_REQUIRE(n >= 0 && n < sm_count(), CPT_ERR_INVALID, "tc_reserve_sms: %d outside [0, %d)", n, sm_count());
+  tc::g_reserved_sms = n & ~1;  // keep SM pairs whole for the 2-CTA kernels
+  return CPT_OK;
 }
 
 // Debug/test helper: synchronises the device and returns the pipeline-timeout flag of the tensor-core kernels

@@ -81,6 +81,7 @@ class Optimizer:
         # and step (no shared parameters)
         self.overlap_grad_sync = False
         self.bucket_bytes = 32 << 20
+        self.reserve_sms = 16       # SMs the persistent tensor-core kernels leave to NCCL while all-reduces are in flight
         self._buckets = None
         self._bucket_pending: list[int] = []
         self._bucket_work: list[Any] = []
@@ -104,7 +105,7 @@ class Optimizer:
 
     def get_state_dict(self) -> dict[str, dict[Any, Any]]:
         skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel", "_live", "overlap_grad_sync",
-                "bucket_bytes", "_buckets", "_bucket_pending", "_bucket_work", "_bucket_launched", "_offsets", "_bucket_of"}
+                "bucket_bytes", "reserve_sms", "_buckets", "_bucket_pending", "_bucket_work", "_bucket_launched", "_offsets", "_bucket_of"}
         return {"state": self._state, "vars": {k: v for k, v in vars(self).items() if k not in skip}}
 
     def load_state_dict(self, state_dict: dict[str, dict[Any, Any]]) -> None:
@@ -196,6 +197,8 @@ class Optimizer:
 
     def _launch_bucket(self, b: int) -> None:
         lo, hi, _ = self._buckets[b]
+        if not any(self._bucket_launched) and self.reserve_sms > 0:
+            _lib.check(_lib.lib().cpt_tc_reserve_sms(int(self.reserve_sms)))
         self._bucket_launched[b] = True
         self._bucket_work.append(distributed.all_reduce_sum_async(self._arena._buf[lo:hi]))
 
@@ -270,6 +273,8 @@ class Optimizer:
                     self._launch_bucket(b)
             for w in self._bucket_work:
                 w.wait()  # the compute stream waits for NCCL's stream; no host sync
+            if self.reserve_sms > 0:
+                _lib.check(_lib.lib().cpt_tc_reserve_sms(0))
             self._reset_buckets()
         else:
             distributed.all_reduce_sum(self._arena)

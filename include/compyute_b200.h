@@ -264,6 +264,10 @@ int cpt_sgd_step(const cpt_param_entry* table, int n_entries, int64_t max_n, flo
 int cpt_tc_check_status(void);
 /* Number of kernels this library has launched since it was loaded (bench.py's gpu_launches). */
 uint64_t cpt_launch_count(void);
+/* The tensor-core kernels are persistent (one CTA per SM).  n > 0 makes them leave n SMs (rounded down to whole pairs)
+ * free, so that a concurrent kernel of another stream — the NCCL all-reduce of the overlapped data-parallel exchange —
+ * finds an SM to run on; 0 restores the full grid.  Takes effect for subsequent launches. */
+int cpt_tc_reserve_sms(int n);
 
 #ifdef __cplusplus
 }
