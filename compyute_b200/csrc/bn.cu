@@ -306,6 +306,65 @@ int cpt_bn_act_fwd_train(const float* x, const float* w, const float* b, const f
   return CPT_OK;
 }
 
+size_t cpt_bn_cl_workspace_size(int N, int C, int HW) {
+  if (N <= 0 || C <= 0 || HW <= 0) return 0;
+  return cpt_bn_workspace_size(N, C, HW) + tc::bn_bwd_apply_cl_ws(N, C, HW) + 256;
+}
+
+int cpt_bn_act_fwd_train_cl(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,
+                            void* y_cl, float* rmean_out, float* rvar_out, float* save_mean, float* save_rstd, int N, int C,
+                            int HW, float m, float eps, int act, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = bn_check("bn_fwd_train_cl", N, C, HW)) return e;
+  if (int e = check_act("bn_fwd_train_cl", act)) return e;
+  CPT_REQUIRE(y_cl, CPT_ERR_INVALID, "bn_fwd_train_cl: y_cl is NULL");
+  CPT_REQUIRE(ws && ws_bytes >= cpt_bn_workspace_size(N, C, HW), CPT_ERR_WORKSPACE, "bn_fwd_train_cl: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int S = (HW == 1) ? (int)((N / 8 / 64 > 0) ? ((N / 8 / 64 > 64) ? 64 : N / 8 / 64) : 1) : bn_splits(N, C, HW);
+  float2* partial = reinterpret_cast<float2*>(ws);
+  launch_partial<0>(x, nullptr, nullptr, nullptr, nullptr, nullptr, partial, N, C, HW, S, st);
+  CPT_LAUNCH_CHECK("bn_stats");
+  const float count = (float)((int64_t)N * HW);
+  bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(x, partial, S, rmean, rvar, rmean_out, rvar_out, save_mean,
+                                                          save_rstd, C, HW, count, m, eps);
+  CPT_LAUNCH_CHECK("bn_fwd_finalize");
+  return tc::bn_apply_cl(x, w, b, save_mean, save_rstd, y, y_cl, N, C, HW, act, st);
+}
+
+int cpt_bn_act_fwd_eval_cl(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,
+                           void* y_cl, float* save_mean, float* save_rstd, int N, int C, int HW, float eps, int act,
+                           void* stream) {
+  if (int e = bn_check("bn_fwd_eval_cl", N, C, HW)) return e;
+  if (int e = check_act("bn_fwd_eval_cl", act)) return e;
+  CPT_REQUIRE(y_cl, CPT_ERR_INVALID, "bn_fwd_eval_cl: y_cl is NULL");
+  cudaStream_t st = as_stream(stream);
+  bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(rmean, rvar, save_mean, save_rstd, C, eps);
+  CPT_LAUNCH_CHECK("bn_eval_stats");
+  return tc::bn_apply_cl(x, w, b, save_mean, save_rstd, y, y_cl, N, C, HW, act, st);
+}
+
+int cpt_bn_act_bwd_cl(const float* x, const float* dy, const float* w, const float* b, const float* save_mean,
+                      const float* save_rstd, float* dx, void* dx_cl, float* dx_chan_sum, float* dw, float* db, int N, int C,
+                      int HW, int act, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = bn_check("bn_bwd_cl", N, C, HW)) return e;
+  if (int e = check_act("bn_bwd_cl", act)) return e;
+  CPT_REQUIRE(dx_cl, CPT_ERR_INVALID, "bn_bwd_cl: dx_cl is NULL");
+  CPT_REQUIRE(act == CPT_ACT_NONE || b, CPT_ERR_INVALID, "bn_bwd_cl: the fused ReLU mask needs the bias");
+  CPT_REQUIRE(ws && ws_bytes >= cpt_bn_cl_workspace_size(N, C, HW), CPT_ERR_WORKSPACE, "bn_bwd_cl: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int S = (HW == 1) ? (int)((N / 8 / 64 > 0) ? ((N / 8 / 64 > 64) ? 64 : N / 8 / 64) : 1) : bn_splits(N, C, HW);
+  float2* partial = reinterpret_cast<float2*>(ws);
+  float* coef = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + (size_t)C * 64 * sizeof(float2));
+  char* ws2 = reinterpret_cast<char*>(ws) + ((cpt_bn_workspace_size(N, C, HW) + 255) / 256) * 256;
+  if (act) launch_partial<2>(x, dy, save_mean, save_rstd, w, b, partial, N, C, HW, S, st);
+  else launch_partial<1>(x, dy, save_mean, save_rstd, w, b, partial, N, C, HW, S, st);
+  CPT_LAUNCH_CHECK("bn_bwd_partial");
+  const float count = (float)((int64_t)N * HW);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, S, w, save_rstd, dw, db, coef, C, count);
+  CPT_LAUNCH_CHECK("bn_bwd_finalize");
+  return tc::bn_bwd_apply_cl(x, dy, w, b, save_mean, save_rstd, coef, count, dx, dx_cl, dx_chan_sum, N, C, HW, act, ws2,
+                             ws_bytes - (size_t)(ws2 - reinterpret_cast<char*>(ws)), st);
+}
+
 int cpt_bn_fwd_train(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,
                      float* rmean_out, float* rvar_out, float* save_mean, float* save_rstd, int N, int C, int HW,
                      float m, float eps, void* ws, size_t ws_bytes, void* stream) {

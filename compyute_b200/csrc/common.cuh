@@ -89,4 +89,15 @@ __device__ __forceinline__ void st_stream(float4* p, float4 v) {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// BatchNorm apply / backward-apply passes that also emit the channels-last bf16 copy for the neighbouring tensor-core
+// convolution (fused_cl.cuh, compiled in tc_host.cu; called by bn.cu)
+namespace tc {
+int bn_apply_cl(const float* x, const float* w, const float* b, const float* mean, const float* rstd, float* y, void* y_cl, int N,
+                int C, int HW, int act, cudaStream_t st);
+size_t bn_bwd_apply_cl_ws(int N, int C, int HW);
+int bn_bwd_apply_cl(const float* x, const float* dy, const float* w, const float* b, const float* mean, const float* rstd,
+                    const float* coef, float count, float* dx, void* dx_cl, float* dx_chan_sum, int N, int C, int HW, int act,
+                    void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace tc
+
 }  // namespace cpt

@@ -439,6 +439,8 @@ int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, in
   return CPT_OK;
 }
 
+#include "fused_cl.cuh"
+
 // Geometry of one implicit-GEMM launch over a channels-last activation tensor.
 struct ConvPlan {
   int ntaps;

@@ -68,9 +68,13 @@ class Conv2DFn(Function):
             _lib.check(L.cpt_conv2d_fprop_packed(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, ws, wsb, st))
             mode = _MODE_PACKED
         else:
-            # stage x once as channels-last; kept in the cache so wgrad does not convert it again
-            x_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Ci, d.H, d.W, mode),), np.uint8)
-            _lib.check(L.cpt_to_channels_last(f32ptr(x), x_cl.ptr, d.B, d.Ci, d.H, d.W, mode, None, None, 0, st))
+            shadow = getattr(x.data, "cl", None)
+            if shadow is not None and shadow[0] == mode:
+                x_cl = shadow[1]  # the producer (BatchNorm/ReLU pass) already wrote the channels-last operand
+            else:
+                # stage x once as channels-last; kept in the cache so wgrad does not convert it again
+                x_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Ci, d.H, d.W, mode),), np.uint8)
+                _lib.check(L.cpt_to_channels_last(f32ptr(x), x_cl.ptr, d.B, d.Ci, d.H, d.W, mode, None, None, 0, st))
             ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_FPROP, ctypes.byref(d), mode))
             _lib.check(L.cpt_conv2d_fprop_cl(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, mode, ws, wsb, st))
         cache.push(x, f, b is not None, d, mode, x_cl)
@@ -93,9 +97,7 @@ class Conv2DFn(Function):
         dbp = db.ptr if db is not None else None
         ho, wo = dy.shape[2], dy.shape[3]
         if mode == _MODE_PACKED:
-            dy_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Co, ho, wo, _lib.MODE_BF16),), np.uint8)
-            ws, wsb = workspace(L.cpt_to_channels_last_workspace_size(d.B, d.Co, ho, wo))
-            _lib.check(L.cpt_to_channels_last(f32ptr(dy), dy_cl.ptr, d.B, d.Co, ho, wo, _lib.MODE_BF16, dbp, ws, wsb, st))
+            dy_cl = _staged_dy(L, dy, d, ho, wo, _lib.MODE_BF16, db, st)
             ws, wsb = workspace(L.cpt_conv2d_packed_workspace_size(_lib.OP_DGRAD, dref))
             _lib.check(L.cpt_conv2d_dgrad_packed(dref, dy_cl.ptr, f32ptr(f), dx.ptr, ws, wsb, st))
             ws, wsb = workspace(L.cpt_conv2d_packed_workspace_size(_lib.OP_WGRAD, dref))
@@ -109,9 +111,7 @@ class Conv2DFn(Function):
             _lib.check(L.cpt_conv2d_wgrad(dref, f32ptr(x), f32ptr(dy), df.ptr, dbp, mode, ws, wsb, st))
         else:
             # dy staged once (db fused into the staging pass), shared by dgrad and wgrad
-            dy_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Co, ho, wo, mode),), np.uint8)
-            ws, wsb = workspace(L.cpt_to_channels_last_workspace_size(d.B, d.Co, ho, wo))
-            _lib.check(L.cpt_to_channels_last(f32ptr(dy), dy_cl.ptr, d.B, d.Co, ho, wo, mode, dbp, ws, wsb, st))
+            dy_cl = _staged_dy(L, dy, d, ho, wo, mode, db, st)
             if tc_dgrad:
                 ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_DGRAD, dref, mode))
                 _lib.check(L.cpt_conv2d_dgrad_cl(dref, dy_cl.ptr, f32ptr(f), dx.ptr, mode, ws, wsb, st))
@@ -121,6 +121,24 @@ class Conv2DFn(Function):
             ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_WGRAD, dref, mode))
             _lib.check(L.cpt_conv2d_wgrad_cl(dref, x_cl.ptr, dy_cl.ptr, df.ptr, mode, ws, wsb, st))
         return Tensor(dx), Tensor(df), (Tensor(db) if db is not None else None)
+
+
+def _staged_dy(L, dy: Tensor, d, ho: int, wo: int, mode: int, db: Optional[DeviceArray], st) -> DeviceArray:
+    """Channels-last copy of dy (+ db = dy.sum((0, 2, 3)), convolution_funcs.py:252).  When dy was produced by a
+    BatchNorm backward pass that already emitted it (``dy.data.cl``), nothing is staged."""
+    shadow = getattr(dy.data, "cl", None)
+    if shadow is not None and shadow[0] == mode:
+        if db is not None:
+            if shadow[2] is not None:
+                db.copy_from(shadow[2])
+            else:
+                ws, wsb = workspace(d.Co * 64 * 4)
+                _lib.check(L.cpt_channel_sum(f32ptr(dy), db.ptr, d.B, d.Co, ho * wo, ws, wsb, st))
+        return shadow[1]
+    dy_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Co, ho, wo, mode),), np.uint8)
+    ws, wsb = workspace(L.cpt_to_channels_last_workspace_size(d.B, d.Co, ho, wo))
+    _lib.check(L.cpt_to_channels_last(f32ptr(dy), dy_cl.ptr, d.B, d.Co, ho, wo, mode, db.ptr if db is not None else None, ws, wsb, st))
+    return dy_cl
 
 
 def conv2d(x: Tensor, f: Tensor, b: Optional[Tensor] = None, padding: int = 0, stride: int = 1,

@@ -5,6 +5,7 @@ from __future__ import annotations
 import numpy as np
 
 from ... import _lib, graph
+from ...backend import get_compute_mode
 from ...tensors import DeviceArray, ShapeError, Tensor, f32ptr, require_cuda, stream_ptr, workspace
 from .functions import Function, FunctionCache, PseudoCache
 
@@ -14,11 +15,20 @@ __all__ = ["batchnorm1d", "batchnorm2d", "BatchNorm1DFn", "BatchNorm2DFn", "Batc
 ACT_NONE, ACT_RELU = 0, 1  # CPT_ACT_*
 
 
-def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW, act=ACT_NONE):
+def _cl_ok(x) -> bool:
+    """The producer-side channels-last copy is for the bf16 tensor-core convolutions and 4-D activations only."""
+    return x.ndim == 4 and get_compute_mode() == _lib.MODE_BF16
+
+
+def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW, act=ACT_NONE, emit_cl=False):
     require_cuda(x, rmean, rvar, w, b)
     L = _lib.lib()
     st = stream_ptr()
     y = DeviceArray.empty(x.shape, np.float32)
+    y_cl = None
+    if emit_cl and _cl_ok(x):  # the consumer is a tensor-core convolution: write its bf16 NHWC operand in the same pass
+        y_cl = DeviceArray.empty((L.cpt_channels_last_bytes(N, C, HW, 1, _lib.MODE_BF16),), np.uint8)
+        y.cl = (_lib.MODE_BF16, y_cl, None)
     save_mean = DeviceArray.empty((C,), np.float32)
     save_rstd = DeviceArray.empty((C,), np.float32)
     if training:
@@ -28,9 +38,18 @@ def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW, act=ACT
             new_rmean = DeviceArray.empty((C,), np.float32)
             new_rvar = DeviceArray.empty((C,), np.float32)
         ws, wsb = workspace(L.cpt_bn_workspace_size(N, C, HW))
-        _lib.check(L.cpt_bn_act_fwd_train(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, new_rmean.ptr,
-                                          new_rvar.ptr, save_mean.ptr, save_rstd.ptr, N, C, HW, float(m), float(eps), act, ws, wsb, st))
+        if y_cl is not None:
+            _lib.check(L.cpt_bn_act_fwd_train_cl(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, y_cl.ptr,
+                                                 new_rmean.ptr, new_rvar.ptr, save_mean.ptr, save_rstd.ptr, N, C, HW, float(m),
+                                                 float(eps), act, ws, wsb, st))
+        else:
+            _lib.check(L.cpt_bn_act_fwd_train(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, new_rmean.ptr,
+                                              new_rvar.ptr, save_mean.ptr, save_rstd.ptr, N, C, HW, float(m), float(eps), act, ws,
+                                              wsb, st))
         rmean, rvar = Tensor(new_rmean), Tensor(new_rvar)
+    elif y_cl is not None:
+        _lib.check(L.cpt_bn_act_fwd_eval_cl(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, y_cl.ptr,
+                                            save_mean.ptr, save_rstd.ptr, N, C, HW, float(eps), act, st))
     else:
         _lib.check(L.cpt_bn_act_fwd_eval(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, save_mean.ptr,
                                          save_rstd.ptr, N, C, HW, float(eps), act, st))
@@ -40,13 +59,23 @@ def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW, act=ACT
     return Tensor(y), rmean, rvar
 
 
-def _bn_backward(cache, dy, dw_out=None, db_out=None):
+def _bn_backward(cache, dy, dw_out=None, db_out=None, emit_cl=False, emit_sum=False):
+    """``emit_cl``: also write dx as channels-last bf16 (the dy operand of the producing convolution's backward);
+    ``emit_sum``: and its per-channel sums (that convolution's bias gradient)."""
     x, w, b, save_mean, save_rstd, (N, C, HW), act = cache.pop()
     require_cuda(dy)
     L = _lib.lib()
     dx = DeviceArray.empty(x.shape, np.float32)
     dw = dw_out.reshape((C,)) if dw_out is not None else DeviceArray.empty((C,), np.float32)
     db = db_out.reshape((C,)) if db_out is not None else DeviceArray.empty((C,), np.float32)
+    if emit_cl and _cl_ok(x):
+        dx_cl = DeviceArray.empty((L.cpt_channels_last_bytes(N, C, HW, 1, _lib.MODE_BF16),), np.uint8)
+        csum = DeviceArray.empty((C,), np.float32) if emit_sum else None
+        ws, wsb = workspace(L.cpt_bn_cl_workspace_size(N, C, HW))
+        _lib.check(L.cpt_bn_act_bwd_cl(f32ptr(x), f32ptr(dy), f32ptr(w), f32ptr(b), save_mean.ptr, save_rstd.ptr, dx.ptr, dx_cl.ptr,
+                                       csum.ptr if csum is not None else None, dw.ptr, db.ptr, N, C, HW, act, ws, wsb, stream_ptr()))
+        dx.cl = (_lib.MODE_BF16, dx_cl, csum)
+        return Tensor(dx), Tensor(dw), Tensor(db)
     ws, wsb = workspace(L.cpt_bn_workspace_size(N, C, HW))
     _lib.check(L.cpt_bn_act_bwd(f32ptr(x), f32ptr(dy), f32ptr(w), f32ptr(b), save_mean.ptr, save_rstd.ptr, dx.ptr, dw.ptr, db.ptr,
                                 N, C, HW, act, ws, wsb, stream_ptr()))
@@ -58,15 +87,17 @@ class BatchNorm2DFn(Function):
 
     @staticmethod
     def forward(cache: FunctionCache, x: Tensor, rmean: Tensor, rvar: Tensor, w: Tensor, b: Tensor, m: float, eps: float,
-                training: bool) -> tuple[Tensor, Tensor, Tensor]:
+                training: bool, emit_cl: bool = False) -> tuple[Tensor, Tensor, Tensor]:
+        """``emit_cl`` (extension): also write y as channels-last bf16 for a tensor-core convolution that consumes it."""
         if x.ndim != 4:
             raise ShapeError(f"Expected input to be 4D, got {x.ndim}D.")
         B, C, H, W = x.shape
-        return _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, B, C, H * W)
+        return _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, B, C, H * W, ACT_NONE, emit_cl)
 
     @staticmethod
-    def backward(cache: FunctionCache, dy: Tensor, dw_out=None, db_out=None) -> tuple[Tensor, Tensor, Tensor]:
-        return _bn_backward(cache, dy, dw_out, db_out)
+    def backward(cache: FunctionCache, dy: Tensor, dw_out=None, db_out=None, emit_cl: bool = False,
+                 emit_sum: bool = False) -> tuple[Tensor, Tensor, Tensor]:
+        return _bn_backward(cache, dy, dw_out, db_out, emit_cl, emit_sum)
 
 
 class BatchNorm1DFn(Function):
@@ -93,15 +124,16 @@ class BatchNormReLU2DFn(Function):
 
     @staticmethod
     def forward(cache: FunctionCache, x: Tensor, rmean: Tensor, rvar: Tensor, w: Tensor, b: Tensor, m: float, eps: float,
-                training: bool) -> tuple[Tensor, Tensor, Tensor]:
+                training: bool, emit_cl: bool = False) -> tuple[Tensor, Tensor, Tensor]:
         if x.ndim != 4:
             raise ShapeError(f"Expected input to be 4D, got {x.ndim}D.")
         B, C, H, W = x.shape
-        return _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, B, C, H * W, ACT_RELU)
+        return _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, B, C, H * W, ACT_RELU, emit_cl)
 
     @staticmethod
-    def backward(cache: FunctionCache, dy: Tensor, dw_out=None, db_out=None) -> tuple[Tensor, Tensor, Tensor]:
-        return _bn_backward(cache, dy, dw_out, db_out)
+    def backward(cache: FunctionCache, dy: Tensor, dw_out=None, db_out=None, emit_cl: bool = False,
+                 emit_sum: bool = False) -> tuple[Tensor, Tensor, Tensor]:
+        return _bn_backward(cache, dy, dw_out, db_out, emit_cl, emit_sum)
 
 
 class BatchNormReLU1DFn(Function):

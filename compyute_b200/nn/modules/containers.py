@@ -37,6 +37,37 @@ class Sequential(Module):
             raise EmptyContainerError()
         self.layers = ModuleList(modules)
 
+    def _plan_staging_hints(self) -> None:
+        """Tells every BatchNorm2D of this container whether its neighbours are convolutions, so that it writes their
+        channels-last bf16 operand in its own apply pass (forward: the consumer of its — possibly ReLU-fused — output;
+        backward: the convolution that produced its input).  Recomputed when the layer list or the fusion switch changes."""
+        from .layers import BatchNorm2D, Conv2D, ReLU
+        key = (tuple(id(m) for m in self.layers), _fusion)
+        if getattr(self, "_hint_key", None) == key:
+            return
+        object.__setattr__(self, "_hint_key", key)
+
+        def wants_cl(m) -> bool:  # does m feed its input straight into a Conv2D (and into nothing that mutates it)?
+            if isinstance(m, Conv2D):
+                return True
+            if isinstance(m, Sequential):
+                return wants_cl(m.layers[0])
+            if isinstance(m, ResidualConnection):
+                return wants_cl(m.residual_block) and (m.residual_proj is None or wants_cl(m.residual_proj))
+            return False
+
+        n = len(self.layers)
+        for i, m in enumerate(self.layers):
+            if not isinstance(m, BatchNorm2D):
+                continue
+            j = i + 1
+            if j < n and type(self.layers[j]) is ReLU:
+                j = j + 1 if _fusion else n  # unfused: the BatchNorm output feeds the ReLU, not the convolution
+            m._emit_cl_fwd = _fusion and j < n and wants_cl(self.layers[j])
+            prev = self.layers[i - 1] if i > 0 else None
+            m._emit_cl_bwd = _fusion and isinstance(prev, Conv2D)
+            m._emit_cl_bwd_sum = bool(m._emit_cl_bwd and prev.b is not None)
+
     def _fusable(self, i: int, x: Tensor) -> bool:
         """layers[i] is a BatchNorm directly followed by a ReLU and nothing observes the tensor between them."""
         from .layers import ReLU, _BatchNorm
@@ -48,6 +79,7 @@ class Sequential(Module):
 
     @Module.register_forward
     def forward(self, x: Tensor) -> Tensor:
+        self._plan_staging_hints()
         i, n = 0, len(self.layers)
         while i < n:
             layer = self.layers[i]

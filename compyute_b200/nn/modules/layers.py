@@ -120,6 +120,11 @@ class AvgPooling2D(Module):
 class _BatchNorm(Module):
     _fn = None
     _fn_relu = None  # fused BatchNorm -> ReLU (Sequential peephole)
+    # producer-side staging hints set by the enclosing Sequential: the consumer of the output is a tensor-core convolution
+    # (forward), the producer of the input is one (backward; with_sum: it has a bias whose gradient is dx's channel sum)
+    _emit_cl_fwd = False
+    _emit_cl_bwd = False
+    _emit_cl_bwd_sum = False
 
     def __init__(self, channels: int, eps: float = 1e-5, m: float = 0.1, label: Optional[str] = None) -> None:
         super().__init__(label)
@@ -139,13 +144,16 @@ class _BatchNorm(Module):
         return self._forward(self._fn_relu, x)
 
     def _forward(self, fn, x: Tensor) -> Tensor:
-        y, rmean, rvar = fn.forward(self.fcache, x, self.rmean, self.rvar, self.w, self.b, self.m, self.eps, self._is_training)
+        extra = (True,) if (self._emit_cl_fwd and x.ndim == 4) else ()
+        y, rmean, rvar = fn.forward(self.fcache, x, self.rmean, self.rvar, self.w, self.b, self.m, self.eps, self._is_training,
+                                    *extra)
         self.rmean.data = rmean.data  # rebinding, like normalizations.py:163-164
         self.rvar.data = rvar.data
         return y
 
     def backward(self, dy: Tensor) -> Tensor:  # not wrapped in the reference either (normalizations.py:89, 167)
-        dx, dw, db = self._fn.backward(self.fcache, dy, self.grad_slot(self.w), self.grad_slot(self.b))
+        extra = (True, self._emit_cl_bwd_sum) if (self._emit_cl_bwd and dy.ndim == 4) else ()
+        dx, dw, db = self._fn.backward(self.fcache, dy, self.grad_slot(self.w), self.grad_slot(self.b), *extra)
         self.update_parameter_grad(self.w, dw)
         self.update_parameter_grad(self.b, db)
         return dx

@@ -190,6 +190,23 @@ int cpt_bn_act_fwd_eval(const float* x, const float* w, const float* b, const fl
 int cpt_bn_act_bwd(const float* x, const float* dy, const float* w, const float* b,
                    const float* save_mean, const float* save_rstd, float* dx, float* dw, float* db,
                    int N, int C, int HW, int act, void* ws, size_t ws_bytes, void* stream);
+/* Producer-side staging for the tensor-core convolutions: same computation as cpt_bn_act_*, but the apply pass also writes
+ * the channels-last bf16 copy (layout of cpt_to_channels_last, CPT_MODE_BF16, with H*W = HW) of its output — y_cl for the
+ * convolution that consumes y in forward, dx_cl for the backward of the convolution that produced x.  dx_chan_sum (C floats,
+ * may be NULL) receives the per-channel sums of dx, i.e. that convolution's bias gradient (convolution_funcs.py:252).
+ * fp32 results are bit-identical to cpt_bn_act_*. */
+size_t cpt_bn_cl_workspace_size(int N, int C, int HW);
+int cpt_bn_act_fwd_train_cl(const float* x, const float* w, const float* b, const float* rmean,
+                            const float* rvar, float* y, void* y_cl, float* rmean_out, float* rvar_out,
+                            float* save_mean, float* save_rstd, int N, int C, int HW, float m,
+                            float eps, int act, void* ws, size_t ws_bytes, void* stream);
+int cpt_bn_act_fwd_eval_cl(const float* x, const float* w, const float* b, const float* rmean,
+                           const float* rvar, float* y, void* y_cl, float* save_mean, float* save_rstd,
+                           int N, int C, int HW, float eps, int act, void* stream);
+int cpt_bn_act_bwd_cl(const float* x, const float* dy, const float* w, const float* b,
+                      const float* save_mean, const float* save_rstd, float* dx, void* dx_cl,
+                      float* dx_chan_sum, float* dw, float* db, int N, int C, int HW, int act, void* ws,
+                      size_t ws_bytes, void* stream);
 
 /* ---- activations / elementwise ------------------------------------------------------------- */
 /* ReLUFn.forward activation_funcs.py:26-29.  mask = bit-packed (y > 0), 4 * ((n + 31) / 32) bytes, 4-byte aligned, in a

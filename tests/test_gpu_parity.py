@@ -443,6 +443,50 @@ def test_bn_relu_peephole_is_bit_exact(cp):
     assert close(y, ar) and close(dx, dxr, 2e-5) and close(dw, dwr, 2e-5) and close(db, dbr, 2e-5)
 
 
+@pytest.mark.parametrize("shape", [(4, 8, 12, 12), (3, 70, 9, 9), (2, 64, 28, 28)], ids=str)
+def test_producer_side_staging_is_bit_exact(cp, shape):
+    """bf16 mode: a BatchNorm next to a Conv2D writes that convolution's channels-last bf16 operand in its own apply pass
+    (cpt_bn_act_*_cl: forward y_cl, backward dx_cl + the bias gradient's channel sums).  Everything the model returns must equal
+    the layer-by-layer evaluation (separate staging passes) bit for bit: odd channel counts, pixel tails, bias / no bias,
+    residual blocks with projection, stride 2."""
+    from compyute_b200 import nn
+    B, C, H, _ = shape
+    rng = np.random.RandomState(11)
+    x = rng.normal(0, 1, shape).astype(np.float32)
+
+    def build():
+        np.random.seed(5)
+        with cp.use_device(cp.cuda):
+            return nn.Sequential(
+                nn.Conv2D(C, C + 2, 3, padding="same", bias=True), nn.BatchNorm2D(C + 2), nn.ReLU(),
+                nn.Conv2D(C + 2, 16, 3, padding="same", bias=False), nn.BatchNorm2D(16), nn.ReLU(),
+                nn.ResidualConnection(nn.Conv2D(16, 24, 3, padding=1, stride=2, bias=False), nn.BatchNorm2D(24), nn.ReLU(),
+                                      nn.Conv2D(24, 24, 3, padding=1, bias=True), nn.BatchNorm2D(24),
+                                      residual_proj=nn.Sequential(nn.Conv2D(16, 24, 1, stride=2, bias=False), nn.BatchNorm2D(24))),
+                nn.ReLU(), nn.Conv2D(24, 8, 1), nn.BatchNorm2D(8), nn.Flatten(), nn.Linear(8 * ((H + 1) // 2) ** 2, 5))
+
+    def run(fused):
+        nn.set_fusion_enabled(fused)
+        try:
+            model = build()
+            model.training()
+            with cp.compute_mode("bf16"):
+                y = model(cp.tensor(x, device=cp.cuda))
+                dy = np.random.RandomState(12).normal(0, 1, y.shape).astype(np.float32)
+                dx = model.backward(cp.tensor(dy, device=cp.cuda))
+            tc_ok()
+            assert all(not m.fcache.cache for m in model.get_modules())
+            return [y.to_numpy(), dx.to_numpy()] + [p.grad.to_numpy() for p in model.get_parameters()] + \
+                   [b.to_numpy() for b in model.get_buffers()]
+        finally:
+            nn.set_fusion_enabled(True)
+
+    a, b = run(True), run(False)
+    assert len(a) == len(b)
+    for k, (u, v) in enumerate(zip(a, b)):
+        assert np.array_equal(u, v, equal_nan=True), (k, u.shape, float(np.abs(u - v).max()))
+
+
 def test_dataloader_and_checkpoint_on_device(cp, tmp_path):
     """Dataloader uploads batches through pinned double-buffered staging (values identical to host slicing), and a
     model/optimizer checkpoint of device state round-trips through cp.save / cp.load (README.md:197-213)."""
