@@ -3,6 +3,8 @@
 // of the SM count.  Roofline bound: HBM (bytes per element stated per kernel).
 #include <stdarg.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace cpt {
@@ -41,8 +43,16 @@ int sm_count() {
 // float4s at (j*32 + l), j = 0..7, of the chunk and owns mask word chunk*32 + l (bit 4j+i = element i of its j-th float4),
 // so both the eight 128-bit loads per thread and the 128-byte mask store per warp are fully coalesced.  The tail
 // (< 1024 elements) uses plain bit order after the last full chunk.
+// `lp` (optional): the same values as bf16, same linear order — the pre-cast operand of a Linear layer that consumes the result
+// (row pitch == row length, i.e. the layout of cpt_cast_bf16 for a feature count that is a multiple of 8).
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
 __global__ void __launch_bounds__(256) relu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                       uint32_t* __restrict__ mask, int64_t n_chunks, int64_t n) {
+                                                       uint32_t* __restrict__ mask, int64_t n_chunks, int64_t n,
+                                                       __nv_bfloat16* __restrict__ lp) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t c = warp0; c < n_chunks; c += nwarps) {
@@ -62,6 +72,7 @@ __global__ void __launch_bounds__(256) relu_fwd_kernel(const float* __restrict__
         e[i] = r;
       }
       st_stream(yp + j * 32, make_float4(e[0], e[1], e[2], e[3]));
+      if (lp) reinterpret_cast<uint2*>(lp)[c * 256 + lane + j * 32] = pack_bf16x4(e[0], e[1], e[2], e[3]);
     }
     if (mask) mask[c * 32 + lane] = bits;
   }
@@ -75,6 +86,7 @@ __global__ void __launch_bounds__(256) relu_fwd_kernel(const float* __restrict__
         const float xv = x[i];
         r = (xv != xv) ? xv : fmaxf(xv, 0.f);
         y[i] = r;
+        if (lp) lp[i] = __float2bfloat16_rn(r);
       }
       const uint32_t b = __ballot_sync(0xffffffffu, i < n && r > 0.f);
       if (mask && lane == 0) mask[n_chunks * 32 + (base - t0) / 32] = b;
@@ -83,7 +95,8 @@ __global__ void __launch_bounds__(256) relu_fwd_kernel(const float* __restrict__
 }
 
 __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ dy, const uint32_t* __restrict__ mask,
-                                                       float* __restrict__ dx, int64_t n_chunks, int64_t n) {
+                                                       float* __restrict__ dx, int64_t n_chunks, int64_t n,
+                                                       __nv_bfloat16* __restrict__ lp) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t c = warp0; c < n_chunks; c += nwarps) {
@@ -96,8 +109,10 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       // dy * mask (keeps -0.0 / NaN like numpy's float * bool)
-      st_stream(xp + j * 32, make_float4(v[j].x * (float)((bits >> (4 * j)) & 1u), v[j].y * (float)((bits >> (4 * j + 1)) & 1u),
-                                         v[j].z * (float)((bits >> (4 * j + 2)) & 1u), v[j].w * (float)((bits >> (4 * j + 3)) & 1u)));
+      const float4 o = make_float4(v[j].x * (float)((bits >> (4 * j)) & 1u), v[j].y * (float)((bits >> (4 * j + 1)) & 1u),
+                                   v[j].z * (float)((bits >> (4 * j + 2)) & 1u), v[j].w * (float)((bits >> (4 * j + 3)) & 1u));
+      st_stream(xp + j * 32, o);
+      if (lp) reinterpret_cast<uint2*>(lp)[c * 256 + lane + j * 32] = pack_bf16x4(o.x, o.y, o.z, o.w);
     }
   }
   if (warp0 == 0) {
@@ -105,7 +120,11 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__
     for (int64_t base = t0; base < n; base += 32) {
       const int64_t i = base + lane;
       const uint32_t b = mask[n_chunks * 32 + (base - t0) / 32];
-      if (i < n) dx[i] = dy[i] * (float)((b >> lane) & 1u);
+      if (i < n) {
+        const float o = dy[i] * (float)((b >> lane) & 1u);
+        dx[i] = o;
+        if (lp) lp[i] = __float2bfloat16_rn(o);
+      }
     }
   }
 }
@@ -200,24 +219,33 @@ int cpt_device_info(int device, int* sm, int* major, int* minor, size_t* smem_op
 }
 
 int cpt_relu_fwd(const float* x, float* y, uint8_t* mask, int64_t n, void* stream) {
+  return cpt_relu_fwd_lp(x, y, mask, nullptr, n, stream);
+}
+int cpt_relu_bwd(const float* dy, const uint8_t* mask, float* dx, int64_t n, void* stream) {
+  return cpt_relu_bwd_lp(dy, mask, dx, nullptr, n, stream);
+}
+
+int cpt_relu_fwd_lp(const float* x, float* y, uint8_t* mask, void* y_bf16, int64_t n, void* stream) {
   CPT_REQUIRE(n >= 0 && x && y, CPT_ERR_INVALID, "relu_fwd: bad arguments");
+  CPT_REQUIRE(!y_bf16 || (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0, CPT_ERR_INVALID, "relu_fwd: y_bf16 must be 8-byte aligned");
   if (n == 0) return CPT_OK;
   CPT_REQUIRE(aligned16(x) && aligned16(y) && (!mask || (reinterpret_cast<uintptr_t>(mask) & 3) == 0), CPT_ERR_INVALID,
               "relu_fwd: x, y must be 16-byte aligned and mask 4-byte aligned");
   const int64_t n_chunks = n / 1024;
   relu_fwd_kernel<<<ew_grid((n_chunks > 0 ? n_chunks : 1) * 32, 256), 256, 0, as_stream(stream)>>>(
-      x, y, reinterpret_cast<uint32_t*>(mask), n_chunks, n);
+      x, y, reinterpret_cast<uint32_t*>(mask), n_chunks, n, reinterpret_cast<__nv_bfloat16*>(y_bf16));
   CPT_LAUNCH_CHECK("relu_fwd");
   return CPT_OK;
 }
 
-int cpt_relu_bwd(const float* dy, const uint8_t* mask, float* dx, int64_t n, void* stream) {
+int cpt_relu_bwd_lp(const float* dy, const uint8_t* mask, float* dx, void* dx_bf16, int64_t n, void* stream) {
   CPT_REQUIRE(n >= 0 && dy && dx && mask, CPT_ERR_INVALID, "relu_bwd: bad arguments");
+  CPT_REQUIRE(!dx_bf16 || (reinterpret_cast<uintptr_t>(dx_bf16) & 7) == 0, CPT_ERR_INVALID, "relu_bwd: dx_bf16 must be 8-byte aligned");
   if (n == 0) return CPT_OK;
   CPT_REQUIRE(aligned16(dy) && aligned16(dx), CPT_ERR_INVALID, "relu_bwd: pointers must be 16-byte aligned");
   const int64_t n_chunks = n / 1024;
   relu_bwd_kernel<<<ew_grid((n_chunks > 0 ? n_chunks : 1) * 32, 256), 256, 0, as_stream(stream)>>>(
-      dy, reinterpret_cast<const uint32_t*>(mask), dx, n_chunks, n);
+      dy, reinterpret_cast<const uint32_t*>(mask), dx, n_chunks, n, reinterpret_cast<__nv_bfloat16*>(dx_bf16));
   CPT_LAUNCH_CHECK("relu_bwd");
   return CPT_OK;
 }

@@ -5,6 +5,7 @@ from __future__ import annotations
 import numpy as np
 
 from ... import _lib
+from ...backend import get_compute_mode
 from ...tensors import DeviceArray, Tensor, f32ptr, require_cuda, stream_ptr
 from .functions import Function, FunctionCache, PseudoCache, get_caching_enabled
 
@@ -15,28 +16,42 @@ __all__ = ["relu", "ReLUFn", "FUSED_INTO_PRODUCER"]
 FUSED_INTO_PRODUCER = "fused-into-producer"
 
 
+def _lp_buffer(a: DeviceArray):
+    """bf16 copy of a 2-D (N, C) array for the neighbouring Linear layer, attached as ``a.cl``; only in bf16 mode and when
+    C is a multiple of 8 (then the bf16 row pitch of cpt_cast_bf16 equals the row length)."""
+    if get_compute_mode() != _lib.MODE_BF16 or a.ndim != 2 or a.shape[1] % 8 != 0:
+        return None
+    lp = DeviceArray.empty((_lib.lib().cpt_cast_bf16_bytes(a.shape[0], a.shape[1]),), np.uint8)
+    a.cl = (_lib.MODE_BF16, lp, None)
+    return lp
+
+
 class ReLUFn(Function):
     """y = max(x, 0); caches the mask ``y > 0`` (:26-34) — bit-packed here (1 bit/element instead of 1 byte)."""
 
     @staticmethod
-    def forward(cache: FunctionCache, x: Tensor) -> Tensor:
+    def forward(cache: FunctionCache, x: Tensor, emit_lp: bool = False) -> Tensor:
+        """``emit_lp`` (extension): also write y as bf16 rows — the pre-cast operand of a Linear layer that consumes it."""
         require_cuda(x)
         n = x.size
         y = DeviceArray.empty(x.shape, np.float32)
         want_mask = get_caching_enabled() and not isinstance(cache, PseudoCache)
         mask = DeviceArray.empty(((n + 31) // 32 * 4,), np.uint8) if want_mask else None
-        _lib.check(_lib.lib().cpt_relu_fwd(f32ptr(x), y.ptr, mask.ptr if mask is not None else None, n, stream_ptr()))
+        lp = _lp_buffer(y) if emit_lp else None
+        _lib.check(_lib.lib().cpt_relu_fwd_lp(f32ptr(x), y.ptr, mask.ptr if mask is not None else None,
+                                              lp.ptr if lp is not None else None, n, stream_ptr()))
         cache.push(mask)
         return Tensor(y)
 
     @staticmethod
-    def backward(cache: FunctionCache, dy: Tensor) -> Tensor:
+    def backward(cache: FunctionCache, dy: Tensor, emit_lp: bool = False) -> Tensor:
         (mask,) = cache.pop()
         if mask is FUSED_INTO_PRODUCER:
             return dy
         require_cuda(dy)
         dx = DeviceArray.empty(dy.shape, np.float32)
-        _lib.check(_lib.lib().cpt_relu_bwd(f32ptr(dy), mask.ptr, dx.ptr, dy.size, stream_ptr()))
+        lp = _lp_buffer(dx) if emit_lp else None
+        _lib.check(_lib.lib().cpt_relu_bwd_lp(f32ptr(dy), mask.ptr, dx.ptr, lp.ptr if lp is not None else None, dy.size, stream_ptr()))
         return Tensor(dx)
 
 

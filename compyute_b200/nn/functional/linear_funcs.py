@@ -32,9 +32,13 @@ class LinearFn(Function):
         x_bf = w_bf = None
         if mode == _lib.MODE_BF16:
             # operands staged once as bf16 and kept in the cache: x_bf16 is reused by wgrad, w_bf16 by dgrad
-            x_bf = DeviceArray.empty((L.cpt_cast_bf16_bytes(n, in_f),), np.uint8)
+            shadow = getattr(x.data, "cl", None) if x.ndim == 2 else None
             w_bf = DeviceArray.empty((L.cpt_cast_bf16_bytes(out_f, in_f),), np.uint8)
-            _lib.check(L.cpt_cast_bf16(f32ptr(x), x_bf.ptr, n, in_f, st))
+            if shadow is not None and shadow[0] == mode:
+                x_bf = shadow[1]  # written by the producing ReLU pass
+            else:
+                x_bf = DeviceArray.empty((L.cpt_cast_bf16_bytes(n, in_f),), np.uint8)
+                _lib.check(L.cpt_cast_bf16(f32ptr(x), x_bf.ptr, n, in_f, st))
             _lib.check(L.cpt_cast_bf16(f32ptr(w), w_bf.ptr, out_f, in_f, st))
             _lib.check(L.cpt_linear_fwd_bf16(x_bf.ptr, w_bf.ptr, f32ptr(b), y.ptr, n, in_f, out_f, st))
         else:
@@ -58,8 +62,12 @@ class LinearFn(Function):
         if has_bias:
             db = db_out.reshape((out_f,)) if db_out is not None else DeviceArray.empty((out_f,), np.float32)
         if mode == _lib.MODE_BF16:
-            dy_bf = DeviceArray.empty((L.cpt_cast_bf16_bytes(n, out_f),), np.uint8)
-            _lib.check(L.cpt_cast_bf16(f32ptr(dy), dy_bf.ptr, n, out_f, st))
+            shadow = getattr(dy.data, "cl", None) if dy.ndim == 2 else None
+            if shadow is not None and shadow[0] == mode:
+                dy_bf = shadow[1]  # written by the ReLU backward pass that produced dy
+            else:
+                dy_bf = DeviceArray.empty((L.cpt_cast_bf16_bytes(n, out_f),), np.uint8)
+                _lib.check(L.cpt_cast_bf16(f32ptr(dy), dy_bf.ptr, n, out_f, st))
             _lib.check(L.cpt_linear_dgrad_bf16(dy_bf.ptr, w_bf.ptr, dx.ptr, n, in_f, out_f, st))
             ws, wsb = workspace(L.cpt_linear_workspace_size(_lib.OP_WGRAD, n, in_f, out_f, mode))
             _lib.check(L.cpt_linear_wgrad_bf16(x_bf.ptr, dy_bf.ptr, dw.ptr, n, in_f, out_f, ws, wsb, st))

@@ -41,7 +41,7 @@ class Sequential(Module):
         """Tells every BatchNorm2D of this container whether its neighbours are convolutions, so that it writes their
         channels-last bf16 operand in its own apply pass (forward: the consumer of its — possibly ReLU-fused — output;
         backward: the convolution that produced its input).  Recomputed when the layer list or the fusion switch changes."""
-        from .layers import BatchNorm2D, Conv2D, ReLU
+        from .layers import BatchNorm2D, Conv2D, Linear, ReLU
         key = (tuple(id(m) for m in self.layers), _fusion)
         if getattr(self, "_hint_key", None) == key:
             return
@@ -58,6 +58,9 @@ class Sequential(Module):
 
         n = len(self.layers)
         for i, m in enumerate(self.layers):
+            if type(m) is ReLU:  # ReLU between Linear layers writes their bf16 operands (x of the next, dy of the previous)
+                m._emit_lp_fwd = _fusion and i + 1 < n and isinstance(self.layers[i + 1], Linear)
+                m._emit_lp_bwd = _fusion and i > 0 and isinstance(self.layers[i - 1], Linear)
             if not isinstance(m, BatchNorm2D):
                 continue
             j = i + 1

@@ -170,13 +170,18 @@ class BatchNorm2D(_BatchNorm):
 
 
 class ReLU(Module):
+    # hints set by the enclosing Sequential: a Linear layer consumes the output (forward) / produced the input (backward),
+    # so the pass also writes the bf16 operand that layer would otherwise cast
+    _emit_lp_fwd = False
+    _emit_lp_bwd = False
+
     @Module.register_forward
     def forward(self, x: Tensor) -> Tensor:
-        return ReLUFn.forward(self.fcache, x)
+        return ReLUFn.forward(self.fcache, x, self._emit_lp_fwd and x.ndim == 2)
 
     @Module.register_backward
     def backward(self, dy: Tensor) -> Tensor:
-        return ReLUFn.backward(self.fcache, dy)
+        return ReLUFn.backward(self.fcache, dy, self._emit_lp_bwd and dy.ndim == 2)
 
 
 class Flatten(Module):

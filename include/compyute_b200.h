@@ -214,6 +214,11 @@ int cpt_bn_act_bwd_cl(const float* x, const float* dy, const float* w, const flo
 int cpt_relu_fwd(const float* x, float* y, uint8_t* mask, int64_t n, void* stream);
 /* ReLUFn.backward :32-34   dx = dy * mask */
 int cpt_relu_bwd(const float* dy, const uint8_t* mask, float* dx, int64_t n, void* stream);
+/* Same passes, additionally writing the result as bf16 in the same linear order (y_bf16 / dx_bf16, 8-byte aligned, may be NULL):
+ * the pre-cast operand of a neighbouring Linear layer in bf16 mode (cpt_linear_*_bf16), when the feature count is a multiple
+ * of 8 so that the bf16 row pitch equals the row length. */
+int cpt_relu_fwd_lp(const float* x, float* y, uint8_t* mask, void* y_bf16, int64_t n, void* stream);
+int cpt_relu_bwd_lp(const float* dy, const uint8_t* mask, float* dx, void* dx_bf16, int64_t n, void* stream);
 /* a += b  (ResidualConnection containers.py:153-162; grad accumulation module.py:399-400) */
 int cpt_add_inplace(float* a, const float* b, int64_t n, void* stream);
 /* y = alpha * x (+ y if accumulate) */

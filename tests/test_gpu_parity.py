@@ -487,6 +487,38 @@ def test_producer_side_staging_is_bit_exact(cp, shape):
         assert np.array_equal(u, v, equal_nan=True), (k, u.shape, float(np.abs(u - v).max()))
 
 
+def test_relu_writes_the_bf16_operand_of_linear_layers(cp):
+    """bf16 mode: a ReLU between Linear layers also writes the bf16 operand they would otherwise cast (cpt_relu_*_lp);
+    model outputs and gradients must equal the layer-by-layer evaluation bit for bit (widths that are / are not multiples of 8,
+    row counts with a tail below one 1024-element chunk)."""
+    from compyute_b200 import nn
+    rng = np.random.RandomState(21)
+    for N, widths in ((37, (40, 64, 32, 8)), (256, (128, 256, 256, 10)), (9, (12, 20, 24, 6))):
+        x = rng.normal(0, 1, (N, widths[0])).astype(np.float32)
+        dy = rng.normal(0, 1, (N, widths[-1])).astype(np.float32)
+
+        def run(fused):
+            nn.set_fusion_enabled(fused)
+            try:
+                np.random.seed(2)
+                with cp.use_device(cp.cuda):
+                    layers = []
+                    for a, b in zip(widths[:-1], widths[1:]):
+                        layers += [nn.Linear(a, b), nn.ReLU()]
+                    model = nn.Sequential(*layers[:-1])
+                model.training()
+                with cp.compute_mode("bf16"):
+                    y = model(cp.tensor(x, device=cp.cuda))
+                    dx = model.backward(cp.tensor(dy, device=cp.cuda))
+                tc_ok()
+                return [y.to_numpy(), dx.to_numpy()] + [p.grad.to_numpy() for p in model.get_parameters()]
+            finally:
+                nn.set_fusion_enabled(True)
+
+        for u, v in zip(run(True), run(False)):
+            assert np.array_equal(u, v), (N, widths, float(np.abs(u - v).max()))
+
+
 def test_dataloader_and_checkpoint_on_device(cp, tmp_path):
     """Dataloader uploads batches through pinned double-buffered staging (values identical to host slicing), and a
     model/optimizer checkpoint of device state round-trips through cp.save / cp.load (README.md:197-213)."""
