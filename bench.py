@@ -359,8 +359,9 @@ def run_ours(args) -> None:
                 "peak_source": pk["source"] + " (burst cuBLAS bf16)", "ms_per_launch": round(kms, 4), "launches_timed": len(probe["ev"]),
                 "flops_per_launch": fl,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture
-                # (profiles/r01_conv512_ncu_summary.md); algorithmic bytes = 2.47e9 (x_cl bf16 + y fp32 + filters)
-                "traffic": 3.254e9, "algorithmic_bytes": 2.47e9}
+                # (profiles/r01_conv512_ncu_summary.md, launch 1: 1.776 GB read + 1.605 GB written); algorithmic bytes = 2.47e9
+                # (x_cl bf16 0.82 GB + y fp32 1.64 GB + filters)
+                "traffic": 3.382e9, "algorithmic_bytes": 2.47e9}
     cpu_tf, cpu_desc, cpu_times = cpu_conv_sample(12.0, 1)
     value = world * step_flops / ms / 1e9
     line = {"metric": "conv2d_fwd_bwd_tflops", "value": round(value, 2), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -483,6 +484,8 @@ def run_model(args) -> None:
         return ms / steps, L.cpt_launch_count() - n0
 
     graphed = None
+    if args.workload == "mnist" and world == 1 and not args.no_graph:
+        args.graph = True  # config 1 is launch-bound (645 launches of a few microseconds per step): replayed as one CUDA graph
     if args.graph and world == 1:
         # CUDA-graph replay of the whole step (fwd + loss + bwd + fused Adam): static input tensors, one launch per step
         xs_t, ts_t = wrapf(dx), wrapi(dt)
@@ -594,7 +597,8 @@ def main() -> None:
     ap.add_argument("--no-extra-modes", action="store_true")
     ap.add_argument("--workload", default="conv2d_sweep", choices=["conv2d_sweep", "mnist", "vgg", "resnet18", "mlp"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of a model workload")
-    ap.add_argument("--graph", action="store_true", help="model workloads: replay the train step as one CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="model workloads: replay the train step as one CUDA graph (default for mnist)")
+    ap.add_argument("--no-graph", action="store_true", help="mnist: eager launches instead of the default CUDA-graph replay")
     ap.add_argument("--overlap", action="store_true",
                     help="data-parallel model runs: bucketed all-reduces launched during backward (Optimizer.overlap_grad_sync) "
                          "instead of one all-reduce of the whole gradient arena at step(); measured gain at 2 GPUs is ~1 %% because "

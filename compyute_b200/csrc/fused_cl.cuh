@@ -26,6 +26,7 @@ struct BnTileParams {
   const float* coef;    // OP 1: [C][3] = (g, s1, s2) from bn_bwd_finalize_kernel
   float count;
   int C, HW, Cp;
+  long long Q;          // B * HW: pixel tiles run over the flattened (image, pixel) index
   float* partial;       // SUMS: [blocks][groups * 64] per-block channel sums of `out`
 };
 
@@ -34,9 +35,9 @@ __global__ void __launch_bounds__(256) bn_tile_cl_kernel(const BnTileParams p) {
   __shared__ uint32_t tile[32][CL_PX + 1];
   __shared__ float prm[7][CL_CH];  // mean, rstd, w, b, g, s1, s2 of this block's 64 channels
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c0 = blockIdx.y * CL_CH, b = blockIdx.z;
+  const int c0 = blockIdx.y * CL_CH;
   const int C = p.C, HW = p.HW, Cp = p.Cp;
-  const int n_tiles = (HW + CL_PX - 1) / CL_PX;
+  const int64_t Q = p.Q, n_tiles = (Q + CL_PX - 1) / CL_PX;
   if (threadIdx.x < CL_CH) {
     const int c = c0 + threadIdx.x;
     const bool ok = c < C;
@@ -51,16 +52,22 @@ __global__ void __launch_bounds__(256) bn_tile_cl_kernel(const BnTileParams p) {
     }
   }
   __syncthreads();
-  const int64_t img = (int64_t)b * C * HW;
-  const float* xs = p.x + img;
-  const float* gs = OP == 1 ? p.dy + img : nullptr;
-  float* os = p.out + img;
+  const float* xs = p.x;
+  const float* gs = OP == 1 ? p.dy : nullptr;
+  float* os = p.out;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int p0 = t * CL_PX;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t p0 = t * CL_PX;
+    int64_t soff[4];  // offset of (image, channel 0, pixel) for this lane's four pixels; -1 = past the end
+#pragma unroll
+    for (int pi = 0; pi < 4; ++pi) {
+      const int64_t q = p0 + lane + 32 * pi;
+      const uint32_t b = (uint32_t)q / (uint32_t)HW;  // Q < 2^31 (checked on the host): 32-bit division
+      soff[pi] = q < Q ? (int64_t)b * C * HW + ((uint32_t)q - b * (uint32_t)HW) : -1;
+    }
     float v0[4][4], v1[4][4];
     float g0[4][4], g1[4][4];
 #pragma unroll
@@ -68,13 +75,12 @@ __global__ void __launch_bounds__(256) bn_tile_cl_kernel(const BnTileParams p) {
       const int c = c0 + 2 * (warp + 8 * ci);
 #pragma unroll
       for (int pi = 0; pi < 4; ++pi) {
-        const int px = p0 + lane + 32 * pi;
-        const bool okp = px < HW;
-        v0[ci][pi] = (okp && c < C) ? xs[(int64_t)c * HW + px] : 0.f;
-        v1[ci][pi] = (okp && c + 1 < C) ? xs[(int64_t)(c + 1) * HW + px] : 0.f;
+        const bool okp = soff[pi] >= 0;
+        v0[ci][pi] = (okp && c < C) ? xs[soff[pi] + (int64_t)c * HW] : 0.f;
+        v1[ci][pi] = (okp && c + 1 < C) ? xs[soff[pi] + (int64_t)(c + 1) * HW] : 0.f;
         if (OP == 1) {
-          g0[ci][pi] = (okp && c < C) ? gs[(int64_t)c * HW + px] : 0.f;
-          g1[ci][pi] = (okp && c + 1 < C) ? gs[(int64_t)(c + 1) * HW + px] : 0.f;
+          g0[ci][pi] = (okp && c < C) ? gs[soff[pi] + (int64_t)c * HW] : 0.f;
+          g1[ci][pi] = (okp && c + 1 < C) ? gs[soff[pi] + (int64_t)(c + 1) * HW] : 0.f;
         }
       }
     }
@@ -99,8 +105,7 @@ __global__ void __launch_bounds__(256) bn_tile_cl_kernel(const BnTileParams p) {
             if (RELU) gd = gd * (fmaf(ww, (xv - mu) * rs, bb) > 0.f ? 1.f : 0.f);
             r = gc * (p.count * gd - s1 - (xv - mu) * rs * s2);
           }
-          const int px = p0 + lane + 32 * pi;
-          if (px < HW && c + h < C) os[(int64_t)(c + h) * HW + px] = r;
+          if (soff[pi] >= 0 && c + h < C) os[soff[pi] + (int64_t)(c + h) * HW] = r;
           else r = 0.f;  // padding channels / pixels of the bf16 tile are zero
           v[pi] = r;
         }
@@ -117,15 +122,16 @@ __global__ void __launch_bounds__(256) bn_tile_cl_kernel(const BnTileParams p) {
     if (cpair < Cp) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const int pp = warp + 8 * i, px = p0 + pp;
-        if (px < HW) p.out_cl[(((int64_t)b * HW + px) * Cp + cpair) >> 1] = tile[lane][pp];
+        const int pp = warp + 8 * i;
+        const int64_t q = p0 + pp;
+        if (q < Q) p.out_cl[(q * Cp + cpair) >> 1] = tile[lane][pp];
       }
     }
     __syncthreads();  // tile is reused by the next pixel tile
   }
 
   if (SUMS) {
-    const int64_t blk = (int64_t)blockIdx.z * gridDim.x + blockIdx.x;
+    const int64_t blk = blockIdx.x;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float t = warp_sum(acc[i]);
@@ -141,11 +147,11 @@ int bn_apply_cl(const float* x, const float* w, const float* b, const float* mea
   BnTileParams p{};
   p.x = x; p.out = y; p.out_cl = reinterpret_cast<uint32_t*>(y_cl);
   p.mean = mean; p.rstd = rstd; p.w = w; p.b = b;
-  p.C = C; p.HW = HW; p.Cp = round_up(C, 8);
+  p.C = C; p.HW = HW; p.Cp = round_up(C, 8); p.Q = (long long)N * HW;
   int gx, groups;
   cl_grid(N, C, HW, 1, gx, groups);
-  dim3 grid(gx, groups, N);
-  CPT_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CPT_ERR_UNSUPPORTED, "bn_apply_cl: grid too large");
+  dim3 grid(gx, groups, 1);
+  CPT_REQUIRE(grid.y <= 65535 && p.Q < (1LL << 31), CPT_ERR_UNSUPPORTED, "bn_apply_cl: tensor too large");
   if (act) bn_tile_cl_kernel<0, true, false><<<grid, 256, 0, st>>>(p);
   else bn_tile_cl_kernel<0, false, false><<<grid, 256, 0, st>>>(p);
   CPT_LAUNCH_CHECK("bn_apply_cl");
@@ -160,18 +166,18 @@ int bn_bwd_apply_cl(const float* x, const float* dy, const float* w, const float
   BnTileParams p{};
   p.x = x; p.dy = dy; p.out = dx; p.out_cl = reinterpret_cast<uint32_t*>(dx_cl);
   p.mean = mean; p.rstd = rstd; p.w = w; p.b = b; p.coef = coef; p.count = count;
-  p.C = C; p.HW = HW; p.Cp = round_up(C, 8);
+  p.C = C; p.HW = HW; p.Cp = round_up(C, 8); p.Q = (long long)N * HW;
   int gx, groups;
   cl_grid(N, C, HW, 1, gx, groups);
-  dim3 grid(gx, groups, N);
-  CPT_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CPT_ERR_UNSUPPORTED, "bn_bwd_apply_cl: grid too large");
+  dim3 grid(gx, groups, 1);
+  CPT_REQUIRE(grid.y <= 65535 && p.Q < (1LL << 31), CPT_ERR_UNSUPPORTED, "bn_bwd_apply_cl: tensor too large");
   if (dx_chan_sum) {
     CPT_REQUIRE(ws && ws_bytes >= bn_bwd_apply_cl_ws(N, C, HW), CPT_ERR_WORKSPACE, "bn_bwd_apply_cl: workspace too small");
     p.partial = reinterpret_cast<float*>(ws);
     if (act) bn_tile_cl_kernel<1, true, true><<<grid, 256, 0, st>>>(p);
     else bn_tile_cl_kernel<1, false, true><<<grid, 256, 0, st>>>(p);
     CPT_LAUNCH_CHECK("bn_bwd_apply_cl");
-    chan_partial_reduce_kernel<<<(C + 31) / 32, 1024, 0, st>>>(p.partial, dx_chan_sum, C, (int64_t)N * gx, groups * CL_CH);
+    chan_partial_reduce_kernel<<<(C + 31) / 32, 1024, 0, st>>>(p.partial, dx_chan_sum, C, (int64_t)gx, groups * CL_CH);
     CPT_LAUNCH_CHECK("chan_partial_reduce");
   } else {
     if (act) bn_tile_cl_kernel<1, true, false><<<grid, 256, 0, st>>>(p);

@@ -115,19 +115,29 @@ constexpr int CL_PX = 128, CL_CH = 64;
 
 template <bool BF16>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW,
-                                                           int Cp, float* __restrict__ chan_sum, float* __restrict__ partial) {
+                                                           int Cp, float* __restrict__ chan_sum, float* __restrict__ partial,
+                                                           int64_t Q) {
+  // pixel tiles run over the flattened (image, pixel) index q in [0, Q = B*HW): small feature maps (HW < 128) fill the
+  // 128-pixel tile with pixels of several images instead of leaving lanes idle
   __shared__ uint32_t tile[BF16 ? 32 : 64][CL_PX + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c0 = blockIdx.y * CL_CH, b = blockIdx.z;
-  const int n_tiles = (HW + CL_PX - 1) / CL_PX;
-  const float* s = src + (int64_t)b * C * HW;
+  const int c0 = blockIdx.y * CL_CH;
+  const int64_t n_tiles = (Q + CL_PX - 1) / CL_PX;
   uint32_t* d = reinterpret_cast<uint32_t*>(dst);
   float acc[8];  // per-thread channel partial sums, reduced once per block (not once per tile)
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int p0 = t * CL_PX;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t p0 = t * CL_PX;
+    int64_t soff[4];  // source offset of (image, channel 0, pixel) for this lane's four pixels; -1 = past the end
+#pragma unroll
+    for (int pi = 0; pi < 4; ++pi) {
+      const int64_t q = p0 + lane + 32 * pi;
+      const uint32_t b = (uint32_t)q / (uint32_t)HW;  // Q < 2^31 (checked on the host): 32-bit division
+      soff[pi] = q < Q ? (int64_t)b * C * HW + ((uint32_t)q - b * (uint32_t)HW) : -1;
+    }
+    const float* s = src;
     if (BF16) {
       float v0[4][4], v1[4][4];
 #pragma unroll
@@ -135,10 +145,9 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
         const int c = c0 + 2 * (warp + 8 * ci);
 #pragma unroll
         for (int pi = 0; pi < 4; ++pi) {
-          const int px = p0 + lane + 32 * pi;
-          const bool okp = px < HW;
-          v0[ci][pi] = (okp && c < C) ? s[(int64_t)c * HW + px] : 0.f;
-          v1[ci][pi] = (okp && c + 1 < C) ? s[(int64_t)(c + 1) * HW + px] : 0.f;
+          const bool okp = soff[pi] >= 0;
+          v0[ci][pi] = (okp && c < C) ? s[soff[pi] + (int64_t)c * HW] : 0.f;
+          v1[ci][pi] = (okp && c + 1 < C) ? s[soff[pi] + (int64_t)(c + 1) * HW] : 0.f;
         }
       }
 #pragma unroll
@@ -156,8 +165,9 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
       if (c < Cp) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int pp = warp + 8 * i, px = p0 + pp;
-          if (px < HW) d[(((int64_t)b * HW + px) * Cp + c) >> 1] = tile[lane][pp];
+          const int pp = warp + 8 * i;
+          const int64_t q = p0 + pp;
+          if (q < Q) d[(q * Cp + c) >> 1] = tile[lane][pp];
         }
       }
     } else {
@@ -166,10 +176,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
       for (int ci = 0; ci < 8; ++ci) {
         const int c = c0 + warp + 8 * ci;
 #pragma unroll
-        for (int pi = 0; pi < 4; ++pi) {
-          const int px = p0 + lane + 32 * pi;
-          v[ci][pi] = (px < HW && c < C) ? s[(int64_t)c * HW + px] : 0.f;
-        }
+        for (int pi = 0; pi < 4; ++pi) v[ci][pi] = (soff[pi] >= 0 && c < C) ? s[soff[pi] + (int64_t)c * HW] : 0.f;
       }
 #pragma unroll
       for (int ci = 0; ci < 8; ++ci) {
@@ -184,8 +191,9 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
         if (c < Cp) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int pp = warp + 8 * i, px = p0 + pp;
-            if (px < HW) d[((int64_t)b * HW + px) * Cp + c] = tile[lane + 32 * h][pp];
+            const int pp = warp + 8 * i;
+            const int64_t q = p0 + pp;
+            if (q < Q) d[q * Cp + c] = tile[lane + 32 * h][pp];
           }
         }
       }
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 
   if (chan_sum || partial) {  // warp-shuffle tree, then one value per (block, channel)
-    const int64_t blk = (int64_t)blockIdx.z * gridDim.x + blockIdx.x;  // row of the partial matrix [B*gx][groups*64]
+    const int64_t blk = blockIdx.x;  // row of the partial matrix [gx][groups*64]
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float t = warp_sum(acc[i]);
@@ -273,6 +281,36 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * n + i];
     dw[((int64_t)co * Ci + ci) * T + tap] = s;
   }
+}
+// Same reduction, one block per output channel: partial[k][co] is a contiguous [tap][ci] matrix and dw[co] a contiguous
+// [ci][tap] one, so the split sum is read coalesced, transposed through shared memory (odd T: conflict-free) and written
+// coalesced — no per-element 64-bit divisions, no stride-T scatter.  Needs Ci*T floats of dynamic shared memory.
+__global__ void __launch_bounds__(256) wgrad_reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Co,
+                                                                int Ci, int T, int splits) {
+  extern __shared__ float row[];  // [ci][tap]
+  const int co = blockIdx.x, n_row = Ci * T;
+  const int64_t n = (int64_t)Co * n_row;
+  const float* src = partial + (int64_t)co * n_row;
+  for (int idx = threadIdx.x; idx < n_row; idx += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += src[(int64_t)k * n + idx];
+    const int tap = idx / Ci, ci = idx - tap * Ci;
+    row[ci * T + tap] = s;
+  }
+  __syncthreads();
+  float* dst = dw + (int64_t)co * n_row;
+  for (int idx = threadIdx.x; idx < n_row; idx += blockDim.x) dst[idx] = row[idx];
+}
+static int launch_wgrad_reduce(const float* partial, float* dw, int Co, int Ci, int T, int splits, cudaStream_t st) {
+  const size_t smem = (size_t)Ci * T * sizeof(float);
+  if (smem <= 48 * 1024) {
+    wgrad_reduce_rows_kernel<<<Co, 256, smem, st>>>(partial, dw, Co, Ci, T, splits);
+  } else {
+    const int64_t n = (int64_t)Co * Ci * T;
+    wgrad_reduce_kernel<<<ew_grid(n, 256), 256, 0, st>>>(partial, dw, Co, Ci, T, splits);
+  }
+  CPT_LAUNCH_CHECK("wgrad_reduce");
+  return CPT_OK;
 }
 // [R][C] fp32 -> [R][Cp] bf16 (zero padded columns)
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t R, int C, int Cp) {
@@ -402,20 +440,21 @@ static int wgrad_splits(const G& g, int mode) {
 }
 
 static void cl_grid(int B, int C, int H, int W, int& gx, int& groups) {
-  const int Cp = round_up(C, 8), HW = H * W;
-  // each block walks several pixel tiles of its (image, 64-channel group) so the per-channel partial sums are reduced
-  // once per block; keep >= ~16 blocks per SM overall (several waves)
-  const int n_tiles = (HW + CL_PX - 1) / CL_PX;
+  const int Cp = round_up(C, 8);
+  // each block walks several 128-pixel tiles of its 64-channel group (tiles run over the flattened (image, pixel) index) so
+  // the per-channel partial sums are reduced once per block; ~16 blocks per SM overall (several waves)
+  const int64_t n_tiles = ((int64_t)B * H * W + CL_PX - 1) / CL_PX;
   groups = (Cp + CL_CH - 1) / CL_CH;
-  gx = (int)((16LL * sm_count() + (int64_t)groups * B - 1) / ((int64_t)groups * B));
-  if (gx < 1) gx = 1;
-  if (gx > n_tiles) gx = n_tiles;
+  int64_t want = (16LL * sm_count() + groups - 1) / groups;
+  if (want < 1) want = 1;
+  if (want > n_tiles) want = n_tiles;
+  gx = (int)want;
 }
 
 size_t to_channels_last_ws(int B, int C, int H, int W) {
   int gx, groups;
   cl_grid(B, C, H, W, gx, groups);
-  return align_up((size_t)B * gx * groups * CL_CH * sizeof(float), 256);
+  return align_up((size_t)gx * groups * CL_CH * sizeof(float), 256);
 }
 
 // chan_sum != NULL: per-channel sums of src.  With a workspace they are reduced deterministically (per-block partials +
@@ -425,15 +464,16 @@ int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, in
   const int Cp = round_up(C, 8), HW = H * W;
   int gx, groups;
   cl_grid(B, C, H, W, gx, groups);
-  dim3 grid(gx, groups, B);
-  CPT_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CPT_ERR_UNSUPPORTED, "to_channels_last: grid too large");
+  dim3 grid(gx, groups, 1);
+  CPT_REQUIRE(grid.y <= 65535 && (int64_t)B * HW < (1LL << 31), CPT_ERR_UNSUPPORTED, "to_channels_last: tensor too large");
   float* partial = nullptr;
   if (chan_sum && ws && ws_bytes >= to_channels_last_ws(B, C, H, W)) partial = reinterpret_cast<float*>(ws);
-  if (mode == CPT_MODE_BF16) nchw_to_nhwc_kernel<true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial);
-  else nchw_to_nhwc_kernel<false><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial);
+  const int64_t Q = (int64_t)B * HW;
+  if (mode == CPT_MODE_BF16) nchw_to_nhwc_kernel<true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial, Q);
+  else nchw_to_nhwc_kernel<false><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial, Q);
   CPT_LAUNCH_CHECK("nchw_to_nhwc");
   if (partial) {
-    chan_partial_reduce_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partial, chan_sum, C, (int64_t)B * gx, groups * CL_CH);
+    chan_partial_reduce_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partial, chan_sum, C, (int64_t)gx, groups * CL_CH);
     CPT_LAUNCH_CHECK("chan_partial_reduce");
   }
   return CPT_OK;
@@ -654,10 +694,7 @@ int conv_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl,
   p.taps = g.T;
   p.out_s = 1;
   if (int e = launch_bn<true, true, OP_WGRAD>(p, mode, BN, want_2cta(BN, (g.Ci + 127) / 128), st)) return e;
-  const int64_t n = (int64_t)g.Co * g.Ci * g.T;
-  wgrad_reduce_kernel<<<ew_grid(n, 256), 256, 0, st>>>(reinterpret_cast<float*>(ws), dw, g.Co, g.Ci, g.T, splits);
-  CPT_LAUNCH_CHECK("wgrad_reduce");
-  return CPT_OK;
+  return launch_wgrad_reduce(reinterpret_cast<float*>(ws), dw, g.Co, g.Ci, g.T, splits, st);
 }
 
 size_t conv_workspace_size(int op, const cpt_conv2d_desc* d, int mode) {
