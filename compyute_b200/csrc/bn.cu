@@ -139,6 +139,45 @@ __global__ void bn_fwd_finalize_kernel(const float* __restrict__ x, const float2
   rvar_out[c] = rvar[c] * (1.0f - m) + var_unbiased * m;
 }
 
+// Batch statistics from the column sums a convolution's epilogue left behind (cpt_conv2d_fprop_*_stats): block per 32
+// channels, lanes = channels (coalesced float2 loads), the 32 warps split the slots and their partials are combined in fixed
+// order -> deterministic; sums in double; var = E[a²] - E[a]² on the bias-free accumulators a (the convolution's bias only
+// shifts the mean).
+__global__ void __launch_bounds__(1024) bn_fwd_finalize_presum_kernel(const float* __restrict__ stats, int slots,
+                                                                      const float* __restrict__ conv_bias,
+                                                                      const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                                                      float* __restrict__ rmean_out, float* __restrict__ rvar_out,
+                                                                      float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                                                                      int C, float count, float m, float eps) {
+  __shared__ double sh1[32][33], sh2[32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C) {
+    for (int s = warp; s < slots; s += 32) {
+      const float2 v = reinterpret_cast<const float2*>(stats)[(int64_t)s * C + c];
+      s1 += (double)v.x;
+      s2 += (double)v.y;
+    }
+  }
+  sh1[warp][lane] = s1;
+  sh2[warp][lane] = s2;
+  __syncthreads();
+  if (warp != 0 || c >= C) return;
+  s1 = s2 = 0.0;
+#pragma unroll
+  for (int w = 0; w < 32; ++w) { s1 += sh1[w][lane]; s2 += sh2[w][lane]; }
+  const double n = (double)count, mu = s1 / n;
+  double var = s2 / n - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)mu + (conv_bias ? conv_bias[c] : 0.f);
+  save_mean[c] = mean;
+  save_rstd[c] = 1.0f / sqrtf((float)var + eps);
+  const float var_unbiased = (float)(var * n / (n - 1.0));
+  rmean_out[c] = rmean[c] * (1.0f - m) + mean * m;
+  rvar_out[c] = rvar[c] * (1.0f - m) + var_unbiased * m;
+}
+
 __global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar,
                                      float* __restrict__ save_mean, float* __restrict__ save_rstd, int C, float eps) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,6 +367,24 @@ int cpt_bn_act_fwd_train_cl(const float* x, const float* w, const float* b, cons
                                                           save_rstd, C, HW, count, m, eps);
   CPT_LAUNCH_CHECK("bn_fwd_finalize");
   return tc::bn_apply_cl(x, w, b, save_mean, save_rstd, y, y_cl, N, C, HW, act, st);
+}
+
+int cpt_bn_act_fwd_train_presum(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,
+                                void* y_cl, float* rmean_out, float* rvar_out, float* save_mean, float* save_rstd, int N, int C,
+                                int HW, float m, float eps, int act, const float* stats, int stat_slots, const float* conv_bias,
+                                void* stream) {
+  if (int e = bn_check("bn_fwd_train_presum", N, C, HW)) return e;
+  if (int e = check_act("bn_fwd_train_presum", act)) return e;
+  CPT_REQUIRE(stats && stat_slots > 0, CPT_ERR_INVALID, "bn_fwd_train_presum: no statistics");
+  cudaStream_t st = as_stream(stream);
+  const float count = (float)((int64_t)N * HW);
+  bn_fwd_finalize_presum_kernel<<<(C + 31) / 32, 1024, 0, st>>>(stats, stat_slots, conv_bias, rmean, rvar, rmean_out, rvar_out,
+                                                                save_mean, save_rstd, C, count, m, eps);
+  CPT_LAUNCH_CHECK("bn_fwd_finalize_presum");
+  if (y_cl) return tc::bn_apply_cl(x, w, b, save_mean, save_rstd, y, y_cl, N, C, HW, act, st);
+  launch_apply(x, w, b, save_mean, save_rstd, y, N, C, HW, act, st);
+  CPT_LAUNCH_CHECK("bn_apply");
+  return CPT_OK;
 }
 
 int cpt_bn_act_fwd_eval_cl(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,

@@ -31,7 +31,7 @@ struct BnTileParams {
 };
 
 template <int OP, bool RELU, bool SUMS>
-__global__ void __launch_bounds__(256) bn_tile_cl_kernel(const BnTileParams p) {
+__global__ void __launch_bounds__(256, 2) bn_tile_cl_kernel(const BnTileParams p) {
   __shared__ uint32_t tile[32][CL_PX + 1];
   __shared__ float prm[7][CL_CH];  // mean, rstd, w, b, g, s1, s2 of this block's 64 channels
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -61,12 +61,14 @@ __global__ void __launch_bounds__(256) bn_tile_cl_kernel(const BnTileParams p) {
 
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int64_t p0 = t * CL_PX;
-    int64_t soff[4];  // offset of (image, channel 0, pixel) for this lane's four pixels; -1 = past the end
+    // element offset of (image, channel 0, pixel) for this lane's four pixels (32-bit: the host checks B*C*HW < 2^32 - 2^20)
+    uint32_t soff[4];
+    constexpr uint32_t PAST_END = 0xFFFFFFFFu;
 #pragma unroll
     for (int pi = 0; pi < 4; ++pi) {
       const int64_t q = p0 + lane + 32 * pi;
-      const uint32_t b = (uint32_t)q / (uint32_t)HW;  // Q < 2^31 (checked on the host): 32-bit division
-      soff[pi] = q < Q ? (int64_t)b * C * HW + ((uint32_t)q - b * (uint32_t)HW) : -1;
+      const uint32_t b = (uint32_t)q / (uint32_t)HW;
+      soff[pi] = q < Q ? b * (uint32_t)(C * HW) + ((uint32_t)q - b * (uint32_t)HW) : PAST_END;
     }
     float v0[4][4], v1[4][4];
     float g0[4][4], g1[4][4];
@@ -75,12 +77,12 @@ __global__ void __launch_bounds__(256) bn_tile_cl_kernel(const BnTileParams p) {
       const int c = c0 + 2 * (warp + 8 * ci);
 #pragma unroll
       for (int pi = 0; pi < 4; ++pi) {
-        const bool okp = soff[pi] >= 0;
-        v0[ci][pi] = (okp && c < C) ? xs[soff[pi] + (int64_t)c * HW] : 0.f;
-        v1[ci][pi] = (okp && c + 1 < C) ? xs[soff[pi] + (int64_t)(c + 1) * HW] : 0.f;
+        const bool okp = soff[pi] != PAST_END;
+        v0[ci][pi] = (okp && c < C) ? xs[soff[pi] + (uint32_t)(c * HW)] : 0.f;
+        v1[ci][pi] = (okp && c + 1 < C) ? xs[soff[pi] + (uint32_t)((c + 1) * HW)] : 0.f;
         if (OP == 1) {
-          g0[ci][pi] = (okp && c < C) ? gs[soff[pi] + (int64_t)c * HW] : 0.f;
-          g1[ci][pi] = (okp && c + 1 < C) ? gs[soff[pi] + (int64_t)(c + 1) * HW] : 0.f;
+          g0[ci][pi] = (okp && c < C) ? gs[soff[pi] + (uint32_t)(c * HW)] : 0.f;
+          g1[ci][pi] = (okp && c + 1 < C) ? gs[soff[pi] + (uint32_t)((c + 1) * HW)] : 0.f;
         }
       }
     }
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(256) bn_tile_cl_kernel(const BnTileParams p) {
             if (RELU) gd = gd * (fmaf(ww, (xv - mu) * rs, bb) > 0.f ? 1.f : 0.f);
             r = gc * (p.count * gd - s1 - (xv - mu) * rs * s2);
           }
-          if (soff[pi] >= 0 && c + h < C) os[soff[pi] + (int64_t)(c + h) * HW] = r;
+          if (soff[pi] != PAST_END && c + h < C) os[soff[pi] + (uint32_t)((c + h) * HW)] = r;
           else r = 0.f;  // padding channels / pixels of the bf16 tile are zero
           v[pi] = r;
         }
@@ -151,7 +153,8 @@ int bn_apply_cl(const float* x, const float* w, const float* b, const float* mea
   int gx, groups;
   cl_grid(N, C, HW, 1, gx, groups);
   dim3 grid(gx, groups, 1);
-  CPT_REQUIRE(grid.y <= 65535 && p.Q < (1LL << 31), CPT_ERR_UNSUPPORTED, "bn_apply_cl: tensor too large");
+  CPT_REQUIRE(grid.y <= 65535 && p.Q < (1LL << 31) && (int64_t)N * C * HW < (1LL << 32) - (1 << 20), CPT_ERR_UNSUPPORTED,
+              "bn_apply_cl: tensor too large");
   if (act) bn_tile_cl_kernel<0, true, false><<<grid, 256, 0, st>>>(p);
   else bn_tile_cl_kernel<0, false, false><<<grid, 256, 0, st>>>(p);
   CPT_LAUNCH_CHECK("bn_apply_cl");
@@ -170,7 +173,8 @@ int bn_bwd_apply_cl(const float* x, const float* dy, const float* w, const float
   int gx, groups;
   cl_grid(N, C, HW, 1, gx, groups);
   dim3 grid(gx, groups, 1);
-  CPT_REQUIRE(grid.y <= 65535 && p.Q < (1LL << 31), CPT_ERR_UNSUPPORTED, "bn_bwd_apply_cl: tensor too large");
+  CPT_REQUIRE(grid.y <= 65535 && p.Q < (1LL << 31) && (int64_t)N * C * HW < (1LL << 32) - (1 << 20), CPT_ERR_UNSUPPORTED,
+              "bn_bwd_apply_cl: tensor too large");
   if (dx_chan_sum) {
     CPT_REQUIRE(ws && ws_bytes >= bn_bwd_apply_cl_ws(N, C, HW), CPT_ERR_WORKSPACE, "bn_bwd_apply_cl: workspace too small");
     p.partial = reinterpret_cast<float*>(ws);

@@ -114,7 +114,7 @@ __device__ __forceinline__ float round_tf32(float x) {
 constexpr int CL_PX = 128, CL_CH = 64;
 
 template <bool BF16>
-__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW,
+__global__ void __launch_bounds__(256, 4) nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW,
                                                            int Cp, float* __restrict__ chan_sum, float* __restrict__ partial,
                                                            int64_t Q) {
   // pixel tiles run over the flattened (image, pixel) index q in [0, Q = B*HW): small feature maps (HW < 128) fill the
@@ -130,12 +130,14 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int64_t p0 = t * CL_PX;
-    int64_t soff[4];  // source offset of (image, channel 0, pixel) for this lane's four pixels; -1 = past the end
+    // element offset of (image, channel 0, pixel) for this lane's four pixels (32-bit: the host checks B*C*HW < 2^32 - 2^20)
+    uint32_t soff[4];
+    constexpr uint32_t PAST_END = 0xFFFFFFFFu;
 #pragma unroll
     for (int pi = 0; pi < 4; ++pi) {
       const int64_t q = p0 + lane + 32 * pi;
-      const uint32_t b = (uint32_t)q / (uint32_t)HW;  // Q < 2^31 (checked on the host): 32-bit division
-      soff[pi] = q < Q ? (int64_t)b * C * HW + ((uint32_t)q - b * (uint32_t)HW) : -1;
+      const uint32_t b = (uint32_t)q / (uint32_t)HW;
+      soff[pi] = q < Q ? b * (uint32_t)(C * HW) + ((uint32_t)q - b * (uint32_t)HW) : PAST_END;
     }
     const float* s = src;
     if (BF16) {
@@ -145,9 +147,9 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
         const int c = c0 + 2 * (warp + 8 * ci);
 #pragma unroll
         for (int pi = 0; pi < 4; ++pi) {
-          const bool okp = soff[pi] >= 0;
-          v0[ci][pi] = (okp && c < C) ? s[soff[pi] + (int64_t)c * HW] : 0.f;
-          v1[ci][pi] = (okp && c + 1 < C) ? s[soff[pi] + (int64_t)(c + 1) * HW] : 0.f;
+          const bool okp = soff[pi] != PAST_END;
+          v0[ci][pi] = (okp && c < C) ? s[soff[pi] + (uint32_t)(c * HW)] : 0.f;
+          v1[ci][pi] = (okp && c + 1 < C) ? s[soff[pi] + (uint32_t)((c + 1) * HW)] : 0.f;
         }
       }
 #pragma unroll
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
       for (int ci = 0; ci < 8; ++ci) {
         const int c = c0 + warp + 8 * ci;
 #pragma unroll
-        for (int pi = 0; pi < 4; ++pi) v[ci][pi] = (soff[pi] >= 0 && c < C) ? s[soff[pi] + (int64_t)c * HW] : 0.f;
+        for (int pi = 0; pi < 4; ++pi) v[ci][pi] = (soff[pi] != PAST_END && c < C) ? s[soff[pi] + (uint32_t)(c * HW)] : 0.f;
       }
 #pragma unroll
       for (int ci = 0; ci < 8; ++ci) {
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_rows_kernel(const float* __r
 }
 static int launch_wgrad_reduce(const float* partial, float* dw, int Co, int Ci, int T, int splits, cudaStream_t st) {
   const size_t smem = (size_t)Ci * T * sizeof(float);
-  if (smem <= 48 * 1024) {
+  if (smem <= 48 * 1024 && Co >= 256) {  // one block per output channel: needs enough channels to fill the GPU
     wgrad_reduce_rows_kernel<<<Co, 256, smem, st>>>(partial, dw, Co, Ci, T, splits);
   } else {
     const int64_t n = (int64_t)Co * Ci * T;
@@ -465,7 +467,8 @@ int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, in
   int gx, groups;
   cl_grid(B, C, H, W, gx, groups);
   dim3 grid(gx, groups, 1);
-  CPT_REQUIRE(grid.y <= 65535 && (int64_t)B * HW < (1LL << 31), CPT_ERR_UNSUPPORTED, "to_channels_last: tensor too large");
+  CPT_REQUIRE(grid.y <= 65535 && (int64_t)B * HW < (1LL << 31) && (int64_t)B * C * HW < (1LL << 32) - (1 << 20),
+              CPT_ERR_UNSUPPORTED, "to_channels_last: tensor too large");
   float* partial = nullptr;
   if (chan_sum && ws && ws_bytes >= to_channels_last_ws(B, C, H, W)) partial = reinterpret_cast<float*>(ws);
   const int64_t Q = (int64_t)B * HW;
@@ -492,8 +495,10 @@ struct ConvPlan {
 
 // out[b, n, out_r0 + out_s*r, out_c0 + out_s*c] = Σ_{t, ch} act_cl[b, lower_h + r*trav + off_h[t], lower_w + c*trav + off_w[t], ch]
 //                                                          * wmat[n][t][ch]     (+ bias[n])
+static size_t stats_bytes(int Ncols) { return (size_t)sm_count() * 4 * Ncols * 2 * sizeof(float); }
+
 static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Win, const void* wmat, int Ncols, const ConvPlan& pl,
-                            const float* bias, float* out, int mode, cudaStream_t st) {
+                            const float* bias, float* out, int mode, cudaStream_t st, float* stats = nullptr) {
   const int kc = kc_of(mode), Cp = round_up(Cact, 8), Ck = round_up(Cact, kc), T = pl.ntaps;
   const int BN = pick_bn(Ncols);
   TcParams p{};
@@ -505,6 +510,10 @@ static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Wi
   p.out = out;
   p.bias = bias;
   p.bias_mode = bias ? BIAS_COL : BIAS_NONE;
+  if (stats) {  // slots of CTAs / N-tiles that never run stay zero
+    CPT_CUDA(cudaMemsetAsync(stats, 0, stats_bytes(Ncols), st));
+    p.stats = stats;
+  }
   if (int e = get_status_ptr(&p.status)) return e;
   p.M = (int)M;
   p.N = Ncols;
@@ -533,7 +542,7 @@ static bool fprop_tc_ok(const G& g) {
 }
 
 int conv_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w, const float* bias, float* y, int mode, void* ws,
-                  size_t ws_bytes, cudaStream_t st) {
+                  size_t ws_bytes, cudaStream_t st, float* stats = nullptr) {
   const G g = geom(d);
   CPT_REQUIRE(fprop_tc_ok(g), CPT_ERR_UNSUPPORTED, "conv2d_fprop_cl: kernel %d / padding %d / dilation %d outside the TMA im2col limits", g.K, g.P, g.D);
   const size_t need = wmat_bytes(g.Co, g.T, g.Ci, mode);
@@ -554,7 +563,7 @@ int conv_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w, co
   pl.trav = g.S;
   pl.sub_H = g.Ho; pl.sub_W = g.Wo;
   pl.out_H = g.Ho; pl.out_W = g.Wo; pl.out_s = 1; pl.out_r0 = pl.out_c0 = 0;
-  return conv_im2col_gemm(x_cl, g.B, g.Ci, g.H, g.W, ws, g.Co, pl, bias, y, mode, st);
+  return conv_im2col_gemm(x_cl, g.B, g.Ci, g.H, g.W, ws, g.Co, pl, bias, y, mode, st, stats);
 }
 
 // taps (j, kk) of stride class (rh, rw) — same rule as the exact path (conv.cu class_taps)
@@ -995,14 +1004,14 @@ __global__ void w_packT_kernel(const float* __restrict__ w, __nv_bfloat16* __res
 // The loops run over the output positions (ho, wo) that can reach (h, w) — about (K/S)^2 of them — instead of over all
 // K^2 taps; DIL1 removes the divisibility test of the dilated case.
 template <bool DIL1>
-__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int Ci, int H, int W,
+__global__ void __launch_bounds__(256) col2im_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dx, int Ci, int H, int W,
                                                      int K, int P, int S, int D, int Ho, int Wo) {
   const int T = K * K;
   const int64_t plane = (int64_t)Ho * Wo;
   const int w = blockIdx.x * blockDim.x + threadIdx.x, h = blockIdx.y;
   const int bc = blockIdx.z;  // b * Ci + c
   if (w >= W) return;
-  const float* base = dcol + (int64_t)bc * T * plane;
+  const __nv_bfloat16* base = dcol + (int64_t)bc * T * plane;
   const int span = (K - 1) * D;
   // ho in [ceil((h + P - span) / S), floor((h + P) / S)] ∩ [0, Ho)
   const int hp = h + P, wp = w + P;
@@ -1018,7 +1027,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
     const int hh = hp - ho * S;
     int j = hh;
     if (!DIL1) { j = hh / D; if (j * D != hh) continue; }
-    const float* rowp = base + (int64_t)(j * K) * plane + (int64_t)ho * Wo;
+    const __nv_bfloat16* rowp = base + (int64_t)(j * K) * plane + (int64_t)ho * Wo;
     for (int wo0 = wo_hi; wo0 >= wo_lo; wo0 -= 4) {
       float v[4];
 #pragma unroll
@@ -1027,7 +1036,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
         int kk = ww;
         bool ok = wo >= wo_lo;
         if (!DIL1) { kk = ww / D; ok = ok && kk * D == ww; }
-        v[u] = ok ? __ldg(rowp + (int64_t)kk * plane + wo) : 0.f;
+        v[u] = ok ? __bfloat162float(rowp[(int64_t)kk * plane + wo]) : 0.f;
       }
       acc += v[0]; acc += v[1]; acc += v[2]; acc += v[3];
     }
@@ -1047,7 +1056,7 @@ size_t conv_packed_workspace_size(int op, const cpt_conv2d_desc* d) {
   const PackGeom q = pack_geom(g);
   if (op == CPT_OP_FPROP) return cast_bytes(g.Co, q.Kdim) + 1024;
   if (op == CPT_OP_DGRAD)
-    return align_up((size_t)q.Kdim * round_up(g.Co, 8) * 2, 1024) + align_up((size_t)g.B * q.Kdim * g.Ho * g.Wo * sizeof(float), 1024) + 1024;
+    return align_up((size_t)q.Kdim * round_up(g.Co, 8) * 2, 1024) + align_up((size_t)g.B * q.Kdim * g.Ho * g.Wo * 2, 1024) + 1024;
   return align_up((size_t)64 * g.Co * q.Kdim * sizeof(float), 1024) + 1024;
 }
 
@@ -1074,7 +1083,7 @@ int conv_im2col_pack(const cpt_conv2d_desc* d, const float* x, void* col, cudaSt
 }
 
 int conv_fprop_packed(const cpt_conv2d_desc* d, const void* col, const float* w, const float* bias, float* y, void* ws,
-                      size_t ws_bytes, cudaStream_t st) {
+                      size_t ws_bytes, cudaStream_t st, float* stats = nullptr) {
   const G g = geom(d);
   const int mode = CPT_MODE_BF16;
   CPT_REQUIRE(packed_ok(g, mode), CPT_ERR_UNSUPPORTED, "conv2d_fprop_packed: geometry not covered by the packed-K path");
@@ -1087,6 +1096,10 @@ int conv_fprop_packed(const cpt_conv2d_desc* d, const void* col, const float* w,
   if (int e = make_map_2d(&p.tmA, col, mode, q.Kdim, (uint64_t)q.px, q.Kp, kc, 128)) return e;
   if (int e = make_map_2d(&p.tmB, ws, mode, q.Kdim, g.Co, q.Kp, kc, use2 ? BN / 2 : BN)) return e;
   p.out = y; p.bias = bias; p.bias_mode = bias ? BIAS_COL : BIAS_NONE;
+  if (stats) {
+    CPT_CUDA(cudaMemsetAsync(stats, 0, stats_bytes(g.Co), st));
+    p.stats = stats;
+  }
   if (int e = get_status_ptr(&p.status)) return e;
   p.M = (int)q.px; p.N = g.Co;
   p.m_tiles = (int)((q.px + 127) / 128); p.n_tiles = (g.Co + BN - 1) / BN; p.z_tiles = 1;
@@ -1117,7 +1130,9 @@ int conv_dgrad_packed(const cpt_conv2d_desc* d, const void* dy_cl, const float* 
   const int Cop = round_up(g.Co, 8), kc = kc_of(mode);
   char* base = reinterpret_cast<char*>(ws);
   __nv_bfloat16* wT = reinterpret_cast<__nv_bfloat16*>(base);
-  float* dcol = reinterpret_cast<float*>(base + align_up((size_t)q.Kdim * Cop * 2, 1024));
+  // dcol is kept in bf16: each of its entries is one tap's contribution to a dx element (a 64..512-term fp32 dot product rounded
+  // once); dx sums <= ceil(K/S)^2 of them in fp32.  Halves the traffic of the two passes that dominate this path.
+  __nv_bfloat16* dcol = reinterpret_cast<__nv_bfloat16*>(base + align_up((size_t)q.Kdim * Cop * 2, 1024));
   w_packT_kernel<<<ew_grid((int64_t)q.Kdim * Cop, 256), 256, 0, st>>>(w, wT, g.Co, q.Kdim, Cop);
   CPT_LAUNCH_CHECK("w_packT");
   const int BN = pick_bn(q.Kdim);
@@ -1126,7 +1141,7 @@ int conv_dgrad_packed(const cpt_conv2d_desc* d, const void* dy_cl, const float* 
   // dcol[b][k][ho][wo]: lanes = pixels (A = dy_cl [px][Cop], K-major), columns = k (B = wT [Kdim][Cop], K-major)
   if (int e = make_map_2d(&p.tmA, dy_cl, mode, g.Co, (uint64_t)q.px, Cop, kc, 128)) return e;
   if (int e = make_map_2d(&p.tmB, wT, mode, g.Co, q.Kdim, Cop, kc, use2 ? BN / 2 : BN)) return e;
-  p.out = dcol; p.bias = nullptr; p.bias_mode = BIAS_NONE;
+  p.out = reinterpret_cast<float*>(dcol); p.out_bf16 = 1; p.bias = nullptr; p.bias_mode = BIAS_NONE;
   if (int e = get_status_ptr(&p.status)) return e;
   p.M = (int)q.px; p.N = q.Kdim;
   p.m_tiles = (int)((q.px + 127) / 128); p.n_tiles = (q.Kdim + BN - 1) / BN; p.z_tiles = 1;
@@ -1226,6 +1241,25 @@ int cpt_conv2d_wgrad_packed(const cpt_conv2d_desc* d, const void* col, const voi
                             void* stream) {
   if (int e = check_tc(d, CPT_MODE_BF16, "conv2d_wgrad_packed")) return e;
   return tc::conv_wgrad_packed(d, col, dy_cl, dw, ws, ws_bytes, as_stream(stream));
+}
+
+/* forward passes that also leave the batch statistics of their output for a BatchNorm that consumes it */
+size_t cpt_conv2d_stats_bytes(const cpt_conv2d_desc* d) {
+  if (!d || d->Co <= 0) return 0;
+  return tc::stats_bytes(d->Co);
+}
+int cpt_conv2d_stats_slots(void) { return sm_count() * 4; }
+int cpt_conv2d_fprop_cl_stats(const cpt_conv2d_desc* d, const void* x_cl, const float* w, const float* bias, float* y, float* stats,
+                              int mode, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = check_tc(d, mode, "conv2d_fprop_cl_stats")) return e;
+  CPT_REQUIRE(stats, CPT_ERR_INVALID, "conv2d_fprop_cl_stats: stats is NULL");
+  return tc::conv_fprop_cl(d, x_cl, w, bias, y, mode, ws, ws_bytes, as_stream(stream), stats);
+}
+int cpt_conv2d_fprop_packed_stats(const cpt_conv2d_desc* d, const void* col, const float* w, const float* bias, float* y,
+                                  float* stats, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = check_tc(d, CPT_MODE_BF16, "conv2d_fprop_packed_stats")) return e;
+  CPT_REQUIRE(stats, CPT_ERR_INVALID, "conv2d_fprop_packed_stats: stats is NULL");
+  return tc::conv_fprop_packed(d, col, w, bias, y, ws, ws_bytes, as_stream(stream), stats);
 }
 
 size_t cpt_cast_bf16_bytes(int64_t rows, int cols) { return rows > 0 && cols > 0 ? tc::cast_bytes(rows, cols) : 0; }

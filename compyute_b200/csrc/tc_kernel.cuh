@@ -15,6 +15,8 @@
 // NCHW conv outputs, the feature dimension for row-major Linear outputs, Ci for wgrad partials) so that the
 // epilogue's 32-lane stores are 128-byte coalesced without a shared-memory transpose.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "tc_ptx.cuh"
 
 namespace cpt {
@@ -30,6 +32,9 @@ struct alignas(64) TcParams {
   const float* bias;
   int* status;      // device int: set non-zero on a pipeline timeout
   int bias_mode;
+  int out_bf16;     // 1: `out` is bf16 (no bias): the packed-K dgrad intermediate dcol
+  float* stats;     // optional [gridDim.x * 4][N][2]: per-epilogue-warp column sums (Σ acc, Σ acc²) of the raw accumulators
+                    // (without bias) over the valid lanes — the batch statistics of a BatchNorm that consumes the output
   int M, N;         // valid extents of the lane / column dimensions
   int m_tiles, n_tiles, z_tiles;  // m_tiles counts 128-row (1-CTA) or 256-row (2-CTA) tiles; z = split / tap*split
   int k_iters_total;              // k iterations of the whole reduction (GEMM / WGRAD) or per tile (CONV)
@@ -55,6 +60,25 @@ struct Elem {
   static constexpr int UMMA_K = 32 / BYTES;   // 16 bf16 / 8 tf32
   static constexpr int BK = KC;               // reduction elements per stage (also k-rows of an MN-major stage)
 };
+
+// Column sums of a 32 x 32 block held one row per lane (a[j] = column j of this lane's row): five exchange rounds, each
+// halving the columns a lane still owns; lane L ends up with the sum of column L.  31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float col_sums_32x32(float (&a)[32], int lane) {
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const int o = 16 >> r;  // exchange distance == number of columns kept
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < o) {
+        const float send = up ? a[j] : a[j + o];
+        const float keep = up ? a[j + o] : a[j];
+        a[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+  }
+  return a[0];
+}
 
 template <int BN, bool CTA2>
 struct StageCfg {
@@ -254,9 +278,32 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
+    // batch statistics for a consuming BatchNorm (only the K-major x K-major instantiations that produce activations)
+    constexpr bool STATS_OK = (OP == OP_CONV) || (OP == OP_GEMM && !A_MN && !B_MN);
+    __shared__ float stat_acc[STATS_OK ? 4 : 1][STATS_OK ? BN : 1][2];
+    const bool do_stats = STATS_OK && p.stats != nullptr;
+    int stat_n_tile = -1;
+    auto stats_flush = [&]() {  // this warp's column sums of the finished N-tile -> its slot of the partial buffer
+      if (STATS_OK && stat_n_tile >= 0) {
+        float* dstp = p.stats + ((long long)(blockIdx.x * 4 + ew) * p.N) * 2;
+        for (int c = lane; c < BN; c += 32) {
+          const int col = stat_n_tile * BN + c;
+          if (col < p.N) {
+            dstp[2 * col] = stat_acc[STATS_OK ? ew : 0][STATS_OK ? c : 0][0];
+            dstp[2 * col + 1] = stat_acc[STATS_OK ? ew : 0][STATS_OK ? c : 0][1];
+          }
+        }
+      }
+    };
     for (int t = group; t < total_tiles; t += n_groups) {
       const int m_tile = t % p.m_tiles, r = t / p.m_tiles, n_tile = r % p.n_tiles, z = r / p.n_tiles;
       const int m = m_tile * (128 * NCTA) + cta_rank * 128 + ew * 32 + lane, n0 = n_tile * BN;
+      if (do_stats && n_tile != stat_n_tile) {
+        stats_flush();
+        stat_n_tile = n_tile;
+        for (int c = lane; c < BN; c += 32) stat_acc[STATS_OK ? ew : 0][STATS_OK ? c : 0][0] = stat_acc[STATS_OK ? ew : 0][STATS_OK ? c : 0][1] = 0.f;
+        __syncwarp();
+      }
       const int iters = tile_k_iters(z);
       long long z_off = 0;
       if (OP == OP_WGRAD) z_off = (long long)(z / p.taps) * p.split_stride + (long long)(z % p.taps) * p.tap_stride;
@@ -293,6 +340,26 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
       };
       auto store_chunk = [&](const uint32_t (&v)[32], int c) {
         const int cbase = n0 + c * 32;
+        if (do_stats) {
+          float a[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = m_ok ? __uint_as_float(v[j]) : 0.f;
+          const float s1 = col_sums_32x32(a, lane);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float x = m_ok ? __uint_as_float(v[j]) : 0.f; a[j] = x * x; }
+          const float s2 = col_sums_32x32(a, lane);
+          stat_acc[STATS_OK ? ew : 0][STATS_OK ? c * 32 + lane : 0][0] += s1;   // lane L owns column c*32 + L of this warp's slot
+          stat_acc[STATS_OK ? ew : 0][STATS_OK ? c * 32 + lane : 0][1] += s2;
+        }
+        if (p.out_bf16) {  // same addressing in 2-byte elements: 64-byte stores per warp and column
+          __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(p.out) + z_off + lane_off + (long long)cbase * cs;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (m_ok && cbase + j < p.N) *qb = __float2bfloat16_rn(__uint_as_float(v[j]));
+            qb += cs;
+          }
+          return;
+        }
         float* q = dst + (long long)(c * 32) * cs;
         float bl = 0.f;  // this lane's column bias; column j's value is fetched with a shuffle (one LDG per chunk)
         if (col_bias && cbase + lane < p.N) bl = __ldg(p.bias + cbase + lane);
@@ -339,6 +406,7 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (do_stats) { __syncwarp(); stats_flush(); }
   }
 
   tc_fence_before();

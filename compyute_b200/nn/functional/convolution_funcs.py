@@ -44,7 +44,9 @@ class Conv2DFn(Function):
 
     @staticmethod
     def forward(cache: FunctionCache, x: Tensor, f: Tensor, b: Optional[Tensor], padding: int, stride: int,
-                dilation: int) -> Tensor:
+                dilation: int, emit_stats: bool = False) -> Tensor:
+        """``emit_stats`` (extension, tensor-core modes): the epilogue also leaves per-channel Σy / Σy² partials on the
+        result (``y.data.stats``) for a BatchNorm that consumes it, which then skips its statistics pass."""
         if x.ndim != 4:
             raise ShapeError(f"Expected input to be 4D, got {x.ndim}D.")
         require_cuda(x, f, b)
@@ -65,7 +67,12 @@ class Conv2DFn(Function):
             x_cl = DeviceArray.empty((L.cpt_conv2d_packed_bytes(ctypes.byref(d), mode),), np.uint8)
             _lib.check(L.cpt_conv2d_im2col_pack(ctypes.byref(d), f32ptr(x), x_cl.ptr, st))
             ws, wsb = workspace(L.cpt_conv2d_packed_workspace_size(_lib.OP_FPROP, ctypes.byref(d)))
-            _lib.check(L.cpt_conv2d_fprop_packed(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, ws, wsb, st))
+            if emit_stats:
+                stats = DeviceArray.empty((L.cpt_conv2d_stats_bytes(ctypes.byref(d)),), np.uint8)
+                _lib.check(L.cpt_conv2d_fprop_packed_stats(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, stats.ptr, ws, wsb, st))
+                y.stats = (stats, L.cpt_conv2d_stats_slots(), b)
+            else:
+                _lib.check(L.cpt_conv2d_fprop_packed(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, ws, wsb, st))
             mode = _MODE_PACKED
         else:
             shadow = getattr(x.data, "cl", None)
@@ -76,7 +83,12 @@ class Conv2DFn(Function):
                 x_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Ci, d.H, d.W, mode),), np.uint8)
                 _lib.check(L.cpt_to_channels_last(f32ptr(x), x_cl.ptr, d.B, d.Ci, d.H, d.W, mode, None, None, 0, st))
             ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_FPROP, ctypes.byref(d), mode))
-            _lib.check(L.cpt_conv2d_fprop_cl(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, mode, ws, wsb, st))
+            if emit_stats:
+                stats = DeviceArray.empty((L.cpt_conv2d_stats_bytes(ctypes.byref(d)),), np.uint8)
+                _lib.check(L.cpt_conv2d_fprop_cl_stats(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, stats.ptr, mode, ws, wsb, st))
+                y.stats = (stats, L.cpt_conv2d_stats_slots(), b)
+            else:
+                _lib.check(L.cpt_conv2d_fprop_cl(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, mode, ws, wsb, st))
         cache.push(x, f, b is not None, d, mode, x_cl)
         return Tensor(y)
 

@@ -37,8 +37,14 @@ def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW, act=ACT
         else:
             new_rmean = DeviceArray.empty((C,), np.float32)
             new_rvar = DeviceArray.empty((C,), np.float32)
+        pre = getattr(x.data, "stats", None)
         ws, wsb = workspace(L.cpt_bn_workspace_size(N, C, HW))
-        if y_cl is not None:
+        if pre is not None:  # the producing convolution's epilogue already summed the batch statistics
+            _lib.check(L.cpt_bn_act_fwd_train_presum(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr,
+                                                     y_cl.ptr if y_cl is not None else None, new_rmean.ptr, new_rvar.ptr,
+                                                     save_mean.ptr, save_rstd.ptr, N, C, HW, float(m), float(eps), act,
+                                                     pre[0].ptr, pre[1], f32ptr(pre[2]), st))
+        elif y_cl is not None:
             _lib.check(L.cpt_bn_act_fwd_train_cl(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y.ptr, y_cl.ptr,
                                                  new_rmean.ptr, new_rvar.ptr, save_mean.ptr, save_rstd.ptr, N, C, HW, float(m),
                                                  float(eps), act, ws, wsb, st))

@@ -9,6 +9,19 @@ from ..functional.activation_funcs import FUSED_INTO_PRODUCER
 from .module import Module, ModuleList, get_debug_mode
 
 _fusion = True
+_epilogue_stats = True
+
+
+def set_epilogue_stats_enabled(enabled: bool) -> None:
+    """BatchNorm batch statistics from the producing convolution's epilogue (tensor-core modes).  Unlike the other
+    peepholes this changes the summation order / variance formula of the statistics (not bit-identical to the two-pass
+    computation, well inside the tf32 / bf16 tolerances); on by default."""
+    global _epilogue_stats
+    _epilogue_stats = bool(enabled)
+
+
+def get_epilogue_stats_enabled() -> bool:
+    return _epilogue_stats
 
 
 def set_fusion_enabled(enabled: bool) -> None:
@@ -21,7 +34,8 @@ def set_fusion_enabled(enabled: bool) -> None:
 def get_fusion_enabled() -> bool:
     return _fusion
 
-__all__ = ["Sequential", "ResidualConnection", "EmptyContainerError", "set_fusion_enabled", "get_fusion_enabled"]
+__all__ = ["Sequential", "ResidualConnection", "EmptyContainerError", "set_fusion_enabled", "get_fusion_enabled",
+           "set_epilogue_stats_enabled", "get_epilogue_stats_enabled"]
 
 
 class EmptyContainerError(Exception):
@@ -42,7 +56,7 @@ class Sequential(Module):
         channels-last bf16 operand in its own apply pass (forward: the consumer of its — possibly ReLU-fused — output;
         backward: the convolution that produced its input).  Recomputed when the layer list or the fusion switch changes."""
         from .layers import BatchNorm2D, Conv2D, Linear, ReLU
-        key = (tuple(id(m) for m in self.layers), _fusion)
+        key = (tuple(id(m) for m in self.layers), _fusion, _epilogue_stats)
         if getattr(self, "_hint_key", None) == key:
             return
         object.__setattr__(self, "_hint_key", key)
@@ -58,6 +72,8 @@ class Sequential(Module):
 
         n = len(self.layers)
         for i, m in enumerate(self.layers):
+            if isinstance(m, Conv2D):  # its epilogue sums the batch statistics of a BatchNorm2D that follows
+                m._emit_stats = _fusion and _epilogue_stats and i + 1 < n and isinstance(self.layers[i + 1], BatchNorm2D)
             if type(m) is ReLU:  # ReLU between Linear layers writes their bf16 operands (x of the next, dy of the previous)
                 m._emit_lp_fwd = _fusion and i + 1 < n and isinstance(self.layers[i + 1], Linear)
                 m._emit_lp_bwd = _fusion and i > 0 and isinstance(self.layers[i - 1], Linear)

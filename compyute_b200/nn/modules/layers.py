@@ -57,9 +57,12 @@ class Conv2D(Module):
         self.w = Parameter(_uniform((out_channels, in_channels, kernel_size, kernel_size), k))
         self.b = Parameter(_uniform((out_channels,), k)) if bias else None
 
+    _emit_stats = False  # hint set by the enclosing Sequential: a BatchNorm2D consumes the output
+
     @Module.register_forward
     def forward(self, x: Tensor) -> Tensor:
-        return Conv2DFn.forward(self.fcache, x, self.w, self.b, self.padding, self.stride, self.dilation)
+        return Conv2DFn.forward(self.fcache, x, self.w, self.b, self.padding, self.stride, self.dilation,
+                                self._emit_stats and self._is_training)
 
     @Module.register_backward
     def backward(self, dy: Tensor) -> Tensor:

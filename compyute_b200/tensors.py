@@ -47,13 +47,16 @@ _NP2TORCH = {"float32": "float32", "int32": "int32", "int64": "int64", "int8": "
 class DeviceArray:
     """C-contiguous array in HBM.  ``ptr`` is what the C ABI receives (== CuPy's ``arr.data.ptr``)."""
 
-    __slots__ = ("_buf", "shape", "dtype", "cl")
+    __slots__ = ("_buf", "shape", "dtype", "cl", "stats")
 
     def __init__(self, buf, shape: ShapeLike, dtype: np.dtype):
         # cl: optional (mode, DeviceArray, chan_sum | None) — the channels-last low-precision copy of this array that its
         # PRODUCER kernel wrote alongside it (cpt_bn_act_*_cl), consumed by the next tensor-core convolution instead of a
         # staging pass; every in-place mutation drops it
-        self.cl = None
+        self.cl = self.stats = None
+        # stats: optional (slots array, n_slots, conv bias | None) — per-channel Σ / Σ² partials of this array left by the
+        # convolution epilogue that produced it, consumed by a BatchNorm forward instead of its statistics pass
+        self.stats = None
         self._buf = buf  # torch tensor owning the memory (1-D or any shape, contiguous)
         self.shape = tuple(int(s) for s in shape)
         self.dtype = np.dtype(dtype)
@@ -127,13 +130,13 @@ class DeviceArray:
         return DeviceArray(self._buf.clone(), self.shape, self.dtype)  # cudaMemcpyAsync D2D
 
     def copy_from(self, other: "DeviceArray") -> None:
-        self.cl = None
+        self.cl = self.stats = None
         if other.size != self.size or other.dtype != self.dtype:
             raise ShapeError(f"copy_from: {other.shape}/{other.dtype} into {self.shape}/{self.dtype}")
         self._buf.view(-1).copy_(other._buf.view(-1))
 
     def upload(self, a) -> None:
-        self.cl = None
+        self.cl = self.stats = None
         """In-place H2D copy into this buffer (keeps the address: used to feed CUDA-graph-captured steps)."""
         torch = _t()
         if isinstance(a, DeviceArray):
@@ -160,7 +163,7 @@ class DeviceArray:
 
     def __iadd__(self, other) -> "DeviceArray":
         self._f32("+=")
-        self.cl = None
+        self.cl = self.stats = None
         if isinstance(other, DeviceArray):
             if other.size != self.size:
                 raise ShapeError(f"+=: shapes {self.shape} and {other.shape} differ (no broadcasting on device)")
@@ -169,7 +172,7 @@ class DeviceArray:
         raise TypeError(f"+=: unsupported operand {type(other)}")
 
     def fill(self, value: float) -> None:
-        self.cl = None
+        self.cl = self.stats = None
         self._f32("fill")
         _lib.check(_lib.lib().cpt_fill(self.ptr, float(value), self.size, stream_ptr()))
 

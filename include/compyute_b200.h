@@ -207,6 +207,25 @@ int cpt_bn_act_bwd_cl(const float* x, const float* dy, const float* w, const flo
                       const float* save_mean, const float* save_rstd, float* dx, void* dx_cl,
                       float* dx_chan_sum, float* dw, float* db, int N, int C, int HW, int act, void* ws,
                       size_t ws_bytes, void* stream);
+/* Batch statistics from the producing convolution's epilogue (tensor-core modes).  cpt_conv2d_fprop_*_stats are the forward
+ * passes above that additionally leave, in `stats` (cpt_conv2d_stats_bytes bytes = cpt_conv2d_stats_slots() x Co x 2 floats),
+ * per-epilogue-warp column sums (Σ a, Σ a²) of the bias-free accumulators; cpt_bn_act_fwd_train_presum is the training forward
+ * of normalization_funcs.py:138-147 that adds the slots in fixed order (double) instead of reading x a first time:
+ * mean = Σa/n + conv_bias, var = Σa²/n - (Σa/n)².  y_cl may be NULL.  Not bit-identical to the two-pass statistics (different
+ * summation order / variance formula), so only the tf32 / bf16 modes use it. */
+size_t cpt_conv2d_stats_bytes(const cpt_conv2d_desc* d);
+int cpt_conv2d_stats_slots(void);
+int cpt_conv2d_fprop_cl_stats(const cpt_conv2d_desc* d, const void* x_cl, const float* w,
+                              const float* bias, float* y, float* stats, int mode, void* ws,
+                              size_t ws_bytes, void* stream);
+int cpt_conv2d_fprop_packed_stats(const cpt_conv2d_desc* d, const void* col, const float* w,
+                                  const float* bias, float* y, float* stats, void* ws, size_t ws_bytes,
+                                  void* stream);
+int cpt_bn_act_fwd_train_presum(const float* x, const float* w, const float* b, const float* rmean,
+                                const float* rvar, float* y, void* y_cl, float* rmean_out,
+                                float* rvar_out, float* save_mean, float* save_rstd, int N, int C, int HW,
+                                float m, float eps, int act, const float* stats, int stat_slots,
+                                const float* conv_bias, void* stream);
 
 /* ---- activations / elementwise ------------------------------------------------------------- */
 /* ReLUFn.forward activation_funcs.py:26-29.  mask = bit-packed (y > 0), 4 * ((n + 31) / 32) bytes, 4-byte aligned, in a
