@@ -8,9 +8,10 @@
 Hand-written CUDA for sm_100a (compyute_b200/csrc) behind a C ABI (include/compyute_b200.h); no CPU fallback.
 """
 
-from . import distributed, graph, nn
+from . import distributed, graph, nn, random, tensor_ops
 from .backend import *
 from .tensors import DeviceArray, ShapeError, Tensor, tensor
 from .utils import load, save
+from .tensor_ops import *  # noqa: F401,F403  (cp.zeros, cp.exp, cp.sum, cp.concat, ... like the reference's top level)
 
 __version__ = "0.1.0"

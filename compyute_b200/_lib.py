@@ -38,7 +38,7 @@ class ParamEntry(ctypes.Structure):
 
 
 _SCALARS = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,
-            "float": ctypes.c_float, "uint64_t": ctypes.c_uint64, "void": None}
+            "float": ctypes.c_float, "double": ctypes.c_double, "uint64_t": ctypes.c_uint64, "void": None}
 
 
 def parse_header(path: str = HEADER) -> dict[str, tuple[object, list[object]]]:

@@ -161,16 +161,6 @@ class DeviceArray:
         if self.dtype != np.float32:
             raise TypeError(f"{who}: only float32 device arrays are supported, got {self.dtype}")
 
-    def __iadd__(self, other) -> "DeviceArray":
-        self._f32("+=")
-        self.cl = self.stats = None
-        if isinstance(other, DeviceArray):
-            if other.size != self.size:
-                raise ShapeError(f"+=: shapes {self.shape} and {other.shape} differ (no broadcasting on device)")
-            _lib.check(_lib.lib().cpt_add_inplace(self.ptr, other.ptr, self.size, stream_ptr()))
-            return self
-        raise TypeError(f"+=: unsupported operand {type(other)}")
-
     def fill(self, value: float) -> None:
         self.cl = self.stats = None
         self._f32("fill")
@@ -182,11 +172,142 @@ class DeviceArray:
         _lib.check(_lib.lib().cpt_axpby(out.ptr, self.ptr, float(alpha), 0, self.size, stream_ptr()))
         return out
 
-    def sum(self) -> float:
-        self._f32("sum")
-        out = DeviceArray.empty((1,), np.float32)
-        _lib.check(_lib.lib().cpt_sum(self.ptr, self.size, out.ptr, stream_ptr()))
-        return out.item()
+    # -- NumPy-style operator surface: what `Tensor.data <op> other` reaches on a CuPy array in the reference
+    # (tensors.py:196-292); kernels in csrc/tensor_ops.cu, host-side shape logic in device_ops.py
+    def _bin(self, op, other, reverse=False):
+        from . import device_ops as D
+        if other is None and op == "add" and reverse:  # tensors.py:199-201: None + grad
+            return self.copy()
+        return D.binary(op, self, other, reverse=reverse)
+
+    def _ibin(self, op, other):
+        from . import device_ops as D
+        self.cl = self.stats = None
+        if op == "add" and isinstance(other, DeviceArray) and other.shape == self.shape and other.dtype == self.dtype == np.float32:
+            _lib.check(_lib.lib().cpt_add_inplace(self.ptr, other.ptr, self.size, stream_ptr()))  # residual / grad accumulation
+            return self
+        return D.binary(op, self, other, out=self)
+
+    def __add__(self, o): return self._bin("add", o)
+    def __radd__(self, o): return self._bin("add", o, True)
+    def __iadd__(self, o): return self._ibin("add", o)
+    def __sub__(self, o): return self._bin("sub", o)
+    def __rsub__(self, o): return self._bin("sub", o, True)
+    def __isub__(self, o): return self._ibin("sub", o)
+    def __mul__(self, o): return self._bin("mul", o)
+    def __rmul__(self, o): return self._bin("mul", o, True)
+    def __imul__(self, o): return self._ibin("mul", o)
+    def __truediv__(self, o): return self._bin("div", o)
+    def __rtruediv__(self, o): return self._bin("div", o, True)
+    def __itruediv__(self, o): return self._ibin("div", o)
+    def __floordiv__(self, o): return self._bin("floordiv", o)
+    def __rfloordiv__(self, o): return self._bin("floordiv", o, True)
+    def __ifloordiv__(self, o): return self._ibin("floordiv", o)
+    def __pow__(self, o): return self._bin("pow", o)
+    def __rpow__(self, o): return self._bin("pow", o, True)
+    def __ipow__(self, o): return self._ibin("pow", o)
+    def __mod__(self, o): return self._bin("mod", o)
+    def __rmod__(self, o): return self._bin("mod", o, True)
+    def __imod__(self, o): return self._ibin("mod", o)
+    def __lt__(self, o): return self._bin("lt", o)
+    def __gt__(self, o): return self._bin("gt", o)
+    def __le__(self, o): return self._bin("le", o)
+    def __ge__(self, o): return self._bin("ge", o)
+    def __eq__(self, o): return self._bin("eq", o)  # noqa: elementwise like NumPy
+    def __ne__(self, o): return self._bin("ne", o)
+    __hash__ = object.__hash__
+
+    def __neg__(self):
+        from . import device_ops as D
+        return D.unary("neg", self)
+
+    def __abs__(self):
+        from . import device_ops as D
+        return D.unary("abs", self)
+
+    def __invert__(self):
+        from . import device_ops as D
+        if self.dtype != np.bool_:
+            raise TypeError("~ is defined for bool device arrays only")
+        return D.logic("not", self)
+
+    def __and__(self, o):
+        from . import device_ops as D
+        return D.logic("and", self, o)
+
+    def __or__(self, o):
+        from . import device_ops as D
+        return D.logic("or", self, o)
+
+    def __xor__(self, o):
+        from . import device_ops as D
+        return D.logic("xor", self, o)
+
+    def __matmul__(self, o):
+        from . import device_ops as D
+        return D.matmul(self, o)
+
+    def __getitem__(self, key):
+        from . import device_ops as D
+        return D.getitem(self, key)
+
+    def __setitem__(self, key, value) -> None:
+        from . import device_ops as D
+        D.setitem(self, key, value)
+
+    def __len__(self) -> int:
+        if not self.shape:
+            raise TypeError("len() of unsized object")
+        return self.shape[0]
+
+    def astype(self, dtype, copy: bool = True) -> "DeviceArray":
+        from . import device_ops as D
+        return self if (not copy and np.dtype(dtype) == self.dtype) else D.astype(self, dtype)
+
+    def tolist(self) -> list:
+        return self.numpy().tolist()
+
+    def _red(self, op, dim, keepdims):
+        from . import device_ops as D
+        return D.reduce(op, self, dim, keepdims)
+
+    def sum(self, dim=None, keepdims: bool = False) -> "DeviceArray":
+        from . import device_ops as D
+        return D.sum_(self, dim, keepdims)
+
+    def mean(self, dim=None, keepdims: bool = False) -> "DeviceArray":
+        from . import device_ops as D
+        return D.mean(self, dim, keepdims)
+
+    def var(self, dim=None, ddof: int = 0, keepdims: bool = False) -> "DeviceArray":
+        from . import device_ops as D
+        return D.var(self, dim, ddof, keepdims)
+
+    def std(self, dim=None, keepdims: bool = False) -> "DeviceArray":
+        from . import device_ops as D
+        return D.std(self, dim, keepdims)
+
+    def max(self, dim=None, keepdims: bool = False): return self._red("max", dim, keepdims)
+    def min(self, dim=None, keepdims: bool = False): return self._red("min", dim, keepdims)
+    def prod(self, dim=None, keepdims: bool = False): return self._red("prod", dim, keepdims)
+    def any(self, dim=None, keepdims: bool = False): return self._red("any", dim, keepdims)
+    def all(self, dim=None, keepdims: bool = False): return self._red("all", dim, keepdims)
+
+    def argmax(self, dim=None, keepdims: bool = False) -> "DeviceArray":
+        from . import device_ops as D
+        return D.argmax(self, dim, keepdims)
+
+    def transpose(self, *dims) -> "DeviceArray":
+        from . import device_ops as D
+        dims = dims[0] if len(dims) == 1 and isinstance(dims[0], (tuple, list)) else dims
+        return D.permute(self, dims if dims else tuple(reversed(range(self.ndim))))
+
+    def swapaxes(self, d1: int, d2: int) -> "DeviceArray":
+        from . import device_ops as D
+        return D.swapaxes(self, d1, d2)
+
+    def squeeze(self) -> "DeviceArray":
+        return self.reshape(tuple(d for d in self.shape if d != 1))
 
     def has_nan(self) -> bool:
         """``is_nan(x).any().item()`` (module.py:332) — one reduction kernel + one 4-byte D2H."""
@@ -265,9 +386,7 @@ class Tensor:
 
     @property
     def T(self) -> "Tensor":
-        if self.device is cuda:
-            raise NotImplementedError("transpose of device tensors is not part of the CNN hot path")
-        return Tensor(np.swapaxes(self.data, -1, -2))
+        return Tensor(self.data.swapaxes(-1, -2))  # tensors.py:131-135: last two dims
 
     def __bool__(self) -> bool:  # tensors.py:305-306: `if b:` means `b is not None`
         return True
@@ -313,22 +432,109 @@ class Tensor:
     def to_contiguous(self) -> "Tensor":
         return self if isinstance(self.data, DeviceArray) else Tensor(np.ascontiguousarray(self.data))
 
-    # ---- arithmetic used by the callers of the hot path
-    def __iadd__(self, other: "Tensor") -> "Tensor":
-        o = other.data if isinstance(other, Tensor) else other
-        if isinstance(self.data, DeviceArray):
-            self.data += o
-        else:
-            self.data += o
+    # ---- operators (tensors.py:176-306): `.data` is a NumPy array on cpu and a DeviceArray on cuda; both implement them
+    def __getitem__(self, key: Any) -> "Tensor":
+        return Tensor(self.data[_unwrap_key(key)])
+
+    def __setitem__(self, key: Any, value) -> None:
+        self.data[_unwrap_key(key)] = _unwrap(value)
+
+    def __iter__(self) -> "Tensor":
+        self._iterator = 0
         return self
 
-    def __add__(self, other: "Tensor") -> "Tensor":
-        out = self.copy()
-        out += other
-        return out
+    def __next__(self) -> "Tensor":
+        if self._iterator == self.shape[0]:
+            raise StopIteration
+        y = self[self._iterator]
+        self._iterator += 1
+        return y
 
-    def sum(self) -> float:
-        return self.data.sum() if isinstance(self.data, DeviceArray) else float(self.data.sum())
+    def __add__(self, o): return Tensor(self.data + _unwrap(o))
+    def __radd__(self, o): return Tensor(self.data + o) if o is not None else self.copy()  # tensors.py:199-201
+    def __sub__(self, o): return Tensor(self.data - _unwrap(o))
+    def __rsub__(self, o): return Tensor(o - self.data)
+    def __mul__(self, o): return Tensor(self.data * _unwrap(o))
+    def __rmul__(self, o): return Tensor(o * self.data)
+    def __truediv__(self, o): return Tensor(self.data / _unwrap(o))
+    def __rtruediv__(self, o): return Tensor(o / self.data)
+    def __floordiv__(self, o): return Tensor(self.data // _unwrap(o))
+    def __rfloordiv__(self, o): return Tensor(o // self.data)
+    def __pow__(self, o): return Tensor(self.data ** _unwrap(o))
+    def __rpow__(self, o): return Tensor(o ** self.data)
+    def __mod__(self, o): return Tensor(self.data % _unwrap(o))
+    def __rmod__(self, o): return Tensor(o % self.data)
+    def __neg__(self): return Tensor(-self.data)
+    def __invert__(self): return Tensor(~self.data)
+    def __matmul__(self, o): return Tensor(self.data @ _unwrap(o))
+    def __lt__(self, o): return Tensor(self.data < _unwrap(o))
+    def __gt__(self, o): return Tensor(self.data > _unwrap(o))
+    def __le__(self, o): return Tensor(self.data <= _unwrap(o))
+    def __ge__(self, o): return Tensor(self.data >= _unwrap(o))
+    def __eq__(self, o): return Tensor(self.data == _unwrap(o))  # type: ignore[override]
+    def __ne__(self, o): return Tensor(self.data != _unwrap(o))  # type: ignore[override]
+
+    def __hash__(self) -> int:
+        return id(self)
+
+    def __array__(self, dtype=None, copy=None) -> np.ndarray:
+        a = self.to_numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def _inplace(self, name: str, o) -> "Tensor":
+        d = getattr(self.data, name)(_unwrap(o))  # NumPy / DeviceArray in-place operator: same array comes back
+        if d is not NotImplemented:
+            self.data = d
+        return self
+
+    def __iadd__(self, o): return self._inplace("__iadd__", o)
+    def __isub__(self, o): return self._inplace("__isub__", o)
+    def __imul__(self, o): return self._inplace("__imul__", o)
+    def __itruediv__(self, o): return self._inplace("__itruediv__", o)
+    def __ifloordiv__(self, o): return self._inplace("__ifloordiv__", o)
+    def __ipow__(self, o): return self._inplace("__ipow__", o)
+    def __imod__(self, o): return self._inplace("__imod__", o)
+
+    # ---- dtype conversions (tensors.py:372-455)
+    def to_type(self, dtype) -> "Tensor":
+        dtype = np.dtype(dtype)
+        return self if dtype == self.dtype else Tensor(self.data.astype(dtype))
+
+    def ito_type(self, dtype) -> None:
+        self.data = self.to_type(dtype).data
+
+    def to_int(self): return self.to_type(np.int32)
+    def to_long(self): return self.to_type(np.int64)
+    def to_float(self): return self.to_type(np.float32)
+    def to_list(self) -> list: return self.to_numpy().tolist()
+    def to_cpu(self): return self.to_device(cpu)
+    def to_cuda(self): return self.to_device(cuda)
+
+    # ---- unary / reductions / shape (tensors.py:543-682); dim and keepdims as in the reference
+    def abs(self): return Tensor(abs(self.data))
+    def all(self, dim=None, *, keepdims=False): return Tensor(self.data.all(dim, keepdims=keepdims))
+    def any(self, dim=None, *, keepdims=False): return Tensor(self.data.any(dim, keepdims=keepdims))
+    def argmax(self, dim=None, *, keepdims=False): return Tensor(self.data.argmax(dim, keepdims=keepdims))
+    def max(self, dim=None, *, keepdims=False): return Tensor(self.data.max(dim, keepdims=keepdims))
+    def mean(self, dim=None, *, keepdims=False): return Tensor(self.data.mean(dim, keepdims=keepdims))
+    def min(self, dim=None, *, keepdims=False): return Tensor(self.data.min(dim, keepdims=keepdims))
+    def std(self, dim=None, *, keepdims=False): return Tensor(self.data.std(dim, keepdims=keepdims))
+    def sum(self, dim=None, *, keepdims=False): return Tensor(self.data.sum(dim, keepdims=keepdims))
+    def var(self, dim=None, *, ddof=0, keepdims=False): return Tensor(self.data.var(dim, ddof=ddof, keepdims=keepdims))
+    def permute(self, dims): return Tensor(self.data.transpose(tuple(dims)))
+    def transpose(self, dim1: int, dim2: int): return Tensor(self.data.swapaxes(dim1, dim2))
+    def squeeze(self): return Tensor(self.data.squeeze())
+
+
+def _unwrap(v: Any) -> Any:
+    """``to_arraylike`` (tensors.py:685-689)"""
+    return v.data if isinstance(v, Tensor) else v
+
+
+def _unwrap_key(key: Any) -> Any:
+    if isinstance(key, tuple):
+        return tuple(_unwrap(k) for k in key)
+    return _unwrap(key)
 
 
 def tensor(data: Any, device: Optional[Device] = None, dtype=None) -> Tensor:

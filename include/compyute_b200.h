@@ -299,6 +299,95 @@ int cpt_sgd_step(const cpt_param_entry* table, int n_entries, int64_t max_n, flo
                  float momentum, int nesterov, float weight_decay, float grad_scale,
                  const float* live_scalars, void* stream);
 
+/* ---- generic device-tensor operators -------------------------------------------
+ * What the reference reaches as `Tensor.data <op> other` / `Tensor.data.<reduction>(dim)` (compyute/tensors.py:196-292,
+ * 552-682) and `device.module.<fn>` (compyute/tensor_ops/ modules) on CuPy arrays.  Values are fp32 unless a dtype code says
+ * otherwise; booleans are uint8 0/1 (NumPy bool layout).  Shapes of up to CPT_MAX_DIMS dims, strides in ELEMENTS,
+ * innermost dim last; `dims`/strides/`reduced` are HOST arrays read during the call. */
+#define CPT_MAX_DIMS 6
+#define CPT_DT_F32 0
+#define CPT_DT_I32 1
+#define CPT_DT_I64 2
+#define CPT_DT_U8 3 /* bool */
+#define CPT_DT_F64 4
+/* binary ops: arithmetic → fp32 out, comparisons → uint8 out  (tensors.py:196-292, selection_ops.py:89-144) */
+#define CPT_EW_ADD 0
+#define CPT_EW_SUB 1
+#define CPT_EW_MUL 2
+#define CPT_EW_DIV 3
+#define CPT_EW_POW 4
+#define CPT_EW_MAX 5
+#define CPT_EW_MIN 6
+#define CPT_EW_FLOORDIV 7
+#define CPT_EW_MOD 8
+#define CPT_EW_LT 9
+#define CPT_EW_GT 10
+#define CPT_EW_LE 11
+#define CPT_EW_GE 12
+#define CPT_EW_EQ 13
+#define CPT_EW_NE 14
+/* out[i] = a[ia] op b[ib] with NumPy broadcasting: `dims` is the OUTPUT shape, sa / sb the operands' element strides over
+ * it (0 on broadcast dims); out is C-contiguous and may alias a (in-place operators).  b == NULL: the second operand is
+ * `scalar` (scalar_mode 1: a op scalar, 2: scalar op a; a must then be contiguous). */
+int cpt_ew_binary(int op, void* out, const float* a, const float* b, float scalar, int scalar_mode, int ndim,
+                  const int64_t* dims, const int64_t* sa, const int64_t* sb, void* stream);
+/* unary ops (tensors.py:267,543; unary_ops.py:33-438); ISNAN writes uint8; CLIP uses p0 = min, p1 = max; ROUND p0 = 10^decimals */
+#define CPT_UN_NEG 0
+#define CPT_UN_ABS 1
+#define CPT_UN_EXP 2
+#define CPT_UN_LOG 3
+#define CPT_UN_LOG2 4
+#define CPT_UN_LOG10 5
+#define CPT_UN_SQRT 6
+#define CPT_UN_TANH 7
+#define CPT_UN_SIN 8
+#define CPT_UN_COS 9
+#define CPT_UN_TAN 10
+#define CPT_UN_SINH 11
+#define CPT_UN_COSH 12
+#define CPT_UN_CLIP 13
+#define CPT_UN_ISNAN 14
+#define CPT_UN_ROUND 15
+#define CPT_UN_SQUARE 16
+#define CPT_UN_RECIP 17
+int cpt_ew_unary(int op, void* out, const float* a, float p0, float p1, int64_t n, void* stream);
+/* boolean arrays: op 0 and, 1 or, 2 xor, 3 not (b ignored)   tensors.py:270 (__invert__) */
+int cpt_logic(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, int64_t n, void* stream);
+/* reductions over the axes flagged in `reduced` (tensors.py:552-682, reduction_ops.py, selection_ops.py:22-127).
+ * x: C-contiguous fp32 (CPT_DT_F32) or bool (CPT_DT_U8).  out: C-contiguous over the kept axes — fp32 for SUM (× scale, so
+ * mean = SUM with scale 1/n) / SUMSQ / PROD / MAX / MIN (NaN propagates like NumPy), uint8 for ANY / ALL, int64 for COUNT
+ * (non-zeros) and ARGMAX (first maximum, NaN counts as the maximum; one axis or the whole tensor).  Deterministic: the
+ * reduced range is split over the grid and the partials are combined in fixed order (ws from cpt_reduce_workspace_size). */
+#define CPT_RED_SUM 0
+#define CPT_RED_SUMSQ 1
+#define CPT_RED_PROD 2
+#define CPT_RED_MAX 3
+#define CPT_RED_MIN 4
+#define CPT_RED_ANY 5
+#define CPT_RED_ALL 6
+#define CPT_RED_COUNT 7
+#define CPT_RED_ARGMAX 8
+size_t cpt_reduce_workspace_size(int64_t n_out);
+int cpt_reduce(int op, void* out, const void* x, int x_dtype, int ndim, const int64_t* dims, const int32_t* reduced,
+               float scale, void* ws, size_t ws_bytes, void* stream);
+/* dst[Σ i_k·dst_strides[k]] = src[Σ i_k·src_strides[k]] over `dims` — slicing / __setitem__ / permute / flip / concat / pad /
+ * broadcast_to (tensors.py:176-183, 615-667; shape_ops.py:34-458).  elem_size 1, 4 or 8 bytes; strides may be negative
+ * or 0 (source only); base offsets are folded into the pointers by the caller. */
+int cpt_strided_copy(void* dst, const void* src, int elem_size, int ndim, const int64_t* dims,
+                     const int64_t* dst_strides, const int64_t* src_strides, void* stream);
+/* dst[i, :] = src[idx[i], :] — integer-array indexing of the leading axis (Dataloader batch gather
+ * nn/utils/dataloaders.py:65-66, one-hot identity(n)[t] preprocessing/basic.py:125).  Negative indices wrap; an index
+ * out of range sets *err_flag (device int, may be NULL) and is clamped. */
+int cpt_gather_rows(void* dst, const void* src, const void* idx, int idx_dtype, int64_t n_idx, int64_t row_bytes,
+                    int64_t n_src_rows, int* err_flag, void* stream);
+/* astype (tensors.py:372-455) between CPT_DT_* types; → bool is `!= 0` */
+int cpt_cast(void* dst, int dst_dtype, const void* src, int src_dtype, int64_t n, void* stream);
+/* arange (creation_ops.py:24-57): dst[i] = start + i·step */
+int cpt_arange(void* dst, int dtype, double start, double step, int64_t n, void* stream);
+/* random/random.py:54-184 on a counter-based device RNG (statistical contract, not NumPy's stream): kind 0 uniform
+ * [p0, p1), 1 normal(mean p0, std p1), 2 integers in [p0, p1) stored as fp32 */
+int cpt_random_fill(float* dst, int64_t n, int kind, float p0, float p1, uint64_t seed, void* stream);
+
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 /* Synchronises the device and returns (then clears) the tensor-core pipeline watchdog flag: 0 = healthy,
  * non-zero = an mbarrier wait timed out inside a tcgen05 kernel (results invalid).  Test/debug helper. */

@@ -490,11 +490,12 @@ def test_producer_side_staging_is_bit_exact(cp, shape):
     # batch statistics summed in the convolution epilogue (cpt_conv2d_fprop_*_stats + cpt_bn_act_fwd_train_presum): another
     # summation order and E[a^2] - E[a]^2 instead of the shifted two-pass variance: the statistics agree to fp32 rounding, but
     # a 1e-7 change of an activation can flip its bf16 rounding in the next convolution's operand, so downstream tensors are
-    # compared at the bf16-mode tolerance (both paths are within it of the oracle, tests/test_gpu_models.py)
+    # compared at twice the bf16-mode tolerance: each path is within TOL of the oracle (tests/test_gpu_models.py), hence
+    # within 2*TOL of the other (measured: <= 1.3e-2 on dx after six bf16 convolutions, <= 1e-2 elsewhere)
     c = run(True, stats=True)
     for k, (u, v) in enumerate(zip(c, a)):
         scale = max(float(np.abs(v).max()), 1e-6)
-        assert float(np.abs(u - v).max()) <= TOL["bf16"] * scale + 1e-5, (k, u.shape, float(np.abs(u - v).max()), scale)
+        assert float(np.abs(u - v).max()) <= 2 * TOL["bf16"] * scale + 1e-5, (k, u.shape, float(np.abs(u - v).max()), scale)
     # first BatchNorm's running statistics come straight from the epilogue sums: fp32-rounding agreement
     n_par = len(list(build().get_parameters()))
     for u, v in zip(c[2 + n_par:2 + n_par + 2], a[2 + n_par:2 + n_par + 2]):

@@ -1,0 +1,310 @@
+"""GPU parity of the generic device-tensor operator set (run with ``-m gpu``).
+
+The oracle for this row is NumPy itself: the reference evaluates these operators by calling NumPy (cpu) / CuPy (cuda) on
+``Tensor.data`` (compyute/tensors.py:196-292, 552-682; compyute/tensor_ops/*.py), so every test evaluates the same
+expression on a ``cpu`` tensor (NumPy) and on a ``cuda`` tensor (csrc/tensor_ops.cu through the C ABI).
+Tolerances: bit-exact for comparisons, indexing, data movement, casts, max/min/argmax/any/all, add/sub/mul/div/neg/abs/sqrt
+(IEEE-exact in both); ``allclose(rtol=atol=1e-5)`` (the reference's tests/utils.py:54-60) for sums / means / variances (other
+summation order) and 1e-6 relative for transcendental functions (CUDA libm vs NumPy differ by <= 2 ulp)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cp():
+    import compyute_b200 as cp
+    from compyute_b200 import _lib
+    _lib.lib()
+    assert cp.gpu_available(), "no CUDA device"
+    return cp
+
+
+def dev(cp, a):
+    return cp.tensor(a, device=cp.cuda)
+
+
+def same(t, ref):
+    a = t.to_numpy() if hasattr(t, "to_numpy") else np.asarray(t)
+    ref = np.asarray(ref)
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    assert np.array_equal(a, ref, equal_nan=a.dtype.kind == "f"), float(np.nanmax(np.abs(a.astype(np.float64) - ref)))
+
+
+def near(t, ref, tol=1e-5):
+    a = t.to_numpy() if hasattr(t, "to_numpy") else np.asarray(t)
+    ref = np.asarray(ref)
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    assert np.allclose(a, ref, rtol=tol, atol=tol, equal_nan=True), float(np.nanmax(np.abs(a - ref)))
+
+
+RNG = np.random.RandomState(42)
+A = RNG.uniform(-2, 2, (6, 5, 7, 9)).astype(np.float32)
+SHAPES_B = [(6, 5, 7, 9), (5, 1, 1), (1, 5, 7, 9), (9,), (6, 1, 7, 1), (1,), (7, 9), (6, 5, 1, 1)]
+
+
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "truediv", "lt", "gt", "le", "ge", "eq", "ne"])
+@pytest.mark.parametrize("bshape", SHAPES_B, ids=str)
+def test_binary_broadcast_exact(cp, op, bshape):
+    import operator
+    f = getattr(operator, op)
+    b = RNG.uniform(0.5, 2, bshape).astype(np.float32)
+    b.reshape(-1)[::3] = A.reshape(-1)[:b.size:3]  # some equal elements for eq / le / ge
+    same(f(dev(cp, A), dev(cp, b)), f(A, b))
+    same(f(dev(cp, b), dev(cp, A)), f(b, A))
+
+
+@pytest.mark.parametrize("op", ["pow", "floordiv", "mod"])
+def test_binary_other(cp, op):
+    import operator
+    f = getattr(operator, op)
+    a = np.abs(A) + 0.25
+    b = RNG.uniform(0.5, 3, (5, 1, 1)).astype(np.float32)
+    near(f(dev(cp, a), dev(cp, b)), f(a, b), 1e-5 if op == "pow" else 1e-6)
+    near(f(dev(cp, A), 1.5) if op != "pow" else f(dev(cp, a), 1.5), f(A, np.float32(1.5)) if op != "pow" else f(a, np.float32(1.5)), 2e-6)
+    if op != "pow":  # sign conventions of floor division / modulo with negative operands
+        same(f(dev(cp, np.array([-7., 7., -7., 7., 5.5, -5.5], np.float32)), dev(cp, np.array([2., -2., -2., 2., 2., 2.], np.float32))),
+             f(np.array([-7., 7., -7., 7., 5.5, -5.5], np.float32), np.array([2., -2., -2., 2., 2., 2.], np.float32)))
+
+
+def test_scalar_and_reverse_and_inplace(cp):
+    x = dev(cp, A)
+    same(x + 2, A + np.float32(2)); same(2 + x, np.float32(2) + A); same(x - 2, A - np.float32(2)); same(2 - x, np.float32(2) - A)
+    same(x * 3, A * np.float32(3)); same(3 * x, A * np.float32(3)); same(x / 4, A / np.float32(4)); same(4 / x, np.float32(4) / A)
+    same(x > 0.5, A > 0.5); same(x == A[0, 0, 0, 0], A == A[0, 0, 0, 0]); same(-x, -A); same(x.abs(), np.abs(A))
+    near(2 ** x, np.float32(2) ** A, 2e-6); near(x ** 2, A ** 2, 1e-6)
+    y = dev(cp, A.copy()); p = y.data.ptr
+    y += dev(cp, A); y -= 1; y *= dev(cp, A[:, :, :1, :1].copy()); y /= 2; y += dev(cp, np.ones((5, 1, 1), np.float32))
+    ref = A.copy(); ref += A; ref -= 1; ref *= A[:, :, :1, :1]; ref /= 2; ref += np.ones((5, 1, 1), np.float32)
+    same(y, ref)
+    assert y.data.ptr == p, "in-place operators must keep the buffer"
+    with pytest.raises(cp.ShapeError):
+        dev(cp, A) + dev(cp, np.ones((4, 9), np.float32))
+    with pytest.raises(cp.ShapeError):
+        z = dev(cp, np.ones((5, 1, 1), np.float32)); z += dev(cp, A)
+    assert (None + dev(cp, A[0])).shape == A[0].shape  # tensors.py:199-201
+    # odd sizes / unaligned views go through the scalar tail
+    v = dev(cp, A.reshape(-1))[3:1000]
+    same(v * 2 + v, A.reshape(-1)[3:1000] * 2 + A.reshape(-1)[3:1000])
+
+
+def test_nan_semantics(cp):
+    a = np.array([1., np.nan, -3., np.inf, -np.inf, 0., -0.], np.float32); b = np.array([np.nan, 2., 5., 1., 1., -0., 0.], np.float32)
+    same(cp.maximum(dev(cp, a), dev(cp, b)), np.maximum(a, b)); same(cp.minimum(dev(cp, a), dev(cp, b)), np.minimum(a, b))
+    same(cp.is_nan(dev(cp, a)), np.isnan(a)); same(dev(cp, a) == dev(cp, a), a == a); same(cp.clip(dev(cp, a), -1, 2), np.clip(a, -1, 2))
+    same(dev(cp, a).max(), a.max()); same(dev(cp, a).min(), a.min()); same(dev(cp, a).argmax(), a.argmax())
+    same(dev(cp, a[2:]).max(), a[2:].max()); same(dev(cp, a[2:]).argmax(), a[2:].argmax())
+
+
+@pytest.mark.parametrize("name", ["exp", "log", "log2", "log10", "sqrt", "tanh", "sin", "cos", "tan", "sinh", "cosh", "sech", "abs"])
+def test_unary(cp, name):
+    a = (np.abs(A) + 0.1) if name in ("log", "log2", "log10", "sqrt") else A
+    ref = 1 / np.cosh(a) if name == "sech" else getattr(np, name)(a)
+    got = getattr(cp, name)(dev(cp, a))
+    if name in ("sqrt", "abs"):
+        same(got, ref)
+    else:
+        near(got, ref, 2e-6)
+    assert got.dtype == np.float32 and got.device == cp.cuda
+
+
+def test_round_clip_logic(cp):
+    a = np.array([0.5, 1.5, 2.5, -0.5, 1.234567, -1.23449, 12.3451], np.float32)
+    same(cp.round(dev(cp, a), 0), np.round(a, 0)); near(cp.round(dev(cp, a), 3), np.round(a, 3), 1e-6)
+    same(cp.clip(dev(cp, A), -0.5, None), np.clip(A, -0.5, None)); same(cp.clip(dev(cp, A), None, 0.25), np.clip(A, None, 0.25))
+    m1, m2 = A > 0, A < 1
+    d1, d2 = dev(cp, A) > 0, dev(cp, A) < 1
+    assert d1.dtype == np.bool_
+    same(~d1, ~m1); same(Tensor_and(d1, d2), m1 & m2); same(cp.Tensor(d1.data | d2.data), m1 | m2); same(cp.Tensor(d1.data ^ d2.data), m1 ^ m2)
+    same(d1.sum(), m1.sum()); same(d1.sum(1), m1.sum(1)); same(d1.any((0, 2)), m1.any((0, 2))); same(Tensor_and(d1, d2).all(), (m1 & m2).all())
+
+
+def Tensor_and(a, b):
+    from compyute_b200 import Tensor
+    return Tensor(a.data & b.data)
+
+
+DIMS = [None, 0, 1, 2, 3, -1, (0, 2, 3), (0, 1), (2, 3), (1, 3), (0, 3), (0, 1, 2, 3), (1, 2)]
+
+
+@pytest.mark.parametrize("keepdims", [False, True])
+@pytest.mark.parametrize("dim", DIMS, ids=str)
+def test_reductions(cp, dim, keepdims):
+    x = dev(cp, A)
+    near(x.sum(dim, keepdims=keepdims), A.sum(dim, keepdims=keepdims), 2e-5)
+    near(x.mean(dim, keepdims=keepdims), A.mean(dim, keepdims=keepdims))
+    near(x.var(dim, keepdims=keepdims), A.var(dim, keepdims=keepdims))
+    near(x.var(dim, ddof=1, keepdims=keepdims), A.var(dim, ddof=1, keepdims=keepdims))
+    near(x.std(dim, keepdims=keepdims), A.std(dim, keepdims=keepdims))
+    same(x.max(dim, keepdims=keepdims), A.max(dim, keepdims=keepdims))
+    same(x.min(dim, keepdims=keepdims), A.min(dim, keepdims=keepdims))
+    same((x > 1.9).any(dim, keepdims=keepdims), (A > 1.9).any(dim, keepdims=keepdims))
+    same((x > -1.9).all(dim, keepdims=keepdims), (A > -1.9).all(dim, keepdims=keepdims))
+    near(cp.norm(x, dim, keepdims=keepdims), np.sqrt((A.astype(np.float64) ** 2).sum(dim, keepdims=keepdims)), 1e-5)
+    if dim is None or isinstance(dim, int):
+        q = np.round(A * 2) / 2  # many ties: the first maximum wins
+        same(dev(cp, q).argmax(dim, keepdims=keepdims), q.argmax(dim, keepdims=keepdims))
+        assert dev(cp, q).argmax(dim).dtype == np.int64
+
+
+@pytest.mark.parametrize("shape,dim", [((1 << 20,), None), ((8192, 512), 0), ((8192, 512), 1), ((64, 32, 56, 56), (0, 2, 3)),
+                                       ((3, 1000003), 1), ((100003, 3), 0), ((2, 3, 5, 7, 4, 6, 2), (1, 2, 5)), ((513,), 0), ((1,), None), ((), None)], ids=str)
+def test_reductions_large_and_odd(cp, shape, dim):
+    """Grid-split reductions (fixed-order second pass), vectorised / scalar row form, column form, 7-d input."""
+    a = np.random.RandomState(1).normal(0.1, 1, shape).astype(np.float32)
+    x = dev(cp, a)
+    ref = a.astype(np.float64).sum(dim)
+    got = x.sum(dim).to_numpy()
+    assert got.shape == ref.shape and np.allclose(got, ref, rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(a).sum(dim).max())) ** 0.5)
+    near(x.mean(dim), a.astype(np.float64).mean(dim), 1e-5)
+    same(x.max(dim), a.max(dim)); same(x.min(dim), a.min(dim))
+    if dim is None or isinstance(dim, int):
+        same(x.argmax(dim), a.argmax(dim))
+    # determinism
+    assert np.array_equal(x.sum(dim).to_numpy(), got)
+
+
+def test_getitem_setitem(cp):
+    x = dev(cp, A)
+    keys = [0, -1, (1, 2), (slice(1, 4),), (slice(None), 2), (Ellipsis, 3), (slice(None), slice(None), slice(1, 6, 2), slice(None, None, -1)),
+            (slice(4, 1, -1), Ellipsis, slice(2, 3)), (None, 2, Ellipsis), (slice(0, 0),), (2, slice(None), None, 3, slice(8, 2, -3)),
+            (slice(None), slice(1, 2)), (Ellipsis,), (5, 4, 6, 8)]
+    for k in keys:
+        same(x[k], A[k])
+    idx = np.array([5, 0, 0, -1, 3], np.int64)
+    same(x[idx], A[idx]); same(x[cp.tensor(idx.astype(np.int32), device=cp.cuda)], A[idx]); same(x[[1, 2]], A[[1, 2]])
+    same(x[cp.tensor(idx)], A[idx])  # host index tensor (Dataloader, dataloaders.py:65-66)
+    eye = cp.identity(7, device=cp.cuda)
+    same(eye[dev(cp, np.array([3, 0, 6], np.int32))], np.identity(7, np.float32)[[3, 0, 6]])  # one-hot (preprocessing/basic.py:125)
+    with pytest.raises(IndexError):
+        x[6]
+    with pytest.raises(NotImplementedError):
+        x[x > 0]
+    # contiguous regions are views (writes go through, like NumPy); others are copies
+    y = dev(cp, A.copy()); ref = A.copy()
+    v = y[2]; v += 1; ref[2] += 1
+    same(y, ref)
+    for k, val in [((slice(None), 1), 7.0), ((slice(1, 3), slice(None), slice(0, 7, 3)), ref[1:3, :, 0:7:3] * 2), ((Ellipsis, slice(None, None, -2)), 3.5),
+                   ((0, 0), np.arange(9, dtype=np.float32)), ((slice(None), slice(None), 2, 2), np.float32(-1))]:
+        y[k] = dev(cp, val) if isinstance(val, np.ndarray) else val
+        ref[k] = val
+        same(y, ref)
+    with pytest.raises(cp.ShapeError):
+        y[0] = dev(cp, np.zeros((4, 4), np.float32))
+    assert len(x) == 6 and [t.shape for t in x][0] == A[0].shape
+
+
+def test_shape_ops(cp):
+    x = dev(cp, A)
+    same(x.T, np.swapaxes(A, -1, -2)); same(x.transpose(0, 2), A.swapaxes(0, 2)); same(x.permute((3, 1, 0, 2)), A.transpose(3, 1, 0, 2))
+    same(cp.movedim(x, 1, 3), np.moveaxis(A, 1, 3)); same(cp.flip(x), np.flip(A)); same(cp.flip(x, (1, 3)), np.flip(A, (1, 3)))
+    same(cp.flatten(x), A.reshape(-1)); same(cp.reshape(x, (30, 63)), A.reshape(30, 63)); same(cp.insert_dim(x, 2), np.expand_dims(A, 2))
+    same(dev(cp, A[:1, :, :1]).squeeze(), A[:1, :, :1].squeeze())
+    same(cp.pad(x, 2), np.pad(A, 2)); same(cp.pad(x, ((0, 0), (1, 2), (3, 0), (0, 1))), np.pad(A, ((0, 0), (1, 2), (3, 0), (0, 1))))
+    same(cp.pad_to_shape(x, (6, 8, 7, 12)), np.pad(A, ((0, 0), (0, 3), (0, 0), (0, 3))))
+    for d in (0, 1, -1):
+        same(cp.concat([x, x * 2, x], d), np.concatenate([A, A * 2, A], d))
+        same(cp.stack([x, x + 1], d), np.stack([A, A + 1], d))
+        same(cp.tile(x, 3, d), np.concatenate([A] * 3, d))
+    for got, ref in zip(cp.split(x, 3, 0), np.split(A, 3, 0)):
+        same(got, ref)
+    for got, ref in zip(cp.split(x, [2, 3, 8], -1), np.split(A, [2, 3, 8], -1)):
+        same(got, ref)
+    same(cp.repeat1d(x, 3), np.repeat(A, 3, -1)); same(cp.repeat2d(x, 2), np.repeat(np.repeat(A, 2, -1), 2, -2))
+    same(cp.broadcast_to(dev(cp, A[:, :1]), (2, 6, 5, 7, 9)), np.broadcast_to(A[:, :1], (2, 6, 5, 7, 9)))
+    same(cp.outer(dev(cp, A[0, 0, 0]), dev(cp, A[0, 0, 1])), np.outer(A[0, 0, 0], A[0, 0, 1]))
+    near(cp.inner(dev(cp, A[0, 0, 0]), dev(cp, A[0, 0, 1])), np.inner(A[0, 0, 0], A[0, 0, 1]))
+
+
+def test_creation_cast_random(cp):
+    with cp.use_device(cp.cuda):
+        same(cp.zeros((3, 4)), np.zeros((3, 4), np.float32)); same(cp.ones((5,)), np.ones(5, np.float32)); same(cp.full((2, 3), 2.5), np.full((2, 3), 2.5, np.float32))
+        same(cp.zeros((3,), dtype=np.int32), np.zeros(3, np.int32)); same(cp.ones((3,), dtype=np.int64), np.ones(3, np.int64))
+        same(cp.full((4,), 7, dtype=np.int32), np.full(4, 7, np.int32)); same(cp.ones((2, 2), dtype=np.bool_), np.ones((2, 2), np.bool_))
+        same(cp.arange(10), np.arange(10)); same(cp.arange(10, 2, 3, dtype=np.float32), np.arange(2, 10, 3, dtype=np.float32))
+        same(cp.identity(5), np.identity(5, np.float32)); near(cp.linspace(0, 1, 11), np.linspace(0, 1, 11, dtype=np.float32), 1e-6)
+        assert cp.zeros((2,)).device == cp.cuda and cp.ones_like(cp.zeros((2, 3))).shape == (2, 3)
+    x = dev(cp, A * 3)
+    same(x.to_int(), (A * 3).astype(np.int32)); same(x.to_long(), (A * 3).astype(np.int64)); same(x.to_type(np.bool_), (A * 3).astype(np.bool_))
+    same(x.to_int().to_float(), (A * 3).astype(np.int32).astype(np.float32)); same(x.to_type(np.float64), (A * 3).astype(np.float64))
+    i = dev(cp, np.arange(-5, 5, dtype=np.int64))
+    same(i + 1, (np.arange(-5, 5) + 1).astype(np.float32))  # integer arithmetic is carried in float32 on the device (documented)
+    same(i > 0, np.arange(-5, 5) > 0)
+    cp.random.set_seed(7)
+    u = cp.random.uniform((1 << 16,), -1, 3, device=cp.cuda).to_numpy(); n = cp.random.normal((1 << 16,), 2, 0.5, device=cp.cuda).to_numpy()
+    k = cp.random.uniform_int((1 << 14,), 3, 9, device=cp.cuda).to_numpy(); r = cp.random.random((1 << 12,), device=cp.cuda).to_numpy()
+    assert u.min() >= -1 and u.max() < 3 and abs(u.mean() - 1) < 0.03 and abs(u.var() - 16 / 12) < 0.05
+    assert abs(n.mean() - 2) < 0.01 and abs(n.std() - 0.5) < 0.01 and np.isfinite(n).all()
+    assert k.dtype == np.int32 and set(np.unique(k)) == set(range(3, 9)) and r.min() >= 0 and r.max() < 1
+    cp.random.set_seed(7)
+    assert np.array_equal(cp.random.uniform((1 << 16,), -1, 3, device=cp.cuda).to_numpy(), u)  # reproducible
+    assert not np.array_equal(cp.random.uniform((1 << 16,), -1, 3, device=cp.cuda).to_numpy(), u)  # a fresh draw per call
+    p = cp.random.permutation(100, device=cp.cuda)
+    assert sorted(p.to_numpy().tolist()) == list(range(100))
+    xs, idx = cp.random.shuffle(dev(cp, A))
+    same(xs, A[idx.to_numpy()])
+    b = cp.random.bernoulli(0.3, (1 << 16,), device=cp.cuda).to_numpy()
+    assert b.dtype == np.bool_ and abs(b.mean() - 0.3) < 0.01
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("bf16", 1e-2)])
+def test_matmul(cp, mode, tol):
+    rng = np.random.RandomState(3)
+    a = rng.uniform(-1, 1, (48, 64)).astype(np.float32); b = rng.uniform(-1, 1, (64, 40)).astype(np.float32)
+    a3 = rng.uniform(-1, 1, (3, 16, 64)).astype(np.float32); b3 = rng.uniform(-1, 1, (3, 64, 24)).astype(np.float32)
+    with cp.compute_mode(mode):
+        for x, y in ((a, b), (a3, b), (a3, b3), (a[0], b), (a, b[:, 0]), (a[0], b[:, 0])):
+            ref = x.astype(np.float64) @ y.astype(np.float64)
+            got = (dev(cp, x) @ dev(cp, y)).to_numpy()
+            assert got.shape == ref.shape and np.abs(got - ref).max() <= tol * max(1.0, np.abs(ref).max())
+    with pytest.raises(cp.ShapeError):
+        dev(cp, a) @ dev(cp, a)
+
+
+def test_allclose_and_clip_grad_norm(cp):
+    from compyute_b200 import nn
+    from compyute_b200.nn.utils import clip_grad_norm
+    x = dev(cp, A)
+    assert cp.allclose(x, dev(cp, A + 1e-7)) and not cp.allclose(x, dev(cp, A + 1e-2))
+    np.random.seed(0)
+    with cp.use_device(cp.cuda):
+        model = nn.Sequential(nn.Conv2D(3, 4, 3, padding="same"), nn.ReLU(), nn.Flatten(), nn.Linear(4 * 36, 5))
+    model.training()
+    y = model(dev(cp, RNG.normal(0, 1, (8, 3, 6, 6)).astype(np.float32)))
+    model.backward(dev(cp, RNG.normal(0, 1, y.shape).astype(np.float32)))
+    grads = [p.grad.to_numpy().copy() for p in model.get_parameters()]
+    total = float(np.sqrt(sum((g.astype(np.float64) ** 2).sum() for g in grads)))
+    assert abs(clip_grad_norm(model.get_parameters(), 1e9) - total) <= 1e-5 * total
+    for p, g in zip(model.get_parameters(), grads):
+        same(p.grad, g)
+    got = clip_grad_norm(model.get_parameters(), total / 4)  # training.py:31-37
+    assert abs(got - total) <= 1e-5 * total
+    for p, g in zip(model.get_parameters(), grads):
+        near(p.grad, g * np.float32(0.25), 1e-6)
+
+
+def test_memory_bound_ops_reach_bandwidth(cp):
+    """Throughput sanity at a size far above L2 (256 MiB operands): the flat binary kernel and the full reduction must
+    run at a sizeable fraction of HBM bandwidth (the exact figures are in profiles/, tools/membound_bench.py)."""
+    import torch
+    n = 64 << 20
+    a = cp.tensor(np.ones(1, np.float32), device=cp.cuda)
+    from compyute_b200.tensors import DeviceArray
+    x = cp.Tensor(DeviceArray.empty((n,), np.float32)); x.data.fill(1.0)
+    y = cp.Tensor(DeviceArray.empty((n,), np.float32)); y.data.fill(2.0)
+
+    def timed(f, reps=5):
+        f(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            f()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    t_add = timed(lambda: x + y); t_sum = timed(lambda: x.sum())
+    assert float(x.sum().item()) == float(n)
+    gbs_add, gbs_sum = 12 * n / t_add / 1e9, 4 * n / t_sum / 1e9
+    print(f"add {gbs_add:.0f} GB/s, sum {gbs_sum:.0f} GB/s")
+    assert gbs_add > 2500 and gbs_sum > 2500, (gbs_add, gbs_sum)

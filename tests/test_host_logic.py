@@ -208,3 +208,67 @@ def test_plan_grad_buckets_tiles_the_arena_from_the_end():
                 assert lo == offs[members[-1]]
                 seen += members
             assert seen == list(range(len(sizes) - 1, -1, -1))
+
+
+# ---------------------------------------------------------------- device_ops host logic, no GPU needed
+def test_basic_index_regions_match_numpy():
+    """``_basic_index`` turns a NumPy basic index into (offset, dims, strides) of a C-contiguous array; checked by reading the
+    region back through as_strided and comparing with NumPy's own indexing."""
+    from numpy.lib.stride_tricks import as_strided
+    from compyute_b200.device_ops import _basic_index
+    a = np.arange(6 * 5 * 7 * 9, dtype=np.int64).reshape(6, 5, 7, 9)
+    keys = [0, -1, (1, 2), (slice(1, 4),), (slice(None), 2), (Ellipsis, 3), (slice(None), slice(None), slice(1, 6, 2), slice(None, None, -1)),
+            (slice(4, 1, -1), Ellipsis, slice(2, 3)), (None, 2, Ellipsis), (slice(0, 0),), (2, slice(None), None, 3, slice(8, 2, -3)),
+            (Ellipsis,), (5, 4, 6, 8), (slice(10, 20),), (slice(-3, None), slice(None, -2)), (Ellipsis, None), (slice(None, None, -1),) * 4]
+    for k in keys:
+        off, dims, strides = _basic_index(a.shape, k)
+        ref = a[k]
+        assert tuple(dims) == ref.shape, (k, dims, ref.shape)
+        if ref.size:
+            got = as_strided(a.reshape(-1)[off:], shape=dims, strides=[s * 8 for s in strides]) if all(s >= 0 for s in strides) else None
+            if got is None:  # negative strides: evaluate element by element
+                got = np.empty(dims, np.int64)
+                for idx in np.ndindex(*dims):
+                    got[idx] = a.reshape(-1)[off + sum(i * s for i, s in zip(idx, strides))]
+            assert np.array_equal(got, ref), k
+    for bad in [(6,), (0, 0, 0, 0, 0), (Ellipsis, Ellipsis)]:
+        with pytest.raises(IndexError):
+            _basic_index(a.shape, bad)
+
+
+def test_broadcast_strides_and_merge():
+    from compyute_b200.device_ops import _bstrides, _contig_strides, _merge
+    assert _contig_strides((6, 5, 7, 9)) == [315, 63, 9, 1]
+    assert _bstrides((5, 1, 1), (6, 5, 7, 9)) == [0, 1, 0, 0]
+    assert _bstrides((6, 1, 7, 1), (6, 5, 7, 9)) == [7, 0, 1, 0]
+    assert _bstrides((1,), (3, 4)) == [0, 0]
+    # same-shape operands collapse to one flat dim; a per-channel operand to (B, C, HW)
+    assert _merge((6, 5, 7, 9), [315, 63, 9, 1], [315, 63, 9, 1]) == ([1890], [[1], [1]])
+    assert _merge((6, 5, 7, 9), [315, 63, 9, 1], [0, 1, 0, 0]) == ([6, 5, 63], [[315, 63, 1], [0, 1, 0]])
+    # every merged form addresses the same elements as the unmerged one
+    rng = np.random.RandomState(0)
+    for _ in range(50):
+        nd = rng.randint(1, 7)
+        shape = tuple(int(v) for v in rng.randint(1, 4, nd))
+        bshape = tuple(d if rng.rand() < 0.5 else 1 for d in shape)
+        sa, sb = _bstrides(shape, shape), _bstrides(bshape, shape)
+        md, (ma, mb) = _merge(shape, sa, sb)
+        full = [(sum(i * s for i, s in zip(idx, sa)), sum(i * s for i, s in zip(idx, sb))) for idx in np.ndindex(*shape)]
+        merged = [(sum(i * s for i, s in zip(idx, ma)), sum(i * s for i, s in zip(idx, mb))) for idx in np.ndindex(*md)] if md else [(0, 0)]
+        assert full == merged, (shape, bshape)
+
+
+def test_tensor_ops_namespace_matches_reference_names():
+    """Every function exported by compyute_b200.tensor_ops carries a reference name; on cpu tensors they evaluate with NumPy
+    (host staging), which also pins the argument conventions (stop-first arange, dim / keepdims keywords)."""
+    import compyute_b200 as cp
+    t = cp.tensor(np.arange(12, dtype=np.float32).reshape(3, 4))
+    assert np.array_equal(cp.arange(10, 2, 3).to_numpy(), np.arange(2, 10, 3))
+    assert np.array_equal(cp.sum(t, 0, keepdims=True).to_numpy(), t.to_numpy().sum(0, keepdims=True))
+    assert np.array_equal(cp.concat([t, t], 0).to_numpy(), np.concatenate([t.to_numpy()] * 2, 0))
+    assert np.array_equal(cp.pad_to_shape(t, (4, 6)).to_numpy(), np.pad(t.to_numpy(), ((0, 1), (0, 2))))
+    assert np.array_equal((t @ t.T).to_numpy(), t.to_numpy() @ t.to_numpy().T)
+    assert np.array_equal(cp.maximum(t, 5).to_numpy(), np.maximum(t.to_numpy(), 5))
+    assert (None + t).shape == (3, 4) and bool(t == t) is True  # tensors.py:199-201, 305-306
+    for name in cp.tensor_ops.__all__:
+        assert callable(getattr(cp, name))
