@@ -1,4 +1,4 @@
-"""Host-side utilities around the path.
+"""Input pipeline.
 
 ``Dataloader`` mirrors compyute/nn/utils/dataloaders.py:18-69 (same constructor, ``__call__`` yields tuples of batch
 Tensors on ``device``, ``__len__``).  It is the H2D boundary of a train step and the natural data-parallel shard point
@@ -13,11 +13,11 @@ from typing import Iterator, Optional
 
 import numpy as np
 
-from .. import distributed
-from ..backend import Device, cpu
-from ..tensors import DeviceArray, Tensor
+from ... import distributed
+from ...backend import Device, cpu
+from ...tensors import DeviceArray, Tensor
 
-__all__ = ["Dataloader", "clip_grad_norm"]
+__all__ = ["Dataloader"]
 
 
 class Dataloader:
@@ -92,30 +92,3 @@ class Dataloader:
                 d.record_stream(main)
                 out.append(Tensor(DeviceArray(d, h.shape, h.dtype)))
             yield tuple(out)
-
-
-def clip_grad_norm(parameters, max_norm: float) -> float:
-    """compyute/nn/utils/training.py:12-39: scales all gradients so that their joint L2 norm is at most ``max_norm``;
-    returns the unclipped norm.  On the device: one sum-of-squares reduction per gradient, one 4-byte D2H for the norm (the
-    reference concatenates every gradient into one array first), one in-place scale per gradient when clipping."""
-    params = [p for p in parameters if p.grad]
-    if not params:
-        return 0.0
-    from .. import device_ops as D
-    sq = 0.0
-    parts = []
-    for p in params:
-        g = p.grad.data
-        if isinstance(g, DeviceArray):
-            parts.append(D.reduce("sumsq", g))
-        else:
-            sq += float(np.sum(np.square(g, dtype=np.float64)))
-    if parts:
-        sq += float(D.reduce("sum", D.concat([s.reshape(1) for s in parts], 0)).item())
-    grad_norm = float(np.sqrt(sq))
-    if grad_norm <= max_norm:
-        return grad_norm
-    clip_coef = max_norm / grad_norm
-    for p in params:
-        p.grad *= clip_coef
-    return grad_norm

@@ -1,0 +1,36 @@
+"""Training utilities (compyute/nn/utils/training.py)."""
+
+from __future__ import annotations
+
+import numpy as np
+
+from ...tensors import DeviceArray
+
+__all__ = ["clip_grad_norm"]
+
+
+def clip_grad_norm(parameters, max_norm: float) -> float:
+    """compyute/nn/utils/training.py:12-39: scales all gradients so that their joint L2 norm is at most ``max_norm``;
+    returns the unclipped norm.  On the device: one sum-of-squares reduction per gradient, one 4-byte D2H for the norm (the
+    reference concatenates every gradient into one array first), one in-place scale per gradient when clipping."""
+    params = [p for p in parameters if p.grad]
+    if not params:
+        return 0.0
+    from ... import device_ops as D
+    sq = 0.0
+    parts = []
+    for p in params:
+        g = p.grad.data
+        if isinstance(g, DeviceArray):
+            parts.append(D.reduce("sumsq", g))
+        else:
+            sq += float(np.sum(np.square(g, dtype=np.float64)))
+    if parts:
+        sq += float(D.reduce("sum", D.concat([s.reshape(1) for s in parts], 0)).item())
+    grad_norm = float(np.sqrt(sq))
+    if grad_norm <= max_norm:
+        return grad_norm
+    clip_coef = max_norm / grad_norm
+    for p in params:
+        p.grad *= clip_coef
+    return grad_norm

@@ -7,6 +7,8 @@ import re
 import numpy as np
 import pytest
 
+from tests.conftest import GOLDEN
+
 import compyute_b200 as cp
 from compyute_b200 import _lib, nn
 from compyute_b200.nn.functional import FunctionCache, PseudoCache, conv2d, no_caching, relu
@@ -272,3 +274,44 @@ def test_tensor_ops_namespace_matches_reference_names():
     assert (None + t).shape == (3, 4) and bool(t == t) is True  # tensors.py:199-201, 305-306
     for name in cp.tensor_ops.__all__:
         assert callable(getattr(cp, name))
+
+
+# ---------------------------------------------------------------- LR schedulers, gradient clipping (golden = real reference)
+def test_lr_schedulers_match_reference_sequences():
+    """tests/golden/lr_schedulers.json holds the learning-rate histories the reference's schedulers produce over 30 steps
+    (oracle/gen_golden_next.py); ours must reproduce them exactly (same float operations in the same order)."""
+    import json
+    from compyute_b200.nn import optimizers
+    from compyute_b200.nn.utils import lr_schedulers
+    cases = json.load(open(os.path.join(GOLDEN, "lr_schedulers.json")))
+    assert len(cases) == 5
+    for c in cases:
+        opt = optimizers.SGD([], lr=c["lr0"])
+        sched = getattr(lr_schedulers, c["scheduler"])(opt, **c["kwargs"])
+        for i in range(c["steps"]):
+            opt.t += 1
+            if c["metrics"]:
+                sched.step(loss=c["metrics"][i])
+            else:
+                sched.step()
+        assert sched.cache["lr_history"] == c["lr_history"], c["scheduler"]
+        assert opt.lr == c["final_lr"]
+    with pytest.raises(ValueError):
+        lr_schedulers.AdaptiveLrScheduler(optimizers.SGD([], lr=0.1)).step()
+
+
+def test_clip_grad_norm_host_path_matches_reference():
+    import compyute_b200 as cp
+    from compyute_b200.nn.parameter import Parameter
+    from compyute_b200.nn.utils import clip_grad_norm
+    g = np.load(os.path.join(GOLDEN, "clip_grad_norm.npz"))
+    for tag in ("loose", "tight"):
+        ps = []
+        for i in range(5):
+            p = Parameter(cp.tensor(np.zeros_like(g[f"g{i}"])))
+            p.grad = cp.tensor(g[f"g{i}"].copy())
+            ps.append(p)
+        norm = clip_grad_norm(iter(ps), float(g[f"{tag}_max_norm"]))
+        assert abs(norm - float(g[f"{tag}_norm"])) <= 1e-6 * float(g[f"{tag}_norm"])
+        for i, p in enumerate(ps):
+            assert np.allclose(p.grad.to_numpy(), g[f"{tag}_g{i}"], rtol=1e-6, atol=1e-8)

@@ -105,3 +105,25 @@ if __name__ == "__main__":
     cc = FunctionCache()
     n = 8192 * 4096
     report("softmax_ce_fwd 8192x4096", 8 * n, timeit(lambda: (cc.cache.clear(), CrossEntropyLossFn.forward(cc, logits, t, 1e-8))), "logits read + probs write (sub-L2 size)")
+    del logits, ps, adam, sgd
+    torch.cuda.empty_cache()
+    # generic device-tensor operators (csrc/tensor_ops.cu) on the ResNet-18 stem activation shape
+    xs = wrap(torch.randn(B, C, H, H, device="cuda")); ys = wrap(torch.randn(B, C, H, H, device="cuda"))
+    ch = wrap(torch.randn(C, 1, 1, device="cuda"))
+    report("ew_binary add (same shape)", 12 * N, timeit(lambda: xs + ys), "a, b read + out write")
+    report("ew_binary mul scalar", 8 * N, timeit(lambda: xs * 1.5))
+    report("ew_binary add (C,1,1) broadcast", 8 * N, timeit(lambda: xs + ch), "strided index path")
+    report("ew_binary gt -> bool", 5 * N, timeit(lambda: xs > 0.5), "4 B read + 1 B write")
+    report("ew_unary exp", 8 * N, timeit(lambda: cp.exp(xs)))
+    report("reduce sum (all)", 4 * N, timeit(lambda: xs.sum()), "row form, split over the grid + fixed-order finish")
+    report("reduce sum dims (0,2,3)", 4 * N, timeit(lambda: xs.sum((0, 2, 3))), "row form, 2 reduced dims")
+    report("reduce max last dim", 4 * N, timeit(lambda: xs.max(-1)), "row form, 112-element rows")
+    x2 = wrap(torch.randn(8192 * 8, 4096, device="cuda")); n2 = x2.size
+    report("reduce sum dim 0 of (65536,4096)", 4 * n2, timeit(lambda: x2.sum(0)), "column form")
+    report("reduce argmax dim 1 of (65536,4096)", 4 * n2, timeit(lambda: x2.argmax(1)))
+    report("permute NCHW->NHWC (strided copy)", 8 * N, timeit(lambda: xs.permute((0, 2, 3, 1))), "generic gather; the staging kernel is the tuned form")
+    report("slice copy x[:, :, 1:-1, 1:-1]", 8 * (B * C * (H - 2) ** 2), timeit(lambda: xs[:, :, 1:-1, 1:-1]))
+    idx = Tensor(DeviceArray(torch.randperm(B, device="cuda").to(torch.int32), (B,), np.int32))
+    report("gather_rows (batch shuffle)", 8 * N, timeit(lambda: xs[idx]))
+    report("cast f32 -> int32", 8 * N, timeit(lambda: xs.to_int()))
+    report("random normal", 4 * N, timeit(lambda: cp.random.normal((B, C, H, H), device=cp.cuda)), "write only")
