@@ -178,6 +178,81 @@ __global__ void __launch_bounds__(1024) bn_fwd_finalize_presum_kernel(const floa
   rvar_out[c] = rvar[c] * (1.0f - m) + var_unbiased * m;
 }
 
+// ---- synchronised BatchNorm (statistics over the global batch of all data-parallel ranks) ----
+// local (mean, M2 = Σ(x - mean)², count) of this rank's shard from the shifted partial sums -> stats[3][C]
+__global__ void bn_local_stats_kernel(const float* __restrict__ x, const float2* __restrict__ partial, int S,
+                                      float* __restrict__ stats, int C, int HW, float count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sa = 0.0, sb = 0.0;
+  for (int s = 0; s < S; ++s) {
+    const float2 p = partial[(int64_t)c * S + s];
+    sa += (double)p.x;
+    sb += (double)p.y;
+  }
+  const double dm = sa / (double)count;
+  double m2 = sb - (double)count * dm * dm;
+  stats[c] = (float)((double)x[(int64_t)c * HW] + dm);
+  stats[C + c] = (float)(m2 > 0.0 ? m2 : 0.0);
+  stats[2 * C + c] = count;
+}
+
+// merges the ranks' (mean, M2, count) in rank order with the pairwise update of Chan et al. — every rank runs the same
+// arithmetic on the same gathered values, so all replicas get bit-identical statistics
+__global__ void bn_fwd_finalize_merged_kernel(const float* __restrict__ gathered, int world, const float* __restrict__ rmean,
+                                              const float* __restrict__ rvar, float* __restrict__ rmean_out,
+                                              float* __restrict__ rvar_out, float* __restrict__ save_mean,
+                                              float* __restrict__ save_rstd, float* __restrict__ global_count, int C, float m,
+                                              float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int r = 0; r < world; ++r) {
+    const float* g = gathered + (int64_t)r * 3 * C;
+    const double nb = (double)g[2 * C + c];
+    if (nb <= 0.0) continue;
+    const double delta = (double)g[c] - mean, tot = n + nb;
+    mean += delta * nb / tot;
+    m2 += (double)g[C + c] + delta * delta * n * nb / tot;
+    n = tot;
+  }
+  const double var = m2 / n;
+  if (c == 0) *global_count = (float)n;
+  save_mean[c] = (float)mean;
+  save_rstd[c] = 1.0f / sqrtf((float)var + eps);
+  rmean_out[c] = rmean[c] * (1.0f - m) + (float)mean * m;
+  rvar_out[c] = rvar[c] * (1.0f - m) + (float)(m2 / (n - 1.0)) * m;
+}
+
+// local backward sums -> sums[2][C] = (Σdy, Σdy·x̂) (to be all-reduced), dw / db (local: the gradient exchange averages them)
+__global__ void bn_bwd_local_sums_kernel(const float2* __restrict__ partial, int S, float* __restrict__ sums,
+                                         float* __restrict__ dw, float* __restrict__ db, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sa = 0.f, sb = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float2 p = partial[(int64_t)c * S + s];
+    sa += p.x;
+    sb += p.y;
+  }
+  sums[c] = sa;
+  sums[C + c] = sb;
+  db[c] = sa;
+  dw[c] = sb;
+}
+
+// the global element count lives on the device (written by the merged forward), so the apply kernels run with count = 1 and
+// coefficients pre-divided by n: dx = w·rstd·(dy - Σdy/n - x̂·Σ(dy·x̂)/n)
+__global__ void bn_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ w, const float* __restrict__ rstd,
+                                   float* __restrict__ coef, int C, const float* __restrict__ global_count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float n = *global_count;
+  coef[3 * c + 0] = w[c] * rstd[c];
+  coef[3 * c + 1] = sums[c] / n;
+  coef[3 * c + 2] = sums[C + c] / n;
+}
+
 __global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar,
                                      float* __restrict__ save_mean, float* __restrict__ save_rstd, int C, float eps) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,6 +340,59 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
   }
 }
 
+// y = relu(bn(x) + skip): the tail of a residual block (BatchNorm2D -> `y += skip` -> ReLU; containers.py:153-157 followed by
+// activations.py:114-120) in one pass — 12 1/8 B/elem instead of 8 + 12 + 8 1/8.  Same arithmetic in the same order as the three
+// separate kernels (fmaf(w, (x-mu)*rstd, b); + skip; NaN-propagating max), so results are bit-identical.  Thread mapping and
+// mask layout are those of relu_fwd_kernel (eltwise.cu): warp per 1024-element chunk, lane l owns the float4s at j*32 + l and
+// mask word chunk*32 + l; tail in plain bit order — cpt_relu_bwd consumes the mask unchanged.  Requires HW % 4 == 0.
+__global__ void __launch_bounds__(256) bn_add_relu_kernel(const float* __restrict__ x, const float* __restrict__ skip,
+                                                          const float* __restrict__ w, const float* __restrict__ b,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          float* __restrict__ y, uint32_t* __restrict__ mask, uint32_t n_chunks,
+                                                          uint32_t n, uint32_t C, uint32_t HW) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t c = warp0; c < n_chunks; c += nwarps) {
+    const float4* xp = reinterpret_cast<const float4*>(x) + (size_t)c * 256 + lane;
+    const float4* sp = reinterpret_cast<const float4*>(skip) + (size_t)c * 256 + lane;
+    float4* yp = reinterpret_cast<float4*>(y) + (size_t)c * 256 + lane;
+    float4 v[8], k[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] = ld_stream(xp + j * 32); k[j] = ld_stream(sp + j * 32); }
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t e0 = (c * 256 + lane + j * 32) * 4;  // first element of this float4 (one channel: HW % 4 == 0)
+      const uint32_t ch = (e0 / HW) % C;
+      const float mu = __ldg(mean + ch), rs = __ldg(rstd + ch), ww = __ldg(w + ch), bb = __ldg(b + ch);
+      float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+      const float sk[4] = {k[j].x, k[j].y, k[j].z, k[j].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float r = relu_fwd_val(fmaf(ww, (e[i] - mu) * rs, bb) + sk[i]);
+        bits |= (r > 0.f ? 1u : 0u) << (4 * j + i);
+        e[i] = r;
+      }
+      st_stream(yp + j * 32, make_float4(e[0], e[1], e[2], e[3]));
+    }
+    if (mask) mask[c * 32 + lane] = bits;
+  }
+  if (warp0 == 0) {
+    const uint32_t t0 = n_chunks * 1024;
+    for (uint32_t base = t0; base < n; base += 32) {
+      const uint32_t i = base + lane;
+      float r = 0.f;
+      if (i < n) {
+        const uint32_t ch = (i / HW) % C;
+        r = relu_fwd_val(fmaf(__ldg(w + ch), (x[i] - __ldg(mean + ch)) * __ldg(rstd + ch), __ldg(b + ch)) + skip[i]);
+        y[i] = r;
+      }
+      const uint32_t bl = __ballot_sync(0xffffffffu, i < n && r > 0.f);
+      if (mask && lane == 0) mask[n_chunks * 32 + (base - t0) / 32] = bl;
+    }
+  }
+}
+
 static int bn_splits(int N, int C, int HW) {
   // aim for >= 4 CTAs per SM in total, each with at least ~4K elements
   const int64_t per_channel = (int64_t)N * HW;
@@ -340,6 +468,7 @@ int cpt_bn_act_fwd_train(const float* x, const float* w, const float* b, const f
   bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(x, partial, S, rmean, rvar, rmean_out, rvar_out, save_mean,
                                                           save_rstd, C, HW, count, m, eps);
   CPT_LAUNCH_CHECK("bn_fwd_finalize");
+  if (!y) return CPT_OK;  // statistics only: the caller applies them itself (cpt_bn_add_relu_apply)
   launch_apply(x, w, b, save_mean, save_rstd, y, N, C, HW, act, st);
   CPT_LAUNCH_CHECK("bn_apply");
   return CPT_OK;
@@ -381,6 +510,7 @@ int cpt_bn_act_fwd_train_presum(const float* x, const float* w, const float* b, 
   bn_fwd_finalize_presum_kernel<<<(C + 31) / 32, 1024, 0, st>>>(stats, stat_slots, conv_bias, rmean, rvar, rmean_out, rvar_out,
                                                                 save_mean, save_rstd, C, count, m, eps);
   CPT_LAUNCH_CHECK("bn_fwd_finalize_presum");
+  if (!y) return CPT_OK;
   if (y_cl) return tc::bn_apply_cl(x, w, b, save_mean, save_rstd, y, y_cl, N, C, HW, act, st);
   launch_apply(x, w, b, save_mean, save_rstd, y, N, C, HW, act, st);
   CPT_LAUNCH_CHECK("bn_apply");
@@ -436,6 +566,7 @@ int cpt_bn_act_fwd_eval(const float* x, const float* w, const float* b, const fl
   cudaStream_t st = as_stream(stream);
   bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(rmean, rvar, save_mean, save_rstd, C, eps);
   CPT_LAUNCH_CHECK("bn_eval_stats");
+  if (!y) return CPT_OK;
   launch_apply(x, w, b, save_mean, save_rstd, y, N, C, HW, act, st);
   CPT_LAUNCH_CHECK("bn_apply");
   return CPT_OK;
@@ -477,6 +608,105 @@ int cpt_bn_act_bwd(const float* x, const float* dy, const float* w, const float*
 int cpt_bn_bwd(const float* x, const float* dy, const float* w, const float* save_mean, const float* save_rstd,
                float* dx, float* dw, float* db, int N, int C, int HW, void* ws, size_t ws_bytes, void* stream) {
   return cpt_bn_act_bwd(x, dy, w, nullptr, save_mean, save_rstd, dx, dw, db, N, C, HW, CPT_ACT_NONE, ws, ws_bytes, stream);
+}
+
+// ---- synchronised BatchNorm: the three-step forms of the passes above (the caller runs the collective in between) ----
+static int bn_S(int N, int C, int HW) {
+  return (HW == 1) ? (int)((N / 8 / 64 > 0) ? ((N / 8 / 64 > 64) ? 64 : N / 8 / 64) : 1) : bn_splits(N, C, HW);
+}
+
+int cpt_bn_local_stats(const float* x, float* stats, int N, int C, int HW, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = bn_check("bn_local_stats", N, C, HW)) return e;
+  CPT_REQUIRE(x && stats, CPT_ERR_INVALID, "bn_local_stats: null pointer");
+  CPT_REQUIRE(ws && ws_bytes >= cpt_bn_workspace_size(N, C, HW), CPT_ERR_WORKSPACE, "bn_local_stats: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int S = bn_S(N, C, HW);
+  float2* partial = reinterpret_cast<float2*>(ws);
+  launch_partial<0>(x, nullptr, nullptr, nullptr, nullptr, nullptr, partial, N, C, HW, S, st);
+  CPT_LAUNCH_CHECK("bn_stats");
+  bn_local_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(x, partial, S, stats, C, HW, (float)((int64_t)N * HW));
+  CPT_LAUNCH_CHECK("bn_local_stats");
+  return CPT_OK;
+}
+
+int cpt_bn_act_fwd_train_merged(const float* x, const float* w, const float* b, const float* rmean, const float* rvar, float* y,
+                                void* y_cl, float* rmean_out, float* rvar_out, float* save_mean, float* save_rstd, int N, int C,
+                                int HW, float m, float eps, int act, const float* gathered, int world, float* global_count,
+                                void* stream) {
+  if (int e = bn_check("bn_fwd_train_merged", N, C, HW)) return e;
+  if (int e = check_act("bn_fwd_train_merged", act)) return e;
+  CPT_REQUIRE(gathered && world > 0 && global_count, CPT_ERR_INVALID, "bn_fwd_train_merged: no gathered statistics");
+  cudaStream_t st = as_stream(stream);
+  bn_fwd_finalize_merged_kernel<<<(C + 127) / 128, 128, 0, st>>>(gathered, world, rmean, rvar, rmean_out, rvar_out, save_mean,
+                                                                 save_rstd, global_count, C, m, eps);
+  CPT_LAUNCH_CHECK("bn_fwd_finalize_merged");
+  if (!y) return CPT_OK;
+  if (y_cl) return tc::bn_apply_cl(x, w, b, save_mean, save_rstd, y, y_cl, N, C, HW, act, st);
+  launch_apply(x, w, b, save_mean, save_rstd, y, N, C, HW, act, st);
+  CPT_LAUNCH_CHECK("bn_apply");
+  return CPT_OK;
+}
+
+int cpt_bn_act_bwd_local_sums(const float* x, const float* dy, const float* w, const float* b, const float* save_mean,
+                              const float* save_rstd, float* sums, float* dw, float* db, int N, int C, int HW, int act, void* ws,
+                              size_t ws_bytes, void* stream) {
+  if (int e = bn_check("bn_bwd_local_sums", N, C, HW)) return e;
+  if (int e = check_act("bn_bwd_local_sums", act)) return e;
+  CPT_REQUIRE(act == CPT_ACT_NONE || b, CPT_ERR_INVALID, "bn_bwd_local_sums: the fused ReLU mask needs the bias");
+  CPT_REQUIRE(ws && ws_bytes >= cpt_bn_workspace_size(N, C, HW), CPT_ERR_WORKSPACE, "bn_bwd_local_sums: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int S = bn_S(N, C, HW);
+  float2* partial = reinterpret_cast<float2*>(ws);
+  if (act) launch_partial<2>(x, dy, save_mean, save_rstd, w, b, partial, N, C, HW, S, st);
+  else launch_partial<1>(x, dy, save_mean, save_rstd, w, b, partial, N, C, HW, S, st);
+  CPT_LAUNCH_CHECK("bn_bwd_partial");
+  bn_bwd_local_sums_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, S, sums, dw, db, C);
+  CPT_LAUNCH_CHECK("bn_bwd_local_sums");
+  return CPT_OK;
+}
+
+int cpt_bn_act_bwd_apply_global(const float* x, const float* dy, const float* w, const float* b, const float* save_mean,
+                                const float* save_rstd, const float* sums, const float* global_count, float* dx, void* dx_cl,
+                                float* dx_chan_sum, int N, int C, int HW, int act, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = bn_check("bn_bwd_apply_global", N, C, HW)) return e;
+  if (int e = check_act("bn_bwd_apply_global", act)) return e;
+  CPT_REQUIRE(sums && global_count, CPT_ERR_INVALID, "bn_bwd_apply_global: no sums / count");
+  CPT_REQUIRE(ws && ws_bytes >= (dx_cl ? cpt_bn_cl_workspace_size(N, C, HW) : cpt_bn_workspace_size(N, C, HW)), CPT_ERR_WORKSPACE,
+              "bn_bwd_apply_global: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  float* coef = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + (size_t)C * 64 * sizeof(float2));
+  bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, w, save_rstd, coef, C, global_count);
+  CPT_LAUNCH_CHECK("bn_bwd_coef");
+  if (dx_cl) {
+    char* ws2 = reinterpret_cast<char*>(ws) + ((cpt_bn_workspace_size(N, C, HW) + 255) / 256) * 256;
+    return tc::bn_bwd_apply_cl(x, dy, w, b, save_mean, save_rstd, coef, 1.0f, dx, dx_cl, dx_chan_sum, N, C, HW, act, ws2,
+                               ws_bytes - (size_t)(ws2 - reinterpret_cast<char*>(ws)), st);
+  }
+  const int64_t total = (int64_t)N * C * HW;
+  if (HW % 4 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx)) {
+    if (act) bn_bwd_apply_kernel<4, true><<<ew_grid(total / 4, 256), 256, 0, st>>>(x, dy, save_mean, save_rstd, w, b, coef, dx, total / 4, C, HW / 4, 1.0f);
+    else bn_bwd_apply_kernel<4, false><<<ew_grid(total / 4, 256), 256, 0, st>>>(x, dy, save_mean, save_rstd, w, b, coef, dx, total / 4, C, HW / 4, 1.0f);
+  } else {
+    if (act) bn_bwd_apply_kernel<1, true><<<ew_grid(total, 256), 256, 0, st>>>(x, dy, save_mean, save_rstd, w, b, coef, dx, total, C, HW, 1.0f);
+    else bn_bwd_apply_kernel<1, false><<<ew_grid(total, 256), 256, 0, st>>>(x, dy, save_mean, save_rstd, w, b, coef, dx, total, C, HW, 1.0f);
+  }
+  CPT_LAUNCH_CHECK("bn_bwd_apply");
+  return CPT_OK;
+}
+
+int cpt_bn_add_relu_apply(const float* x, const float* skip, const float* w, const float* b, const float* save_mean,
+                          const float* save_rstd, float* y, uint8_t* mask, int N, int C, int HW, void* stream) {
+  if (int e = bn_check("bn_add_relu_apply", N, C, HW)) return e;
+  CPT_REQUIRE(x && skip && w && b && save_mean && save_rstd && y, CPT_ERR_INVALID, "bn_add_relu_apply: null pointer");
+  const int64_t n = (int64_t)N * C * HW;
+  CPT_REQUIRE(HW % 4 == 0 && n < (1LL << 31), CPT_ERR_UNSUPPORTED, "bn_add_relu_apply: needs H*W %% 4 == 0 and < 2^31 elements");
+  CPT_REQUIRE(aligned16(x) && aligned16(skip) && aligned16(y) && (!mask || (reinterpret_cast<uintptr_t>(mask) & 3) == 0), CPT_ERR_INVALID,
+              "bn_add_relu_apply: x, skip, y must be 16-byte aligned and mask 4-byte aligned");
+  const uint32_t n_chunks = (uint32_t)(n / 1024);
+  bn_add_relu_kernel<<<ew_grid((int64_t)(n_chunks > 0 ? n_chunks : 1) * 32, 256), 256, 0, as_stream(stream)>>>(
+      x, skip, w, b, save_mean, save_rstd, y, reinterpret_cast<uint32_t*>(mask), n_chunks, (uint32_t)n, (uint32_t)C, (uint32_t)HW);
+  CPT_LAUNCH_CHECK("bn_add_relu_apply");
+  return CPT_OK;
 }
 
 }  // extern "C"

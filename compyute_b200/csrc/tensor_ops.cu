@@ -141,6 +141,58 @@ __global__ void __launch_bounds__(256) ew_bin_bcast_kernel(OutT* __restrict__ ou
   }
 }
 
+// Row form of the broadcast kernel: the innermost merged dim (length L) is contiguous in the output and walked with stride
+// 0 or 1 by each operand.  Work item = (row of the outer dims, ROW_SEG-element segment of that row), one warp per item: the
+// outer index is decomposed once per item, a broadcast operand is loaded once per item, the rest streams — with 128-bit
+// accesses when every row start is 16-byte aligned (VEC).
+constexpr int ROW_SEG = 2048;
+struct RowItem {
+  int64_t row, oa, ob, e0, e1;
+};
+__device__ __forceinline__ RowItem row_item(int64_t w, int segs, const Dims& D, int64_t L) {
+  RowItem it;
+  it.row = (w < 0x7fffffff) ? (int64_t)((uint32_t)w / (uint32_t)segs) : w / segs;
+  const int seg = (int)(w - it.row * segs);
+  int64_t r = it.row;
+  it.oa = it.ob = 0;
+#pragma unroll
+  for (int k = CPT_MAX_DIMS - 1; k >= 0; --k) {
+    if (k < D.nd) {
+      int64_t q, c;
+      if (r < 0x7fffffff && D.d[k] < 0x7fffffff) { q = (uint32_t)r / (uint32_t)D.d[k]; c = (uint32_t)r - (uint32_t)q * (uint32_t)D.d[k]; }
+      else { q = r / D.d[k]; c = r - q * D.d[k]; }
+      it.oa += c * D.sa[k]; it.ob += c * D.sb[k]; r = q;
+    }
+  }
+  it.e0 = (int64_t)seg * ROW_SEG;
+  it.e1 = it.e0 + ROW_SEG < L ? it.e0 + ROW_SEG : L;
+  return it;
+}
+
+template <int OP, typename OutT, bool VEC>
+__global__ void __launch_bounds__(256) ew_bin_rows_kernel(OutT* __restrict__ out, const float* __restrict__ a,
+                                                          const float* __restrict__ b, Dims D, int64_t L, int sa_in, int sb_in,
+                                                          int64_t items, int segs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = w0; w < items; w += nw) {
+    const RowItem it = row_item(w, segs, D, L);
+    const float* ap = a + it.oa;
+    const float* bp = b + it.ob;
+    OutT* op = out + it.row * L;
+    const float a0 = sa_in ? 0.f : __ldg(ap), b0 = sb_in ? 0.f : __ldg(bp);
+    if constexpr (VEC) {
+      for (int64_t i = it.e0 + lane * 4; i < it.e1; i += 128) {
+        const float4 u = sa_in ? ld_stream(reinterpret_cast<const float4*>(ap + i)) : make_float4(a0, a0, a0, a0);
+        const float4 v = sb_in ? ld_stream(reinterpret_cast<const float4*>(bp + i)) : make_float4(b0, b0, b0, b0);
+        store4(op, i >> 2, make_float4(bin<OP>(u.x, v.x), bin<OP>(u.y, v.y), bin<OP>(u.z, v.z), bin<OP>(u.w, v.w)));
+      }
+    } else {
+      for (int64_t i = it.e0 + lane; i < it.e1; i += 32) store_out(op, i, bin<OP>(sa_in ? ap[i] : a0, sb_in ? bp[i] : b0));
+    }
+  }
+}
+
 template <int OP, typename OutT>
 __global__ void __launch_bounds__(256) ew_un_kernel(OutT* __restrict__ out, const float* __restrict__ a, float p0, float p1,
                                                     int64_t n4, int64_t n) {
@@ -225,6 +277,7 @@ struct RedGeom {
   int64_t K, R;  // products
 };
 __device__ __forceinline__ int64_t offs(int64_t idx, int n, const int64_t* d, const int64_t* s) {
+  if (n <= 1) return n == 1 ? idx * s[0] : 0;
   int64_t o = 0;
 #pragma unroll
   for (int k = 2; k >= 0; --k) {
@@ -251,12 +304,31 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const T* __restrict__ 
   const T* xo = x + offs(o, G.nk, G.kd, G.ks);
   Acc a = red_init<OP>();
   if constexpr (VEC) {
-    for (int64_t r = r0 + threadIdx.x * 4; r < r1; r += 256 * 4) {
+    int64_t r = r0 + threadIdx.x * 4;
+    for (; r + 3 * 1024 < r1; r += 4 * 1024) {  // four independent 128-bit loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ld_stream(reinterpret_cast<const float4*>(xo + offs(r + u * 1024, G.nr, G.rd, G.rs)));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t q = r + u * 1024;
+        red_step<OP>(a, v[u].x, q); red_step<OP>(a, v[u].y, q + 1); red_step<OP>(a, v[u].z, q + 2); red_step<OP>(a, v[u].w, q + 3);
+      }
+    }
+    for (; r < r1; r += 1024) {
       const float4 v = ld_stream(reinterpret_cast<const float4*>(xo + offs(r, G.nr, G.rd, G.rs)));
       red_step<OP>(a, v.x, r); red_step<OP>(a, v.y, r + 1); red_step<OP>(a, v.z, r + 2); red_step<OP>(a, v.w, r + 3);
     }
   } else {
-    for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) red_step<OP>(a, (float)xo[offs(r, G.nr, G.rd, G.rs)], r);
+    int64_t r = r0 + threadIdx.x;
+    for (; r + 3 * 256 < r1; r += 4 * 256) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (float)xo[offs(r + u * 256, G.nr, G.rd, G.rs)];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) red_step<OP>(a, v[u], r + u * 256);
+    }
+    for (; r < r1; r += 256) red_step<OP>(a, (float)xo[offs(r, G.nr, G.rd, G.rs)], r);
   }
   a = warp_red<OP>(a);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
@@ -265,6 +337,27 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const T* __restrict__ 
     for (int w = 1; w < 8; ++w) red_merge<OP>(a, sh[w]);
     if (S == 1) red_store<OP>(out, o, a, scale);
     else part[(int64_t)s * G.K + o] = a;
+  }
+}
+
+// Row form for short reductions (R <= a few thousand, many outputs): one warp per output, no shared memory, no split.
+template <int OP, typename T, bool VEC>
+__global__ void __launch_bounds__(256) reduce_rows_warp_kernel(const T* __restrict__ x, void* __restrict__ out, RedGeom G, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t o = w0; o < G.K; o += nw) {
+    const T* xo = x + offs(o, G.nk, G.kd, G.ks);
+    Acc a = red_init<OP>();
+    if constexpr (VEC) {
+      for (int64_t r = lane * 4; r < G.R; r += 128) {
+        const float4 v = ld_stream(reinterpret_cast<const float4*>(xo + offs(r, G.nr, G.rd, G.rs)));
+        red_step<OP>(a, v.x, r); red_step<OP>(a, v.y, r + 1); red_step<OP>(a, v.z, r + 2); red_step<OP>(a, v.w, r + 3);
+      }
+    } else {
+      for (int64_t r = lane; r < G.R; r += 32) red_step<OP>(a, (float)xo[offs(r, G.nr, G.rd, G.rs)], r);
+    }
+    a = warp_red<OP>(a);
+    if (lane == 0) red_store<OP>(out, o, a, scale);
   }
 }
 
@@ -281,7 +374,15 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const T* __restrict__ 
   Acc a = red_init<OP>();
   if (ki < kin) {
     const T* xo = x + offs(ko, G.nk - 1, G.kd, G.ks) + ki;
-    for (int64_t r = r0 + row; r < r1; r += 8) red_step<OP>(a, (float)xo[offs(r, G.nr, G.rd, G.rs)], r);
+    int64_t r = r0 + row;
+    for (; r + 24 < r1; r += 32) {  // four independent loads in flight per thread
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (float)xo[offs(r + 8 * u, G.nr, G.rd, G.rs)];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) red_step<OP>(a, v[u], r + 8 * u);
+    }
+    for (; r < r1; r += 8) red_step<OP>(a, (float)xo[offs(r, G.nr, G.rd, G.rs)], r);
   }
   sh[row][lane] = a;
   __syncthreads();
@@ -333,20 +434,75 @@ __global__ void __launch_bounds__(256) strided_copy_kernel(T* __restrict__ dst, 
   }
 }
 
-// dst[i, :] = src[idx[i], :]; rows of `row_words` 4-byte words (or bytes when BYTES)
+// Row form of the strided copy (innermost merged dim contiguous in dst, stride 0 or 1 in src): warp per (row, segment).
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) strided_copy_rows_kernel(T* __restrict__ dst, const T* __restrict__ src, Dims D, int64_t L,
+                                                                int ss_in, int64_t items, int segs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = w0; w < items; w += nw) {
+    const RowItem it = row_item(w, segs, D, L);
+    T* dp = dst + it.oa;
+    const T* sp = src + it.ob;
+    if constexpr (VEC) {  // T is 4 bytes, rows 16-byte aligned on both sides
+      for (int64_t i = it.e0 + lane * 4; i < it.e1; i += 128) *reinterpret_cast<uint4*>(dp + i) = *reinterpret_cast<const uint4*>(sp + i);
+    } else if (ss_in) {
+      for (int64_t i = it.e0 + lane; i < it.e1; i += 32) dp[i] = sp[i];
+    } else {
+      const T v = sp[0];
+      for (int64_t i = it.e0 + lane; i < it.e1; i += 32) dp[i] = v;
+    }
+  }
+}
+
+// Batched 2-D transposition of 4-byte elements: dst[bt][r][c] (C-contiguous) = src[bt*sB + r + c*sC] — 32x32 tiles through
+// shared memory, coalesced on both sides (permute / transpose / NCHW <-> NHWC of the generic operator set).
+__global__ void __launch_bounds__(256) transpose_tile_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int64_t R,
+                                                             int64_t Cc, int64_t sB, int64_t sC, int64_t tiles_r, int64_t tiles_c,
+                                                             int64_t total_tiles) {
+  __shared__ uint32_t t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int64_t bt = tile / (tiles_r * tiles_c), rem = tile - bt * tiles_r * tiles_c;
+    const int64_t tr = rem / tiles_c, tc = rem - tr * tiles_c;
+    const int64_t r0 = tr * 32, c0 = tc * 32;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+      const int64_t r = r0 + tx, c = c0 + j;
+      if (r < R && c < Cc) t[j][tx] = src[bt * sB + r + c * sC];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+      const int64_t r = r0 + j, c = c0 + tx;
+      if (r < R && c < Cc) dst[(bt * R + r) * Cc + c] = t[tx][j];
+    }
+    __syncthreads();
+  }
+}
+
+// dst[i, :] = src[idx[i], :]: warp per (index, 8 KB segment of the row); W = widest word the row size / alignment allows
+constexpr int GATHER_SEG_BYTES = 8192;
 template <typename I, typename W>
 __global__ void __launch_bounds__(256) gather_rows_kernel(W* __restrict__ dst, const W* __restrict__ src, const I* __restrict__ idx,
-                                                          int64_t n_idx, int64_t row_w, int64_t n_src_rows, int* __restrict__ err) {
-  const int64_t total = n_idx * row_w, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t r = i / row_w, c = i - r * row_w;
+                                                          int64_t row_w, int64_t n_src_rows, int* __restrict__ err, int64_t items,
+                                                          int segs) {
+  constexpr int SEG_W = GATHER_SEG_BYTES / (int)sizeof(W);
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = w0; w < items; w += nw) {
+    const int64_t r = w / segs;
+    const int seg = (int)(w - r * segs);
     int64_t j = (int64_t)idx[r];
     if (j < 0) j += n_src_rows;
     if (j < 0 || j >= n_src_rows) {
-      if (err) *err = 1;
+      if (err && lane == 0) *err = 1;
       j = j < 0 ? 0 : n_src_rows - 1;
     }
-    dst[i] = src[j * row_w + c];
+    const int64_t e0 = (int64_t)seg * SEG_W, e1 = e0 + SEG_W < row_w ? e0 + SEG_W : row_w;
+    const W* sp = src + j * row_w;
+    W* dp = dst + r * row_w;
+    for (int64_t i = e0 + lane; i < e1; i += 32) dp[i] = sp[i];
   }
 }
 
@@ -382,6 +538,23 @@ __global__ void __launch_bounds__(256) random_kernel(float* __restrict__ dst, in
       dst[i] = lo + hi * sqrtf(-2.f * logf(1.f - u)) * cospif(2.f * u2);
     }
   }
+}
+
+// grid of 256-thread CTAs for warp-per-item kernels: ~8 resident CTAs per SM, never more warps than items
+static int warp_grid(int64_t items) {
+  int64_t need = (items + 7) / 8, cap = (int64_t)sm_count() * 8;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// splits the innermost merged dim off D (nd >= 1): returns its length and leaves the outer dims in D
+static int64_t pop_inner(Dims& D, int64_t& sa_in, int64_t& sb_in) {
+  const int k = D.nd - 1;
+  const int64_t L = D.d[k];
+  sa_in = D.sa[k]; sb_in = D.sb[k];
+  D.d[k] = 1; D.sa[k] = D.sb[k] = 0;
+  D.nd = k;
+  return L;
 }
 
 static int merge_and_check(int ndim, const int64_t* dims, const int64_t* sa, const int64_t* sb, Dims& D, int64_t& n, const char* who) {
@@ -439,11 +612,30 @@ int cpt_ew_binary(int op, void* out, const float* a, const float* b, float scala
     });
   } else {
     CPT_REQUIRE(b, CPT_ERR_INVALID, "ew_binary: a scalar operand needs a contiguous tensor operand");
-    ok = dispatch_bin(op, [&](auto tag) {
-      constexpr int OP = decltype(tag)::value;
-      using OutT = std::conditional_t<is_cmp(OP), uint8_t, float>;
-      ew_bin_bcast_kernel<OP, OutT><<<ew_grid(n, 256), 256, 0, st>>>(reinterpret_cast<OutT*>(out), a, b, D, n);
-    });
+    const int ki = D.nd - 1;
+    const bool rows_ok = D.d[ki] >= 32 && (D.sa[ki] == 0 || D.sa[ki] == 1) && (D.sb[ki] == 0 || D.sb[ki] == 1);
+    if (rows_ok) {
+      Dims Do = D;
+      int64_t sa_in, sb_in;
+      const int64_t L = pop_inner(Do, sa_in, sb_in);
+      const int segs = (int)((L + ROW_SEG - 1) / ROW_SEG);
+      const int64_t items = (n / L) * segs;
+      bool vec = L % 4 == 0 && aligned16(a) && aligned16(b) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+      for (int k = 0; k < Do.nd; ++k) vec = vec && (sa_in == 0 || Do.sa[k] % 4 == 0) && (sb_in == 0 || Do.sb[k] % 4 == 0);
+      ok = dispatch_bin(op, [&](auto tag) {
+        constexpr int OP = decltype(tag)::value;
+        using OutT = std::conditional_t<is_cmp(OP), uint8_t, float>;
+        OutT* o = reinterpret_cast<OutT*>(out);
+        if (vec) ew_bin_rows_kernel<OP, OutT, true><<<warp_grid(items), 256, 0, st>>>(o, a, b, Do, L, (int)sa_in, (int)sb_in, items, segs);
+        else ew_bin_rows_kernel<OP, OutT, false><<<warp_grid(items), 256, 0, st>>>(o, a, b, Do, L, (int)sa_in, (int)sb_in, items, segs);
+      });
+    } else {
+      ok = dispatch_bin(op, [&](auto tag) {
+        constexpr int OP = decltype(tag)::value;
+        using OutT = std::conditional_t<is_cmp(OP), uint8_t, float>;
+        ew_bin_bcast_kernel<OP, OutT><<<ew_grid(n, 256), 256, 0, st>>>(reinterpret_cast<OutT*>(out), a, b, D, n);
+      });
+    }
   }
   CPT_REQUIRE(ok, CPT_ERR_UNSUPPORTED, "ew_binary: unknown op %d", op);
   CPT_LAUNCH_CHECK("ew_binary");
@@ -541,12 +733,20 @@ int cpt_reduce(int op, void* out, const void* x, int x_dtype, int ndim, const in
   const bool f32 = x_dtype == CPT_DT_F32;
   bool vec = f32 && !cols && aligned16(x) && G.rs[nr > 0 ? nr - 1 : 0] == 1 && (G.rd[nr > 0 ? nr - 1 : 0] % 4 == 0);
   for (int j = 0; j < 3; ++j) vec = vec && (j >= nk || G.ks[j] % 4 == 0 || G.kd[j] == 1) && (j >= nr - 1 || G.rs[j] % 4 == 0);
+  // short rows, many outputs: one warp per output instead of one CTA (no split, no second pass)
+  const bool warp_rows = !cols && G.R <= 4096 && G.K >= (int64_t)sm_count() * 16;
+  if (warp_rows) S = 1;
   const bool ok = dispatch_red(op, [&](auto tag) {
     constexpr int OP = decltype(tag)::value;
     dim3 grid((unsigned)blocks, (unsigned)S);
     if (cols) {
       if (f32) reduce_cols_kernel<OP, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), out, part, G, (int)S, scale, inner_blocks);
       else reduce_cols_kernel<OP, uint8_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(x), out, part, G, (int)S, scale, inner_blocks);
+    } else if (warp_rows) {
+      const int wg = warp_grid(G.K);
+      if (!f32) reduce_rows_warp_kernel<OP, uint8_t, false><<<wg, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(x), out, G, scale);
+      else if (vec) reduce_rows_warp_kernel<OP, float, true><<<wg, 256, 0, st>>>(reinterpret_cast<const float*>(x), out, G, scale);
+      else reduce_rows_warp_kernel<OP, float, false><<<wg, 256, 0, st>>>(reinterpret_cast<const float*>(x), out, G, scale);
     } else if (f32) {
       if (vec) reduce_rows_kernel<OP, float, true><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), out, part, G, (int)S, scale);
       else reduce_rows_kernel<OP, float, false><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), out, part, G, (int)S, scale);
@@ -570,11 +770,41 @@ int cpt_strided_copy(void* dst, const void* src, int elem_size, int ndim, const 
   if (rc != CPT_OK) return rc;
   if (n == 0) return CPT_OK;
   cudaStream_t st = as_stream(stream);
+  CPT_REQUIRE(elem_size == 1 || elem_size == 4 || elem_size == 8, CPT_ERR_UNSUPPORTED, "strided_copy: element size %d", elem_size);
+  const int ki = D.nd - 1;
+  // (1) batched 2-D transposition (dst contiguous, src contiguous along the second-to-last dim): tiled through shared memory
+  if (elem_size == 4 && (D.nd == 2 || D.nd == 3) && D.sa[ki] == 1 && D.sa[ki - 1] == D.d[ki] && D.sb[ki - 1] == 1 &&
+      (D.nd == 2 || D.sa[0] == D.d[1] * D.d[2]) && D.d[ki] >= 8 && D.d[ki - 1] >= 8 && D.sb[ki] > 0 && (D.nd == 2 || D.sb[0] >= 0)) {
+    const int64_t R = D.d[ki - 1], Cc = D.d[ki], Bt = D.nd == 3 ? D.d[0] : 1, sB = D.nd == 3 ? D.sb[0] : 0;
+    const int64_t tr = (R + 31) / 32, tc = (Cc + 31) / 32, total = Bt * tr * tc;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    transpose_tile_kernel<<<(unsigned)(total < cap ? total : cap), 256, 0, st>>>((uint32_t*)dst, (const uint32_t*)src, R, Cc, sB, D.sb[ki], tr,
+                                                                                tc, total);
+    CPT_LAUNCH_CHECK("transpose_tile");
+    return CPT_OK;
+  }
+  // (2) rows: innermost dim contiguous in dst and stride 0 / 1 in src
+  if (D.nd >= 1 && D.d[ki] >= 32 && D.sa[ki] == 1 && (D.sb[ki] == 0 || D.sb[ki] == 1)) {
+    Dims Do = D;
+    int64_t sd_in, ss_in;
+    const int64_t L = pop_inner(Do, sd_in, ss_in);
+    const int segs = (int)((L + ROW_SEG - 1) / ROW_SEG);
+    const int64_t items = (n / L) * segs;
+    bool vec = elem_size == 4 && ss_in == 1 && L % 4 == 0 && aligned16(dst) && aligned16(src);
+    for (int k = 0; k < Do.nd; ++k) vec = vec && Do.sa[k] % 4 == 0 && Do.sb[k] % 4 == 0;
+    const int g = warp_grid(items);
+    if (elem_size == 1) strided_copy_rows_kernel<uint8_t, false><<<g, 256, 0, st>>>((uint8_t*)dst, (const uint8_t*)src, Do, L, (int)ss_in, items, segs);
+    else if (elem_size == 8) strided_copy_rows_kernel<uint64_t, false><<<g, 256, 0, st>>>((uint64_t*)dst, (const uint64_t*)src, Do, L, (int)ss_in, items, segs);
+    else if (vec) strided_copy_rows_kernel<uint32_t, true><<<g, 256, 0, st>>>((uint32_t*)dst, (const uint32_t*)src, Do, L, (int)ss_in, items, segs);
+    else strided_copy_rows_kernel<uint32_t, false><<<g, 256, 0, st>>>((uint32_t*)dst, (const uint32_t*)src, Do, L, (int)ss_in, items, segs);
+    CPT_LAUNCH_CHECK("strided_copy_rows");
+    return CPT_OK;
+  }
+  // (3) anything else: one index decomposition per element
   const int grid = ew_grid(n, 256);
   if (elem_size == 1) strided_copy_kernel<uint8_t><<<grid, 256, 0, st>>>((uint8_t*)dst, (const uint8_t*)src, D, n);
   else if (elem_size == 4) strided_copy_kernel<uint32_t><<<grid, 256, 0, st>>>((uint32_t*)dst, (const uint32_t*)src, D, n);
-  else if (elem_size == 8) strided_copy_kernel<uint64_t><<<grid, 256, 0, st>>>((uint64_t*)dst, (const uint64_t*)src, D, n);
-  else CPT_REQUIRE(false, CPT_ERR_UNSUPPORTED, "strided_copy: element size %d", elem_size);
+  else strided_copy_kernel<uint64_t><<<grid, 256, 0, st>>>((uint64_t*)dst, (const uint64_t*)src, D, n);
   CPT_LAUNCH_CHECK("strided_copy");
   return CPT_OK;
 }
@@ -585,12 +815,15 @@ int cpt_gather_rows(void* dst, const void* src, const void* idx, int idx_dtype, 
   CPT_REQUIRE(idx_dtype == CPT_DT_I32 || idx_dtype == CPT_DT_I64, CPT_ERR_UNSUPPORTED, "gather_rows: int32 / int64 indices only");
   if (n_idx == 0) return CPT_OK;
   cudaStream_t st = as_stream(stream);
-  const bool w4 = row_bytes % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0;
-  const int64_t row_w = w4 ? row_bytes / 4 : row_bytes;
-  const int grid = ew_grid(n_idx * row_w, 256);
-#define GO(I, W) gather_rows_kernel<I, W><<<grid, 256, 0, st>>>((W*)dst, (const W*)src, (const I*)idx, n_idx, row_w, n_src_rows, err_flag)
-  if (idx_dtype == CPT_DT_I32) { if (w4) GO(int32_t, uint32_t); else GO(int32_t, uint8_t); }
-  else { if (w4) GO(int64_t, uint32_t); else GO(int64_t, uint8_t); }
+  const uintptr_t al = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | (uintptr_t)row_bytes;
+  const int wbytes = (al & 15) == 0 ? 16 : (al & 3) == 0 ? 4 : 1;
+  const int64_t row_w = row_bytes / wbytes;
+  const int segs = (int)((row_bytes + GATHER_SEG_BYTES - 1) / GATHER_SEG_BYTES);
+  const int64_t items = n_idx * segs;
+  const int grid = warp_grid(items);
+#define GO(I, W) gather_rows_kernel<I, W><<<grid, 256, 0, st>>>((W*)dst, (const W*)src, (const I*)idx, row_w, n_src_rows, err_flag, items, segs)
+  if (idx_dtype == CPT_DT_I32) { if (wbytes == 16) GO(int32_t, uint4); else if (wbytes == 4) GO(int32_t, uint32_t); else GO(int32_t, uint8_t); }
+  else { if (wbytes == 16) GO(int64_t, uint4); else if (wbytes == 4) GO(int64_t, uint32_t); else GO(int64_t, uint8_t); }
 #undef GO
   CPT_LAUNCH_CHECK("gather_rows");
   return CPT_OK;

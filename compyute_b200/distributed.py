@@ -15,8 +15,8 @@ from typing import Iterable
 
 import numpy as np
 
-__all__ = ["init", "is_initialized", "rank", "world_size", "all_reduce_sum", "all_reduce_sum_async", "broadcast_parameters", "shard_batch",
-           "shard_bounds", "barrier"]
+__all__ = ["init", "is_initialized", "rank", "world_size", "all_reduce_sum", "all_reduce_sum_async", "all_gather", "broadcast_parameters",
+           "shard_batch", "shard_bounds", "barrier", "set_sync_batchnorm", "sync_batchnorm_active"]
 
 _dist = None
 
@@ -68,6 +68,31 @@ def all_reduce_sum(arr) -> None:
         return
     buf = getattr(arr, "_buf", arr)
     _d().all_reduce(buf, op=_d().ReduceOp.SUM)
+
+
+def all_gather(arr):
+    """Gathers a DeviceArray from every rank into a new DeviceArray of shape (world, *arr.shape), in rank order."""
+    from .tensors import DeviceArray
+    out = DeviceArray.empty((world_size(),) + tuple(arr.shape), arr.dtype)
+    _d().all_gather_into_tensor(out._buf.view(-1), arr._buf.view(-1))
+    return out
+
+
+_sync_bn = False
+
+
+def set_sync_batchnorm(enabled: bool) -> None:
+    """Synchronised BatchNorm: in training mode every BatchNorm1D/2D takes its batch statistics — and the two
+    sums of its backward pass — over the GLOBAL batch of all ranks instead of the local shard, which makes data-parallel
+    training at n ranks equal to single-process training on the full batch.  Costs one small all-gather (3·C floats per
+    rank) per forward and one all-reduce (2·C floats) per backward and layer; off by default (per-shard statistics, DDP
+    semantics).  No effect without an initialised process group."""
+    global _sync_bn
+    _sync_bn = bool(enabled)
+
+
+def sync_batchnorm_active() -> bool:
+    return _sync_bn and is_initialized() and world_size() > 1
 
 
 def all_reduce_sum_async(buf):

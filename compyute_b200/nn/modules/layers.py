@@ -146,6 +146,15 @@ class _BatchNorm(Module):
         records the fusion).  Called by ``Sequential`` for a BatchNorm directly followed by a ReLU."""
         return self._forward(self._fn_relu, x)
 
+    def forward_add_relu(self, x: Tensor, skip: Tensor, relu: Module) -> Tensor:
+        """``relu(self(x) + skip)`` in one pass (residual tail): this module's cache entry is the plain BatchNorm one, the
+        ReLU mask is pushed on ``relu``'s cache, so both backward methods run unchanged."""
+        y, rmean, rvar = self._fn.forward(self.fcache, x, self.rmean, self.rvar, self.w, self.b, self.m, self.eps, self._is_training,
+                                          False, skip, relu.fcache)
+        self.rmean.data = rmean.data
+        self.rvar.data = rvar.data
+        return y
+
     def _forward(self, fn, x: Tensor) -> Tensor:
         extra = (True,) if (self._emit_cl_fwd and x.ndim == 4) else ()
         y, rmean, rvar = fn.forward(self.fcache, x, self.rmean, self.rvar, self.w, self.b, self.m, self.eps, self._is_training,

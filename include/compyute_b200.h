@@ -227,6 +227,41 @@ int cpt_bn_act_fwd_train_presum(const float* x, const float* w, const float* b, 
                                 float m, float eps, int act, const float* stats, int stat_slots,
                                 const float* conv_bias, void* stream);
 
+/* Tail of a residual block in one pass: y = relu(bn(x) + skip), i.e. BatchNorm2D.forward (normalizations.py:150-165), the
+ * `y += skip` of ResidualConnection.forward (containers.py:153-157) and ReLUFn.forward (activation_funcs.py:26-29).  The batch
+ * statistics come from a statistics-only call of the forward entry points above (cpt_bn_act_fwd_train / _presum / _merged /
+ * _fwd_eval with y == NULL), this call applies them.  mask: the bit-packed (y > 0) of cpt_relu_fwd (same layout, consumed by
+ * cpt_relu_bwd), may be NULL.  Bit-identical to the three separate passes; needs H*W % 4 == 0 and < 2^31 elements
+ * (CPT_ERR_UNSUPPORTED otherwise: the caller then runs the separate passes). */
+int cpt_bn_add_relu_apply(const float* x, const float* skip, const float* w, const float* b,
+                          const float* save_mean, const float* save_rstd, float* y, uint8_t* mask, int N,
+                          int C, int HW, void* stream);
+/* Synchronised BatchNorm for the batch-sharded data-parallel mode: the statistics of
+ * normalization_funcs.py:139-147 / the sums of :169-175 taken over the GLOBAL batch.  Each pass is split around the
+ * collective the caller runs (torch.distributed / NCCL):
+ *   forward : cpt_bn_local_stats -> all-gather of stats[3][C] = (mean, M2 = Σ(x-mean)², count) -> cpt_bn_act_fwd_train_merged,
+ *             which merges the `world` triples in rank order (Chan's pairwise update, double) — the same arithmetic on the
+ *             same values on every rank, so replicas stay bit-identical — writes the global element count to the device
+ *             float *global_count and applies (y_cl may be NULL);
+ *   backward: cpt_bn_act_bwd_local_sums -> SUM all-reduce of sums[2][C] = (Σdy, Σdy·x̂) -> cpt_bn_act_bwd_apply_global with the
+ *             forward's device-resident global count (no host synchronisation anywhere).  dw / db are the LOCAL sums (the gradient exchange averages them like every other
+ *             parameter gradient).  dx_cl / dx_chan_sum as in cpt_bn_act_bwd_cl, may be NULL.
+ * ws: cpt_bn_workspace_size (cpt_bn_cl_workspace_size when dx_cl is given). */
+int cpt_bn_local_stats(const float* x, float* stats, int N, int C, int HW, void* ws, size_t ws_bytes, void* stream);
+int cpt_bn_act_fwd_train_merged(const float* x, const float* w, const float* b, const float* rmean,
+                                const float* rvar, float* y, void* y_cl, float* rmean_out,
+                                float* rvar_out, float* save_mean, float* save_rstd, int N, int C, int HW,
+                                float m, float eps, int act, const float* gathered, int world,
+                                float* global_count, void* stream);
+int cpt_bn_act_bwd_local_sums(const float* x, const float* dy, const float* w, const float* b,
+                              const float* save_mean, const float* save_rstd, float* sums, float* dw,
+                              float* db, int N, int C, int HW, int act, void* ws, size_t ws_bytes,
+                              void* stream);
+int cpt_bn_act_bwd_apply_global(const float* x, const float* dy, const float* w, const float* b,
+                                const float* save_mean, const float* save_rstd, const float* sums,
+                                const float* global_count, float* dx, void* dx_cl, float* dx_chan_sum, int N,
+                                int C, int HW, int act, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- activations / elementwise ------------------------------------------------------------- */
 /* ReLUFn.forward activation_funcs.py:26-29.  mask = bit-packed (y > 0), 4 * ((n + 31) / 32) bytes, 4-byte aligned, in a
  * layout private to cpt_relu_fwd / cpt_relu_bwd; may be NULL. */

@@ -570,3 +570,55 @@ def test_dataloader_and_checkpoint_on_device(cp, tmp_path):
     model.inference(); model2.inference()
     xb = cp.tensor(X[:8], device=cp.cuda)
     assert np.array_equal(model(xb).to_numpy(), model2(xb).to_numpy())
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("proj", [False, True], ids=["identity", "projection"])
+def test_residual_tail_fusion_is_bit_exact(cp, proj, mode):
+    """ResidualConnection(..., BatchNorm2D) -> ReLU: the block's last BatchNorm apply, the ``y += skip`` and the ReLU run as one
+    pass (cpt_bn_add_relu_apply).  Outputs, input gradient, every parameter gradient and the running statistics must equal the
+    layer-by-layer evaluation bit for bit — training and inference, identity and projected skip, H*W % 4 == 0 (fused kernel) and
+    != 0 (falls back to the separate passes) — and the fused walk must launch fewer kernels."""
+    from compyute_b200 import _lib, nn
+    for H in (8, 7):
+        x = np.random.RandomState(3).normal(0, 1, (5, 8, H, H)).astype(np.float32)
+        co, st = (12, 2) if proj else (8, 1)
+
+        def build():
+            np.random.seed(9)
+            with cp.use_device(cp.cuda):
+                rp = nn.Sequential(nn.Conv2D(8, co, 1, stride=st, bias=False), nn.BatchNorm2D(co)) if proj else None
+                return nn.Sequential(
+                    nn.Conv2D(8, 8, 3, padding="same"), nn.ReLU(),
+                    nn.ResidualConnection(nn.Conv2D(8, co, 3, padding=1, stride=st, bias=False), nn.BatchNorm2D(co), nn.ReLU(),
+                                          nn.Conv2D(co, co, 3, padding=1, bias=False), nn.BatchNorm2D(co), residual_proj=rp),
+                    nn.ReLU(),
+                    nn.ResidualConnection(nn.Conv2D(co, co, 3, padding=1), nn.BatchNorm2D(co)), nn.ReLU(),
+                    nn.AvgPooling2D(2), nn.Flatten(), nn.Linear(co * (((H + st - 1) // st) // 2) ** 2, 3))
+
+        def run(fused):
+            nn.set_fusion_enabled(fused)
+            try:
+                model = build()
+                model.training()
+                n0 = _lib.lib().cpt_launch_count()
+                with cp.compute_mode(mode):
+                    y = model(cp.tensor(x, device=cp.cuda))
+                    dy = np.random.RandomState(4).normal(0, 1, y.shape).astype(np.float32)
+                    dx = model.backward(cp.tensor(dy, device=cp.cuda))
+                    launches = _lib.lib().cpt_launch_count() - n0
+                    tc_ok()
+                    assert all(not m.fcache.cache for m in model.get_modules())
+                    out = [y.to_numpy(), dx.to_numpy()] + [p.grad.to_numpy() for p in model.get_parameters()] + \
+                          [b.to_numpy() for b in model.get_buffers()]
+                    model.inference()
+                    out.append(model(cp.tensor(x, device=cp.cuda)).to_numpy())
+                return out, launches
+            finally:
+                nn.set_fusion_enabled(True)
+
+        (a, la), (b, lb) = run(True), run(False)
+        assert len(a) == len(b)
+        for k, (u, v) in enumerate(zip(a, b)):
+            assert np.array_equal(u, v, equal_nan=True), (H, k, u.shape, float(np.abs(u - v).max()))
+        assert la < lb, (la, lb)
