@@ -598,6 +598,7 @@ def test_residual_tail_fusion_is_bit_exact(cp, proj, mode):
 
         def run(fused):
             nn.set_fusion_enabled(fused)
+            nn.set_epilogue_stats_enabled(False)  # epilogue statistics change the summation order (not bit-identical by design)
             try:
                 model = build()
                 model.training()
@@ -616,6 +617,7 @@ def test_residual_tail_fusion_is_bit_exact(cp, proj, mode):
                 return out, launches
             finally:
                 nn.set_fusion_enabled(True)
+                nn.set_epilogue_stats_enabled(True)
 
         (a, la), (b, lb) = run(True), run(False)
         assert len(a) == len(b)
