@@ -71,6 +71,72 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
   }
 }
 
+// k = 2 fast paths (every MaxPooling2D of the BASELINE configs): W % 4 == 0, H even, 16-byte aligned rows.
+// Work item = (image-channel bc, output row p, group of 4 input columns): two 128-bit loads of x (rows 2p and 2p+1) serve two
+// outputs; two items per thread and loop iteration keep four independent 128-bit loads in flight.  Same comparison order as
+// the generic kernel (bit-exact, NaN in the window -> NaN).
+struct Pool2Item {
+  int64_t row0;  // element offset of x[bc][2p][4*wv]
+  int64_t out;   // element offset of y[bc][p][2*wv]
+};
+__device__ __forceinline__ Pool2Item pool2_item(int64_t it, int Wv, int Ho, int H, int W, int Wo) {
+  int64_t t;
+  int wv, p;
+  if (it < 0x7fffffff) {
+    const uint32_t u = (uint32_t)it, t32 = u / (uint32_t)Wv;
+    wv = (int)(u - t32 * (uint32_t)Wv);
+    const uint32_t bc = t32 / (uint32_t)Ho;
+    p = (int)(t32 - bc * (uint32_t)Ho);
+    t = bc;
+  } else {
+    const int64_t t64 = it / Wv;
+    wv = (int)(it - t64 * Wv);
+    t = t64 / Ho;
+    p = (int)(t64 - t * Ho);
+  }
+  Pool2Item r;
+  r.row0 = (t * H + 2 * (int64_t)p) * W + 4 * (int64_t)wv;
+  r.out = (t * Ho + p) * Wo + 2 * (int64_t)wv;
+  return r;
+}
+
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n_items,
+                                                           int H, int W, int Ho, int Wo) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int Wv = W / 4;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += 2 * stride) {
+    const bool two = it + stride < n_items;
+    const Pool2Item a = pool2_item(it, Wv, Ho, H, W, Wo), b = pool2_item(two ? it + stride : it, Wv, Ho, H, W, Wo);
+    const float4 a0 = ld_stream(reinterpret_cast<const float4*>(x + a.row0)), a1 = ld_stream(reinterpret_cast<const float4*>(x + a.row0 + W));
+    const float4 b0 = ld_stream(reinterpret_cast<const float4*>(x + b.row0)), b1 = ld_stream(reinterpret_cast<const float4*>(x + b.row0 + W));
+    *reinterpret_cast<float2*>(y + a.out) = make_float2(max_nan(max_nan(a0.x, a0.y), max_nan(a1.x, a1.y)),
+                                                        max_nan(max_nan(a0.z, a0.w), max_nan(a1.z, a1.w)));
+    if (two)
+      *reinterpret_cast<float2*>(y + b.out) = make_float2(max_nan(max_nan(b0.x, b0.y), max_nan(b1.x, b1.y)),
+                                                          max_nan(max_nan(b0.z, b0.w), max_nan(b1.z, b1.w)));
+  }
+}
+
+__device__ __forceinline__ float4 pool2_mask(float4 xv, float2 yv, float2 g) {
+  // reference: upsample(dy) * (upsample(y) == x): the bool mask multiplies dy (dy * 0 keeps the sign of dy)
+  return make_float4(g.x * (yv.x == xv.x ? 1.0f : 0.0f), g.x * (yv.x == xv.y ? 1.0f : 0.0f), g.y * (yv.y == xv.z ? 1.0f : 0.0f),
+                     g.y * (yv.y == xv.w ? 1.0f : 0.0f));
+}
+
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                           const float* __restrict__ dy, float* __restrict__ dx, int64_t n_items,
+                                                           int H, int W, int Ho, int Wo) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int Wv = W / 4;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
+    const Pool2Item a = pool2_item(it, Wv, Ho, H, W, Wo);
+    const float4 x0 = ld_stream(reinterpret_cast<const float4*>(x + a.row0)), x1 = ld_stream(reinterpret_cast<const float4*>(x + a.row0 + W));
+    const float2 yv = *reinterpret_cast<const float2*>(y + a.out), g = *reinterpret_cast<const float2*>(dy + a.out);
+    st_stream(reinterpret_cast<float4*>(dx + a.row0), pool2_mask(x0, yv, g));
+    st_stream(reinterpret_cast<float4*>(dx + a.row0 + W), pool2_mask(x1, yv, g));
+  }
+}
+
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n_out,
                                                           int H, int W, int Ho, int Wo, int k) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -119,7 +185,10 @@ int cpt_maxpool2d_fwd(const float* x, float* y, int B, int C, int H, int W, int 
   const int Ho = H / k, Wo = W / k;
   const int64_t n_out = (int64_t)B * C * Ho * Wo;
   const int grid = ew_grid(n_out, 256);
-  if (k == 2) {
+  if (k == 2 && W % 4 == 0 && H % 2 == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(y) & 7) == 0) {
+    const int64_t items = (int64_t)B * C * Ho * (W / 4);
+    maxpool2_fwd_kernel<<<ew_grid((items + 1) / 2, 256), 256, 0, as_stream(stream)>>>(x, y, items, H, W, Ho, Wo);
+  } else if (k == 2) {
     const int vec2 = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
     maxpool_fwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, y, n_out, H, W, Ho, Wo, k, vec2);
   } else {
@@ -133,7 +202,10 @@ int cpt_maxpool2d_bwd(const float* x, const float* y, const float* dy, float* dx
                       void* stream) {
   if (int e = check_pool("maxpool2d_bwd", B, C, H, W, k)) return e;
   const int Ho = H / k, Wo = W / k;
-  if (W % 4 == 0 && aligned16(x) && aligned16(dx)) {
+  if (k == 2 && W % 4 == 0 && H % 2 == 0 && aligned16(x) && aligned16(dx) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy)) & 7) == 0) {
+    const int64_t items = (int64_t)B * C * Ho * (W / 4);
+    maxpool2_bwd_kernel<<<ew_grid(items, 256), 256, 0, as_stream(stream)>>>(x, y, dy, dx, items, H, W, Ho, Wo);
+  } else if (W % 4 == 0 && aligned16(x) && aligned16(dx)) {
     const int64_t items = (int64_t)B * C * H * (W / 4);
     maxpool_bwd_kernel<4><<<ew_grid(items, 256), 256, 0, as_stream(stream)>>>(x, y, dy, dx, items, H, W, Ho, Wo, k);
   } else {

@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 
 #include "simt_gemm.cuh"
+#include <stdlib.h>
+
 #include "tc.cuh"
 #include "tc_kernel.cuh"
 
@@ -1044,6 +1046,93 @@ __global__ void __launch_bounds__(256) col2im_kernel(const __nv_bfloat16* __rest
   dx[((int64_t)bc * H + h) * W + w] = acc;
 }
 
+// Same sum, staged through shared memory: one block per (image-channel, dx row h).  The <= ceil(K/S) output rows ho that
+// reach h contribute K dcol rows each ((j, kk) planes, Wo contiguous bf16): they are copied once, coalesced, into
+// rows[hi][kk][Wo + 1] (fp32, odd pitch: the two lane parities of a stride-2 gather land in different banks), then every
+// thread sums its (ho, wo) pairs from shared memory in the order of col2im_kernel (bit-identical).  Every dcol element is
+// read from HBM exactly once by a 4-byte coalesced load instead of a 2-byte gather (the stem's col2im went from 21 % of
+// HBM bandwidth to the streaming rate of the 0.94 GB it has to read).
+template <bool DIL1, int SS>
+__global__ void __launch_bounds__(256) col2im_rows_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dx, int H, int W,
+                                                          int K, int P, int S_rt, int D, int Ho, int Wo, int nrows_max) {
+  extern __shared__ float rows[];                                                       // [nho][K][Wo + 1] fp32
+  const __nv_bfloat16** rowptr = reinterpret_cast<const __nv_bfloat16**>(rows + (size_t)nrows_max * (Wo + 1) + ((nrows_max * (Wo + 1)) & 1));
+  const int S = SS ? SS : S_rt;  // compile-time stride: the index divisions below become shifts
+  const int h = blockIdx.x, bc = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int pitch = Wo + 1, span = (K - 1) * D, hp = h + P;
+  const int64_t plane = (int64_t)Ho * Wo;
+  const int ho_lo = hp - span > 0 ? (hp - span + S - 1) / S : 0;
+  int ho_hi = hp / S;
+  if (ho_hi > Ho - 1) ho_hi = Ho - 1;
+  const int nho = ho_hi - ho_lo + 1, nrows = nho * K;
+  // source row of every staged row (NULL: this ho does not reach h under dilation), one thread per row
+  if ((int)threadIdx.x < nrows) {
+    const int r = threadIdx.x, hi = r / K, kk = r - hi * K, ho = ho_hi - hi, hh = hp - ho * S;
+    int j = hh;
+    bool ok = true;
+    if (!DIL1) { j = hh / D; ok = j * D == hh; }
+    rowptr[r] = ok ? dcol + ((int64_t)bc * K * K + j * K + kk) * plane + (int64_t)ho * Wo : nullptr;
+  }
+  __syncthreads();
+  if ((Wo & 1) == 0) {
+    // each warp stages four rows at a time, two 4-byte words per lane and row: eight independent loads in flight per lane
+    const int wpr = Wo >> 1;
+    for (int r0 = warp; r0 < nrows; r0 += nwarps * 4) {
+      for (int i0 = 0; i0 < wpr; i0 += 64) {
+        uint32_t v[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u * nwarps;
+          const uint32_t* p = r < nrows ? reinterpret_cast<const uint32_t*>(rowptr[r]) : nullptr;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = i0 + lane + 32 * e;
+            v[u][e] = (p && i < wpr) ? __ldg(p + i) : 0u;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u * nwarps;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = i0 + lane + 32 * e;
+            if (r < nrows && i < wpr) {
+              rows[r * pitch + 2 * i] = __uint_as_float(v[u][e] << 16);
+              rows[r * pitch + 2 * i + 1] = __uint_as_float(v[u][e] & 0xffff0000u);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    for (int r = warp; r < nrows; r += nwarps) {
+      const __nv_bfloat16* src = rowptr[r];
+      if (!src) continue;
+      for (int i = lane; i < Wo; i += 32) rows[r * pitch + i] = __bfloat162float(src[i]);
+    }
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < W; w += blockDim.x) {
+    const int wp = w + P;
+    const int wo_lo = wp - span > 0 ? (wp - span + S - 1) / S : 0;
+    int wo_hi = wp / S;
+    if (wo_hi > Wo - 1) wo_hi = Wo - 1;
+    float acc = 0.f;
+    for (int hi = 0; hi < nho; ++hi) {
+      if (!DIL1 && rowptr[hi * K] == nullptr) continue;
+      const float* rp = rows + hi * K * pitch;
+      for (int wo = wo_hi; wo >= wo_lo; --wo) {
+        const int ww = wp - wo * S;
+        int kk = ww;
+        if (!DIL1) { kk = ww / D; if (kk * D != ww) continue; }
+        acc += rp[kk * pitch + wo];
+      }
+    }
+    dx[((int64_t)bc * H + h) * W + w] = acc;
+  }
+}
+
 size_t conv_packed_bytes(const cpt_conv2d_desc* d, int mode) {
   const G g = geom(d);
   if (!packed_ok(g, mode)) return 0;
@@ -1152,10 +1241,23 @@ int conv_dgrad_packed(const cpt_conv2d_desc* d, const void* dy_cl, const float* 
   if (int e = launch_bn<false, false, OP_GEMM>(p, mode, BN, use2, st)) return e;
   {
     CPT_REQUIRE(g.H <= 65535 && (int64_t)g.B * g.Ci <= 65535, CPT_ERR_UNSUPPORTED, "conv2d_dgrad_packed: grid too large");
-    const int bx = g.W >= 256 ? 256 : (g.W >= 128 ? 128 : (g.W >= 64 ? 64 : 32));
-    dim3 grid((g.W + bx - 1) / bx, g.H, g.B * g.Ci);
-    if (g.D == 1) col2im_kernel<true><<<grid, bx, 0, st>>>(dcol, dx, g.Ci, g.H, g.W, g.K, g.P, g.S, g.D, g.Ho, g.Wo);
-    else col2im_kernel<false><<<grid, bx, 0, st>>>(dcol, dx, g.Ci, g.H, g.W, g.K, g.P, g.S, g.D, g.Ho, g.Wo);
+    const int nho_max = ((g.K - 1) * g.D) / g.S + 1, nrows_max = nho_max * g.K;
+    const size_t smem = ((size_t)nrows_max * (g.Wo + 1) + 1) * sizeof(float) + (size_t)nrows_max * sizeof(void*);
+    static const bool gather_form = getenv("CPT_COL2IM_GATHER") != nullptr;  // A/B switch for tools/stem_bench.py
+    if (smem <= 48 * 1024 && nrows_max <= 256 && !gather_form) {  // rows of one dx line fit in shared memory: streaming form
+      int bx = g.W >= 256 ? 256 : ((g.W + 31) / 32) * 32;
+      if (bx < nrows_max) bx = ((nrows_max + 31) / 32) * 32;
+      dim3 grid(g.H, g.B * g.Ci);
+#define CPT_C2I(DIL, SS) col2im_rows_kernel<DIL, SS><<<grid, bx, smem, st>>>(dcol, dx, g.H, g.W, g.K, g.P, g.S, g.D, g.Ho, g.Wo, nrows_max)
+      if (g.D == 1) { if (g.S == 1) CPT_C2I(true, 1); else if (g.S == 2) CPT_C2I(true, 2); else CPT_C2I(true, 0); }
+      else CPT_C2I(false, 0);
+#undef CPT_C2I
+    } else {
+      const int bx = g.W >= 256 ? 256 : (g.W >= 128 ? 128 : (g.W >= 64 ? 64 : 32));
+      dim3 grid((g.W + bx - 1) / bx, g.H, g.B * g.Ci);
+      if (g.D == 1) col2im_kernel<true><<<grid, bx, 0, st>>>(dcol, dx, g.Ci, g.H, g.W, g.K, g.P, g.S, g.D, g.Ho, g.Wo);
+      else col2im_kernel<false><<<grid, bx, 0, st>>>(dcol, dx, g.Ci, g.H, g.W, g.K, g.P, g.S, g.D, g.Ho, g.Wo);
+    }
   }
   CPT_LAUNCH_CHECK("col2im");
   return CPT_OK;

@@ -243,6 +243,19 @@ def test_maxpool_nan_and_large(cp):
         dx = MaxPooling2DFn.backward(c, T(dy))
         assert np.array_equal(y.to_numpy(), y_ref) and np.array_equal(dx.to_numpy(), dx_ref)
         assert np.array_equal(np.signbit(dx.to_numpy()), np.signbit(dx_ref))
+    # k = 2 fast path (W % 4 == 0, H even) with NaN, +-0.0 and +-inf in the windows
+    x = np.round(rng.uniform(-2, 2, (4, 8, 16, 24)), 1).astype(np.float32)
+    x.reshape(-1)[::97] = np.nan; x.reshape(-1)[5::89] = -0.0; x.reshape(-1)[7::83] = np.inf; x.reshape(-1)[11::79] = -np.inf
+    with np.errstate(invalid="ignore"):
+        y_ref = x.reshape(4, 8, 8, 2, 12, 2).max((3, 5))
+        dy = rng.uniform(-1, 1, y_ref.shape).astype(np.float32)
+        up = lambda a: np.repeat(np.repeat(a, 2, 2), 2, 3)
+        dx_ref = up(dy) * (up(y_ref) == x)
+    c = FunctionCache()
+    y = MaxPooling2DFn.forward(c, T(x), 2)
+    dx = MaxPooling2DFn.backward(c, T(dy))
+    assert np.array_equal(y.to_numpy(), y_ref, equal_nan=True) and np.array_equal(dx.to_numpy(), dx_ref)
+    assert np.array_equal(np.signbit(dx.to_numpy()), np.signbit(dx_ref))
 
 
 # ------------------------------------------------------------------ BatchNorm / ReLU / CE / dropout
