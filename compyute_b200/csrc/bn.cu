@@ -393,6 +393,122 @@ __global__ void __launch_bounds__(256) bn_add_relu_kernel(const float* __restric
   }
 }
 
+// ---- BatchNorm2D -> ReLU -> MaxPooling2D(2) as one forward pass and one backward pass pair -------------------------------
+// (normalizations.py:150-171, activations.py:114-120, pooling_funcs.py:71-82.)  The full-resolution activation
+// a = relu(bn(x)) is never written: forward reads x and writes the pooled maximum; backward recomputes a for the four
+// elements of a window from x, rebuilds the pooling tie mask (a == max, every tie receives the gradient) and the ReLU
+// mask (bn(x) > 0), and feeds g = dy_pool * tie * relu into the usual two BatchNorm backward passes.  Same expressions
+// and the same summation order as the three separate layers -> bit-identical results.  Requires H even, W % 4 == 0.
+__device__ __forceinline__ float max_nan_bn(float a, float b) { return (a > b || a != a) ? a : b; }
+
+struct BnPoolWin {  // one 2 x 4 patch: activations of both rows, the two window maxima
+  float a0[4], a1[4], m[2];
+};
+__device__ __forceinline__ BnPoolWin bn_pool_window(const float4 x0, const float4 x1, float mu, float rs, float ww, float bb) {
+  BnPoolWin r;
+  const float r0[4] = {x0.x, x0.y, x0.z, x0.w}, r1[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.a0[i] = relu_fwd_val(fmaf(ww, (r0[i] - mu) * rs, bb));
+    r.a1[i] = relu_fwd_val(fmaf(ww, (r1[i] - mu) * rs, bb));
+  }
+  r.m[0] = max_nan_bn(max_nan_bn(r.a0[0], r.a0[1]), max_nan_bn(r.a1[0], r.a1[1]));  // order of maxpool_fwd_kernel
+  r.m[1] = max_nan_bn(max_nan_bn(r.a0[2], r.a0[3]), max_nan_bn(r.a1[2], r.a1[3]));
+  return r;
+}
+// gradient w.r.t. bn(x) of element (row, i): dy_pool * (max == a) [pooling_funcs.py:81-82] * (bn(x) > 0) [activation_funcs.py:28,33]
+__device__ __forceinline__ float bn_pool_grad(float g, float mx, float a) { return (g * (mx == a ? 1.0f : 0.0f)) * (a > 0.f ? 1.f : 0.f); }
+
+// item = (image-channel bc, output row p, group of 4 input columns)
+__global__ void __launch_bounds__(256) bn_relu_pool2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ b, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, float* __restrict__ y,
+                                                                int64_t n_items, int C, int H, int W) {
+  const int Wv = W >> 2, Ho = H >> 1, Wo = W >> 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
+    const int wv = (int)(it % Wv);
+    const int64_t t = it / Wv;
+    const int p = (int)(t % Ho);
+    const int64_t bc = t / Ho;
+    const int c = (int)(bc % C);
+    const float* src = x + (bc * H + 2 * (int64_t)p) * W + 4 * wv;
+    const float4 x0 = ld_stream(reinterpret_cast<const float4*>(src)), x1 = ld_stream(reinterpret_cast<const float4*>(src + W));
+    const BnPoolWin r = bn_pool_window(x0, x1, __ldg(mean + c), __ldg(rstd + c), __ldg(w + c), __ldg(b + c));
+    *reinterpret_cast<float2*>(y + (bc * Ho + p) * Wo + 2 * wv) = make_float2(r.m[0], r.m[1]);
+  }
+}
+
+// Backward partial sums (Σg, Σg·x̂) per channel: the iteration space and accumulation order of bn_partial_kernel<2, 4> (items =
+// float4s of the channel's planes, thread-strided, fixed split), so the sums are bit-identical to the unfused layers; the
+// other row of each window comes through L1 (the same block touches it within the same step).
+__global__ void __launch_bounds__(BN_THREADS) bn_pool2_partial_kernel(const float* __restrict__ x, const float* __restrict__ dyp,
+                                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                       const float* __restrict__ w, const float* __restrict__ b,
+                                                                       float2* __restrict__ partial, int N, int C, int H, int W) {
+  __shared__ float sh[32];
+  const int c = blockIdx.x, S = gridDim.y, s = blockIdx.y;
+  const int HW = H * W, HWv = HW >> 2, Wv = W >> 2, Wo = W >> 1, Ho = H >> 1;
+  const int64_t items = (int64_t)N * HWv;
+  const int64_t per = (items + S - 1) / S;
+  const int64_t lo = per * s, hi = (lo + per < items) ? lo + per : items;
+  const float mu = __ldg(mean + c), rs = __ldg(rstd + c), ww = __ldg(w + c), bb = __ldg(b + c);
+  float sa = 0.f, sb = 0.f;
+  for (int64_t it = lo + threadIdx.x; it < hi; it += BN_THREADS) {
+    const int64_t n = it / HWv;
+    const int j = (int)(it - n * HWv), h = j / Wv, wv = j - h * Wv;
+    const int64_t plane = (n * C + c) * (int64_t)HW;
+    const float* rowp = x + plane + (int64_t)(h & ~1) * W + 4 * wv;
+    const float4 x0 = ld_stream(reinterpret_cast<const float4*>(rowp)), x1 = ld_stream(reinterpret_cast<const float4*>(rowp + W));
+    const float2 g = *reinterpret_cast<const float2*>(dyp + ((n * C + c) * (int64_t)Ho + (h >> 1)) * Wo + 2 * wv);
+    const BnPoolWin r = bn_pool_window(x0, x1, mu, rs, ww, bb);
+    const float* a = (h & 1) ? r.a1 : r.a0;
+    const float xr[4] = {(h & 1) ? x1.x : x0.x, (h & 1) ? x1.y : x0.y, (h & 1) ? x1.z : x0.z, (h & 1) ? x1.w : x0.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float gg = bn_pool_grad(u < 2 ? g.x : g.y, r.m[u >> 1], a[u]);
+      sa += gg;
+      sb = fmaf(gg, (xr[u] - mu) * rs, sb);
+    }
+  }
+  sa = block_sum(sa, sh);
+  sb = block_sum(sb, sh);
+  if (threadIdx.x == 0) partial[(int64_t)c * S + s] = make_float2(sa, sb);
+}
+
+// dx = coef0 * (count * g - coef1 - x̂ * coef2) for both rows of the window (expression of bn_bwd_apply_kernel)
+__global__ void __launch_bounds__(256) bn_pool2_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dyp,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 const float* __restrict__ w, const float* __restrict__ b,
+                                                                 const float* __restrict__ coef, float* __restrict__ dx,
+                                                                 int64_t n_items, int C, int H, int W, float count) {
+  const int Wv = W >> 2, Ho = H >> 1, Wo = W >> 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
+    const int wv = (int)(it % Wv);
+    const int64_t t = it / Wv;
+    const int p = (int)(t % Ho);
+    const int64_t bc = t / Ho;
+    const int c = (int)(bc % C);
+    const int64_t off = (bc * H + 2 * (int64_t)p) * W + 4 * wv;
+    const float4 x0 = ld_stream(reinterpret_cast<const float4*>(x + off)), x1 = ld_stream(reinterpret_cast<const float4*>(x + off + W));
+    const float2 g = *reinterpret_cast<const float2*>(dyp + (bc * Ho + p) * Wo + 2 * wv);
+    const float mu = __ldg(mean + c), rs = __ldg(rstd + c);
+    const BnPoolWin r = bn_pool_window(x0, x1, mu, rs, __ldg(w + c), __ldg(b + c));
+    const float k0 = __ldg(coef + 3 * c), s1 = __ldg(coef + 3 * c + 1), s2 = __ldg(coef + 3 * c + 2);
+    const float r0[4] = {x0.x, x0.y, x0.z, x0.w}, r1[4] = {x1.x, x1.y, x1.z, x1.w};
+    float o0[4], o1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float gd = u < 2 ? g.x : g.y;
+      o0[u] = k0 * (count * bn_pool_grad(gd, r.m[u >> 1], r.a0[u]) - s1 - (r0[u] - mu) * rs * s2);
+      o1[u] = k0 * (count * bn_pool_grad(gd, r.m[u >> 1], r.a1[u]) - s1 - (r1[u] - mu) * rs * s2);
+    }
+    st_stream(reinterpret_cast<float4*>(dx + off), make_float4(o0[0], o0[1], o0[2], o0[3]));
+    st_stream(reinterpret_cast<float4*>(dx + off + W), make_float4(o1[0], o1[1], o1[2], o1[3]));
+  }
+}
+
 static int bn_splits(int N, int C, int HW) {
   // aim for >= 4 CTAs per SM in total, each with at least ~4K elements
   const int64_t per_channel = (int64_t)N * HW;
@@ -706,6 +822,43 @@ int cpt_bn_add_relu_apply(const float* x, const float* skip, const float* w, con
   bn_add_relu_kernel<<<ew_grid((int64_t)(n_chunks > 0 ? n_chunks : 1) * 32, 256), 256, 0, as_stream(stream)>>>(
       x, skip, w, b, save_mean, save_rstd, y, reinterpret_cast<uint32_t*>(mask), n_chunks, (uint32_t)n, (uint32_t)C, (uint32_t)HW);
   CPT_LAUNCH_CHECK("bn_add_relu_apply");
+  return CPT_OK;
+}
+
+int cpt_bn_relu_pool2_fwd(const float* x, const float* w, const float* b, const float* save_mean, const float* save_rstd, float* y,
+                          int N, int C, int H, int W, void* stream) {
+  if (int e = bn_check("bn_relu_pool2_fwd", N, C, H * W)) return e;
+  CPT_REQUIRE(x && w && b && save_mean && save_rstd && y, CPT_ERR_INVALID, "bn_relu_pool2_fwd: null pointer");
+  CPT_REQUIRE(H % 2 == 0 && W % 4 == 0, CPT_ERR_UNSUPPORTED, "bn_relu_pool2_fwd: needs H even and W %% 4 == 0");
+  CPT_REQUIRE(aligned16(x) && (reinterpret_cast<uintptr_t>(y) & 7) == 0, CPT_ERR_INVALID, "bn_relu_pool2_fwd: x must be 16-byte, y 8-byte aligned");
+  const int64_t items = (int64_t)N * C * (H / 2) * (W / 4);
+  bn_relu_pool2_fwd_kernel<<<ew_grid(items, 256), 256, 0, as_stream(stream)>>>(x, w, b, save_mean, save_rstd, y, items, C, H, W);
+  CPT_LAUNCH_CHECK("bn_relu_pool2_fwd");
+  return CPT_OK;
+}
+
+int cpt_bn_relu_pool2_bwd(const float* x, const float* dy_pool, const float* w, const float* b, const float* save_mean,
+                          const float* save_rstd, float* dx, float* dw, float* db, int N, int C, int H, int W, void* ws,
+                          size_t ws_bytes, void* stream) {
+  const int HW = H * W;
+  if (int e = bn_check("bn_relu_pool2_bwd", N, C, HW)) return e;
+  CPT_REQUIRE(x && dy_pool && w && b && save_mean && save_rstd && dx && dw && db, CPT_ERR_INVALID, "bn_relu_pool2_bwd: null pointer");
+  CPT_REQUIRE(H % 2 == 0 && W % 4 == 0, CPT_ERR_UNSUPPORTED, "bn_relu_pool2_bwd: needs H even and W %% 4 == 0");
+  CPT_REQUIRE(aligned16(x) && aligned16(dx) && (reinterpret_cast<uintptr_t>(dy_pool) & 7) == 0, CPT_ERR_INVALID,
+              "bn_relu_pool2_bwd: x, dx must be 16-byte, dy_pool 8-byte aligned");
+  CPT_REQUIRE(ws && ws_bytes >= cpt_bn_workspace_size(N, C, HW), CPT_ERR_WORKSPACE, "bn_relu_pool2_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int S = bn_splits(N, C, HW);  // the split of bn_partial_kernel: same partial boundaries, same sums
+  float2* partial = reinterpret_cast<float2*>(ws);
+  float* coef = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + (size_t)C * 64 * sizeof(float2));
+  bn_pool2_partial_kernel<<<dim3(C, S), BN_THREADS, 0, st>>>(x, dy_pool, save_mean, save_rstd, w, b, partial, N, C, H, W);
+  CPT_LAUNCH_CHECK("bn_pool2_partial");
+  const float count = (float)((int64_t)N * HW);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, S, w, save_rstd, dw, db, coef, C, count);
+  CPT_LAUNCH_CHECK("bn_bwd_finalize");
+  const int64_t items = (int64_t)N * C * (H / 2) * (W / 4);
+  bn_pool2_bwd_apply_kernel<<<ew_grid(items, 256), 256, 0, st>>>(x, dy_pool, save_mean, save_rstd, w, b, coef, dx, items, C, H, W, count);
+  CPT_LAUNCH_CHECK("bn_pool2_bwd_apply");
   return CPT_OK;
 }
 

@@ -10,10 +10,11 @@ from ...tensors import DeviceArray, ShapeError, Tensor, f32ptr, require_cuda, st
 from .functions import Function, FunctionCache, PseudoCache, get_caching_enabled
 
 __all__ = ["batchnorm1d", "batchnorm2d", "BatchNorm1DFn", "BatchNorm2DFn", "BatchNormReLU1DFn", "BatchNormReLU2DFn",
-           "residual_tail_supported"]
+           "residual_tail_supported", "pool2_fusion_supported"]
 
 
 ACT_NONE, ACT_RELU = 0, 1  # CPT_ACT_*
+ACT_RELU_POOL2 = 2          # cache marker only: BatchNorm2D -> ReLU -> MaxPooling2D(2) evaluated as one pass (cpt_bn_relu_pool2_*)
 
 
 def _cl_ok(x) -> bool:
@@ -26,15 +27,26 @@ def residual_tail_supported(x) -> bool:
     return x.ndim == 4 and (x.shape[2] * x.shape[3]) % 4 == 0 and x.size < (1 << 31)
 
 
-def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW, act=ACT_NONE, emit_cl=False, skip=None, relu_cache=None):
+def pool2_fusion_supported(x) -> bool:
+    """cpt_bn_relu_pool2_*: 4-D activations with H even and W % 4 == 0; per-shard statistics only (the synchronised backward
+    sums do not know the pooling mask)."""
+    return x.ndim == 4 and x.shape[2] % 2 == 0 and x.shape[3] % 4 == 0 and not distributed.sync_batchnorm_active()
+
+
+def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW, act=ACT_NONE, emit_cl=False, skip=None, relu_cache=None,
+                pool2=False):
     """``skip`` / ``relu_cache`` (extension): evaluate ``relu(bn(x) + skip)`` — the tail of a residual block — in one pass; the
     ReLU mask goes to ``relu_cache`` exactly as ReLUFn.forward would have pushed it, the BatchNorm cache entry is the plain one
     (its backward receives the ReLU's dx).  The statistics step runs with y == NULL, then cpt_bn_add_relu_apply applies."""
     require_cuda(x, rmean, rvar, w, b)
     L = _lib.lib()
     st = stream_ptr()
-    y = DeviceArray.empty(x.shape, np.float32)
-    y_stats = y.ptr if skip is None else None  # NULL: statistics only
+    if pool2:  # relu(bn(x)) max-pooled 2x2 in the same pass: only the pooled tensor exists
+        act, emit_cl = ACT_NONE, False
+        y = DeviceArray.empty((x.shape[0], x.shape[1], x.shape[2] // 2, x.shape[3] // 2), np.float32)
+    else:
+        y = DeviceArray.empty(x.shape, np.float32)
+    y_stats = y.ptr if (skip is None and not pool2) else None  # NULL: statistics only
     y_cl = sync = None
     if emit_cl and _cl_ok(x):  # the consumer is a tensor-core convolution: write its bf16 NHWC operand in the same pass
         y_cl = DeviceArray.empty((L.cpt_channels_last_bytes(N, C, HW, 1, _lib.MODE_BF16),), np.uint8)
@@ -78,6 +90,11 @@ def _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, N, C, HW, act=ACT
     else:
         _lib.check(L.cpt_bn_act_fwd_eval(f32ptr(x), f32ptr(w), f32ptr(b), f32ptr(rmean), f32ptr(rvar), y_stats, save_mean.ptr,
                                          save_rstd.ptr, N, C, HW, float(eps), act, st))
+    if pool2:
+        _lib.check(L.cpt_bn_relu_pool2_fwd(f32ptr(x), f32ptr(w), f32ptr(b), save_mean.ptr, save_rstd.ptr, y.ptr, x.shape[0], C,
+                                           x.shape[2], x.shape[3], st))
+        cache.push(x, w, b, save_mean, save_rstd, (N, C, HW), ACT_RELU_POOL2, None)
+        return Tensor(y), rmean, rvar
     if skip is not None:
         require_cuda(skip)
         if skip.shape != x.shape:
@@ -103,6 +120,11 @@ def _bn_backward(cache, dy, dw_out=None, db_out=None, emit_cl=False, emit_sum=Fa
     dx = DeviceArray.empty(x.shape, np.float32)
     dw = dw_out.reshape((C,)) if dw_out is not None else DeviceArray.empty((C,), np.float32)
     db = db_out.reshape((C,)) if db_out is not None else DeviceArray.empty((C,), np.float32)
+    if act == ACT_RELU_POOL2:  # dy is the gradient of the POOLED output; tie mask and ReLU mask are recomputed from x
+        ws, wsb = workspace(L.cpt_bn_workspace_size(N, C, HW))
+        _lib.check(L.cpt_bn_relu_pool2_bwd(f32ptr(x), f32ptr(dy), f32ptr(w), f32ptr(b), save_mean.ptr, save_rstd.ptr, dx.ptr, dw.ptr,
+                                           db.ptr, x.shape[0], C, x.shape[2], x.shape[3], ws, wsb, stream_ptr()))
+        return Tensor(dx), Tensor(dw), Tensor(db)
     if sync is not None:  # forward took global statistics: the two backward sums are global too
         want_cl = emit_cl and _cl_ok(x)
         dx_cl = DeviceArray.empty((L.cpt_channels_last_bytes(N, C, HW, 1, _lib.MODE_BF16),), np.uint8) if want_cl else None
@@ -137,14 +159,16 @@ class BatchNorm2DFn(Function):
 
     @staticmethod
     def forward(cache: FunctionCache, x: Tensor, rmean: Tensor, rvar: Tensor, w: Tensor, b: Tensor, m: float, eps: float,
-                training: bool, emit_cl: bool = False, skip: Tensor = None, relu_cache=None) -> tuple[Tensor, Tensor, Tensor]:
+                training: bool, emit_cl: bool = False, skip: Tensor = None, relu_cache=None,
+                pool2: bool = False) -> tuple[Tensor, Tensor, Tensor]:
         """``emit_cl`` (extension): also write y as channels-last bf16 for a tensor-core convolution that consumes it.
-        ``skip`` (extension): return ``relu(bn(x) + skip)`` instead (residual tail, see ``_bn_forward``)."""
+        ``skip`` (extension): return ``relu(bn(x) + skip)`` instead (residual tail, see ``_bn_forward``).
+        ``pool2`` (extension): return ``maxpool2(relu(bn(x)))`` instead; ``backward`` then takes the pooled gradient."""
         if x.ndim != 4:
             raise ShapeError(f"Expected input to be 4D, got {x.ndim}D.")
         B, C, H, W = x.shape
         return _bn_forward(cache, x, rmean, rvar, w, b, m, eps, training, B, C, H * W, ACT_NONE, emit_cl and skip is None, skip,
-                           relu_cache)
+                           relu_cache, pool2)
 
     @staticmethod
     def backward(cache: FunctionCache, dy: Tensor, dw_out=None, db_out=None, emit_cl: bool = False,

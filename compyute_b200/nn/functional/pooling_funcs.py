@@ -6,6 +6,7 @@ import numpy as np
 
 from ... import _lib
 from ...tensors import DeviceArray, ShapeError, Tensor, f32ptr, require_cuda, stream_ptr
+from .activation_funcs import FUSED_INTO_PRODUCER
 from .functions import Function, FunctionCache, PseudoCache
 
 __all__ = ["maxpooling2d", "avgpooling2d", "MaxPooling2DFn", "AvgPooling2DFn"]
@@ -34,6 +35,8 @@ class MaxPooling2DFn(Function):
     @staticmethod
     def backward(cache: FunctionCache, dy: Tensor) -> Tensor:
         x, k, y = cache.pop()
+        if x is FUSED_INTO_PRODUCER:  # evaluated inside the preceding BatchNorm (BatchNorm2D -> ReLU -> MaxPooling2D(2) peephole)
+            return dy
         require_cuda(dy)
         B, C, H, W = x.shape
         dx = DeviceArray.empty(x.shape, np.float32)

@@ -6,7 +6,7 @@ from typing import Optional
 
 from ...tensors import DeviceArray, Tensor
 from ..functional.activation_funcs import FUSED_INTO_PRODUCER
-from ..functional.normalization_funcs import residual_tail_supported
+from ..functional.normalization_funcs import pool2_fusion_supported, residual_tail_supported
 from .module import Module, ModuleList, get_debug_mode
 
 _fusion = True
@@ -111,6 +111,19 @@ class Sequential(Module):
         return (type(bn) is BatchNorm2D and not any(m.retain_values for m in mods)
                 and len({m.is_training for m in mods}) == 1)
 
+    def _pool_fusable(self, i: int, x: Tensor) -> bool:
+        """layers[i : i + 3] is BatchNorm2D -> ReLU -> MaxPooling2D(2): one forward pass that writes only the pooled tensor, one
+        backward pass pair that recomputes both masks from x (cpt_bn_relu_pool2_*) — bit-identical to the three layers."""
+        from .layers import BatchNorm2D, MaxPooling2D, ReLU
+        if not _fusion or i + 2 >= len(self.layers) or get_debug_mode() or not isinstance(x.data, DeviceArray):
+            return False
+        bn, relu, pool = self.layers[i], self.layers[i + 1], self.layers[i + 2]
+        if type(bn) is not BatchNorm2D or type(relu) is not ReLU or type(pool) is not MaxPooling2D or pool.kernel_size != 2:
+            return False
+        mods = (bn, relu, pool)
+        return (not any(m.retain_values for m in mods) and len({m.is_training for m in mods}) == 1
+                and pool2_fusion_supported(x))
+
     def _run(self, x: Tensor, tail=None) -> Tensor:
         """The layer walk.  ``tail = (skip_fn, relu)``: this container is the block of a fused residual connection — its last
         BatchNorm2D evaluates ``relu(bn(x) + skip_fn())``."""
@@ -125,7 +138,12 @@ class Sequential(Module):
                 y = layer(x)  # shapes the fused kernel does not cover: the three separate passes
                 y += skip
                 return tail[1](y)
-            if self._fusable(i, x):
+            if self._pool_fusable(i, x):
+                x = layer.forward_relu_pool2(x)
+                self.layers[i + 1].fcache.push(FUSED_INTO_PRODUCER)                            # ReLU.backward passes dy through
+                self.layers[i + 2].fcache.push(FUSED_INTO_PRODUCER, self.layers[i + 2].kernel_size, None)  # so does MaxPooling2D.backward
+                i += 3
+            elif self._fusable(i, x):
                 x = layer.forward_relu(x)
                 self.layers[i + 1].fcache.push(FUSED_INTO_PRODUCER)  # its backward is folded into the BatchNorm's
                 i += 2

@@ -155,6 +155,15 @@ class _BatchNorm(Module):
         self.rvar.data = rvar.data
         return y
 
+    def forward_relu_pool2(self, x: Tensor) -> Tensor:
+        """``maxpool2(relu(self(x)))`` in one pass; ``backward`` then expects the gradient of the pooled output (the cache entry
+        records the fusion).  Called by ``Sequential`` for BatchNorm2D -> ReLU -> MaxPooling2D(2)."""
+        y, rmean, rvar = self._fn.forward(self.fcache, x, self.rmean, self.rvar, self.w, self.b, self.m, self.eps, self._is_training,
+                                          False, None, None, True)
+        self.rmean.data = rmean.data
+        self.rvar.data = rvar.data
+        return y
+
     def _forward(self, fn, x: Tensor) -> Tensor:
         extra = (True,) if (self._emit_cl_fwd and x.ndim == 4) else ()
         y, rmean, rvar = fn.forward(self.fcache, x, self.rmean, self.rvar, self.w, self.b, self.m, self.eps, self._is_training,

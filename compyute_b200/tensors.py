@@ -156,6 +156,12 @@ class DeviceArray:
     def item(self):
         return self.numpy().reshape(-1)[0].item()
 
+    def __array__(self, dtype=None, copy=None) -> np.ndarray:
+        """``numpy.asarray(device_array)``: an explicit host copy (D2H, synchronising) — without it NumPy would fall back to
+        the sequence protocol and issue one indexing launch per element."""
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
+
     # -- arithmetic through the C ABI (fp32 only)
     def _f32(self, who: str) -> None:
         if self.dtype != np.float32:

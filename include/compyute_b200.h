@@ -236,6 +236,17 @@ int cpt_bn_act_fwd_train_presum(const float* x, const float* w, const float* b, 
 int cpt_bn_add_relu_apply(const float* x, const float* skip, const float* w, const float* b,
                           const float* save_mean, const float* save_rstd, float* y, uint8_t* mask, int N,
                           int C, int HW, void* stream);
+/* BatchNorm2D -> ReLU -> MaxPooling2D(kernel 2) as one forward pass and one backward pass pair (normalizations.py:150-171,
+ * activations.py:114-120, pooling_funcs.py:71-82): the full-resolution activation is neither written nor read.  Forward: the
+ * statistics come from a statistics-only call of the forward entry points above (y == NULL); y is the POOLED output
+ * (N, C, H/2, W/2).  Backward: dy_pool is the gradient of the pooled output; the pooling tie mask and the ReLU mask are
+ * recomputed from x.  Bit-identical to the three separate layers (same expressions, same summation order).  Needs H even and
+ * W % 4 == 0 (CPT_ERR_UNSUPPORTED otherwise).  ws: cpt_bn_workspace_size(N, C, H*W). */
+int cpt_bn_relu_pool2_fwd(const float* x, const float* w, const float* b, const float* save_mean,
+                          const float* save_rstd, float* y, int N, int C, int H, int W, void* stream);
+int cpt_bn_relu_pool2_bwd(const float* x, const float* dy_pool, const float* w, const float* b,
+                          const float* save_mean, const float* save_rstd, float* dx, float* dw, float* db,
+                          int N, int C, int H, int W, void* ws, size_t ws_bytes, void* stream);
 /* Synchronised BatchNorm for the batch-sharded data-parallel mode: the statistics of
  * normalization_funcs.py:139-147 / the sums of :169-175 taken over the GLOBAL batch.  Each pass is split around the
  * collective the caller runs (torch.distributed / NCCL):

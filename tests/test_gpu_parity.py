@@ -637,3 +637,76 @@ def test_residual_tail_fusion_is_bit_exact(cp, proj, mode):
         for k, (u, v) in enumerate(zip(a, b)):
             assert np.array_equal(u, v, equal_nan=True), (H, k, u.shape, float(np.abs(u - v).max()))
         assert la < lb, (la, lb)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_bn_relu_maxpool_fusion_is_bit_exact(cp, mode):
+    """BatchNorm2D -> ReLU -> MaxPooling2D(2) inside a Sequential runs as one forward pass that writes only the pooled tensor and
+    one backward pass pair that recomputes the pooling tie mask and the ReLU mask from x (cpt_bn_relu_pool2_*).  Everything the
+    model returns must equal the layer-by-layer evaluation bit for bit (same expressions, same summation order), in training and
+    inference mode; W % 4 != 0 falls back to the separate layers; the fused walk launches fewer kernels."""
+    from compyute_b200 import _lib, nn
+    for H, expect_fused in ((16, True), (12, True), (10, False)):
+        x = np.round(np.random.RandomState(5).normal(0, 1, (6, 3, H, H)), 1).astype(np.float32)  # coarse grid: ties in the windows
+
+        def build():
+            np.random.seed(13)
+            with cp.use_device(cp.cuda):
+                return nn.Sequential(
+                    nn.Conv2D(3, 8, 3, padding="same"), nn.BatchNorm2D(8), nn.ReLU(), nn.MaxPooling2D(2),
+                    nn.Conv2D(8, 16, 3, padding="same", bias=False), nn.BatchNorm2D(16), nn.ReLU(),
+                    nn.Conv2D(16, 16, 3, padding="same"), nn.BatchNorm2D(16), nn.ReLU(), nn.MaxPooling2D(2) if H != 10 else nn.MaxPooling2D(1),
+                    nn.Flatten(), nn.Linear(16 * ((H // 2) // (2 if H != 10 else 1)) ** 2, 4))
+
+        def run(fused):
+            nn.set_fusion_enabled(fused)
+            nn.set_epilogue_stats_enabled(False)
+            try:
+                model = build()
+                model.training()
+                n0 = _lib.lib().cpt_launch_count()
+                with cp.compute_mode(mode):
+                    y = model(cp.tensor(x, device=cp.cuda))
+                    dy = np.random.RandomState(6).normal(0, 1, y.shape).astype(np.float32)
+                    dx = model.backward(cp.tensor(dy, device=cp.cuda))
+                    launches = _lib.lib().cpt_launch_count() - n0
+                    tc_ok()
+                    assert all(not m.fcache.cache for m in model.get_modules())
+                    out = [y.to_numpy(), dx.to_numpy()] + [p.grad.to_numpy() for p in model.get_parameters()] + \
+                          [b.to_numpy() for b in model.get_buffers()]
+                    model.inference()
+                    out.append(model(cp.tensor(x, device=cp.cuda)).to_numpy())
+                return out, launches
+            finally:
+                nn.set_fusion_enabled(True)
+                nn.set_epilogue_stats_enabled(True)
+
+        (a, la), (b, lb) = run(True), run(False)
+        for k, (u, v) in enumerate(zip(a, b)):
+            assert np.array_equal(u, v, equal_nan=True), (H, k, u.shape, float(np.abs(u - v).max()))
+        assert la < lb, (la, lb)
+
+
+def test_bn_relu_maxpool_function_vs_oracle(cp):
+    """The fused pass through the Function API (``BatchNorm2DFn.forward(..., pool2=True)``) against the oracle's three functions
+    (normalization_funcs.py:124-177, activation_funcs.py:26-34, pooling_funcs.py:71-82), ties and negative gradients included."""
+    from compyute_b200.nn.functional import BatchNorm2DFn, FunctionCache
+    rng = np.random.RandomState(8)
+    x = np.round(rng.normal(0.3, 1.5, (5, 7, 12, 20)), 1).astype(np.float32)
+    w = rng.uniform(0.5, 1.5, (7,)).astype(np.float32); b = rng.uniform(-0.5, 0.5, (7,)).astype(np.float32)
+    dyp = rng.normal(0, 1, (5, 7, 6, 10)).astype(np.float32)
+    # the reference's pooling is square-only (Appendix A.2): restate the three steps per dim from the oracle's BatchNorm
+    rc = []
+    yb, rm_ref, rv_ref = R.batchnorm_forward(rc, x, np.zeros(7, np.float32), np.ones(7, np.float32), w, b, 0.1, 1e-5, True)
+    a = np.maximum(yb, 0)
+    yp_ref = a.reshape(5, 7, 6, 2, 10, 2).max((3, 5))
+    up = lambda t: np.repeat(np.repeat(t, 2, 2), 2, 3)
+    da = up(dyp) * (up(yp_ref) == a)
+    dx_ref, dw_ref, db_ref = R.batchnorm_backward(rc, da * (a > 0))
+    T = lambda t: cp.tensor(t, device=cp.cuda)
+    c = FunctionCache()
+    yp, rm, rv = BatchNorm2DFn.forward(c, T(x), T(np.zeros(7, np.float32)), T(np.ones(7, np.float32)), T(w), T(b), 0.1, 1e-5, True,
+                                       False, None, None, True)
+    dx, dw, db = BatchNorm2DFn.backward(c, T(dyp))
+    assert close(yp, yp_ref) and close(rm, rm_ref) and close(rv, rv_ref)
+    assert close(dx, dx_ref, 2e-5) and close(dw, dw_ref, 2e-5) and close(db, db_ref, 2e-5)
