@@ -410,6 +410,7 @@ def run_model(args) -> None:
     model.training()
     opt = nn.optimizers.Adam(model.get_parameters(), lr=1e-3)
     opt.overlap_grad_sync = world > 1 and args.overlap  # bucketed all-reduces launched during backward
+    distributed.set_sync_batchnorm(world > 1 and args.sync_bn)  # BatchNorm statistics over the global batch (optional)
     opt.reserve_sms = int(os.environ.get("CPT_DP_RESERVE_SMS", opt.reserve_sms))
     opt.bucket_bytes = int(os.environ.get("CPT_DP_BUCKET_BYTES", opt.bucket_bytes))
     loss_fn = nn.CrossEntropyLoss()
@@ -556,6 +557,7 @@ def run_model(args) -> None:
             "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.mode], "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": B, "compute_mode": args.mode, "cuda_graph": bool(graphed), "tolerance": TOL[args.mode], "parallelism": f"dp{world}",
                        "grad_sync": ("bucketed all-reduce overlapped with backward" if opt.overlap_grad_sync else "one all-reduce at step()") if world > 1 else "n/a",
+                       "batchnorm": "synchronised (global-batch statistics)" if distributed.sync_batchnorm_active() else "per-shard statistics",
                        "l2_policy": "activations of one step exceed L2" if B * int(np.prod(xshape)) * 4 > 126e6 else "L2 flushed implicitly: per-step activation traffic exceeds L2"},
             "clocks": clocks, "e2e": {"value": round(world * B / (e2e_ms / 1e3), 1), "unit": "images/s", "h2d_bytes_per_step": int(hx.numel() * 4 + ht.numel() * 4),
                                       "d2h_bytes_per_step": 4, "note": "module API; one batch H2D from pinned memory (prefetched on a copy stream during the previous step) and the loss D2H every step; wall clock incl. host dispatch"},
@@ -603,6 +605,9 @@ def main() -> None:
                     help="data-parallel model runs: bucketed all-reduces launched during backward (Optimizer.overlap_grad_sync) "
                          "instead of one all-reduce of the whole gradient arena at step(); measured gain at 2 GPUs is ~1 %% because "
                          "the persistent GEMM grids leave NCCL little room, so it is opt-in")
+    ap.add_argument("--sync-bn", action="store_true",
+                    help="data-parallel model runs: synchronised BatchNorm (distributed.set_sync_batchnorm): statistics and backward "
+                         "sums over the global batch, one small all-gather / all-reduce per BatchNorm layer and pass")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
