@@ -129,6 +129,27 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__
   }
 }
 
+// dx = dy * mask for a mask in PLAIN bit order (element e = bit e % 32 of word e / 32), as written by the fused
+// Linear + ReLU epilogue (cpt_linear_relu_fwd_bf16); lp as in relu_bwd_kernel.
+__global__ void __launch_bounds__(256) relu_bwd_plain_kernel(const float* __restrict__ dy, const uint32_t* __restrict__ mask,
+                                                             float* __restrict__ dx, int64_t n4, int64_t n,
+                                                             __nv_bfloat16* __restrict__ lp) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = t; i < n4; i += stride) {
+    const float4 v = ld_stream(reinterpret_cast<const float4*>(dy) + i);
+    const uint32_t b = __ldg(mask + (i >> 3)) >> ((i & 7) * 4);
+    const float4 o = make_float4(v.x * (float)(b & 1u), v.y * (float)((b >> 1) & 1u), v.z * (float)((b >> 2) & 1u),
+                                 v.w * (float)((b >> 3) & 1u));
+    st_stream(reinterpret_cast<float4*>(dx) + i, o);
+    if (lp) reinterpret_cast<uint2*>(lp)[i] = pack_bf16x4(o.x, o.y, o.z, o.w);
+  }
+  for (int64_t i = n4 * 4 + t; i < n; i += stride) {
+    const float o = dy[i] * (float)((__ldg(mask + (i >> 5)) >> (i & 31)) & 1u);
+    dx[i] = o;
+    if (lp) lp[i] = __float2bfloat16_rn(o);
+  }
+}
+
 // ------------------------------------------------------------------ a += b (12 B/elem), y = alpha x (+y)
 __global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b,
                                                           int64_t n4, int64_t n) {
@@ -247,6 +268,18 @@ int cpt_relu_bwd_lp(const float* dy, const uint8_t* mask, float* dx, void* dx_bf
   relu_bwd_kernel<<<ew_grid((n_chunks > 0 ? n_chunks : 1) * 32, 256), 256, 0, as_stream(stream)>>>(
       dy, reinterpret_cast<const uint32_t*>(mask), dx, n_chunks, n, reinterpret_cast<__nv_bfloat16*>(dx_bf16));
   CPT_LAUNCH_CHECK("relu_bwd");
+  return CPT_OK;
+}
+
+int cpt_relu_bwd_plain(const float* dy, const uint8_t* mask, float* dx, void* dx_bf16, int64_t n, void* stream) {
+  CPT_REQUIRE(n >= 0 && dy && dx && mask, CPT_ERR_INVALID, "relu_bwd_plain: bad arguments");
+  CPT_REQUIRE((reinterpret_cast<uintptr_t>(mask) & 3) == 0 && (!dx_bf16 || (reinterpret_cast<uintptr_t>(dx_bf16) & 7) == 0), CPT_ERR_INVALID,
+              "relu_bwd_plain: mask must be 4-byte, dx_bf16 8-byte aligned");
+  if (n == 0) return CPT_OK;
+  const int64_t n4 = (aligned16(dy) && aligned16(dx)) ? n / 4 : 0;
+  relu_bwd_plain_kernel<<<ew_grid(n4 > 0 ? n4 : n, 256), 256, 0, as_stream(stream)>>>(dy, reinterpret_cast<const uint32_t*>(mask), dx, n4, n,
+                                                                                     reinterpret_cast<__nv_bfloat16*>(dx_bf16));
+  CPT_LAUNCH_CHECK("relu_bwd_plain");
   return CPT_OK;
 }
 

@@ -782,7 +782,8 @@ size_t linear_workspace_size(int op, int64_t N, int In, int Out, int mode) {
   return s;
 }
 
-int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, int64_t N, int In, int Out, int mode, cudaStream_t st);
+int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, int64_t N, int In, int Out, int mode, cudaStream_t st,
+                  int relu = 0, void* y_lp = nullptr, unsigned int* mask = nullptr);
 int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In, int Out, int mode, cudaStream_t st);
 int linear_wgrad_lp(const void* xa, const void* ga, float* dw, int64_t N, int In, int Out, int mode, void* ws, size_t ws_bytes,
                     cudaStream_t st, int max_splits = 16);
@@ -804,7 +805,8 @@ int linear_fwd(const float* x, const float* w, const float* bias, float* y, int6
 }
 
 // operands already in the mode's element type: bf16 with row pitch round_up(C, 8), or fp32 (tf32) with pitch C
-int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, int64_t N, int In, int Out, int mode, cudaStream_t st) {
+int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, int64_t N, int In, int Out, int mode, cudaStream_t st,
+                  int relu, void* y_lp, unsigned int* mask) {
   const int pitch = mode == CPT_MODE_BF16 ? round_up(In, 8) : In;
   const int kc = kc_of(mode), BN = pick_bn(N);
   TcParams p{};
@@ -813,6 +815,7 @@ int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, i
   const bool use2 = want_2cta(BN, (Out + 127) / 128);
   if (int e = make_map_2d(&p.tmB, xa, mode, In, (uint64_t)N, pitch, kc, use2 ? BN / 2 : BN)) return e;
   p.out = y; p.bias = bias; p.bias_mode = bias ? BIAS_LANE : BIAS_NONE;
+  p.relu = relu; p.relu_lp = y_lp; p.relu_mask = mask;
   if (int e = get_status_ptr(&p.status)) return e;
   p.M = Out; p.N = (int)N;
   p.m_tiles = (Out + 127) / 128; p.n_tiles = (int)((N + BN - 1) / BN); p.z_tiles = 1;
@@ -1436,6 +1439,14 @@ static int check_lp(int64_t N, int In, int Out, int mode, const char* who) {
 int cpt_linear_fwd_bf16(const void* x_bf, const void* w_bf, const float* bias, float* y, int64_t N, int In, int Out, void* stream) {
   if (int e = check_lp(N, In, Out, CPT_MODE_BF16, "linear_fwd_bf16")) return e;
   return tc::linear_fwd_lp(x_bf, w_bf, bias, y, N, In, Out, CPT_MODE_BF16, as_stream(stream));
+}
+int cpt_linear_relu_fwd_bf16(const void* x_bf, const void* w_bf, const float* bias, float* y, void* y_bf16, uint8_t* mask, int64_t N,
+                             int In, int Out, void* stream) {
+  if (int e = check_lp(N, In, Out, CPT_MODE_BF16, "linear_relu_fwd_bf16")) return e;
+  CPT_REQUIRE(Out % 32 == 0, CPT_ERR_UNSUPPORTED, "linear_relu_fwd_bf16: the fused ReLU needs Out %% 32 == 0");
+  CPT_REQUIRE(!mask || (reinterpret_cast<uintptr_t>(mask) & 3) == 0, CPT_ERR_INVALID, "linear_relu_fwd_bf16: mask must be 4-byte aligned");
+  return tc::linear_fwd_lp(x_bf, w_bf, bias, y, N, In, Out, CPT_MODE_BF16, as_stream(stream), 1, y_bf16,
+                           reinterpret_cast<unsigned int*>(mask));
 }
 int cpt_linear_dgrad_bf16(const void* dy_bf, const void* w_bf, float* dx, int64_t N, int In, int Out, void* stream) {
   if (int e = check_lp(N, In, Out, CPT_MODE_BF16, "linear_dgrad_bf16")) return e;

@@ -33,6 +33,12 @@ struct alignas(64) TcParams {
   int* status;      // device int: set non-zero on a pipeline timeout
   int bias_mode;
   int out_bf16;     // 1: `out` is bf16 (no bias): the packed-K dgrad intermediate dcol
+  // fused ReLU of a Linear layer's forward (lanes = output features, columns = rows of the batch; M % 32 == 0): out receives
+  // max(acc + bias, 0); relu_lp (optional) the same values as bf16 rows for the next Linear layer; relu_mask (optional) the
+  // bits (out > 0) in plain order — element e = col * M + m is bit e % 32 of word e / 32 (consumed by cpt_relu_bwd_plain)
+  int relu;
+  void* relu_lp;
+  unsigned int* relu_mask;
   float* stats;     // optional [gridDim.x * 4][N][2]: per-epilogue-warp column sums (Σ acc, Σ acc²) of the raw accumulators
                     // (without bias) over the valid lanes — the batch statistics of a BatchNorm that consumes the output
   int M, N;         // valid extents of the lane / column dimensions
@@ -361,6 +367,25 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
           return;
         }
         float* q = dst + (long long)(c * 32) * cs;
+        if (p.relu) {  // Linear forward + ReLU: one ballot per column gives the mask word of this warp's 32 features
+          __nv_bfloat16* lq = p.relu_lp ? reinterpret_cast<__nv_bfloat16*>(p.relu_lp) + z_off + lane_off + (long long)cbase * cs : nullptr;
+          const int mw = m >> 5;  // m - lane is a multiple of 32: word index of this warp's features within a row
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = __uint_as_float(v[j]) + lane_bias;
+            const float val = (a != a) ? a : fmaxf(a, 0.f);  // numpy.maximum propagates NaN (activation_funcs.py:27)
+            const bool col_ok = cbase + j < p.N;
+            const unsigned int bits = __ballot_sync(0xffffffffu, m_ok && val > 0.f);
+            if (col_ok) {
+              if (m_ok) *q = val;
+              if (lq && m_ok) *lq = __float2bfloat16_rn(val);
+              if (p.relu_mask && lane == 0 && m_ok) p.relu_mask[((long long)(cbase + j) * p.M >> 5) + mw] = bits;
+            }
+            q += cs;
+            if (lq) lq += cs;
+          }
+          return;
+        }
         float bl = 0.f;  // this lane's column bias; column j's value is fetched with a shuffle (one LDG per chunk)
         if (col_bias && cbase + lane < p.N) bl = __ldg(p.bias + cbase + lane);
         if (cbase + 32 <= p.N) {

@@ -9,11 +9,21 @@ from ...backend import get_compute_mode
 from ...tensors import DeviceArray, Tensor, f32ptr, require_cuda, stream_ptr
 from .functions import Function, FunctionCache, PseudoCache, get_caching_enabled
 
-__all__ = ["relu", "ReLUFn", "FUSED_INTO_PRODUCER"]
+__all__ = ["relu", "ReLUFn", "FUSED_INTO_PRODUCER", "PlainMask"]
 
 # cache marker: this ReLU was evaluated inside its producer (Sequential peephole BatchNorm -> ReLU, see
 # normalization_funcs.BatchNormReLU2DFn); the producer's backward already applies dy * (y > 0)
 FUSED_INTO_PRODUCER = "fused-into-producer"
+
+
+class PlainMask:
+    """ReLU mask in plain bit order (element e = bit e % 32 of word e / 32), as written by the fused Linear + ReLU epilogue
+    (``cpt_linear_relu_fwd_bf16``); ``ReLUFn.backward`` then calls ``cpt_relu_bwd_plain``."""
+
+    __slots__ = ("bits",)
+
+    def __init__(self, bits: DeviceArray) -> None:
+        self.bits = bits
 
 
 def _lp_buffer(a: DeviceArray):
@@ -51,6 +61,10 @@ class ReLUFn(Function):
         require_cuda(dy)
         dx = DeviceArray.empty(dy.shape, np.float32)
         lp = _lp_buffer(dx) if emit_lp else None
+        if isinstance(mask, PlainMask):
+            _lib.check(_lib.lib().cpt_relu_bwd_plain(f32ptr(dy), mask.bits.ptr, dx.ptr, lp.ptr if lp is not None else None, dy.size,
+                                                     stream_ptr()))
+            return Tensor(dx)
         _lib.check(_lib.lib().cpt_relu_bwd_lp(f32ptr(dy), mask.ptr, dx.ptr, lp.ptr if lp is not None else None, dy.size, stream_ptr()))
         return Tensor(dx)
 

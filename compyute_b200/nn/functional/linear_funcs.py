@@ -9,7 +9,8 @@ import numpy as np
 from ... import _lib
 from ...backend import get_compute_mode
 from ...tensors import DeviceArray, ShapeError, Tensor, f32ptr, require_cuda, stream_ptr, workspace
-from .functions import Function, FunctionCache, PseudoCache
+from .activation_funcs import PlainMask
+from .functions import Function, FunctionCache, PseudoCache, get_caching_enabled
 
 __all__ = ["linear", "LinearFn"]
 
@@ -19,7 +20,15 @@ class LinearFn(Function):
     what the reference's batched matmul + ``.sum(leading)`` computes (linear_funcs.py:15-35)."""
 
     @staticmethod
-    def forward(cache: FunctionCache, x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+    def relu_fusable(x: Tensor, w: Tensor) -> bool:
+        """The GEMM epilogue can apply a following ReLU: bf16 mode, 2-D input, Out % 32 == 0 (mask words)."""
+        return get_compute_mode() == _lib.MODE_BF16 and x.ndim == 2 and w.shape[0] % 32 == 0
+
+    @staticmethod
+    def forward(cache: FunctionCache, x: Tensor, w: Tensor, b: Optional[Tensor], relu_cache=None, emit_lp: bool = False) -> Tensor:
+        """``relu_cache`` (extension): return ``relu(x @ w.T + b)`` from the GEMM epilogue (``relu_fusable`` must hold); the
+        mask is pushed on ``relu_cache`` as ReLUFn.forward would have, ``emit_lp`` also writes the bf16 rows a following Linear
+        layer consumes."""
         require_cuda(x, w, b)
         out_f, in_f = w.shape
         if x.shape[-1] != in_f:
@@ -40,7 +49,18 @@ class LinearFn(Function):
                 x_bf = DeviceArray.empty((L.cpt_cast_bf16_bytes(n, in_f),), np.uint8)
                 _lib.check(L.cpt_cast_bf16(f32ptr(x), x_bf.ptr, n, in_f, st))
             _lib.check(L.cpt_cast_bf16(f32ptr(w), w_bf.ptr, out_f, in_f, st))
-            _lib.check(L.cpt_linear_fwd_bf16(x_bf.ptr, w_bf.ptr, f32ptr(b), y.ptr, n, in_f, out_f, st))
+            if relu_cache is not None:
+                want_mask = get_caching_enabled() and not isinstance(relu_cache, PseudoCache)
+                mask = DeviceArray.empty(((n * out_f + 31) // 32 * 4,), np.uint8) if want_mask else None
+                lp = None
+                if emit_lp and out_f % 8 == 0:
+                    lp = DeviceArray.empty((L.cpt_cast_bf16_bytes(n, out_f),), np.uint8)
+                    y.cl = (mode, lp, None)
+                _lib.check(L.cpt_linear_relu_fwd_bf16(x_bf.ptr, w_bf.ptr, f32ptr(b), y.ptr, lp.ptr if lp is not None else None,
+                                                      mask.ptr if mask is not None else None, n, in_f, out_f, st))
+                relu_cache.push(PlainMask(mask) if mask is not None else None)
+            else:
+                _lib.check(L.cpt_linear_fwd_bf16(x_bf.ptr, w_bf.ptr, f32ptr(b), y.ptr, n, in_f, out_f, st))
         else:
             ws, wsb = workspace(L.cpt_linear_workspace_size(_lib.OP_FPROP, n, in_f, out_f, mode))
             _lib.check(L.cpt_linear_fwd(f32ptr(x), f32ptr(w), f32ptr(b), y.ptr, n, in_f, out_f, mode, ws, wsb, st))

@@ -124,6 +124,19 @@ class Sequential(Module):
         return (not any(m.retain_values for m in mods) and len({m.is_training for m in mods}) == 1
                 and pool2_fusion_supported(x))
 
+    def _linear_relu_fusable(self, i: int, x: Tensor) -> bool:
+        """layers[i : i + 2] is Linear -> ReLU in bf16 mode with Out % 32 == 0: the ReLU (+ its mask, + the bf16 rows of a following
+        Linear) comes out of the GEMM epilogue (cpt_linear_relu_fwd_bf16) — bit-identical, one pass over y less each way."""
+        from ..functional.linear_funcs import LinearFn
+        from .layers import Linear, ReLU
+        if not _fusion or i + 1 >= len(self.layers) or get_debug_mode() or not isinstance(x.data, DeviceArray):
+            return False
+        lin, relu = self.layers[i], self.layers[i + 1]
+        if type(lin) is not Linear or type(relu) is not ReLU:
+            return False
+        return (not lin.retain_values and not relu.retain_values and lin.is_training == relu.is_training
+                and LinearFn.relu_fusable(x, lin.w))
+
     def _run(self, x: Tensor, tail=None) -> Tensor:
         """The layer walk.  ``tail = (skip_fn, relu)``: this container is the block of a fused residual connection — its last
         BatchNorm2D evaluates ``relu(bn(x) + skip_fn())``."""
@@ -146,6 +159,9 @@ class Sequential(Module):
             elif self._fusable(i, x):
                 x = layer.forward_relu(x)
                 self.layers[i + 1].fcache.push(FUSED_INTO_PRODUCER)  # its backward is folded into the BatchNorm's
+                i += 2
+            elif self._linear_relu_fusable(i, x):
+                x = layer.forward_relu(x, self.layers[i + 1])
                 i += 2
             elif self._residual_fusable(i, x):
                 x = layer.forward_relu(x, self.layers[i + 1])

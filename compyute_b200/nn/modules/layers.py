@@ -84,6 +84,12 @@ class Linear(Module):
     def forward(self, x: Tensor) -> Tensor:
         return LinearFn.forward(self.fcache, x, self.w, self.b)
 
+    def forward_relu(self, x: Tensor, relu: Module) -> Tensor:
+        """``relu(self(x))`` from the GEMM epilogue (bf16 mode; called by ``Sequential`` for Linear -> ReLU): the ReLU mask goes to
+        ``relu``'s cache, so both backward methods run unchanged; the bf16 rows for a following Linear are written as well when
+        the enclosing Sequential planned that hint for the ReLU."""
+        return LinearFn.forward(self.fcache, x, self.w, self.b, relu.fcache, relu._emit_lp_fwd)
+
     @Module.register_backward
     def backward(self, dy: Tensor) -> Tensor:
         dx, dw, db = LinearFn.backward(self.fcache, dy, self.grad_slot(self.w), self.grad_slot(self.b))

@@ -277,6 +277,14 @@ int cpt_bn_act_bwd_apply_global(const float* x, const float* dy, const float* w,
 /* ReLUFn.forward activation_funcs.py:26-29.  mask = bit-packed (y > 0), 4 * ((n + 31) / 32) bytes, 4-byte aligned, in a
  * layout private to cpt_relu_fwd / cpt_relu_bwd; may be NULL. */
 int cpt_relu_fwd(const float* x, float* y, uint8_t* mask, int64_t n, void* stream);
+/* Linear + ReLU in one pass (linear_funcs.py:15-23 followed by activation_funcs.py:26-29; bf16 mode, Out % 32 == 0): the GEMM
+ * epilogue writes y = max(x @ w.T + b, 0), optionally the same values as bf16 rows (y_bf16: the x operand of a following
+ * Linear layer, layout of cpt_cast_bf16) and the mask (y > 0) in PLAIN bit order — element e of the (N, Out) output is bit
+ * e % 32 of 32-bit word e / 32; 4 * ceil(N*Out / 32) bytes.  cpt_relu_bwd_plain is ReLUFn.backward for that mask layout
+ * (dx_bf16 optional, as cpt_relu_bwd_lp).  Bit-identical to cpt_linear_fwd_bf16 followed by cpt_relu_fwd_lp. */
+int cpt_linear_relu_fwd_bf16(const void* x_bf, const void* w_bf, const float* bias, float* y, void* y_bf16,
+                             uint8_t* mask, int64_t N, int In, int Out, void* stream);
+int cpt_relu_bwd_plain(const float* dy, const uint8_t* mask, float* dx, void* dx_bf16, int64_t n, void* stream);
 /* ReLUFn.backward :32-34   dx = dy * mask */
 int cpt_relu_bwd(const float* dy, const uint8_t* mask, float* dx, int64_t n, void* stream);
 /* Same passes, additionally writing the result as bf16 in the same linear order (y_bf16 / dx_bf16, 8-byte aligned, may be NULL):

@@ -710,3 +710,46 @@ def test_bn_relu_maxpool_function_vs_oracle(cp):
     dx, dw, db = BatchNorm2DFn.backward(c, T(dyp))
     assert close(yp, yp_ref) and close(rm, rm_ref) and close(rv, rv_ref)
     assert close(dx, dx_ref, 2e-5) and close(dw, dw_ref, 2e-5) and close(db, db_ref, 2e-5)
+
+
+def test_linear_relu_epilogue_fusion_is_bit_exact(cp):
+    """bf16 mode: Linear -> ReLU with Out % 32 == 0 takes the ReLU, its mask (plain bit order, cpt_relu_bwd_plain) and the bf16
+    rows of a following Linear out of the GEMM epilogue (cpt_linear_relu_fwd_bf16).  Outputs, input gradient and every
+    parameter gradient must equal the layer-by-layer evaluation bit for bit: ragged batch sizes (partial column tiles),
+    feature counts that are / are not multiples of 128, with and without bias, NaN inputs, inference mode."""
+    from compyute_b200 import _lib, nn
+    rng = np.random.RandomState(31)
+    for N, widths, bias in ((37, (40, 64, 32, 8), True), (300, (128, 256, 96, 160, 10), True), (9, (12, 32, 24, 64, 6), False),
+                            (1024, (256, 512, 512, 32), True)):
+        x = rng.normal(0, 1, (N, widths[0])).astype(np.float32)
+        x[3, 5] = np.nan
+        dy = rng.normal(0, 1, (N, widths[-1])).astype(np.float32)
+
+        def run(fused):
+            nn.set_fusion_enabled(fused)
+            try:
+                np.random.seed(2)
+                with cp.use_device(cp.cuda):
+                    layers = []
+                    for a, b in zip(widths[:-1], widths[1:]):
+                        layers += [nn.Linear(a, b, bias=bias), nn.ReLU()]
+                    model = nn.Sequential(*layers[:-1])
+                model.training()
+                n0 = _lib.lib().cpt_launch_count()
+                with cp.compute_mode("bf16"):
+                    y = model(cp.tensor(x, device=cp.cuda))
+                    dx = model.backward(cp.tensor(dy, device=cp.cuda))
+                    launches = _lib.lib().cpt_launch_count() - n0
+                    tc_ok()
+                    assert all(not m.fcache.cache for m in model.get_modules())
+                    out = [y.to_numpy(), dx.to_numpy()] + [p.grad.to_numpy() for p in model.get_parameters()]
+                    model.inference()
+                    out.append(model(cp.tensor(x, device=cp.cuda)).to_numpy())
+                return out, launches
+            finally:
+                nn.set_fusion_enabled(True)
+
+        (a, la), (b, lb) = run(True), run(False)
+        for k, (u, v) in enumerate(zip(a, b)):
+            assert np.array_equal(u, v, equal_nan=True), (N, widths, k, float(np.nanmax(np.abs(u - v))))
+        assert la < lb, (la, lb)
