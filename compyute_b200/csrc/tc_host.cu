@@ -784,7 +784,8 @@ size_t linear_workspace_size(int op, int64_t N, int In, int Out, int mode) {
 
 int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, int64_t N, int In, int Out, int mode, cudaStream_t st,
                   int relu = 0, void* y_lp = nullptr, unsigned int* mask = nullptr);
-int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In, int Out, int mode, cudaStream_t st);
+int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In, int Out, int mode, cudaStream_t st,
+                    const unsigned int* in_mask = nullptr, void* dx_lp = nullptr);
 int linear_wgrad_lp(const void* xa, const void* ga, float* dw, int64_t N, int In, int Out, int mode, void* ws, size_t ws_bytes,
                     cudaStream_t st, int max_splits = 16);
 
@@ -840,7 +841,8 @@ int linear_dgrad(const float* dy, const float* w, float* dx, int64_t N, int In, 
   return linear_dgrad_lp(ga, wa, dx, N, In, Out, mode, st);
 }
 
-int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In, int Out, int mode, cudaStream_t st) {
+int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In, int Out, int mode, cudaStream_t st,
+                    const unsigned int* in_mask, void* dx_lp) {
   const int gpitch = mode == CPT_MODE_BF16 ? round_up(Out, 8) : Out, wpitch = mode == CPT_MODE_BF16 ? round_up(In, 8) : In;
   const int kc = kc_of(mode), BN = pick_bn(N);
   TcParams p{};
@@ -849,6 +851,7 @@ int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In
   const bool use2 = want_2cta(BN, (In + 127) / 128);
   if (int e = make_map_2d(&p.tmB, ga, mode, Out, (uint64_t)N, gpitch, kc, use2 ? BN / 2 : BN)) return e;
   p.out = dx; p.bias = nullptr; p.bias_mode = BIAS_NONE;
+  if (in_mask) { p.relu = 2; p.relu_mask = const_cast<unsigned int*>(in_mask); p.relu_lp = dx_lp; }
   if (int e = get_status_ptr(&p.status)) return e;
   p.M = In; p.N = (int)N;
   p.m_tiles = (In + 127) / 128; p.n_tiles = (int)((N + BN - 1) / BN); p.z_tiles = 1;
@@ -1451,6 +1454,14 @@ int cpt_linear_relu_fwd_bf16(const void* x_bf, const void* w_bf, const float* bi
 int cpt_linear_dgrad_bf16(const void* dy_bf, const void* w_bf, float* dx, int64_t N, int In, int Out, void* stream) {
   if (int e = check_lp(N, In, Out, CPT_MODE_BF16, "linear_dgrad_bf16")) return e;
   return tc::linear_dgrad_lp(dy_bf, w_bf, dx, N, In, Out, CPT_MODE_BF16, as_stream(stream));
+}
+int cpt_linear_dgrad_relu_bf16(const void* dy_bf, const void* w_bf, const uint8_t* mask, float* dx, void* dx_bf16, int64_t N, int In,
+                               int Out, void* stream) {
+  if (int e = check_lp(N, In, Out, CPT_MODE_BF16, "linear_dgrad_relu_bf16")) return e;
+  CPT_REQUIRE(mask && In % 32 == 0, CPT_ERR_UNSUPPORTED, "linear_dgrad_relu_bf16: needs the mask and In %% 32 == 0");
+  CPT_REQUIRE((reinterpret_cast<uintptr_t>(mask) & 3) == 0, CPT_ERR_INVALID, "linear_dgrad_relu_bf16: mask must be 4-byte aligned");
+  return tc::linear_dgrad_lp(dy_bf, w_bf, dx, N, In, Out, CPT_MODE_BF16, as_stream(stream), reinterpret_cast<const unsigned int*>(mask),
+                             dx_bf16);
 }
 int cpt_linear_wgrad_bf16(const void* x_bf, const void* dy_bf, float* dw, int64_t N, int In, int Out, void* ws, size_t ws_bytes,
                           void* stream) {

@@ -36,6 +36,9 @@ struct alignas(64) TcParams {
   // fused ReLU of a Linear layer's forward (lanes = output features, columns = rows of the batch; M % 32 == 0): out receives
   // max(acc + bias, 0); relu_lp (optional) the same values as bf16 rows for the next Linear layer; relu_mask (optional) the
   // bits (out > 0) in plain order — element e = col * M + m is bit e % 32 of word e / 32 (consumed by cpt_relu_bwd_plain)
+  // relu == 2 is the backward counterpart on a Linear layer's dgrad (lanes = input features): out = acc * mask, with the mask
+  // (READ here) of the ReLU that produced this layer's input, relu_lp = the same values as bf16 rows (dy operand of the
+  // previous Linear layer's backward)
   int relu;
   void* relu_lp;
   unsigned int* relu_mask;
@@ -370,20 +373,41 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
         if (p.relu) {  // Linear forward + ReLU: one ballot per column gives the mask word of this warp's 32 features
           __nv_bfloat16* lq = p.relu_lp ? reinterpret_cast<__nv_bfloat16*>(p.relu_lp) + z_off + lane_off + (long long)cbase * cs : nullptr;
           const int mw = m >> 5;  // m - lane is a multiple of 32: word index of this warp's features within a row
+          if (p.relu == 2) {  // dgrad of the layer behind a ReLU: dx = acc * mask (activation_funcs.py:32-34)
+            // lane L fetches the mask word of column cbase + L once per chunk (one load in flight per lane, issued before any
+            // store); column j's word then comes by shuffle — a load per column would serialise behind the stores
+            unsigned int myw = 0u;
+            if (cbase + lane < p.N && m_ok) myw = __ldg(p.relu_mask + ((long long)(cbase + lane) * p.M >> 5) + mw);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const bool col_ok = cbase + j < p.N;
+              const unsigned int bits = __shfl_sync(0xffffffffu, myw, j);
+              const float val = __uint_as_float(v[j]) * (float)((bits >> lane) & 1u);
+              if (col_ok && m_ok) {
+                *q = val;
+                if (lq) *lq = __float2bfloat16_rn(val);
+              }
+              q += cs;
+              if (lq) lq += cs;
+            }
+            return;
+          }
+          unsigned int myw = 0u;  // lane L collects the mask word of column cbase + L: one store instruction per chunk
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float a = __uint_as_float(v[j]) + lane_bias;
             const float val = (a != a) ? a : fmaxf(a, 0.f);  // numpy.maximum propagates NaN (activation_funcs.py:27)
             const bool col_ok = cbase + j < p.N;
             const unsigned int bits = __ballot_sync(0xffffffffu, m_ok && val > 0.f);
-            if (col_ok) {
-              if (m_ok) *q = val;
-              if (lq && m_ok) *lq = __float2bfloat16_rn(val);
-              if (p.relu_mask && lane == 0 && m_ok) p.relu_mask[((long long)(cbase + j) * p.M >> 5) + mw] = bits;
+            if (lane == j) myw = bits;
+            if (col_ok && m_ok) {
+              *q = val;
+              if (lq) *lq = __float2bfloat16_rn(val);
             }
             q += cs;
             if (lq) lq += cs;
           }
+          if (p.relu_mask && m_ok && cbase + lane < p.N) p.relu_mask[((long long)(cbase + lane) * p.M >> 5) + mw] = myw;
           return;
         }
         float bl = 0.f;  // this lane's column bias; column j's value is fetched with a shuffle (one LDG per chunk)

@@ -68,8 +68,11 @@ class LinearFn(Function):
         return Tensor(y)
 
     @staticmethod
-    def backward(cache: FunctionCache, dy: Tensor, dw_out: Optional[DeviceArray] = None,
-                 db_out: Optional[DeviceArray] = None) -> tuple[Tensor, Tensor, Optional[Tensor]]:
+    def backward(cache: FunctionCache, dy: Tensor, dw_out: Optional[DeviceArray] = None, db_out: Optional[DeviceArray] = None,
+                 input_relu_mask=None, emit_lp: bool = False) -> tuple[Tensor, Tensor, Optional[Tensor]]:
+        """``input_relu_mask`` (extension): the cache entry of the ReLU that produced this layer's input; the returned dx is then
+        already that ReLU's dx (``dx * mask``) — from the dgrad epilogue when the mask is a ``PlainMask`` in bf16 mode and
+        In % 32 == 0, else by a separate ReLU backward pass; ``emit_lp`` also writes its bf16 rows."""
         x, w, has_bias, mode, x_bf, w_bf = cache.pop()
         require_cuda(dy)
         out_f, in_f = w.shape
@@ -88,7 +91,16 @@ class LinearFn(Function):
             else:
                 dy_bf = DeviceArray.empty((L.cpt_cast_bf16_bytes(n, out_f),), np.uint8)
                 _lib.check(L.cpt_cast_bf16(f32ptr(dy), dy_bf.ptr, n, out_f, st))
-            _lib.check(L.cpt_linear_dgrad_bf16(dy_bf.ptr, w_bf.ptr, dx.ptr, n, in_f, out_f, st))
+            if isinstance(input_relu_mask, PlainMask) and in_f % 32 == 0 and x.ndim == 2:
+                lp = None
+                if emit_lp and in_f % 8 == 0:
+                    lp = DeviceArray.empty((L.cpt_cast_bf16_bytes(n, in_f),), np.uint8)
+                    dx.cl = (mode, lp, None)
+                _lib.check(L.cpt_linear_dgrad_relu_bf16(dy_bf.ptr, w_bf.ptr, input_relu_mask.bits.ptr, dx.ptr,
+                                                        lp.ptr if lp is not None else None, n, in_f, out_f, st))
+                input_relu_mask = None  # applied
+            else:
+                _lib.check(L.cpt_linear_dgrad_bf16(dy_bf.ptr, w_bf.ptr, dx.ptr, n, in_f, out_f, st))
             ws, wsb = workspace(L.cpt_linear_workspace_size(_lib.OP_WGRAD, n, in_f, out_f, mode))
             _lib.check(L.cpt_linear_wgrad_bf16(x_bf.ptr, dy_bf.ptr, dw.ptr, n, in_f, out_f, ws, wsb, st))
             if db is not None:
@@ -99,7 +111,13 @@ class LinearFn(Function):
             ws, wsb = workspace(L.cpt_linear_workspace_size(_lib.OP_WGRAD, n, in_f, out_f, mode))
             _lib.check(L.cpt_linear_wgrad(f32ptr(x), f32ptr(dy), dw.ptr, db.ptr if db is not None else None, n, in_f, out_f, mode,
                                           ws, wsb, st))
-        return Tensor(dx), Tensor(dw), (Tensor(db) if db is not None else None)
+        dxt = Tensor(dx)
+        if input_relu_mask is not None:  # not fused above: the ReLU's own backward pass
+            from .activation_funcs import ReLUFn
+            tmp = FunctionCache()
+            tmp.push(input_relu_mask)
+            dxt = ReLUFn.backward(tmp, dxt, emit_lp)
+        return dxt, Tensor(dw), (Tensor(db) if db is not None else None)
 
 
 def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:

@@ -177,8 +177,20 @@ class Sequential(Module):
 
     @Module.register_backward
     def backward(self, dy: Tensor) -> Tensor:
-        for layer in reversed(self.layers):
-            dy = layer.backward(dy)  # a ReLU whose cache entry is FUSED_INTO_PRODUCER passes dy through
+        from ..functional.activation_funcs import PlainMask
+        from .layers import Linear, ReLU
+        i = len(self.layers) - 1
+        while i >= 0:
+            layer = self.layers[i]
+            prev = self.layers[i - 1] if i > 0 else None
+            if (_fusion and type(layer) is Linear and type(prev) is ReLU and not get_debug_mode() and prev.is_training and layer.is_training
+                    and not layer.retain_values and not prev.retain_values
+                    and prev.fcache.cache and isinstance(prev.fcache.cache[-1][0], PlainMask)):
+                dy = layer.backward_relu(dy, prev)  # the ReLU's dx * mask comes out of this layer's dgrad epilogue
+                i -= 2
+            else:
+                dy = layer.backward(dy)  # a ReLU whose cache entry is FUSED_INTO_PRODUCER passes dy through
+                i -= 1
         return dy
 
 

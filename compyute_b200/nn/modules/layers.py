@@ -97,6 +97,15 @@ class Linear(Module):
         self.update_parameter_grad(self.b, db)
         return dx
 
+    def backward_relu(self, dy: Tensor, relu: Module) -> Tensor:
+        """``relu.backward(self.backward(dy))`` with the ReLU's ``dx * mask`` applied in the dgrad epilogue (``relu`` produced
+        this layer's input and holds a plain-order mask; called by ``Sequential.backward``)."""
+        (mask,) = relu.fcache.pop()
+        dx, dw, db = LinearFn.backward(self.fcache, dy, self.grad_slot(self.w), self.grad_slot(self.b), mask, relu._emit_lp_bwd)
+        self.update_parameter_grad(self.w, dw)
+        self.update_parameter_grad(self.b, db)
+        return dx
+
 
 class MaxPooling2D(Module):
     def __init__(self, kernel_size: int = 2, label: Optional[str] = None) -> None:

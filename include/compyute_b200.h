@@ -285,6 +285,12 @@ int cpt_relu_fwd(const float* x, float* y, uint8_t* mask, int64_t n, void* strea
 int cpt_linear_relu_fwd_bf16(const void* x_bf, const void* w_bf, const float* bias, float* y, void* y_bf16,
                              uint8_t* mask, int64_t N, int In, int Out, void* stream);
 int cpt_relu_bwd_plain(const float* dy, const uint8_t* mask, float* dx, void* dx_bf16, int64_t n, void* stream);
+/* LinearFn.backward's dx = dy @ w (linear_funcs.py:31) followed by the backward of the ReLU that produced this layer's input
+ * (activation_funcs.py:32-34) in the dgrad epilogue: dx = (dy @ w) * mask, mask in plain bit order over the (N, In) input (as
+ * written by cpt_linear_relu_fwd_bf16 of the previous layer), In % 32 == 0; dx_bf16 (optional) = the same values as bf16 rows,
+ * the dy operand of the previous Linear layer's backward.  Bit-identical to cpt_linear_dgrad_bf16 + cpt_relu_bwd_plain. */
+int cpt_linear_dgrad_relu_bf16(const void* dy_bf, const void* w_bf, const uint8_t* mask, float* dx, void* dx_bf16,
+                               int64_t N, int In, int Out, void* stream);
 /* ReLUFn.backward :32-34   dx = dy * mask */
 int cpt_relu_bwd(const float* dy, const uint8_t* mask, float* dx, int64_t n, void* stream);
 /* Same passes, additionally writing the result as bf16 in the same linear order (y_bf16 / dx_bf16, 8-byte aligned, may be NULL):
