@@ -20,6 +20,7 @@ box, so kind = "port".
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -212,11 +213,15 @@ def run_ours(args) -> None:
         probe["on"] = with_probe
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = L.cpt_launch_count()
-        e0.record()
-        for _ in range(steps):
-            step(layers, opt)
-        e1.record()
-        torch.cuda.synchronize()
+        gc.collect(); gc.disable()  # a cyclic-GC pause on the host starves the launch queue (seen as one stalled step)
+        try:
+            e0.record()
+            for _ in range(steps):
+                step(layers, opt)
+            e1.record()
+            torch.cuda.synchronize()
+        finally:
+            gc.enable()
         probe["on"] = False
         if world > 1:
             distributed.barrier()
@@ -472,11 +477,15 @@ def run_model(args) -> None:
             distributed.barrier()
         n0 = L.cpt_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter(); e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record(); torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) * 1e3
+        gc.collect(); gc.disable()  # a cyclic-GC pause on the host starves the launch queue of the small-image workloads
+        try:
+            t0 = time.perf_counter(); e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3
+        finally:
+            gc.enable()
         if world > 1:
             distributed.barrier()
         ms = e0.elapsed_time(e1) if device_timed else wall

@@ -308,4 +308,5 @@ def test_memory_bound_ops_reach_bandwidth(cp):
     assert float(x.sum().item()) == float(n)
     gbs_add, gbs_sum = 12 * n / t_add / 1e9, 4 * n / t_sum / 1e9
     print(f"add {gbs_add:.0f} GB/s, sum {gbs_sum:.0f} GB/s")
-    assert gbs_add > 2500 and gbs_sum > 1500, (gbs_add, gbs_sum)
+    # measured: add 5.8-6.4 TB/s, sum 3.7-3.9 TB/s; the floors only catch a catastrophic slow path (scalar / uncoalesced fallback)
+    assert gbs_add > 1500 and gbs_sum > 800, (gbs_add, gbs_sum)

@@ -315,3 +315,52 @@ def test_clip_grad_norm_host_path_matches_reference():
         assert abs(norm - float(g[f"{tag}_norm"])) <= 1e-6 * float(g[f"{tag}_norm"])
         for i, p in enumerate(ps):
             assert np.allclose(p.grad.to_numpy(), g[f"{tag}_g{i}"], rtol=1e-6, atol=1e-8)
+
+
+# ---------------------------------------------------------------- Sequential peephole planning (no kernels run)
+def _host_backed(shape):
+    """A DeviceArray handle over HOST memory: enough for the planner predicates, which only look at types, shapes and flags."""
+    import torch
+    from compyute_b200.tensors import DeviceArray, Tensor
+    return Tensor(DeviceArray(torch.zeros(shape), shape, np.float32))
+
+
+def test_sequential_fusion_planning():
+    """Which peepholes the Sequential walk selects (containers.py): BatchNorm->ReLU, BatchNorm2D->ReLU->MaxPooling2D(2),
+    residual tails, Linear->ReLU (bf16 mode only), and the staging / statistics hints — and that retain_values, debug mode,
+    unsupported shapes or the global switch turn them off."""
+    np.random.seed(0)
+    seq = nn.Sequential(nn.Conv2D(3, 8, 3, padding="same"), nn.BatchNorm2D(8), nn.ReLU(), nn.MaxPooling2D(2),
+                        nn.Conv2D(8, 8, 3, padding="same", bias=False), nn.BatchNorm2D(8), nn.ReLU(),
+                        nn.ResidualConnection(nn.Conv2D(8, 8, 3, padding=1), nn.BatchNorm2D(8)), nn.ReLU(),
+                        nn.MaxPooling2D(3), nn.Flatten(), nn.Linear(32, 64), nn.ReLU(), nn.Linear(64, 10), nn.ReLU(), nn.Linear(10, 4))
+    seq.training()
+    x4, x2 = _host_backed((2, 8, 8, 8)), _host_backed((2, 32))
+    assert seq._pool_fusable(1, x4) and not seq._pool_fusable(5, x4)            # BN, ReLU, MaxPool(2) / no pool behind
+    assert not seq._pool_fusable(1, _host_backed((2, 8, 8, 6)))                  # W % 4 != 0 -> separate layers
+    assert not seq._pool_fusable(1, _host_backed((2, 8, 7, 8)))                  # H odd
+    assert seq._fusable(1, x4) and seq._fusable(5, x4) and not seq._fusable(0, x4)
+    assert seq._residual_fusable(7, x4) and not seq._residual_fusable(4, x4)
+    with cp.compute_mode("bf16"):
+        assert seq._linear_relu_fusable(11, x2)                                  # Out = 64
+        assert not seq._linear_relu_fusable(13, _host_backed((2, 64)))           # Out = 10: not a multiple of 32
+        assert not seq._linear_relu_fusable(11, _host_backed((2, 3, 32)))        # 3-D input
+    with cp.compute_mode("fp32"):
+        assert not seq._linear_relu_fusable(11, x2)                              # the epilogue ReLU is a bf16-mode path
+    # host tensors, retain_values, debug mode and the global switch disable every peephole
+    assert not seq._pool_fusable(1, cp.tensor(np.zeros((2, 8, 8, 8), np.float32)))
+    seq.layers[2].retain_values = True
+    assert not seq._pool_fusable(1, x4) and not seq._fusable(1, x4)
+    seq.layers[2].retain_values = False
+    nn.set_fusion_enabled(False)
+    try:
+        assert not (seq._pool_fusable(1, x4) or seq._fusable(1, x4) or seq._residual_fusable(7, x4))
+    finally:
+        nn.set_fusion_enabled(True)
+    # hints: a convolution followed by BatchNorm2D sums its statistics in the epilogue; a BatchNorm between convolutions writes
+    # the channels-last operand of both neighbours; ReLU between Linear layers writes their bf16 rows
+    seq._plan_staging_hints()
+    assert seq.layers[0]._emit_stats and seq.layers[4]._emit_stats
+    assert not seq.layers[1]._emit_cl_fwd and seq.layers[1]._emit_cl_bwd and seq.layers[1]._emit_cl_bwd_sum    # consumer is the pool
+    assert seq.layers[5]._emit_cl_fwd and seq.layers[5]._emit_cl_bwd and not seq.layers[5]._emit_cl_bwd_sum    # conv without bias before it
+    assert seq.layers[12]._emit_lp_fwd and seq.layers[12]._emit_lp_bwd and not seq.layers[8]._emit_lp_fwd
