@@ -339,6 +339,13 @@ def run_ours(args) -> None:
                            "runs); PCIe-bound (6.2 GB each way per step)"}
             del hx, hdy, bufs
 
+    # ---- parity of what was just timed (outside the timed region): the C=512 layer's y / dx / dw of one more pass in the
+    # benchmarked mode against fp64 dot products of sampled entries (operands fetched from the device tensors of this run)
+    parity = None
+    if rank == 0:
+        with cp.compute_mode(args.mode):
+            parity = parity_check(layers[-1], xs[-1], dys[-1], x_t[-1], dy_t[-1], args.mode)
+
     # ---- other compute modes (outside the headline timed region; same step, fewer iterations)
     modes = {}
     if rank == 0 and world == 1 and not args.no_extra_modes:
@@ -350,6 +357,32 @@ def run_ours(args) -> None:
                 mms, _ = timed(lay, op, k, w)
             modes[m] = {"tflops": round(step_flops / mms / 1e9, 1), "ms_per_step": round(mms, 3), "tolerance": TOL[m]}
 
+    # ---- the "CNN train images/s" half of the metric: configs 2-4 through the module API at this world size, a few steps
+    # each (outside the headline timed region; full records: --workload vgg|resnet18|mlp)
+    models = {}
+    if not args.no_models:
+        del layers, opt
+        xs.clear(); dys.clear(); x_t.clear(); dy_t.clear()
+        gc.collect(); torch.cuda.empty_cache()
+        plan = [("resnet18", False), ("vgg", False), ("mlp", False)] + ([("vgg", True)] if world > 1 else [])
+        for wl, strong in plan:
+            sub = argparse.Namespace(**vars(args))
+            sub.workload, sub.batch, sub.strong, sub.steps, sub.warmup = wl, 0, strong, args.model_steps, 3
+            sub.graph = False
+            try:
+                rec = model_record(sub, cpu=False)
+            except Exception as e:  # pragma: no cover - reported, never silent
+                rec = {"error": f"{type(e).__name__}: {e}"} if rank == 0 else None
+            gc.collect(); torch.cuda.empty_cache()
+            if rec is not None:
+                keep = ("value", "unit", "ms_per_step", "scaling", "tflops", "gpu_launches", "steps", "tc_watchdog", "error")
+                slim = {k: rec[k] for k in keep if k in rec}
+                if "config" in rec:
+                    slim.update(batch_per_gpu=rec["config"]["batch_per_gpu"], global_batch=rec["config"]["global_batch"],
+                                cuda_graph=rec["config"]["cuda_graph"], grad_sync=rec["config"]["grad_sync"])
+                    slim["e2e"] = rec["e2e"]["value"]
+                    slim["frac_of_bf16_peak"] = rec["roofline"]["frac"]
+                models[wl + ("_strong" if strong else "")] = slim
     if rank != 0:
         return
     # dominant kernel: tc_kernel<bf16, OP_CONV, BN=256> for the C=512 fprop (same kernel runs dgrad)
@@ -363,10 +396,10 @@ def run_ours(args) -> None:
                 "frac_of_sustained": round(ach / pk["bf16_tflops_sustained"], 4) if pk.get("bf16_tflops_sustained") else None,
                 "peak_source": pk["source"] + " (burst cuBLAS bf16)", "ms_per_launch": round(kms, 4), "launches_timed": len(probe["ev"]),
                 "flops_per_launch": fl,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture
-                # (profiles/r01_conv512_ncu_summary.md, launch 1: 1.776 GB read + 1.605 GB written); algorithmic bytes = 2.47e9
-                # (x_cl bf16 0.82 GB + y fp32 1.64 GB + filters)
-                "traffic": 3.382e9, "algorithmic_bytes": 2.47e9}
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture of THIS
+                # build of the kernel sources (profiles/ncu_traffic.json, keyed by a hash of tc_kernel.cuh + tc_host.cu);
+                # null when the sources changed since the capture.  Algorithmic bytes = x_cl bf16 0.82 GB + y fp32 1.64 GB + filters
+                "algorithmic_bytes": 2.47e9, **ncu_traffic("conv512_fprop")}
     cpu_tf, cpu_desc, cpu_times = cpu_conv_sample(12.0, 1)
     value = world * step_flops / ms / 1e9
     line = {"metric": "conv2d_fwd_bwd_tflops", "value": round(value, 2), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -376,8 +409,67 @@ def run_ours(args) -> None:
             "roofline": roof, "cpu_baseline": {"value": round(cpu_tf, 7), "unit": "TFLOP/s", "cores": 1, "host_cores": os.cpu_count(),
                                                 "kind": "port", "sample": cpu_desc, "seconds": round(cpu_times[0], 2)},
             "images_per_s": round(world * BATCH * len(SWEEP) / (ms / 1e3), 1), "frac_of_bf16_peak": round(value / world / pk["bf16_tflops"], 4),
-            "per_layer": per_layer, "modes": modes, "tc_watchdog": int(status)}
+            "per_layer": per_layer, "modes": modes, "models": models, "parity_check": parity, "tc_watchdog": int(status)}
     emit(line)
+
+
+def kernel_source_hash() -> str:
+    import hashlib
+    h = hashlib.sha1()
+    for f in ("tc_kernel.cuh", "tc_host.cu", "tc_ptx.cuh"):
+        with open(os.path.join(ROOT, "compyute_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
+def ncu_traffic(key: str) -> dict:
+    """DRAM bytes per launch of a kernel from the committed ncu capture of the current kernel sources (never a constant)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            db = json.load(f)
+        rec = db.get(key, {})
+        if rec.get("source_hash") == kernel_source_hash():
+            return {"traffic": rec["dram_bytes"], "traffic_source": rec.get("capture", "profiles/ncu_traffic.json")}
+        return {"traffic": None, "traffic_source": f"no ncu capture for kernel sources {kernel_source_hash()} (last: {rec.get('source_hash')}, {rec.get('dram_bytes')} B)"}
+    except Exception as e:
+        return {"traffic": None, "traffic_source": f"unavailable: {e}"}
+
+
+def parity_check(layer, x_dev, dy_dev, x_t, dy_t, mode: str, samples: int = 96) -> dict:
+    """One more forward + backward of the C=512 layer in the benchmarked mode; sampled entries of y, dx and dw against
+    fp64 dot products.  Errors are relative to the largest magnitude of the tensor (the mode's tolerance convention)."""
+    import torch
+    tol = {"bf16": 1e-2, "tf32": 2e-3, "fp32": 1e-5}[mode]
+    layer.w.grad = None  # first gradient of a step is stored by reference (module.py:392-400), later ones accumulate
+    if layer.b is not None:
+        layer.b.grad = None
+    y = layer(x_t)
+    dx = layer.backward(dy_t)
+    yb, dxb = y.data._buf, dx.data._buf
+    w = layer.w.data._buf.double()
+    b = layer.b.data._buf.double()
+    dw = layer.w.grad.data._buf
+    B, C, H, _ = x_dev.shape
+    g = torch.Generator().manual_seed(0)
+    r = lambda n: int(torch.randint(0, n, (1,), generator=g))
+    xp = lambda t, bi, p, q: torch.nn.functional.pad(t[bi].double(), (1, 1, 1, 1))[:, p:p + 3, q:q + 3]
+    ey = edx = edw = 0.0
+    for _ in range(samples):
+        bi, o, p, q = r(B), r(C), r(H), r(H)
+        ref = (xp(x_dev, bi, p, q) * w[o]).sum() + b[o]
+        ey = max(ey, abs(float(yb[bi, o, p, q]) - float(ref)))
+        ref = (xp(dy_dev, bi, p, q) * w[:, o].flip(-1, -2)).sum()
+        edx = max(edx, abs(float(dxb[bi, o, p, q]) - float(ref)))
+    for _ in range(16):
+        o, i, j, k = r(C), r(C), r(3), r(3)
+        xs = torch.nn.functional.pad(x_dev[:, i].double(), (1, 1, 1, 1))[:, j:j + H, k:k + H]
+        ref = (dy_dev[:, o].double() * xs).sum()
+        edw = max(edw, abs(float(dw[o, i, j, k]) - float(ref)))
+    sy, sdx, sdw = float(yb.abs().max()), float(dxb.abs().max()), float(dw.abs().max())
+    rel = {"y": ey / sy, "dx": edx / sdx, "dw": edw / sdw}
+    return {"layer": "Conv2D(512, 512, 3, same), x = (256, 512, 56, 56)", "mode": mode, "samples": {"y": samples, "dx": samples, "dw": 16},
+            "max_err_over_max_abs": {k: float(f"{v:.3e}") for k, v in rel.items()}, "tolerance": tol,
+            "reference": "fp64 dot products (torch, on the device tensors of the run)", "ok": bool(all(v <= tol for v in rel.values()))}
 
 
 # ------------------------------------------------------------------------------------------------ model workloads
@@ -391,7 +483,14 @@ MODEL_WORKLOADS = {
 
 
 def run_model(args) -> None:
-    """Train-step throughput (images/s) of one of the model configs through the public module API."""
+    line = model_record(args)
+    if line is not None:
+        emit(line)
+
+
+def model_record(args, cpu: bool = True):
+    """Train-step throughput (images/s) of one of the model configs through the public module API.  Returns the JSON
+    record on rank 0 (None elsewhere)."""
     import torch
 
     import bench_workloads as W
@@ -406,6 +505,11 @@ def run_model(args) -> None:
         distributed.init("nccl")
     factory, xshape, classes, B, desc = MODEL_WORKLOADS[args.workload]
     B = args.batch or B
+    scaling = "weak"
+    if getattr(args, "strong", False):  # strong scaling: the GLOBAL batch is fixed, every rank takes its shard
+        assert B % world == 0, "strong scaling needs the global batch to divide by the world size"
+        B //= world
+        scaling = "strong"
     spec = getattr(W, factory)()
     hw = xshape[-1] if len(xshape) == 3 else 1
     flops_img = W.train_flops_per_image(spec, hw)
@@ -520,7 +624,7 @@ def run_model(args) -> None:
         e2e_ms, _ = timed(step_e2e, max(2, args.steps // 2), 2, device_timed=False)
     status = L.cpt_tc_check_status()
     if rank != 0:
-        return
+        return None
     pk = peaks()
     ips = world * B / (ms / 1e3)
     tfl = ips * flops_img / 1e12
@@ -534,6 +638,8 @@ def run_model(args) -> None:
         cpu_spec, cpu_note = spec, f"{nb} images, fwd + bwd"
     cpu_val = None
     try:
+        if not cpu:
+            raise RuntimeError("skipped (sub-record of the default line; run --workload for the CPU sample)")
         rs = np.random.RandomState(0)
         def rand_params(sp):
             ps, bs = [], []
@@ -564,9 +670,9 @@ def run_model(args) -> None:
     except Exception as e:  # pragma: no cover
         cpu_note = f"cpu sample failed: {e}"
     line = {"metric": "cnn_train_images_per_s" if args.workload != "mlp" else "mlp_train_samples_per_s", "value": round(ips, 1), "unit": "images/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.mode], "data": "synthetic",
-            "config": {"workload": desc, "batch_per_gpu": B, "compute_mode": args.mode, "cuda_graph": bool(graphed), "tolerance": TOL[args.mode], "parallelism": f"dp{world}",
+            "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "compute_mode": args.mode, "cuda_graph": bool(graphed), "tolerance": TOL[args.mode], "parallelism": f"dp{world}",
                        "grad_sync": ("bucketed all-reduce overlapped with backward" if opt.overlap_grad_sync else "one all-reduce at step()") if world > 1 else "n/a",
                        "batchnorm": "synchronised (global-batch statistics)" if distributed.sync_batchnorm_active() else "per-shard statistics",
                        "l2_policy": "activations of one step exceed L2" if B * int(np.prod(xshape)) * 4 > 126e6 else "L2 flushed implicitly: per-step activation traffic exceeds L2"},
@@ -577,7 +683,7 @@ def run_model(args) -> None:
                                                         "note": f"whole step: {flops_img / 1e9:.3f} GFLOP/image algorithmic (3 x contraction FLOPs)"},
             "cpu_baseline": {"value": None if cpu_val is None else round(cpu_val, 4), "unit": "images/s", "cores": 1, "host_cores": os.cpu_count(), "kind": "port", "sample": cpu_note},
             "tflops": round(tfl, 2), "tc_watchdog": int(status)}
-    emit(line)
+    return line
 
 
 _REAL_STDOUT = None
@@ -608,6 +714,9 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("COMPYUTE_B200_MODE", "bf16"), choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--no-extra-modes", action="store_true")
+    ap.add_argument("--no-models", action="store_true", help="skip the model sub-records (configs 2-4) of the default line")
+    ap.add_argument("--model-steps", type=int, default=5, help="timed steps of each model sub-record")
+    ap.add_argument("--strong", action="store_true", help="model workloads: strong scaling (the configured batch is the GLOBAL batch)")
     ap.add_argument("--workload", default="conv2d_sweep", choices=["conv2d_sweep", "mnist", "vgg", "resnet18", "mlp"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of a model workload")
     ap.add_argument("--graph", action="store_true", help="model workloads: replay the train step as one CUDA graph (default for mnist and vgg on one GPU)")

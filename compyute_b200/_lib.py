@@ -16,7 +16,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "compyute_b200.h")
 LIB_PATH = os.path.join(_HERE, "lib", "libcompyute_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, -1, -2, -3, -4
-MODE_FP32, MODE_TF32, MODE_BF16 = 0, 1, 2
+MODE_FP32, MODE_TF32, MODE_BF16, MODE_FP32X3 = 0, 1, 2, 3
 OP_FPROP, OP_DGRAD, OP_WGRAD = 0, 1, 2
 
 

@@ -85,8 +85,9 @@ def use_device(device: Device):
         _default_device = prev
 
 
-# ---- compute mode of the contractions (Conv2D / Linear): "fp32" exact FFMA, "tf32" / "bf16" tcgen05
-_MODES = {"fp32": _lib.MODE_FP32, "tf32": _lib.MODE_TF32, "bf16": _lib.MODE_BF16}
+# ---- compute mode of the contractions (Conv2D / Linear): "fp32" exact FFMA, "tf32" / "bf16" tcgen05, "fp32x3" = fp32-exact on
+# tcgen05 (operands split into tf32 hi + lo planes, three MMAs per k-step; same 1e-5 contract as "fp32")
+_MODES = {"fp32": _lib.MODE_FP32, "tf32": _lib.MODE_TF32, "bf16": _lib.MODE_BF16, "fp32x3": _lib.MODE_FP32X3}
 _mode = _MODES[os.environ.get("COMPYUTE_B200_MODE", "fp32")]
 
 

@@ -7,7 +7,7 @@
 #include <stdlib.h>
 
 #include "tc.cuh"
-#include "tc_kernel.cuh"
+#include "tc_launch.cuh"
 
 namespace cpt {
 namespace tc {
@@ -36,6 +36,10 @@ static int load_driver() {
   return CPT_OK;
 }
 
+// CPT_MODE_FP32X3: fp32-exact contraction on the tensor cores — every operand is staged as TWO tf32 planes (hi = rna_tf32(a),
+// lo = rna_tf32(a - hi), the lo plane `plane bytes` after the hi plane) and the kernel issues three MMAs per k-step
+static inline bool is_x3(int mode) { return mode == CPT_MODE_FP32X3; }
+static inline int planes(int mode) { return is_x3(mode) ? 2 : 1; }
 static inline int esize(int mode) { return mode == CPT_MODE_BF16 ? 2 : 4; }
 static inline int kc_of(int mode) { return 128 / esize(mode); }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -118,7 +122,7 @@ constexpr int CL_PX = 128, CL_CH = 64;
 template <bool BF16>
 __global__ void __launch_bounds__(256, 4) nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW,
                                                            int Cp, float* __restrict__ chan_sum, float* __restrict__ partial,
-                                                           int64_t Q) {
+                                                           int64_t Q, float* __restrict__ dst_lo) {
   // pixel tiles run over the flattened (image, pixel) index q in [0, Q = B*HW): small feature maps (HW < 128) fill the
   // 128-pixel tile with pixels of several images instead of leaving lanes idle
   __shared__ uint32_t tile[BF16 ? 32 : 64][CL_PX + 1];
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(256, 4) nchw_to_nhwc_kernel(const float* __res
 #pragma unroll
       for (int ci = 0; ci < 8; ++ci) {
 #pragma unroll
-        for (int pi = 0; pi < 4; ++pi) tile[warp + 8 * ci][lane + 32 * pi] = __float_as_uint(round_tf32(v[ci][pi]));
+        for (int pi = 0; pi < 4; ++pi) tile[warp + 8 * ci][lane + 32 * pi] = __float_as_uint(v[ci][pi]);  // rounded at the store
         acc[ci] += (v[ci][0] + v[ci][1]) + (v[ci][2] + v[ci][3]);
       }
       __syncthreads();
@@ -197,7 +201,11 @@ __global__ void __launch_bounds__(256, 4) nchw_to_nhwc_kernel(const float* __res
           for (int i = 0; i < 16; ++i) {
             const int pp = warp + 8 * i;
             const int64_t q = p0 + pp;
-            if (q < Q) d[q * Cp + c] = tile[lane + 32 * h][pp];
+            if (q < Q) {
+              const float a = __uint_as_float(tile[lane + 32 * h][pp]), hi = round_tf32(a);
+              d[q * Cp + c] = __float_as_uint(hi);
+              if (dst_lo) dst_lo[q * Cp + c] = round_tf32(a - hi);   // FP32X3: a - hi is exact in fp32
+            }
           }
         }
       }
@@ -247,8 +255,9 @@ __global__ void __launch_bounds__(1024) chan_partial_reduce_kernel(const float* 
 }
 
 // w (Co, Ci, K, K) fp32 -> fprop weight matrix [Co][T][Ck] (zero padded, Ck = round_up(Ci, KC))
+// dst_lo (FP32X3 only): the tf32 lo plane, same layout
 template <bool BF16>
-__global__ void w_fprop_kernel(const float* __restrict__ w, void* __restrict__ dst, int Co, int Ci, int T, int Ck) {
+__global__ void w_fprop_kernel(const float* __restrict__ w, void* __restrict__ dst, int Co, int Ci, int T, int Ck, float* __restrict__ dst_lo) {
   const int64_t n = (int64_t)Co * T * Ck;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % Ck);
@@ -256,14 +265,18 @@ __global__ void w_fprop_kernel(const float* __restrict__ w, void* __restrict__ d
     const int tap = (int)(r % T), co = (int)(r / T);
     const float v = c < Ci ? w[((int64_t)co * Ci + c) * T + tap] : 0.f;
     if (BF16) reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
-    else reinterpret_cast<float*>(dst)[i] = round_tf32(v);
+    else {
+      const float hi = round_tf32(v);
+      reinterpret_cast<float*>(dst)[i] = hi;
+      if (dst_lo) dst_lo[i] = round_tf32(v - hi);
+    }
   }
 }
 // dgrad weight matrix [Ci][nt][Cok] for the taps of one stride class: w'[ci][t][co] = w[co][ci][tap_idx[t]]
 struct TapIdx { unsigned char idx[64]; };
 template <bool BF16>
 __global__ void w_dgrad_kernel(const float* __restrict__ w, void* __restrict__ dst, int Co, int Ci, int T, int nt, int Cok,
-                               const TapIdx taps) {
+                               const TapIdx taps, float* __restrict__ dst_lo) {
   const int64_t n = (int64_t)Ci * nt * Cok;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int co = (int)(i % Cok);
@@ -271,7 +284,11 @@ __global__ void w_dgrad_kernel(const float* __restrict__ w, void* __restrict__ d
     const int tap = (int)(r % nt), ci = (int)(r / nt);
     const float v = co < Co ? w[((int64_t)co * Ci + ci) * T + taps.idx[tap]] : 0.f;
     if (BF16) reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
-    else reinterpret_cast<float*>(dst)[i] = round_tf32(v);
+    else {
+      const float hi = round_tf32(v);
+      reinterpret_cast<float*>(dst)[i] = hi;
+      if (dst_lo) dst_lo[i] = round_tf32(v - hi);
+    }
   }
 }
 // dw[co][ci][tap] = Σ_split partial[split][co][tap][ci]   (fixed order)
@@ -327,43 +344,22 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
   }
 }
 
+// [R][C] fp32 -> tf32 hi / lo planes [R][C] each (FP32X3 operands of the Linear GEMMs); C % 4 == 0, 16-byte aligned
+__global__ void split_tf32_kernel(const float4* __restrict__ src, float4* __restrict__ hi, float4* __restrict__ lo, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    float4 h, l;
+    h.x = round_tf32(v.x); h.y = round_tf32(v.y); h.z = round_tf32(v.z); h.w = round_tf32(v.w);
+    l.x = round_tf32(v.x - h.x); l.y = round_tf32(v.y - h.y); l.z = round_tf32(v.z - h.z); l.w = round_tf32(v.w - h.w);
+    hi[i] = h; lo[i] = l;
+  }
+}
+
 // ------------------------------------------------------------------ kernel launch
 __device__ int g_tc_status = 0;
 // SMs left free by the persistent tensor-core kernels (cpt_tc_reserve_sms): room for a concurrent NCCL all-reduce in
 // data-parallel backward passes.  A persistent grid that owns every SM (and nearly every register) serialises with it.
 static int g_reserved_sms = 0;
-
-template <bool BF16, bool A_MN, bool B_MN, int BN, int OP, bool CTA2>
-static int launch_inst(const TcParams& p, cudaStream_t st) {
-  using S = StageCfg<BN, CTA2>;
-  static bool configured = false;
-  auto kern = tc_kernel<BF16, A_MN, B_MN, BN, OP, CTA2>;
-  if (!configured) {
-    CPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
-    configured = true;
-  }
-  const int total = p.m_tiles * p.n_tiles * p.z_tiles;  // tiles (1-CTA) or tile pairs (2-CTA)
-  const int ncta = CTA2 ? 2 : 1;
-  int groups = (sm_count() - g_reserved_sms) / ncta;
-  if (groups < 1) groups = 1;
-  if (total < groups) groups = total;
-  if (groups < 1) return CPT_OK;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(groups * ncta);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = S::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = ncta;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = CTA2 ? 1 : 0;
-  CPT_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
-  CPT_LAUNCH_CHECK("tc_kernel");
-  return CPT_OK;
-}
 
 // 2-CTA (cta_group::2) is used when the tile grid is large enough to keep all SM pairs busy; CPT_TC_2CTA=0/1 overrides.
 // The drivers ask this BEFORE building the B tensor map (its box covers BN/2 columns per CTA in 2-CTA mode).
@@ -380,15 +376,11 @@ static bool want_2cta(int BN, int64_t m_tiles128) {
 
 template <bool A_MN, bool B_MN, int OP>
 static int launch_bn(TcParams p, int mode, int BN, bool use2, cudaStream_t st) {
-  const bool bf = mode == CPT_MODE_BF16;
-  if (use2) {
-    p.m_tiles = (p.m_tiles + 1) / 2;  // 256-row tiles
-    if (BN == 256) return bf ? launch_inst<true, A_MN, B_MN, 256, OP, true>(p, st) : launch_inst<false, A_MN, B_MN, 256, OP, true>(p, st);
-    return bf ? launch_inst<true, A_MN, B_MN, 128, OP, true>(p, st) : launch_inst<false, A_MN, B_MN, 128, OP, true>(p, st);
-  }
-  if (BN == 256) return bf ? launch_inst<true, A_MN, B_MN, 256, OP, false>(p, st) : launch_inst<false, A_MN, B_MN, 256, OP, false>(p, st);
-  if (BN == 128) return bf ? launch_inst<true, A_MN, B_MN, 128, OP, false>(p, st) : launch_inst<false, A_MN, B_MN, 128, OP, false>(p, st);
-  return bf ? launch_inst<true, A_MN, B_MN, 64, OP, false>(p, st) : launch_inst<false, A_MN, B_MN, 64, OP, false>(p, st);
+  if (use2) p.m_tiles = (p.m_tiles + 1) / 2;  // 256-row tiles
+  LaunchSel sel{A_MN, B_MN, OP, BN, use2, (sm_count() - g_reserved_sms) / (use2 ? 2 : 1)};
+  if (mode == CPT_MODE_BF16) return launch_bf16(p, sel, st);
+  if (is_x3(mode)) return launch_x3(p, sel, st);
+  return launch_tf32(p, sel, st);
 }
 
 static int pick_bn(int64_t n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
@@ -428,11 +420,17 @@ static G geom(const cpt_conv2d_desc* d) {
   g.Wo = (d->W + 2 * d->pad - keff) / d->stride + 1;
   return g;
 }
-static size_t cl_bytes(int B, int C, int H, int W, int mode) {
+// one plane of a channels-last activation tensor / of a re-laid-out filter matrix; FP32X3 tensors hold two (hi, then lo)
+static size_t cl_plane_bytes(int B, int C, int H, int W, int mode) {
   return align_up((size_t)B * H * W * round_up(C, 8) * esize(mode), 1024);
 }
-static size_t wmat_bytes(int rows, int T, int C, int mode) {
+static size_t cl_bytes(int B, int C, int H, int W, int mode) { return planes(mode) * cl_plane_bytes(B, C, H, W, mode); }
+static size_t wmat_plane_bytes(int rows, int T, int C, int mode) {
   return align_up((size_t)rows * T * round_up(C, kc_of(mode)) * esize(mode), 1024);
+}
+static size_t wmat_bytes(int rows, int T, int C, int mode) { return planes(mode) * wmat_plane_bytes(rows, T, C, mode); }
+static inline const void* lo_plane(const void* base, size_t plane_bytes, int mode) {
+  return is_x3(mode) ? reinterpret_cast<const char*>(base) + plane_bytes : nullptr;
 }
 static bool dgrad_tc_ok(const G& g);
 
@@ -474,8 +472,9 @@ int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, in
   float* partial = nullptr;
   if (chan_sum && ws && ws_bytes >= to_channels_last_ws(B, C, H, W)) partial = reinterpret_cast<float*>(ws);
   const int64_t Q = (int64_t)B * HW;
-  if (mode == CPT_MODE_BF16) nchw_to_nhwc_kernel<true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial, Q);
-  else nchw_to_nhwc_kernel<false><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial, Q);
+  float* dst_lo = is_x3(mode) ? reinterpret_cast<float*>(reinterpret_cast<char*>(dst) + cl_plane_bytes(B, C, H, W, mode)) : nullptr;
+  if (mode == CPT_MODE_BF16) nchw_to_nhwc_kernel<true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial, Q, nullptr);
+  else nchw_to_nhwc_kernel<false><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial, Q, dst_lo);
   CPT_LAUNCH_CHECK("nchw_to_nhwc");
   if (partial) {
     chan_partial_reduce_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partial, chan_sum, C, (int64_t)gx, groups * CL_CH);
@@ -499,8 +498,9 @@ struct ConvPlan {
 //                                                          * wmat[n][t][ch]     (+ bias[n])
 static size_t stats_bytes(int Ncols) { return (size_t)sm_count() * 4 * Ncols * 2 * sizeof(float); }
 
-static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Win, const void* wmat, int Ncols, const ConvPlan& pl,
-                            const float* bias, float* out, int mode, cudaStream_t st, float* stats = nullptr) {
+// FP32X3: act_cl holds the hi and lo planes back to back (cl_bytes layout); wmat_lo is the lo plane of the filter matrix
+static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Win, const void* wmat, const void* wmat_lo, int Ncols,
+                            const ConvPlan& pl, const float* bias, float* out, int mode, cudaStream_t st, float* stats = nullptr) {
   const int kc = kc_of(mode), Cp = round_up(Cact, 8), Ck = round_up(Cact, kc), T = pl.ntaps;
   const int BN = pick_bn(Ncols);
   TcParams p{};
@@ -509,6 +509,11 @@ static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Wi
   const bool use2 = want_2cta(BN, (M + 127) / 128);
   if (int e = make_map_im2col(&p.tmA, act_cl, mode, Cp, Win, Hin, B, pl.lower_w, pl.lower_h, pl.upper_w, pl.upper_h, pl.trav, kc, 128)) return e;
   if (int e = make_map_2d(&p.tmB, wmat, mode, (uint64_t)T * Ck, Ncols, (uint64_t)T * Ck, kc, use2 ? BN / 2 : BN)) return e;
+  if (is_x3(mode)) {
+    const void* act_lo = lo_plane(act_cl, cl_plane_bytes(B, Cact, Hin, Win, mode), mode);
+    if (int e = make_map_im2col(&p.tmA2, act_lo, mode, Cp, Win, Hin, B, pl.lower_w, pl.lower_h, pl.upper_w, pl.upper_h, pl.trav, kc, 128)) return e;
+    if (int e = make_map_2d(&p.tmB2, wmat_lo, mode, (uint64_t)T * Ck, Ncols, (uint64_t)T * Ck, kc, use2 ? BN / 2 : BN)) return e;
+  }
   p.out = out;
   p.bias = bias;
   p.bias_mode = bias ? BIAS_COL : BIAS_NONE;
@@ -551,8 +556,9 @@ int conv_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w, co
   CPT_REQUIRE(ws && ws_bytes >= need, CPT_ERR_WORKSPACE, "conv2d_fprop_cl: workspace too small (%zu < %zu)", ws_bytes, need);
   const int Ck = round_up(g.Ci, kc_of(mode));
   const int64_t n = (int64_t)g.Co * g.T * Ck;
-  if (mode == CPT_MODE_BF16) w_fprop_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Ck);
-  else w_fprop_kernel<false><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Ck);
+  float* w_lo = const_cast<float*>(reinterpret_cast<const float*>(lo_plane(ws, wmat_plane_bytes(g.Co, g.T, g.Ci, mode), mode)));
+  if (mode == CPT_MODE_BF16) w_fprop_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Ck, nullptr);
+  else w_fprop_kernel<false><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Ck, w_lo);
   CPT_LAUNCH_CHECK("w_fprop");
   ConvPlan pl{};
   pl.ntaps = g.T;
@@ -565,7 +571,7 @@ int conv_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w, co
   pl.trav = g.S;
   pl.sub_H = g.Ho; pl.sub_W = g.Wo;
   pl.out_H = g.Ho; pl.out_W = g.Wo; pl.out_s = 1; pl.out_r0 = pl.out_c0 = 0;
-  return conv_im2col_gemm(x_cl, g.B, g.Ci, g.H, g.W, ws, g.Co, pl, bias, y, mode, st, stats);
+  return conv_im2col_gemm(x_cl, g.B, g.Ci, g.H, g.W, ws, w_lo, g.Co, pl, bias, y, mode, st, stats);
 }
 
 // taps (j, kk) of stride class (rh, rw) — same rule as the exact path (conv.cu class_taps)
@@ -633,7 +639,7 @@ int conv_dgrad_cl(const cpt_conv2d_desc* d, const void* dy_cl, const float* w, f
   CPT_REQUIRE(dgrad_tc_ok(g), CPT_ERR_UNSUPPORTED, "conv2d_dgrad_cl: geometry (K=%d, stride=%d, pad=%d, dil=%d) outside the TMA im2col limits",
               g.K, g.S, g.P, g.D);
   const int Cok = round_up(g.Co, kc_of(mode));
-  const size_t per_class = align_up((size_t)g.Ci * g.T * Cok * esize(mode), 1024);
+  const size_t per_plane = align_up((size_t)g.Ci * g.T * Cok * esize(mode), 1024), per_class = per_plane * planes(mode);
   const size_t need = per_class * g.S * g.S;
   CPT_REQUIRE(ws && ws_bytes >= need, CPT_ERR_WORKSPACE, "conv2d_dgrad_cl: workspace too small (%zu < %zu)", ws_bytes, need);
   bool any_empty = false;
@@ -653,10 +659,11 @@ int conv_dgrad_cl(const cpt_conv2d_desc* d, const void* dy_cl, const float* w, f
     if (pl.ntaps == 0) continue;
     void* wm = reinterpret_cast<char*>(ws) + per_class * c;
     const int64_t n = (int64_t)g.Ci * pl.ntaps * Cok;
-    if (mode == CPT_MODE_BF16) w_dgrad_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w, wm, g.Co, g.Ci, g.T, pl.ntaps, Cok, ti);
-    else w_dgrad_kernel<false><<<ew_grid(n, 256), 256, 0, st>>>(w, wm, g.Co, g.Ci, g.T, pl.ntaps, Cok, ti);
+    float* wm_lo = const_cast<float*>(reinterpret_cast<const float*>(lo_plane(wm, per_plane, mode)));
+    if (mode == CPT_MODE_BF16) w_dgrad_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w, wm, g.Co, g.Ci, g.T, pl.ntaps, Cok, ti, nullptr);
+    else w_dgrad_kernel<false><<<ew_grid(n, 256), 256, 0, st>>>(w, wm, g.Co, g.Ci, g.T, pl.ntaps, Cok, ti, wm_lo);
     CPT_LAUNCH_CHECK("w_dgrad");
-    if (int e = conv_im2col_gemm(dy_cl, g.B, g.Co, g.Ho, g.Wo, wm, g.Ci, pl, nullptr, dx, mode, st)) return e;
+    if (int e = conv_im2col_gemm(dy_cl, g.B, g.Co, g.Ho, g.Wo, wm, wm_lo, g.Ci, pl, nullptr, dx, mode, st)) return e;
   }
   return CPT_OK;
 }
@@ -680,6 +687,12 @@ int conv_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl,
   // B: dy_cl as [pixels][Cop], columns = output channels (MN-major)
   const int Cop = round_up(g.Co, 8);
   if (int e = make_map_2d(&p.tmB, dy_cl, mode, Cop, (uint64_t)pixels, Cop, kc, bk, true)) return e;
+  if (is_x3(mode)) {
+    const void* x_lo = lo_plane(x_cl, cl_plane_bytes(g.B, g.Ci, g.H, g.W, mode), mode);
+    const void* dy_lo = lo_plane(dy_cl, cl_plane_bytes(g.B, g.Co, g.Ho, g.Wo, mode), mode);
+    if (int e = make_map_im2col(&p.tmA2, x_lo, mode, round_up(g.Ci, 8), g.W, g.H, g.B, -g.P, -g.P, upper_w, upper_h, g.S, kc, bk, true)) return e;
+    if (int e = make_map_2d(&p.tmB2, dy_lo, mode, Cop, (uint64_t)pixels, Cop, kc, bk, true)) return e;
+  }
   p.out = reinterpret_cast<float*>(ws);
   p.bias = nullptr;
   p.bias_mode = BIAS_NONE;
@@ -713,7 +726,7 @@ size_t conv_workspace_size(int op, const cpt_conv2d_desc* d, int mode) {
   if (op == CPT_OP_FPROP) return cl_bytes(g.B, g.Ci, g.H, g.W, mode) + wmat_bytes(g.Co, g.T, g.Ci, mode) + 1024;
   if (op == CPT_OP_DGRAD) {
     if (!dgrad_tc_ok(g)) return 8192;  // exact path: tap tables of the stride classes
-    return cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode) + (size_t)g.S * g.S * wmat_bytes(g.Ci, g.T, g.Co, mode) + 1024;
+    return cl_bytes(g.B, g.Co, g.Ho, g.Wo, mode) + (size_t)g.S * g.S * wmat_bytes(g.Ci, g.T, g.Co, mode) + 2048;
   }
   size_t part = align_up((size_t)wgrad_splits(g, mode) * g.Co * g.T * g.Ci * sizeof(float), 1024);
   const size_t csum = to_channels_last_ws(g.B, g.Co, g.Ho, g.Wo);
@@ -767,12 +780,28 @@ static bool tf32_direct_ok(const void* a, const void* b, int In, int Out) {
   return In % 4 == 0 && Out % 4 == 0 && aligned16(a) && aligned16(b);
 }
 
+// FP32X3: hi + lo tf32 planes of an [R][C] fp32 matrix (same pitch as the source)
+static size_t split_bytes(int64_t R, int C) { return 2 * align_up((size_t)R * C * 4, 1024); }
+static int split_to_tf32(const float* src, void* dst, int64_t R, int C, cudaStream_t st) {
+  const int64_t n4 = R * C / 4;
+  float4* hi = reinterpret_cast<float4*>(dst);
+  float4* lo = reinterpret_cast<float4*>(reinterpret_cast<char*>(dst) + split_bytes(R, C) / 2);
+  split_tf32_kernel<<<ew_grid(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), hi, lo, n4);
+  CPT_LAUNCH_CHECK("split_tf32");
+  return CPT_OK;
+}
+static inline const void* split_lo(const void* hi, int64_t R, int C) { return reinterpret_cast<const char*>(hi) + split_bytes(R, C) / 2; }
+
 size_t linear_workspace_size(int op, int64_t N, int In, int Out, int mode) {
   size_t s = 1024;
   if (mode == CPT_MODE_BF16) {
     if (op == CPT_OP_FPROP) s += cast_bytes(N, In) + cast_bytes(Out, In);
     else if (op == CPT_OP_DGRAD) s += cast_bytes(N, Out) + cast_bytes(Out, In);
     else s += cast_bytes(N, In) + cast_bytes(N, Out);
+  } else if (is_x3(mode)) {
+    if (op == CPT_OP_FPROP) s += split_bytes(N, In) + split_bytes(Out, In);
+    else if (op == CPT_OP_DGRAD) s += split_bytes(N, Out) + split_bytes(Out, In);
+    else s += split_bytes(N, In) + split_bytes(N, Out);
   }
   if (op == CPT_OP_WGRAD) {
     // split-K partials + db partials
@@ -782,12 +811,13 @@ size_t linear_workspace_size(int op, int64_t N, int In, int Out, int mode) {
   return s;
 }
 
+// *_lo: the tf32 lo planes of the two operands (FP32X3 mode only)
 int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, int64_t N, int In, int Out, int mode, cudaStream_t st,
-                  int relu = 0, void* y_lp = nullptr, unsigned int* mask = nullptr);
+                  int relu = 0, void* y_lp = nullptr, unsigned int* mask = nullptr, const void* xa_lo = nullptr, const void* wa_lo = nullptr);
 int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In, int Out, int mode, cudaStream_t st,
-                    const unsigned int* in_mask = nullptr, void* dx_lp = nullptr);
+                    const unsigned int* in_mask = nullptr, void* dx_lp = nullptr, const void* ga_lo = nullptr, const void* wa_lo = nullptr);
 int linear_wgrad_lp(const void* xa, const void* ga, float* dw, int64_t N, int In, int Out, int mode, void* ws, size_t ws_bytes,
-                    cudaStream_t st, int max_splits = 16);
+                    cudaStream_t st, int max_splits = 16, const void* xa_lo = nullptr, const void* ga_lo = nullptr);
 
 int linear_fwd(const float* x, const float* w, const float* bias, float* y, int64_t N, int In, int Out, int mode, void* ws,
                size_t ws_bytes, cudaStream_t st) {
@@ -801,13 +831,20 @@ int linear_fwd(const float* x, const float* w, const float* bias, float* y, int6
     xa = base; wa = base + cast_bytes(N, In);
   } else if (!tf32_direct_ok(x, w, In, 4)) {
     return cpt_linear_fwd(x, w, bias, y, N, In, Out, CPT_MODE_FP32, ws, ws_bytes, st);
+  } else if (is_x3(mode)) {
+    CPT_REQUIRE(ws && ws_bytes >= linear_workspace_size(CPT_OP_FPROP, N, In, Out, mode), CPT_ERR_WORKSPACE, "linear_fwd: workspace too small");
+    char* base = reinterpret_cast<char*>(ws);
+    if (int e = split_to_tf32(x, base, N, In, st)) return e;
+    if (int e = split_to_tf32(w, base + split_bytes(N, In), Out, In, st)) return e;
+    xa = base; wa = base + split_bytes(N, In);
+    return linear_fwd_lp(xa, wa, bias, y, N, In, Out, mode, st, 0, nullptr, nullptr, split_lo(xa, N, In), split_lo(wa, Out, In));
   }
   return linear_fwd_lp(xa, wa, bias, y, N, In, Out, mode, st);
 }
 
 // operands already in the mode's element type: bf16 with row pitch round_up(C, 8), or fp32 (tf32) with pitch C
 int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, int64_t N, int In, int Out, int mode, cudaStream_t st,
-                  int relu, void* y_lp, unsigned int* mask) {
+                  int relu, void* y_lp, unsigned int* mask, const void* xa_lo, const void* wa_lo) {
   const int pitch = mode == CPT_MODE_BF16 ? round_up(In, 8) : In;
   const int kc = kc_of(mode), BN = pick_bn(N);
   TcParams p{};
@@ -815,6 +852,10 @@ int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, i
   if (int e = make_map_2d(&p.tmA, wa, mode, In, Out, pitch, kc, 128)) return e;
   const bool use2 = want_2cta(BN, (Out + 127) / 128);
   if (int e = make_map_2d(&p.tmB, xa, mode, In, (uint64_t)N, pitch, kc, use2 ? BN / 2 : BN)) return e;
+  if (is_x3(mode)) {
+    if (int e = make_map_2d(&p.tmA2, wa_lo, mode, In, Out, pitch, kc, 128)) return e;
+    if (int e = make_map_2d(&p.tmB2, xa_lo, mode, In, (uint64_t)N, pitch, kc, use2 ? BN / 2 : BN)) return e;
+  }
   p.out = y; p.bias = bias; p.bias_mode = bias ? BIAS_LANE : BIAS_NONE;
   p.relu = relu; p.relu_lp = y_lp; p.relu_mask = mask;
   if (int e = get_status_ptr(&p.status)) return e;
@@ -837,12 +878,19 @@ int linear_dgrad(const float* dy, const float* w, float* dx, int64_t N, int In, 
     ga = base; wa = base + cast_bytes(N, Out);
   } else if (!tf32_direct_ok(dy, w, In, Out)) {
     return cpt_linear_dgrad(dy, w, dx, N, In, Out, CPT_MODE_FP32, ws, ws_bytes, st);
+  } else if (is_x3(mode)) {
+    CPT_REQUIRE(ws && ws_bytes >= linear_workspace_size(CPT_OP_DGRAD, N, In, Out, mode), CPT_ERR_WORKSPACE, "linear_dgrad: workspace too small");
+    char* base = reinterpret_cast<char*>(ws);
+    if (int e = split_to_tf32(dy, base, N, Out, st)) return e;
+    if (int e = split_to_tf32(w, base + split_bytes(N, Out), Out, In, st)) return e;
+    ga = base; wa = base + split_bytes(N, Out);
+    return linear_dgrad_lp(ga, wa, dx, N, In, Out, mode, st, nullptr, nullptr, split_lo(ga, N, Out), split_lo(wa, Out, In));
   }
   return linear_dgrad_lp(ga, wa, dx, N, In, Out, mode, st);
 }
 
 int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In, int Out, int mode, cudaStream_t st,
-                    const unsigned int* in_mask, void* dx_lp) {
+                    const unsigned int* in_mask, void* dx_lp, const void* ga_lo, const void* wa_lo) {
   const int gpitch = mode == CPT_MODE_BF16 ? round_up(Out, 8) : Out, wpitch = mode == CPT_MODE_BF16 ? round_up(In, 8) : In;
   const int kc = kc_of(mode), BN = pick_bn(N);
   TcParams p{};
@@ -850,6 +898,10 @@ int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In
   if (int e = make_map_2d(&p.tmA, wa, mode, In, Out, wpitch, kc, kc, true)) return e;
   const bool use2 = want_2cta(BN, (In + 127) / 128);
   if (int e = make_map_2d(&p.tmB, ga, mode, Out, (uint64_t)N, gpitch, kc, use2 ? BN / 2 : BN)) return e;
+  if (is_x3(mode)) {
+    if (int e = make_map_2d(&p.tmA2, wa_lo, mode, In, Out, wpitch, kc, kc, true)) return e;
+    if (int e = make_map_2d(&p.tmB2, ga_lo, mode, Out, (uint64_t)N, gpitch, kc, use2 ? BN / 2 : BN)) return e;
+  }
   p.out = dx; p.bias = nullptr; p.bias_mode = BIAS_NONE;
   if (in_mask) { p.relu = 2; p.relu_mask = const_cast<unsigned int*>(in_mask); p.relu_lp = dx_lp; }
   if (int e = get_status_ptr(&p.status)) return e;
@@ -874,8 +926,14 @@ int linear_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t 
     off = cast_bytes(N, In) + cast_bytes(N, Out);
   } else if (!tf32_direct_ok(x, dy, In, Out)) {
     return cpt_linear_wgrad(x, dy, dw, db, N, In, Out, CPT_MODE_FP32, ws, ws_bytes, st);
+  } else if (is_x3(mode)) {
+    if (int e = split_to_tf32(x, base, N, In, st)) return e;
+    if (int e = split_to_tf32(dy, base + split_bytes(N, In), N, Out, st)) return e;
+    xa = base; ga = base + split_bytes(N, In);
+    off = split_bytes(N, In) + split_bytes(N, Out);
   }
-  if (int e = linear_wgrad_lp(xa, ga, dw, N, In, Out, mode, base + off, ws_bytes - off, st)) return e;
+  if (int e = linear_wgrad_lp(xa, ga, dw, N, In, Out, mode, base + off, ws_bytes - off, st, 16,
+                              is_x3(mode) ? split_lo(xa, N, In) : nullptr, is_x3(mode) ? split_lo(ga, N, Out) : nullptr)) return e;
   if (db) {
     const size_t part = align_up((size_t)16 * Out * In * sizeof(float), 1024);
     return channel_sum(dy, db, (int)N, Out, 1, base + off + part, st);
@@ -885,7 +943,7 @@ int linear_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t 
 
 // ws: split-K partials (up to 16 x Out x In floats)
 int linear_wgrad_lp(const void* xa, const void* ga, float* dw, int64_t N, int In, int Out, int mode, void* ws, size_t ws_bytes,
-                    cudaStream_t st, int max_splits) {
+                    cudaStream_t st, int max_splits, const void* xa_lo, const void* ga_lo) {
   char* base = reinterpret_cast<char*>(ws);
   const size_t off = 0;
   const int xpitch = mode == CPT_MODE_BF16 ? round_up(In, 8) : In, gpitch = mode == CPT_MODE_BF16 ? round_up(Out, 8) : Out;
@@ -903,6 +961,10 @@ int linear_wgrad_lp(const void* xa, const void* ga, float* dw, int64_t N, int In
   // dw[o][i]: lanes = i.  A(m=i, k=n) = x[n][i] MN-major; B(col=o, k=n) = dy[n][o] MN-major
   if (int e = make_map_2d(&p.tmA, xa, mode, In, (uint64_t)N, xpitch, kc, bk, true)) return e;
   if (int e = make_map_2d(&p.tmB, ga, mode, Out, (uint64_t)N, gpitch, kc, bk, true)) return e;
+  if (is_x3(mode)) {
+    if (int e = make_map_2d(&p.tmA2, xa_lo, mode, In, (uint64_t)N, xpitch, kc, bk, true)) return e;
+    if (int e = make_map_2d(&p.tmB2, ga_lo, mode, Out, (uint64_t)N, gpitch, kc, bk, true)) return e;
+  }
   p.out = splits > 1 ? partial : dw; p.bias = nullptr; p.bias_mode = BIAS_NONE;
   if (int e = get_status_ptr(&p.status)) return e;
   p.M = In; p.N = Out;
@@ -1348,7 +1410,8 @@ size_t cpt_to_channels_last_workspace_size(int B, int C, int H, int W) {
 int cpt_to_channels_last(const float* src, void* dst, int B, int C, int H, int W, int mode, float* chan_sum, void* ws,
                          size_t ws_bytes, void* stream) {
   CPT_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, CPT_ERR_INVALID, "to_channels_last: bad arguments");
-  CPT_REQUIRE(mode == CPT_MODE_TF32 || mode == CPT_MODE_BF16, CPT_ERR_INVALID, "to_channels_last: mode must be TF32 or BF16");
+  CPT_REQUIRE(mode == CPT_MODE_TF32 || mode == CPT_MODE_BF16 || mode == CPT_MODE_FP32X3, CPT_ERR_INVALID,
+              "to_channels_last: mode must be TF32, BF16 or FP32X3");
   return tc::to_channels_last(src, dst, B, C, H, W, mode, chan_sum, ws, ws_bytes, as_stream(stream));
 }
 
@@ -1356,7 +1419,8 @@ static int check_tc(const cpt_conv2d_desc* d, int mode, const char* who) {
   CPT_REQUIRE(d && d->B > 0 && d->Ci > 0 && d->H > 0 && d->W > 0 && d->Co > 0 && d->K > 0 && d->pad >= 0 && d->stride >= 1 &&
                   d->dil >= 1,
               CPT_ERR_INVALID, "%s: bad descriptor", who);
-  CPT_REQUIRE(mode == CPT_MODE_TF32 || mode == CPT_MODE_BF16, CPT_ERR_INVALID, "%s: mode must be TF32 or BF16", who);
+  CPT_REQUIRE(mode == CPT_MODE_TF32 || mode == CPT_MODE_BF16 || mode == CPT_MODE_FP32X3, CPT_ERR_INVALID,
+              "%s: mode must be TF32, BF16 or FP32X3", who);
   return CPT_OK;
 }
 

@@ -17,58 +17,11 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include "tc_params.cuh"
 #include "tc_ptx.cuh"
 
 namespace cpt {
 namespace tc {
-
-enum { OP_GEMM = 0, OP_CONV = 1, OP_WGRAD = 2 };
-enum { BIAS_NONE = 0, BIAS_COL = 1, BIAS_LANE = 2 };
-
-struct alignas(64) TcParams {
-  CUtensorMap tmA;  // operand A (M side)
-  CUtensorMap tmB;  // operand B (N side)
-  float* out;
-  const float* bias;
-  int* status;      // device int: set non-zero on a pipeline timeout
-  int bias_mode;
-  int out_bf16;     // 1: `out` is bf16 (no bias): the packed-K dgrad intermediate dcol
-  // fused ReLU of a Linear layer's forward (lanes = output features, columns = rows of the batch; M % 32 == 0): out receives
-  // max(acc + bias, 0); relu_lp (optional) the same values as bf16 rows for the next Linear layer; relu_mask (optional) the
-  // bits (out > 0) in plain order — element e = col * M + m is bit e % 32 of word e / 32 (consumed by cpt_relu_bwd_plain)
-  // relu == 2 is the backward counterpart on a Linear layer's dgrad (lanes = input features): out = acc * mask, with the mask
-  // (READ here) of the ReLU that produced this layer's input, relu_lp = the same values as bf16 rows (dy operand of the
-  // previous Linear layer's backward)
-  int relu;
-  void* relu_lp;
-  unsigned int* relu_mask;
-  float* stats;     // optional [gridDim.x * 4][N][2]: per-epilogue-warp column sums (Σ acc, Σ acc²) of the raw accumulators
-                    // (without bias) over the valid lanes — the batch statistics of a BatchNorm that consumes the output
-  int M, N;         // valid extents of the lane / column dimensions
-  int m_tiles, n_tiles, z_tiles;  // m_tiles counts 128-row (1-CTA) or 256-row (2-CTA) tiles; z = split / tap*split
-  int k_iters_total;              // k iterations of the whole reduction (GEMM / WGRAD) or per tile (CONV)
-  int k_iters_per_split;
-  // epilogue addressing: dst = out + z_off + lane_off(m) + col * col_stride
-  long long col_stride, split_stride, tap_stride;
-  int lane_is_pixel;              // 1: lane m -> (image b, sub-grid row r, col c): lane_off = b*img_stride + (out_r0 + out_s*r)*out_W + out_c0 + out_s*c
-  int px_per_img;                 // pixels per image of the lane / reduction grid (CONV lanes: sub_H*sub_W, WGRAD: Ho*Wo)
-  long long img_stride;
-  int out_W, out_s, out_r0, out_c0;  // output scatter of CONV lanes (dense fprop/dgrad: out_W = Wo, out_s = 1, r0 = c0 = 0)
-  // convolution geometry (im2col coordinates): base pixel of grid position (r, c) = (lower_h + r*trav, lower_w + c*trav)
-  int Wo, Ho;                      // width (and, WGRAD, height) of the lane / reduction pixel grid
-  int trav, lower_w, lower_h;      // traversal stride and lower corner of the im2col bounding box
-  int conv_stride, pad, dil, Kw;   // WGRAD: conv geometry for the tap of this tile
-  int taps, cchunks, wk_cols;      // wk_cols: weight-matrix columns per tap (padded C)
-  unsigned short tap_w[64], tap_h[64];  // CONV: im2col offsets of tap t (fprop: kk*dil, j*dil; dgrad: class offsets)
-};
-
-template <bool BF16>
-struct Elem {
-  static constexpr int BYTES = BF16 ? 2 : 4;
-  static constexpr int KC = 128 / BYTES;      // elements per 128-byte swizzle row: 64 bf16 / 32 tf32
-  static constexpr int UMMA_K = 32 / BYTES;   // 16 bf16 / 8 tf32
-  static constexpr int BK = KC;               // reduction elements per stage (also k-rows of an MN-major stage)
-};
 
 // Column sums of a 32 x 32 block held one row per lane (a[j] = column j of this lane's row): five exchange rounds, each
 // halving the columns a lane still owns; lane L ends up with the sum of column L.  31 shuffles instead of 32 x 5.
@@ -89,20 +42,14 @@ __device__ __forceinline__ float col_sums_32x32(float (&a)[32], int lane) {
   return a[0];
 }
 
-template <int BN, bool CTA2>
-struct StageCfg {
-  static constexpr int A_BYTES = 128 * 128;   // 128 lanes x 128 B (K-major) == (128/KC chunks) x BK rows x 128 B
-  static constexpr int BN_CTA = CTA2 ? BN / 2 : BN;  // B columns staged by one CTA
-  static constexpr int B_BYTES = BN_CTA * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-template <bool BF16, bool A_MN, bool B_MN, int BN, int OP, bool CTA2>
+// X3 (fp32-exact mode, BF16 = false only): every fp32 operand element a is staged as two tf32 planes, hi = rna_tf32(a) and
+// lo = rna_tf32(a - hi); a*b is evaluated as lo_a*hi_b + hi_a*lo_b + hi_a*hi_b (the dropped lo*lo term and the rounding of lo are
+// ~2^-22 relative), fp32 accumulation in TMEM: three MMAs per k-step over a stage that holds both planes of both operands.
+template <bool BF16, bool X3, bool A_MN, bool B_MN, int BN, int OP, bool CTA2>
 __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcParams p) {
+  static_assert(!(BF16 && X3), "the hi/lo split applies to fp32 operands");
   using E = Elem<BF16>;
-  using S = StageCfg<BN, CTA2>;
+  using S = StageCfg<BN, CTA2, X3>;
   constexpr int STAGES = S::STAGES;
   constexpr int NCTA = CTA2 ? 2 : 1;
   constexpr uint32_t IDESC = make_idesc(BF16, A_MN, B_MN, 128 * NCTA, BN);
@@ -132,6 +79,7 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
   if (warp == 0 && elect_one_sync()) {
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
+    if (X3) { prefetch_tmap(&p.tmA2); prefetch_tmap(&p.tmB2); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -202,38 +150,43 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
         const uint32_t fb = CTA2 ? mapa_cluster(full_bar(stage), 0) : full_bar(stage);
         if (CTA2 && cta_rank != 0) mbar_arrive_expect_tx_cluster(fb, S::STAGE_BYTES);
         else mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
-        const uint32_t sa = a_smem(stage), sb = b_smem(stage);
+#pragma unroll
+        for (int pl = 0; pl < (X3 ? 2 : 1); ++pl) {   // plane 0: the operands (X3: hi planes), plane 1 (X3 only): lo planes
+        const CUtensorMap* tmA = pl ? &p.tmA2 : &p.tmA;
+        const CUtensorMap* tmB = pl ? &p.tmB2 : &p.tmB;
+        const uint32_t sa = a_smem(stage) + pl * S::PLANE_BYTES, sb = b_smem(stage) + pl * S::PLANE_BYTES;
         if (OP == OP_CONV) {
           // A: 128 output pixels x KC channels of filter tap (j, kk); B: weights [Co][tap][C] rows n0.., K-major
-          tma_load_im2col_4d<CTA2>(&p.tmA, fb, sa, cc * E::KC, cw, ch, cn, p.tap_w[tp], p.tap_h[tp]);
-          tma_load_2d<CTA2>(&p.tmB, fb, sb, tp * p.wk_cols + cc * E::KC, n0);
+          tma_load_im2col_4d<CTA2>(tmA, fb, sa, cc * E::KC, cw, ch, cn, p.tap_w[tp], p.tap_h[tp]);
+          tma_load_2d<CTA2>(tmB, fb, sb, tp * p.wk_cols + cc * E::KC, n0);
         } else if (OP == OP_WGRAD) {
           // reduction over output pixels: chunk of BK pixels starting at flattened pixel k0
           const int k0 = (k_begin + i) * E::BK;
 #pragma unroll
           for (int c = 0; c < 128 / E::KC; ++c)
-            tma_load_im2col_4d<CTA2>(&p.tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, wqx * p.conv_stride - p.pad,
+            tma_load_im2col_4d<CTA2>(tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, wqx * p.conv_stride - p.pad,
                                      wpy * p.conv_stride - p.pad, wb, (uint16_t)(wkk * p.dil), (uint16_t)(wj * p.dil));
 #pragma unroll
           for (int c = 0; c < S::BN_CTA / E::KC; ++c)
-            tma_load_2d<CTA2>(&p.tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, k0);
+            tma_load_2d<CTA2>(tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, k0);
         } else {
           const int kidx = k_begin + i;
           if (A_MN) {
 #pragma unroll
             for (int c = 0; c < 128 / E::KC; ++c)
-              tma_load_2d<CTA2>(&p.tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, kidx * E::BK);
+              tma_load_2d<CTA2>(tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, kidx * E::BK);
           } else {
-            tma_load_2d<CTA2>(&p.tmA, fb, sa, kidx * E::KC, m0);
+            tma_load_2d<CTA2>(tmA, fb, sa, kidx * E::KC, m0);
           }
           if (B_MN) {
 #pragma unroll
             for (int c = 0; c < S::BN_CTA / E::KC; ++c)
-              tma_load_2d<CTA2>(&p.tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, kidx * E::BK);
+              tma_load_2d<CTA2>(tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, kidx * E::BK);
           } else {
-            tma_load_2d<CTA2>(&p.tmB, fb, sb, kidx * E::KC, n0);
+            tma_load_2d<CTA2>(tmB, fb, sb, kidx * E::KC, n0);
           }
         }
+        }  // plane
         }  // elected lane
         __syncwarp();
         if (OP == OP_CONV) {
@@ -267,11 +220,21 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
         for (int s = 0; s < 4; ++s) {
           // K-major: advance 32 B inside the 128-B swizzle row; MN-major: advance UMMA_K k-rows (x128 B)
           // MN-major tf32 uses the 32-byte-atom swizzle: k-groups of 4 rows (512 B) instead of 8 rows (1024 B)
-          const uint64_t da = A_MN ? make_smem_desc(sa + s * (E::UMMA_K * 128), CHUNK_BYTES, MN_SBO, MN_LAYOUT)
-                                   : make_smem_desc(sa + s * 32, 16, 1024);
-          const uint64_t db = B_MN ? make_smem_desc(sb + s * (E::UMMA_K * 128), CHUNK_BYTES, MN_SBO, MN_LAYOUT)
-                                   : make_smem_desc(sb + s * 32, 16, 1024);
-          umma<BF16, CTA2>(d_tmem, da, db, IDESC, (uint32_t)((i | s) != 0));
+          auto desc_a = [&](uint32_t a0) {
+            return A_MN ? make_smem_desc(a0 + s * (E::UMMA_K * 128), CHUNK_BYTES, MN_SBO, MN_LAYOUT) : make_smem_desc(a0 + s * 32, 16, 1024);
+          };
+          auto desc_b = [&](uint32_t b0) {
+            return B_MN ? make_smem_desc(b0 + s * (E::UMMA_K * 128), CHUNK_BYTES, MN_SBO, MN_LAYOUT) : make_smem_desc(b0 + s * 32, 16, 1024);
+          };
+          const uint64_t da = desc_a(sa), db = desc_b(sb);
+          if (X3) {  // small terms first: lo*hi, hi*lo, then hi*hi
+            const uint64_t da2 = desc_a(sa + S::PLANE_BYTES), db2 = desc_b(sb + S::PLANE_BYTES);
+            umma<BF16, CTA2>(d_tmem, da2, db, IDESC, (uint32_t)((i | s) != 0));
+            umma<BF16, CTA2>(d_tmem, da, db2, IDESC, 1u);
+            umma<BF16, CTA2>(d_tmem, da, db, IDESC, 1u);
+          } else {
+            umma<BF16, CTA2>(d_tmem, da, db, IDESC, (uint32_t)((i | s) != 0));
+          }
         }
         umma_commit<CTA2>(empty_bar(stage));  // frees the smem stage (in both CTAs) once these MMAs have read it
         }  // elected lane

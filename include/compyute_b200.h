@@ -40,6 +40,11 @@ extern "C" {
 #define CPT_MODE_FP32 0
 #define CPT_MODE_TF32 1
 #define CPT_MODE_BF16 2
+/* fp32-exact contraction on the tensor cores ("3xTF32"): every fp32 operand a is staged as two tf32 planes, hi = rna(a) and
+ * lo = rna(a - hi); a*b = lo*hi + hi*lo + hi*hi with fp32 accumulation (the dropped terms are ~2^-22 relative).  Meets the
+ * reference's allclose(1e-5) like CPT_MODE_FP32 (the FFMA kernels), which stays the fallback for geometries outside the TMA
+ * limits.  Channels-last / workspace sizes of this mode hold both planes. */
+#define CPT_MODE_FP32X3 3
 
 #define CPT_OP_FPROP 0
 #define CPT_OP_DGRAD 1

@@ -13,7 +13,8 @@ from tests.conftest import load_golden, manifest
 
 pytestmark = pytest.mark.gpu
 M = manifest()
-TOL = {"fp32": None, "tf32": 2e-3, "bf16": 1e-2}
+TOL = {"fp32": None, "fp32x3": None, "tf32": 2e-3, "bf16": 1e-2}
+EXACT_MODES = ("fp32", "fp32x3")  # both promise the reference's own allclose(1e-5)
 
 
 @pytest.fixture(scope="module")
@@ -37,7 +38,7 @@ def relerr(a, ref):
 
 
 def check(a, ref, mode, tol32=1e-5):
-    if mode == "fp32":
+    if mode in EXACT_MODES:
         assert close(a, ref, tol32), f"max abs err {np.abs((a.to_numpy() if hasattr(a, 'to_numpy') else a) - ref).max():.3e}"
     else:
         assert relerr(a, ref) <= TOL[mode], f"{mode}: rel err {relerr(a, ref):.3e}"
@@ -49,7 +50,7 @@ def tc_ok():
 
 
 # ------------------------------------------------------------------ Conv2D
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "tf32", "bf16"])
 @pytest.mark.parametrize("case", M["conv2d"], ids=lambda c: f"conv{c['id']}")
 def test_conv2d_golden(cp, case, mode):
     from compyute_b200.nn.functional import Conv2DFn, FunctionCache
@@ -79,7 +80,7 @@ CONV_ORACLE = [  # (B, Ci, Co, H, K, pad, stride, dil, bias)
 ]
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "tf32", "bf16"])
 @pytest.mark.parametrize("shape", CONV_ORACLE, ids=lambda s: "x".join(map(str, s[:8])))
 def test_conv2d_oracle(cp, shape, mode):
     from compyute_b200.nn.functional import Conv2DFn, FunctionCache
@@ -158,7 +159,7 @@ def test_conv2d_full_size_properties(cp, mode):
 
 
 # ------------------------------------------------------------------ Linear
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "tf32", "bf16"])
 @pytest.mark.parametrize("case", M["linear"], ids=lambda c: f"lin{c['id']}")
 def test_linear_golden(cp, case, mode):
     from compyute_b200.nn.functional import FunctionCache, LinearFn
@@ -174,7 +175,7 @@ def test_linear_golden(cp, case, mode):
         check(db, g[f"c{n}_db"], mode)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "tf32", "bf16"])
 @pytest.mark.parametrize("shape", [(128, 576, 256, True), (300, 84, 10, True), (512, 1024, 768, False), (1000, 333, 130, True),
                                    (4096, 512, 1000, True)], ids=str)
 def test_linear_oracle(cp, shape, mode):
