@@ -1,0 +1,259 @@
+// "Strip" (shared-halo) implicit-GEMM convolution for stride-1 / dilation-1 / same-padded KxK layers with few channels
+// (bf16, tcgen05).  Replaces the tap-per-k-iteration im2col loads of tc_kernel<OP_CONV> where those are L2->SM bound.
+//
+// The activation tensor is staged ZERO-PADDED and channels-last, act_pad[B][Hp][Wp][Cp] (Hp = H + 2P, Wp = W + 2P), and
+// read as one long matrix of pixel rows [R = B*Hp*Wp][Cp].  Output lane m is the padded-linear index of the window's
+// top-left input pixel, m = b*Hp*Wp + h*Wp + w, so filter tap (j, k) of lane m reads row m + j*Wp + k: for a tile of 128
+// consecutive lanes all K*K taps read from ONE strip of 128 + (K-1)*(Wp+1) consecutive rows.  The producer TMA-loads that
+// strip once per (tile, 64-channel chunk); the MMA warp issues the K*K taps as UMMA instructions whose A descriptors start
+// tap_off rows into the strip (the 128B swizzle is a function of the shared-memory address, so a descriptor may start at
+// any 128-byte row of a tile that TMA wrote at a 1024-byte aligned base — tools/halo_probe.cu).  Lanes with h >= H or
+// w >= W (the 2P pad columns / rows: 1 - H*W/(Hp*Wp) of the MMAs) are computed and dropped by the epilogue.
+// Filter tiles [BN][64] per (tap, chunk) either stay RESIDENT in shared memory for the life of the persistent CTA
+// (one N tile and T*chunks*BN*128 bytes fit) or stream through a ring like tc_kernel's B operand.
+//
+//   warp 0  TMA producer (strips + filter tiles)      warp 1  MMA issuer      warp 2  TMEM allocator      warps 4-7  epilogue
+#pragma once
+#include <cuda_bf16.h>
+
+#include "strip_params.cuh"
+#include "tc_kernel.cuh"  // col_sums_32x32, PTX wrappers
+
+namespace cpt {
+namespace tc {
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1) strip_conv_kernel(const __grid_constant__ StripParams p) {
+  constexpr uint32_t IDESC = make_idesc(true, false, false, 128, BN);
+  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr uint32_t B_BYTES = BN * 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // [0, 1024): barriers | strip units | filter tiles
+  auto ufull = [&](int u) { return smem_base + 8u * u; };
+  auto uempty = [&](int u) { return smem_base + 8u * (STRIP_MAX_UNITS + u); };
+  auto bfull = [&](int s) { return smem_base + 8u * (2 * STRIP_MAX_UNITS + s); };
+  auto bempty = [&](int s) { return smem_base + 8u * (2 * STRIP_MAX_UNITS + STRIP_MAX_BSTAGES + s); };
+  auto tfull = [&](int a) { return smem_base + 8u * (2 * STRIP_MAX_UNITS + 2 * STRIP_MAX_BSTAGES + a); };
+  auto tempty = [&](int a) { return smem_base + 8u * (2 * STRIP_MAX_UNITS + 2 * STRIP_MAX_BSTAGES + 2 + a); };
+  const uint32_t tmem_slot = smem_base + 8u * (2 * STRIP_MAX_UNITS + 2 * STRIP_MAX_BSTAGES + 4);
+  const uint32_t unit_base = smem_base + 1024u;
+  const uint32_t b_base = unit_base + (uint32_t)(p.n_units * p.unit_bytes);
+  auto unit_smem = [&](int u) { return unit_base + (uint32_t)(u * p.unit_bytes); };
+  auto b_smem = [&](int s) { return b_base + (uint32_t)s * B_BYTES; };
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (warp == 0 && elect_one_sync()) {
+    prefetch_tmap(&p.tmA);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int u = 0; u < p.n_units; ++u) { mbar_init(ufull(u), 1); mbar_init(uempty(u), 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<false>(tmem_slot, TMEM_COLS);
+    tmem_relinquish<false>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int n_ctas = gridDim.x, cta = blockIdx.x;
+  const int my_tiles = cta < total_tiles ? (total_tiles - cta + n_ctas - 1) / n_ctas : 0;
+  const int T = p.T, cchunks = p.cchunks;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    const int total_units = my_tiles * cchunks;
+    int u_issued = 0, b_cnt = 0;
+    bool ok = true;
+    auto issue_strip = [&](int k) -> bool {  // unit k of this CTA's sequence: (tile, chunk)
+      const int ti = k / cchunks, cc = k - ti * cchunks;
+      const int t = cta + ti * n_ctas;
+      const int m0 = (t % p.m_tiles) * 128;
+      const int slot = k % p.n_units;
+      const uint32_t par = (uint32_t)((k / p.n_units) & 1);
+      if (!__all_sync(0xffffffffu, mbar_wait(uempty(slot), par ^ 1))) { atomicExch(p.status, 11); return false; }
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(ufull(slot), (uint32_t)p.unit_bytes);
+        for (int l = 0; l < p.n_loads; ++l)
+          tma_load_2d<false>(&p.tmA, ufull(slot), unit_smem(slot) + (uint32_t)(l * p.box_rows * 128), cc * 64, m0 + l * p.box_rows);
+      }
+      __syncwarp();
+      return true;
+    };
+    const int la = T > 1 ? 1 : 0;
+    if (total_units > 0) { ok = issue_strip(0); u_issued = 1; }
+    for (int k = 0; k < total_units && ok; ++k) {
+      const int ti = k / cchunks, cc = k - ti * cchunks;
+      const int t = cta + ti * n_ctas;
+      const int n0 = (t / p.m_tiles) * BN;
+      const bool load_b = !p.resident || ti == 0;
+      for (int tap = 0; tap < T && ok; ++tap) {
+        if (tap == la && u_issued < total_units) { ok = issue_strip(u_issued); ++u_issued; if (!ok) break; }
+        if (load_b) {
+          int slot;
+          uint32_t par;
+          if (p.resident) { slot = cc * T + tap; par = 0; }
+          else { slot = b_cnt % p.b_stages; par = (uint32_t)((b_cnt / p.b_stages) & 1); ++b_cnt; }
+          if (!p.resident && !__all_sync(0xffffffffu, mbar_wait(bempty(slot), par ^ 1))) { atomicExch(p.status, 12); ok = false; break; }
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(bfull(slot), B_BYTES);
+            tma_load_2d<false>(&p.tmB, bfull(slot), b_smem(slot), tap * p.wk_cols + cc * 64, n0);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    int acc = 0, k = 0, b_cnt = 0;
+    uint32_t acc_phase = 0;
+    bool ok = true;
+    for (int ti = 0; ti < my_tiles && ok; ++ti) {
+      if (!__all_sync(0xffffffffu, mbar_wait(tempty(acc), acc_phase ^ 1))) { atomicExch(p.status, 13); break; }
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int cc = 0; cc < cchunks && ok; ++cc, ++k) {
+        const int uslot = k % p.n_units;
+        if (!__all_sync(0xffffffffu, mbar_wait(ufull(uslot), (uint32_t)((k / p.n_units) & 1)))) { atomicExch(p.status, 14); ok = false; break; }
+        const uint32_t sa0 = unit_smem(uslot);
+        for (int tap = 0; tap < T; ++tap) {
+          int bslot;
+          if (p.resident) {
+            bslot = cc * T + tap;
+            if (ti == 0 && !__all_sync(0xffffffffu, mbar_wait(bfull(bslot), 0))) { atomicExch(p.status, 15); ok = false; break; }
+          } else {
+            bslot = b_cnt % p.b_stages;
+            const uint32_t par = (uint32_t)((b_cnt / p.b_stages) & 1);
+            ++b_cnt;
+            if (!__all_sync(0xffffffffu, mbar_wait(bfull(bslot), par))) { atomicExch(p.status, 15); ok = false; break; }
+          }
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t sa = sa0 + (uint32_t)p.tap_off[tap] * 128u, sb = b_smem(bslot);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              uint64_t da = make_smem_desc(sa + s * 32, 16, 1024);
+              if (p.base_offset_mode) da |= (uint64_t)(((sa + s * 32) >> 7) & 7u) << 49;
+              const uint64_t db = make_smem_desc(sb + s * 32, 16, 1024);
+              umma<true, false>(d_tmem, da, db, IDESC, (uint32_t)((cc | tap | s) != 0));
+            }
+            if (!p.resident) umma_commit<false>(bempty(bslot));
+            if (tap == T - 1) umma_commit<false>(uempty(uslot));   // strip free once these MMAs have read it
+          }
+          __syncwarp();
+        }
+      }
+      if (!ok) break;
+      if (elect_one_sync()) umma_commit<false>(tfull(acc));
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue ===========================
+    const int ew = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    __shared__ float stat_acc[4][BN][2];
+    const bool do_stats = p.stats != nullptr;
+    int stat_n_tile = -1;
+    auto stats_flush = [&]() {
+      if (stat_n_tile >= 0) {
+        float* dstp = p.stats + ((long long)(blockIdx.x * 4 + ew) * p.N) * 2;
+        for (int c = lane; c < BN; c += 32) {
+          const int col = stat_n_tile * BN + c;
+          if (col < p.N) { dstp[2 * col] = stat_acc[ew][c][0]; dstp[2 * col + 1] = stat_acc[ew][c][1]; }
+        }
+      }
+    };
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int t = cta + ti * n_ctas;
+      const int m_tile = t % p.m_tiles, n_tile = t / p.m_tiles;
+      const int m = m_tile * 128 + ew * 32 + lane, n0 = n_tile * BN;
+      if (do_stats && n_tile != stat_n_tile) {
+        stats_flush();
+        stat_n_tile = n_tile;
+        for (int c = lane; c < BN; c += 32) stat_acc[ew][c][0] = stat_acc[ew][c][1] = 0.f;
+        __syncwarp();
+      }
+      // lane -> (image, row, col) of the padded grid; pad rows / columns are dropped
+      const int b = m / p.HpWp, rem = m - b * p.HpWp, h = rem / p.Wp, w = rem - h * p.Wp;
+      const bool m_ok = m < p.M_lanes && h < p.H && w < p.W;
+      float* dst = p.out + (long long)b * p.img_stride + (long long)h * p.W + w + (long long)n0 * p.col_stride;
+      const long long cs = p.col_stride;
+      if (!mbar_wait(tfull(acc), acc_phase)) { atomicExch(p.status, 16); break; }
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      constexpr int NCH = BN / 32;
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(tbase, va);
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(acc));
+      };
+      auto store_chunk = [&](const uint32_t (&v)[32], int c) {
+        const int cbase = n0 + c * 32;
+        if (do_stats) {
+          float a[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = m_ok ? __uint_as_float(v[j]) : 0.f;
+          const float s1 = col_sums_32x32(a, lane);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float x = m_ok ? __uint_as_float(v[j]) : 0.f; a[j] = x * x; }
+          const float s2 = col_sums_32x32(a, lane);
+          stat_acc[ew][c * 32 + lane][0] += s1;
+          stat_acc[ew][c * 32 + lane][1] += s2;
+        }
+        float* q = dst + (long long)(c * 32) * cs;
+        float bl = 0.f;
+        if (p.bias && cbase + lane < p.N) bl = __ldg(p.bias + cbase + lane);
+        if (cbase + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float val = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j);
+            if (m_ok) *q = val;
+            q += cs;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float val = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j);
+            if (m_ok && cbase + j < p.N) *q = val;
+            q += cs;
+          }
+        }
+      };
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32(tbase + (uint32_t)((c + 1) * 32), vb);
+        store_chunk(va, c);
+        tmem_ld_wait();
+        if (c + 2 < NCH) tmem_ld_32x32(tbase + (uint32_t)((c + 2) * 32), va);
+        if (c + 2 >= NCH) release_acc();
+        store_chunk(vb, c + 1);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (do_stats) { __syncwarp(); stats_flush(); }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<false>(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+}  // namespace cpt

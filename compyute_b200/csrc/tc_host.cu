@@ -8,6 +8,7 @@
 
 #include "tc.cuh"
 #include "tc_launch.cuh"
+#include "strip_params.cuh"
 
 namespace cpt {
 namespace tc {
@@ -119,10 +120,13 @@ __device__ __forceinline__ float round_tf32(float x) {
 // per (block, channel).
 constexpr int CL_PX = 128, CL_CH = 64;
 
-template <bool BF16>
+// Zero-padded destination (strip convolution path): pixel (b, h, w) goes to row b*Hp*Wp + (h + P)*Wp + (w + P)
+struct PadGeom { int W, H, P; };
+
+template <bool BF16, bool PAD = false>
 __global__ void __launch_bounds__(256, 4) nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW,
                                                            int Cp, float* __restrict__ chan_sum, float* __restrict__ partial,
-                                                           int64_t Q, float* __restrict__ dst_lo) {
+                                                           int64_t Q, float* __restrict__ dst_lo, PadGeom pg = PadGeom{0, 0, 0}) {
   // pixel tiles run over the flattened (image, pixel) index q in [0, Q = B*HW): small feature maps (HW < 128) fill the
   // 128-pixel tile with pixels of several images instead of leaving lanes idle
   __shared__ uint32_t tile[BF16 ? 32 : 64][CL_PX + 1];
@@ -171,11 +175,28 @@ __global__ void __launch_bounds__(256, 4) nchw_to_nhwc_kernel(const float* __res
       __syncthreads();
       const int c = c0 + 2 * lane;  // this lane's channel pair
       if (c < Cp) {
+        if (PAD) {
+          // destination row of pixel q = p0 + warp + 8 i, advanced incrementally (one division per tile, not per store)
+          const int Wp = pg.W + 2 * pg.P, HpWp = (pg.H + 2 * pg.P) * Wp;
+          int64_t q = p0 + warp;
+          int b = (int)(q / HW), r = (int)(q - (int64_t)b * HW), h = r / pg.W, w = r - h * pg.W;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int pp = warp + 8 * i;
-          const int64_t q = p0 + pp;
-          if (q < Q) d[(q * Cp + c) >> 1] = tile[lane][pp];
+          for (int i = 0; i < 16; ++i) {
+            if (q < Q) {
+              const int64_t row = (int64_t)b * HpWp + (int64_t)(h + pg.P) * Wp + (w + pg.P);
+              d[(row * Cp + c) >> 1] = tile[lane][warp + 8 * i];
+            }
+            q += 8; w += 8;
+            while (w >= pg.W) { w -= pg.W; ++h; }
+            while (h >= pg.H) { h -= pg.H; ++b; }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int pp = warp + 8 * i;
+            const int64_t q = p0 + pp;
+            if (q < Q) d[(q * Cp + c) >> 1] = tile[lane][pp];
+          }
         }
       }
     } else {
@@ -384,6 +405,8 @@ static int launch_bn(TcParams p, int mode, int BN, bool use2, cudaStream_t st) {
 }
 
 static int pick_bn(int64_t n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
+// FP32X3 accumulates the tile in registers (chunked reduction): at most 128 columns
+static int pick_bn_mode(int64_t n, int mode) { const int bn = pick_bn(n); return (is_x3(mode) && bn > 128) ? 128 : bn; }
 
 static int get_status_ptr(int** ptr) {
   CPT_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(ptr), g_tc_status));
@@ -437,7 +460,7 @@ static bool dgrad_tc_ok(const G& g);
 static int wgrad_splits(const G& g, int mode) {
   const int bk = kc_of(mode);
   const int k_iters = (int)(((int64_t)g.B * g.Ho * g.Wo + bk - 1) / bk);
-  const int tiles = ((g.Ci + 127) / 128) * ((g.Co + pick_bn(g.Co) - 1) / pick_bn(g.Co)) * g.T;
+  const int tiles = ((g.Ci + 127) / 128) * ((g.Co + pick_bn_mode(g.Co, mode) - 1) / pick_bn_mode(g.Co, mode)) * g.T;
   return pick_splits(tiles, k_iters, 8);
 }
 
@@ -502,7 +525,7 @@ static size_t stats_bytes(int Ncols) { return (size_t)sm_count() * 4 * Ncols * 2
 static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Win, const void* wmat, const void* wmat_lo, int Ncols,
                             const ConvPlan& pl, const float* bias, float* out, int mode, cudaStream_t st, float* stats = nullptr) {
   const int kc = kc_of(mode), Cp = round_up(Cact, 8), Ck = round_up(Cact, kc), T = pl.ntaps;
-  const int BN = pick_bn(Ncols);
+  const int BN = pick_bn_mode(Ncols, mode);
   TcParams p{};
   const int64_t M = (int64_t)B * pl.sub_H * pl.sub_W;
   CPT_REQUIRE(M < (1LL << 31), CPT_ERR_UNSUPPORTED, "conv: pixel count exceeds int32");
@@ -679,7 +702,7 @@ int conv_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl,
   const int splits = (k_iters + kps - 1) / kps;  // no empty split
   const size_t need = align_up((size_t)splits * g.Co * g.T * g.Ci * sizeof(float), 1024);
   CPT_REQUIRE(ws && ws_bytes >= need, CPT_ERR_WORKSPACE, "conv2d_wgrad_cl: workspace too small (%zu < %zu)", ws_bytes, need);
-  const int BN = pick_bn(g.Co);
+  const int BN = pick_bn_mode(g.Co, mode);
   TcParams p{};
   const int upper_w = g.P - (g.K - 1) * g.D, upper_h = upper_w;
   // A: x_cl through im2col, lanes = input channels (MN-major), reduction = output pixels
@@ -846,7 +869,7 @@ int linear_fwd(const float* x, const float* w, const float* bias, float* y, int6
 int linear_fwd_lp(const void* xa, const void* wa, const float* bias, float* y, int64_t N, int In, int Out, int mode, cudaStream_t st,
                   int relu, void* y_lp, unsigned int* mask, const void* xa_lo, const void* wa_lo) {
   const int pitch = mode == CPT_MODE_BF16 ? round_up(In, 8) : In;
-  const int kc = kc_of(mode), BN = pick_bn(N);
+  const int kc = kc_of(mode), BN = pick_bn_mode(N, mode);
   TcParams p{};
   // y[n][o]: lanes = o.  A = w [Out][In] K-major, B = x [N][In] K-major
   if (int e = make_map_2d(&p.tmA, wa, mode, In, Out, pitch, kc, 128)) return e;
@@ -892,7 +915,7 @@ int linear_dgrad(const float* dy, const float* w, float* dx, int64_t N, int In, 
 int linear_dgrad_lp(const void* ga, const void* wa, float* dx, int64_t N, int In, int Out, int mode, cudaStream_t st,
                     const unsigned int* in_mask, void* dx_lp, const void* ga_lo, const void* wa_lo) {
   const int gpitch = mode == CPT_MODE_BF16 ? round_up(Out, 8) : Out, wpitch = mode == CPT_MODE_BF16 ? round_up(In, 8) : In;
-  const int kc = kc_of(mode), BN = pick_bn(N);
+  const int kc = kc_of(mode), BN = pick_bn_mode(N, mode);
   TcParams p{};
   // dx[n][i]: lanes = i.  A(m=i, k=o) = w[o][i]: MN-major over the [Out][In] matrix; B = dy [N][Out] K-major
   if (int e = make_map_2d(&p.tmA, wa, mode, In, Out, wpitch, kc, kc, true)) return e;
@@ -947,7 +970,7 @@ int linear_wgrad_lp(const void* xa, const void* ga, float* dw, int64_t N, int In
   char* base = reinterpret_cast<char*>(ws);
   const size_t off = 0;
   const int xpitch = mode == CPT_MODE_BF16 ? round_up(In, 8) : In, gpitch = mode == CPT_MODE_BF16 ? round_up(Out, 8) : Out;
-  const int kc = kc_of(mode), bk = kc, BN = pick_bn(Out);
+  const int kc = kc_of(mode), bk = kc, BN = pick_bn_mode(Out, mode);
   const int k_iters = (int)((N + bk - 1) / bk);
   const int tiles = ((In + 127) / 128) * ((Out + BN - 1) / BN);
   int splits_req = pick_splits(tiles, k_iters, 8);
@@ -1390,12 +1413,256 @@ int conv_dgrad_packed(const cpt_conv2d_desc* d, const void* dy_cl, const float* 
   return CPT_OK;
 }
 
+
+// ------------------------------------------------------------------ strip ("shared halo") path: see strip_kernel.cuh
+// Stride-1 / dilation-1 / same-padded odd-K layers in bf16 mode whose channel counts are multiples of 64.  Activations are
+// staged zero-padded (cpt_to_channels_last_padded); fprop and dgrad run strip_conv_kernel, wgrad reads the same padded
+// tensors through im2col maps whose bounding box is the interior.
+struct StripPlan {
+  int Hp, Wp, box_rows, n_loads, unit_bytes, n_units, b_stages, resident, BN, m_tiles, n_tiles;
+  long long M_lanes;
+  size_t smem;
+};
+static int strip_max_channels() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CPT_STRIP_MAX_C");
+    v = e ? atoi(e) : 128;   // larger layers are tensor-pipe bound on the im2col path already
+  }
+  return v;
+}
+static bool strip_plan(int B, int Cact, int H, int W, int K, int Ncols, StripPlan& q) {
+  const int P = (K - 1) / 2;
+  q.Hp = H + 2 * P; q.Wp = W + 2 * P;
+  const int SR = 128 + (K - 1) * (q.Wp + 1);
+  if (SR <= 256) { q.n_loads = 1; q.box_rows = round_up(SR, 8); }
+  else { q.n_loads = 2; q.box_rows = round_up((SR + 1) / 2, 8); }
+  if (q.box_rows > 256) return false;
+  q.unit_bytes = q.n_loads * q.box_rows * 128;
+  q.BN = pick_bn(Ncols);
+  q.n_tiles = (Ncols + q.BN - 1) / q.BN;
+  q.M_lanes = (long long)(B - 1) * q.Hp * q.Wp + (long long)(H - 1) * q.Wp + W;
+  if (q.M_lanes >= (1LL << 31) - 256 || (long long)B * q.Hp * q.Wp >= (1LL << 31)) return false;
+  q.m_tiles = (int)((q.M_lanes + 127) / 128);
+  const int T = K * K, cchunks = Cact / 64, b_bytes = q.BN * 128;
+  const int avail = 232448 - 2048 - 4 * q.BN * 2 * 4 - 512;   // barriers + alignment slack, static stats accumulators
+  q.resident = q.n_tiles == 1 && T * cchunks <= STRIP_MAX_BSTAGES && 2 * q.unit_bytes + T * cchunks * b_bytes <= avail;
+  if (q.resident) {
+    q.b_stages = T * cchunks;
+    q.n_units = (avail - q.b_stages * b_bytes) / q.unit_bytes;
+    if (q.n_units > STRIP_MAX_UNITS) q.n_units = STRIP_MAX_UNITS;
+  } else {
+    q.n_units = 3;
+    if (avail - 3 * q.unit_bytes < 6 * b_bytes) q.n_units = 2;
+    q.b_stages = (avail - q.n_units * q.unit_bytes) / b_bytes;
+    if (q.b_stages > STRIP_MAX_BSTAGES) q.b_stages = STRIP_MAX_BSTAGES;
+    if (q.b_stages < 3) return false;
+  }
+  q.smem = 1024 + 1024 + (size_t)q.n_units * q.unit_bytes + (size_t)q.b_stages * b_bytes;
+  return q.n_units >= 2;
+}
+
+bool strip_ok(const G& g, int mode) {
+  static const bool off = getenv("CPT_NO_STRIP") != nullptr;
+  if (off || mode != CPT_MODE_BF16 || g.S != 1 || g.D != 1 || g.K < 3 || (g.K & 1) == 0 || g.K > 7 || g.P != (g.K - 1) / 2) return false;
+  if (g.Ci % 64 != 0 || g.Co % 64 != 0 || g.Ci > strip_max_channels() || g.Co > strip_max_channels()) return false;
+  StripPlan a, b;
+  return strip_plan(g.B, g.Ci, g.H, g.W, g.K, g.Co, a) && strip_plan(g.B, g.Co, g.H, g.W, g.K, g.Ci, b);
+}
+
+size_t cl_padded_bytes(int B, int C, int H, int W, int P) {
+  return align_up((size_t)B * (H + 2 * P) * (W + 2 * P) * round_up(C, 8) * 2, 1024);
+}
+
+// zeroes the pad pixels of act_pad[B][Hp][Wp][Cp] (bf16): one warp per border pixel, 16 bytes per lane and step
+__global__ void __launch_bounds__(256) zero_border_kernel(uint4* __restrict__ dst, int B, int H, int W, int P, int vec_per_px) {
+  const int Wp = W + 2 * P, Hp = H + 2 * P;
+  const int per_img = Hp * Wp - H * W, top = P * Wp;
+  const int64_t total = (int64_t)B * per_img;
+  const int lane = threadIdx.x & 31;
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < total; i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int b = (int)(i / per_img), r = (int)(i - (int64_t)b * per_img);
+    int hp, wp;
+    if (r < top) { hp = r / Wp; wp = r - hp * Wp; }
+    else if (r < 2 * top) { const int rr = r - top; hp = H + P + rr / Wp; wp = rr % Wp; }
+    else { const int rr = r - 2 * top, row = rr / (2 * P), k = rr - row * (2 * P); hp = P + row; wp = k < P ? k : W + k; }
+    uint4* px = dst + ((int64_t)b * Hp * Wp + (int64_t)hp * Wp + wp) * vec_per_px;
+    for (int v = lane; v < vec_per_px; v += 32) px[v] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+int to_channels_last_padded(const float* src, void* dst, int B, int C, int H, int W, int P, float* chan_sum, void* ws, size_t ws_bytes,
+                            cudaStream_t st) {
+  const int Cp = round_up(C, 8), HW = H * W;
+  int gx, groups;
+  cl_grid(B, C, H, W, gx, groups);
+  dim3 grid(gx, groups, 1);
+  CPT_REQUIRE(grid.y <= 65535 && (int64_t)B * (H + 2 * P) * (W + 2 * P) < (1LL << 31) && (int64_t)B * C * HW < (1LL << 32) - (1 << 20),
+              CPT_ERR_UNSUPPORTED, "to_channels_last_padded: tensor too large");
+  if (P > 0) {
+    const int64_t border = (int64_t)B * ((H + 2 * P) * (W + 2 * P) - HW);
+    zero_border_kernel<<<ew_grid(border * 32, 256), 256, 0, st>>>(reinterpret_cast<uint4*>(dst), B, H, W, P, Cp * 2 / 16);
+    CPT_LAUNCH_CHECK("zero_border");
+  }
+  float* partial = nullptr;
+  if (chan_sum && ws && ws_bytes >= to_channels_last_ws(B, C, H, W)) partial = reinterpret_cast<float*>(ws);
+  const int64_t Q = (int64_t)B * HW;
+  nchw_to_nhwc_kernel<true, true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial, Q, nullptr, PadGeom{W, H, P});
+  CPT_LAUNCH_CHECK("nchw_to_nhwc_padded");
+  if (partial) {
+    chan_partial_reduce_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partial, chan_sum, C, (int64_t)gx, groups * CL_CH);
+    CPT_LAUNCH_CHECK("chan_partial_reduce");
+  }
+  return CPT_OK;
+}
+
+// out[b, n, h, w] = Σ_{t=(j,k), ch} act_pad[b, h + j, w + k, ch] * wmat[n][t][ch]  (+ bias[n])
+static int conv_strip_gemm(const void* act_pad, int B, int Cact, int H, int W, int K, const void* wmat, int Ncols, const float* bias,
+                           float* out, cudaStream_t st, float* stats) {
+  StripPlan q;
+  CPT_REQUIRE(strip_plan(B, Cact, H, W, K, Ncols, q), CPT_ERR_UNSUPPORTED, "strip convolution: geometry does not fit shared memory");
+  const int mode = CPT_MODE_BF16, T = K * K, Ck = round_up(Cact, 64);
+  StripParams p{};
+  if (int e = make_map_2d(&p.tmA, act_pad, mode, Cact, (uint64_t)B * q.Hp * q.Wp, round_up(Cact, 8), 64, q.box_rows)) return e;
+  if (int e = make_map_2d(&p.tmB, wmat, mode, (uint64_t)T * Ck, Ncols, (uint64_t)T * Ck, 64, q.BN)) return e;
+  p.out = out; p.bias = bias;
+  if (int e = get_status_ptr(&p.status)) return e;
+  if (stats) {
+    CPT_CUDA(cudaMemsetAsync(stats, 0, stats_bytes(Ncols), st));
+    p.stats = stats;
+  }
+  p.M_lanes = (int)q.M_lanes; p.N = Ncols; p.m_tiles = q.m_tiles; p.n_tiles = q.n_tiles;
+  p.T = T; p.cchunks = Cact / 64; p.wk_cols = Ck;
+  p.H = H; p.W = W; p.Wp = q.Wp; p.HpWp = q.Hp * q.Wp;
+  p.box_rows = q.box_rows; p.n_loads = q.n_loads; p.unit_bytes = q.unit_bytes; p.n_units = q.n_units; p.b_stages = q.b_stages;
+  p.resident = q.resident;
+  static const int base_mode = getenv("CPT_STRIP_BASE_OFFSET") ? atoi(getenv("CPT_STRIP_BASE_OFFSET")) : 0;
+  p.base_offset_mode = base_mode;
+  p.col_stride = (long long)H * W; p.img_stride = (long long)Ncols * H * W;
+  for (int j = 0; j < K; ++j)
+    for (int k = 0; k < K; ++k) p.tap_off[j * K + k] = j * q.Wp + k;
+  int grid = sm_count() - g_reserved_sms;
+  const int total = q.m_tiles * q.n_tiles;
+  if (grid > total) grid = total;
+  if (grid < 1) return CPT_OK;
+  return launch_strip(p, q.BN, grid, q.smem, st);
+}
+
+size_t conv_strip_workspace_size(int op, const cpt_conv2d_desc* d) {
+  const G g = geom(d);
+  const int mode = CPT_MODE_BF16;
+  if (op == CPT_OP_FPROP) return wmat_bytes(g.Co, g.T, g.Ci, mode) + 1024;
+  if (op == CPT_OP_DGRAD) return wmat_bytes(g.Ci, g.T, g.Co, mode) + 1024;
+  return align_up((size_t)wgrad_splits(g, mode) * g.Co * g.T * g.Ci * sizeof(float), 1024) + 1024;
+}
+
+int conv_fprop_strip(const cpt_conv2d_desc* d, const void* x_pad, const float* w, const float* bias, float* y, void* ws, size_t ws_bytes,
+                     cudaStream_t st, float* stats) {
+  const G g = geom(d);
+  CPT_REQUIRE(strip_ok(g, CPT_MODE_BF16), CPT_ERR_UNSUPPORTED, "conv2d_fprop_strip: geometry not covered by the strip path");
+  CPT_REQUIRE(ws && ws_bytes >= conv_strip_workspace_size(CPT_OP_FPROP, d), CPT_ERR_WORKSPACE, "conv2d_fprop_strip: workspace too small");
+  const int Ck = round_up(g.Ci, 64);
+  const int64_t n = (int64_t)g.Co * g.T * Ck;
+  w_fprop_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, Ck, nullptr);
+  CPT_LAUNCH_CHECK("w_fprop");
+  return conv_strip_gemm(x_pad, g.B, g.Ci, g.H, g.W, g.K, ws, g.Co, bias, y, st, stats);
+}
+
+int conv_dgrad_strip(const cpt_conv2d_desc* d, const void* dy_pad, const float* w, float* dx, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const G g = geom(d);
+  CPT_REQUIRE(strip_ok(g, CPT_MODE_BF16), CPT_ERR_UNSUPPORTED, "conv2d_dgrad_strip: geometry not covered by the strip path");
+  CPT_REQUIRE(ws && ws_bytes >= conv_strip_workspace_size(CPT_OP_DGRAD, d), CPT_ERR_WORKSPACE, "conv2d_dgrad_strip: workspace too small");
+  // dx[h][w] = Σ_{j',k'} dy_pad[h + j'][w + k'] * w[:, :, K-1-j', K-1-k']: the forward strip over dy with the taps reversed
+  const int Cok = round_up(g.Co, 64);
+  TapIdx ti{};
+  for (int t = 0; t < g.T; ++t) ti.idx[t] = (unsigned char)(g.T - 1 - t);
+  const int64_t n = (int64_t)g.Ci * g.T * Cok;
+  w_dgrad_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w, ws, g.Co, g.Ci, g.T, g.T, Cok, ti, nullptr);
+  CPT_LAUNCH_CHECK("w_dgrad");
+  return conv_strip_gemm(dy_pad, g.B, g.Co, g.H, g.W, g.K, ws, g.Ci, nullptr, dx, st, nullptr);
+}
+
+// wgrad over the padded tensors: A = x_pad through an im2col map with padding 0 (the pad is in the data), B = dy_pad through an
+// im2col map whose bounding box is the interior; both walk the H x W output grid in the same order
+int conv_wgrad_padded(const cpt_conv2d_desc* d, const void* x_pad, const void* dy_pad, float* dw, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const G g = geom(d);
+  const int mode = CPT_MODE_BF16;
+  CPT_REQUIRE(strip_ok(g, mode), CPT_ERR_UNSUPPORTED, "conv2d_wgrad_padded: geometry not covered by the strip path");
+  const int kc = kc_of(mode), bk = kc, P = g.P, Hp = g.H + 2 * P, Wp = g.W + 2 * P;
+  const int splits_req = wgrad_splits(g, mode);
+  const int64_t pixels = (int64_t)g.B * g.Ho * g.Wo;
+  const int k_iters = (int)((pixels + bk - 1) / bk);
+  const int kps = (k_iters + splits_req - 1) / splits_req;
+  const int splits = (k_iters + kps - 1) / kps;
+  const size_t need = align_up((size_t)splits * g.Co * g.T * g.Ci * sizeof(float), 1024);
+  CPT_REQUIRE(ws && ws_bytes >= need, CPT_ERR_WORKSPACE, "conv2d_wgrad_padded: workspace too small (%zu < %zu)", ws_bytes, need);
+  const int BN = pick_bn(g.Co);
+  TcParams p{};
+  if (int e = make_map_im2col(&p.tmA, x_pad, mode, round_up(g.Ci, 8), Wp, Hp, g.B, 0, 0, -(g.K - 1), -(g.K - 1), 1, kc, bk, true)) return e;
+  if (int e = make_map_im2col(&p.tmB, dy_pad, mode, round_up(g.Co, 8), Wp, Hp, g.B, P, P, -P, -P, 1, kc, bk, true)) return e;
+  p.b_im2col = 1; p.b_pad = P;
+  p.out = reinterpret_cast<float*>(ws);
+  p.bias = nullptr; p.bias_mode = BIAS_NONE;
+  if (int e = get_status_ptr(&p.status)) return e;
+  p.M = g.Ci; p.N = g.Co;
+  p.m_tiles = (g.Ci + 127) / 128; p.n_tiles = (g.Co + BN - 1) / BN; p.z_tiles = g.T * splits;
+  p.k_iters_total = k_iters; p.k_iters_per_split = kps;
+  p.col_stride = (long long)g.T * g.Ci; p.split_stride = (long long)g.Co * g.T * g.Ci; p.tap_stride = g.Ci;
+  p.lane_is_pixel = 0; p.px_per_img = g.Ho * g.Wo; p.Wo = g.Wo; p.Ho = g.Ho;
+  p.conv_stride = 1; p.pad = 0; p.dil = 1; p.Kw = g.K; p.taps = g.T; p.out_s = 1;
+  if (int e = launch_bn<true, true, OP_WGRAD>(p, mode, BN, want_2cta(BN, (g.Ci + 127) / 128), st)) return e;
+  return launch_wgrad_reduce(reinterpret_cast<float*>(ws), dw, g.Co, g.Ci, g.T, splits, st);
+}
+
 }  // namespace tc
 }  // namespace cpt
 
 using namespace cpt;
 
 extern "C" {
+
+static int check_tc_desc(const cpt_conv2d_desc* d) {
+  CPT_REQUIRE(d && d->B > 0 && d->Ci > 0 && d->H > 0 && d->W > 0 && d->Co > 0 && d->K > 0 && d->pad >= 0 && d->stride >= 1 && d->dil >= 1,
+              CPT_ERR_INVALID, "bad convolution descriptor");
+  return CPT_OK;
+}
+
+/* strip ("shared halo") path for stride-1 same-padded small-channel layers: see include/compyute_b200.h */
+int cpt_conv2d_strip_supported(const cpt_conv2d_desc* d, int mode) {
+  if (!d || d->B <= 0 || d->Ci <= 0 || d->H <= 0 || d->W <= 0 || d->Co <= 0 || d->K <= 0 || d->pad < 0 || d->stride < 1 || d->dil < 1) return 0;
+  return tc::strip_ok(tc::geom(d), mode) ? 1 : 0;
+}
+size_t cpt_channels_last_padded_bytes(int B, int C, int H, int W, int pad) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || pad < 0) return 0;
+  return tc::cl_padded_bytes(B, C, H, W, pad);
+}
+int cpt_to_channels_last_padded(const float* src, void* dst, int B, int C, int H, int W, int pad, float* chan_sum, void* ws,
+                                size_t ws_bytes, void* stream) {
+  CPT_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0 && pad >= 0 && C % 8 == 0, CPT_ERR_INVALID, "to_channels_last_padded: bad arguments");
+  return tc::to_channels_last_padded(src, dst, B, C, H, W, pad, chan_sum, ws, ws_bytes, as_stream(stream));
+}
+size_t cpt_conv2d_strip_workspace_size(int op, const cpt_conv2d_desc* d) {
+  if (check_tc_desc(d)) return 0;
+  return tc::conv_strip_workspace_size(op, d);
+}
+int cpt_conv2d_fprop_strip(const cpt_conv2d_desc* d, const void* x_pad, const float* w, const float* bias, float* y, float* stats,
+                           void* ws, size_t ws_bytes, void* stream) {
+  if (int e = check_tc_desc(d)) return e;
+  CPT_REQUIRE(x_pad && w && y, CPT_ERR_INVALID, "conv2d_fprop_strip: null pointer");
+  return tc::conv_fprop_strip(d, x_pad, w, bias, y, ws, ws_bytes, as_stream(stream), stats);
+}
+int cpt_conv2d_dgrad_strip(const cpt_conv2d_desc* d, const void* dy_pad, const float* w, float* dx, void* ws, size_t ws_bytes,
+                           void* stream) {
+  if (int e = check_tc_desc(d)) return e;
+  CPT_REQUIRE(dy_pad && w && dx, CPT_ERR_INVALID, "conv2d_dgrad_strip: null pointer");
+  return tc::conv_dgrad_strip(d, dy_pad, w, dx, ws, ws_bytes, as_stream(stream));
+}
+int cpt_conv2d_wgrad_padded(const cpt_conv2d_desc* d, const void* x_pad, const void* dy_pad, float* dw, void* ws, size_t ws_bytes,
+                            void* stream) {
+  if (int e = check_tc_desc(d)) return e;
+  CPT_REQUIRE(x_pad && dy_pad && dw, CPT_ERR_INVALID, "conv2d_wgrad_padded: null pointer");
+  return tc::conv_wgrad_padded(d, x_pad, dy_pad, dw, ws, ws_bytes, as_stream(stream));
+}
 
 size_t cpt_channels_last_bytes(int B, int C, int H, int W, int mode) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || mode == CPT_MODE_FP32) return 0;

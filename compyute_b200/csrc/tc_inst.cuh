@@ -40,11 +40,12 @@ static int launch_inst(const TcParams& p, const LaunchSel& s, cudaStream_t st) {
 
 template <bool BF16, bool X3, bool A_MN, bool B_MN, int OP>
 static int launch_layout(const TcParams& p, const LaunchSel& s, cudaStream_t st) {
-  if (s.use2) {
-    if (s.BN == 256) return launch_inst<BF16, X3, A_MN, B_MN, 256, OP, true>(p, s, st);
-    return launch_inst<BF16, X3, A_MN, B_MN, 128, OP, true>(p, s, st);
+  if constexpr (!X3) {  // the X3 epilogue keeps BN accumulators per thread in registers: BN <= 128 (see pick_bn_mode)
+    if (s.BN == 256) return s.use2 ? launch_inst<BF16, X3, A_MN, B_MN, 256, OP, true>(p, s, st) : launch_inst<BF16, X3, A_MN, B_MN, 256, OP, false>(p, s, st);
+  } else {
+    CPT_REQUIRE(s.BN <= 128, CPT_ERR_INVALID, "tc launch: FP32X3 tiles are at most 128 columns wide");
   }
-  if (s.BN == 256) return launch_inst<BF16, X3, A_MN, B_MN, 256, OP, false>(p, s, st);
+  if (s.use2) return launch_inst<BF16, X3, A_MN, B_MN, 128, OP, true>(p, s, st);
   if (s.BN == 128) return launch_inst<BF16, X3, A_MN, B_MN, 128, OP, false>(p, s, st);
   return launch_inst<BF16, X3, A_MN, B_MN, 64, OP, false>(p, s, st);
 }

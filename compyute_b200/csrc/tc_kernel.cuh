@@ -57,6 +57,13 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
   constexpr uint32_t CHUNK_BYTES = E::BK * 128;  // one MN-major chunk: BK k-rows x 128 B
   constexpr uint32_t MN_SBO = BF16 ? 1024u : 512u;
   constexpr uint32_t MN_LAYOUT = BF16 ? 2u : 1u;
+  // X3: the TMEM accumulator rounds toward zero on every MMA (measured, tools/acc_rounding_probe.py: the relative error of
+  // an all-positive dot product grows linearly, -3e-5 at K = 4096), which would break the 1e-5 contract of the exact mode
+  // for long reductions.  The reduction is therefore cut into chunks of ACC_CHUNK k-iterations (256 elements): the MMA warp
+  // hands each chunk's accumulator to the epilogue warps, which add it to a register accumulator with round-to-nearest
+  // while the next chunk runs in the other TMEM stage.
+  constexpr int ACC_CHUNK = X3 ? 8 : 0x3fffffff;
+  static_assert(!X3 || BN <= 128, "X3 keeps BN fp32 accumulators per epilogue thread in registers");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -166,9 +173,15 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
           for (int c = 0; c < 128 / E::KC; ++c)
             tma_load_im2col_4d<CTA2>(tmA, fb, sa + c * CHUNK_BYTES, m0 + c * E::KC, wqx * p.conv_stride - p.pad,
                                      wpy * p.conv_stride - p.pad, wb, (uint16_t)(wkk * p.dil), (uint16_t)(wj * p.dil));
+          if (p.b_im2col) {
 #pragma unroll
-          for (int c = 0; c < S::BN_CTA / E::KC; ++c)
-            tma_load_2d<CTA2>(tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, k0);
+            for (int c = 0; c < S::BN_CTA / E::KC; ++c)
+              tma_load_im2col_4d<CTA2>(tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, wqx + p.b_pad, wpy + p.b_pad, wb, (uint16_t)0, (uint16_t)0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < S::BN_CTA / E::KC; ++c)
+              tma_load_2d<CTA2>(tmB, fb, sb + c * CHUNK_BYTES, n0 + c * E::KC, k0);
+          }
         } else {
           const int kidx = k_begin + i;
           if (A_MN) {
@@ -208,10 +221,13 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
     for (int t = group; t < total_tiles && ok; t += n_groups) {
       const int z = (t / p.m_tiles) / p.n_tiles;
       const int iters = tile_k_iters(z);
-      if (!__all_sync(0xffffffffu, mbar_wait(tempty_bar(acc), acc_phase ^ 1))) { atomicExch(p.status, 2); break; }
+      int i = 0;
+      do {  // one pass per accumulator hand-off: the whole reduction, or ACC_CHUNK k-iterations of it in X3 mode
+      if (!__all_sync(0xffffffffu, mbar_wait(tempty_bar(acc), acc_phase ^ 1))) { atomicExch(p.status, 2); ok = false; break; }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int i = 0; i < iters; ++i) {
+      const int i0 = i, i_end = (iters - i0 > ACC_CHUNK) ? i0 + ACC_CHUNK : iters;
+      for (; i < i_end; ++i) {
         if (!__all_sync(0xffffffffu, mbar_wait(full_bar(stage), phase))) { atomicExch(p.status, 3); ok = false; break; }
         tc_fence_after();
         if (elect_one_sync()) {
@@ -227,13 +243,14 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
             return B_MN ? make_smem_desc(b0 + s * (E::UMMA_K * 128), CHUNK_BYTES, MN_SBO, MN_LAYOUT) : make_smem_desc(b0 + s * 32, 16, 1024);
           };
           const uint64_t da = desc_a(sa), db = desc_b(sb);
+          const uint32_t accumulate = (uint32_t)(((i - i0) | s) != 0);
           if (X3) {  // small terms first: lo*hi, hi*lo, then hi*hi
             const uint64_t da2 = desc_a(sa + S::PLANE_BYTES), db2 = desc_b(sb + S::PLANE_BYTES);
-            umma<BF16, CTA2>(d_tmem, da2, db, IDESC, (uint32_t)((i | s) != 0));
+            umma<BF16, CTA2>(d_tmem, da2, db, IDESC, accumulate);
             umma<BF16, CTA2>(d_tmem, da, db2, IDESC, 1u);
             umma<BF16, CTA2>(d_tmem, da, db, IDESC, 1u);
           } else {
-            umma<BF16, CTA2>(d_tmem, da, db, IDESC, (uint32_t)((i | s) != 0));
+            umma<BF16, CTA2>(d_tmem, da, db, IDESC, accumulate);
           }
         }
         umma_commit<CTA2>(empty_bar(stage));  // frees the smem stage (in both CTAs) once these MMAs have read it
@@ -241,9 +258,11 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (!ok) break;
       if (elect_one_sync()) umma_commit<CTA2>(tfull_bar(acc));  // accumulator complete -> epilogue warps of both CTAs
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      } while (i < iters);
     }
   } else if (warp >= 4) {
     // =========================== epilogue (every CTA: its own 128 TMEM lanes) ===========================
@@ -287,7 +306,7 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
       }
       const bool m_ok = m < p.M;
       const float lane_bias = (p.bias_mode == BIAS_LANE && m_ok) ? __ldg(p.bias + m) : 0.f;
-      bool ok = mbar_wait(tfull_bar(acc), acc_phase);
+      bool ok = X3 ? true : mbar_wait(tfull_bar(acc), acc_phase);
       if (!ok) { atomicExch(p.status, 4); break; }
       tc_fence_after();
       // Column n of this lane lives col_stride floats after column n-1: a running pointer, one 128-byte store per warp
@@ -301,7 +320,7 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
       static_assert(NCH % 2 == 0, "chunk pairs");
       const bool col_bias = p.bias_mode == BIAS_COL;
       uint32_t va[32], vb[32];
-      if (iters > 0) tmem_ld_32x32(tbase, va);
+      if (!X3 && iters > 0) tmem_ld_32x32(tbase, va);
       auto release_acc = [&]() {
         tc_fence_before();
         __syncwarp();
@@ -399,6 +418,46 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
           }
         }
       };
+      if constexpr (X3) {
+        // chunked reduction: add each hand-off's accumulator (TMEM, truncating) into registers (round to nearest)
+        constexpr int XN = X3 ? NCH : 1;
+        float r[XN][32];
+#pragma unroll
+        for (int c = 0; c < XN; ++c)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[c][j] = 0.f;
+        const int handoffs = iters > 0 ? (iters + ACC_CHUNK - 1) / ACC_CHUNK : 1;
+        bool alive = true;
+        for (int hnd = 0; hnd < handoffs; ++hnd) {
+          if (!mbar_wait(tfull_bar(acc), acc_phase)) { atomicExch(p.status, 4); alive = false; break; }
+          tc_fence_after();
+          const uint32_t tb = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+          if (iters > 0) {
+            tmem_ld_32x32(tb, va);
+#pragma unroll
+            for (int c = 0; c < XN; c += 2) {
+              tmem_ld_wait();
+              tmem_ld_32x32(tb + (uint32_t)((c + 1) * 32), vb);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[c][j] += __uint_as_float(va[j]);
+              tmem_ld_wait();
+              if (c + 2 < XN) tmem_ld_32x32(tb + (uint32_t)((c + 2) * 32), va);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[c + 1][j] += __uint_as_float(vb[j]);
+            }
+          }
+          release_acc();
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (!alive) break;
+#pragma unroll
+        for (int c = 0; c < XN; ++c) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) va[j] = __float_as_uint(r[c][j]);
+          store_chunk(va, c);
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < NCH; c += 2) {
         if (iters > 0) {

@@ -44,6 +44,8 @@ struct alignas(64) TcParams {
   int Wo, Ho;                      // width (and, WGRAD, height) of the lane / reduction pixel grid
   int trav, lower_w, lower_h;      // traversal stride and lower corner of the im2col bounding box
   int conv_stride, pad, dil, Kw;   // WGRAD: conv geometry for the tap of this tile
+  int b_im2col, b_pad;             // WGRAD: operand B (dy) is a zero-padded channels-last tensor read through an im2col map
+                                   // whose bounding box is the un-padded interior (base pixel = output pixel + b_pad)
   int taps, cchunks, wk_cols;      // wk_cols: weight-matrix columns per tap (padded C)
   unsigned short tap_w[64], tap_h[64];  // CONV: im2col offsets of tap t (fprop: kk*dil, j*dil; dgrad: class offsets)
 };

@@ -21,6 +21,7 @@ from .functions import Function, FunctionCache, PseudoCache
 __all__ = ["conv2d", "Conv2DFn"]
 
 _MODE_PACKED = 100  # cache tag: bf16 layer that ran on the packed-K path (x_cl holds the patch matrix)
+_MODE_STRIP = 101   # cache tag: bf16 layer that ran on the strip path (x_cl holds the zero-padded channels-last copy)
 
 
 def _desc(x_shape, f_shape, padding: int, stride: int, dilation: int) -> _lib.ConvDesc:
@@ -76,6 +77,22 @@ class Conv2DFn(Function):
             else:
                 _lib.check(L.cpt_conv2d_fprop_packed(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, ws, wsb, st))
             mode = _MODE_PACKED
+        elif L.cpt_conv2d_strip_supported(ctypes.byref(d), mode) and not _has_dense_shadow(x, mode):
+            # stride-1 same-padded small-channel layer: zero-padded channels-last operand, one strip per 128 outputs
+            shadow = getattr(x.data, "cl", None)
+            if shadow is not None and shadow[0] == (_MODE_STRIP, d.pad):
+                x_cl = shadow[1]  # the producer already wrote the padded operand
+            else:
+                x_cl = DeviceArray.empty((L.cpt_channels_last_padded_bytes(d.B, d.Ci, d.H, d.W, d.pad),), np.uint8)
+                _lib.check(L.cpt_to_channels_last_padded(f32ptr(x), x_cl.ptr, d.B, d.Ci, d.H, d.W, d.pad, None, None, 0, st))
+            ws, wsb = workspace(L.cpt_conv2d_strip_workspace_size(_lib.OP_FPROP, ctypes.byref(d)))
+            stats = None
+            if emit_stats:
+                stats = DeviceArray.empty((L.cpt_conv2d_stats_bytes(ctypes.byref(d)),), np.uint8)
+                y.stats = (stats, L.cpt_conv2d_stats_slots(), b)
+            _lib.check(L.cpt_conv2d_fprop_strip(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr,
+                                                stats.ptr if stats is not None else None, ws, wsb, st))
+            mode = _MODE_STRIP
         else:
             shadow = getattr(x.data, "cl", None)
             if shadow is not None and shadow[0] == mode:
@@ -117,6 +134,13 @@ class Conv2DFn(Function):
             ws, wsb = workspace(L.cpt_conv2d_packed_workspace_size(_lib.OP_WGRAD, dref))
             _lib.check(L.cpt_conv2d_wgrad_packed(dref, x_cl.ptr, dy_cl.ptr, df.ptr, ws, wsb, st))
             return Tensor(dx), Tensor(df), (Tensor(db) if db is not None else None)
+        if mode == _MODE_STRIP:
+            dy_pad = _staged_dy_padded(L, dy, d, db, st)
+            ws, wsb = workspace(L.cpt_conv2d_strip_workspace_size(_lib.OP_DGRAD, dref))
+            _lib.check(L.cpt_conv2d_dgrad_strip(dref, dy_pad.ptr, f32ptr(f), dx.ptr, ws, wsb, st))
+            ws, wsb = workspace(L.cpt_conv2d_strip_workspace_size(_lib.OP_WGRAD, dref))
+            _lib.check(L.cpt_conv2d_wgrad_padded(dref, x_cl.ptr, dy_pad.ptr, df.ptr, ws, wsb, st))
+            return Tensor(dx), Tensor(df), (Tensor(db) if db is not None else None)
         tc_dgrad = mode != _lib.MODE_FP32 and bool(L.cpt_conv2d_dgrad_cl_supported(dref, mode))
         if mode == _lib.MODE_FP32:
             ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_DGRAD, dref, mode))
@@ -153,6 +177,30 @@ def _staged_dy(L, dy: Tensor, d, ho: int, wo: int, mode: int, db: Optional[Devic
     ws, wsb = workspace(L.cpt_to_channels_last_workspace_size(d.B, d.Co, ho, wo))
     _lib.check(L.cpt_to_channels_last(f32ptr(dy), dy_cl.ptr, d.B, d.Co, ho, wo, mode, db.ptr if db is not None else None, ws, wsb, st))
     return dy_cl
+
+
+def _has_dense_shadow(x: Tensor, mode: int) -> bool:
+    """The producer already wrote the dense channels-last operand of the im2col path: using it beats re-staging x padded."""
+    shadow = getattr(x.data, "cl", None)
+    return shadow is not None and shadow[0] == mode
+
+
+def _staged_dy_padded(L, dy: Tensor, d, db: Optional[DeviceArray], st) -> DeviceArray:
+    """Zero-padded channels-last copy of dy for the strip path (+ db fused into the staging pass)."""
+    shadow = getattr(dy.data, "cl", None)
+    if shadow is not None and shadow[0] == (_MODE_STRIP, d.pad):
+        if db is not None:
+            if shadow[2] is not None:
+                db.copy_from(shadow[2])
+            else:
+                ws, wsb = workspace(d.Co * 64 * 4)
+                _lib.check(L.cpt_channel_sum(f32ptr(dy), db.ptr, d.B, d.Co, d.H * d.W, ws, wsb, st))
+        return shadow[1]
+    dy_pad = DeviceArray.empty((L.cpt_channels_last_padded_bytes(d.B, d.Co, d.H, d.W, d.pad),), np.uint8)
+    ws, wsb = workspace(L.cpt_to_channels_last_workspace_size(d.B, d.Co, d.H, d.W))
+    _lib.check(L.cpt_to_channels_last_padded(f32ptr(dy), dy_pad.ptr, d.B, d.Co, d.H, d.W, d.pad, db.ptr if db is not None else None,
+                                             ws, wsb, st))
+    return dy_pad
 
 
 def conv2d(x: Tensor, f: Tensor, b: Optional[Tensor] = None, padding: int = 0, stride: int = 1,

@@ -46,6 +46,13 @@ def notify_grad_written(parameter: Parameter, first: bool) -> None:
         opt._on_grad_ready(owner[1], first)
 
 
+def slot_owner(parameter: Parameter):
+    """The optimizer whose gradient arena holds ``parameter``'s slot, or None."""
+    slot = getattr(parameter, "grad_slot", None)
+    owner = _SLOT_OWNERS.get(slot.ptr) if slot is not None else None
+    return owner[0]() if owner is not None else None
+
+
 def plan_grad_buckets(offsets: list[int], sizes: list[int], bucket_elems: int) -> list[tuple[int, int, list[int]]]:
     """Contiguous buckets over the gradient arena for the overlapped data-parallel exchange.  Backward produces gradients
     from the LAST parameter to the first, so buckets are cut walking the arena from its end: returns
@@ -87,6 +94,7 @@ class Optimizer:
         self._bucket_work: list[Any] = []
         self._bucket_launched: list[bool] = []
         self._live = None           # device float[8]: per-step scalars read by the update kernel in CUDA-graph replays
+        self._synced = False        # sync_grads() already exchanged (and averaged) this step's gradients
         if parameters is not None:
             self.set_parameters(parameters)
 
@@ -104,7 +112,7 @@ class Optimizer:
         self._build_arena()
 
     def get_state_dict(self) -> dict[str, dict[Any, Any]]:
-        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel", "_live", "overlap_grad_sync",
+        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel", "_live", "_synced", "overlap_grad_sync",
                 "bucket_bytes", "reserve_sms", "_buckets", "_bucket_pending", "_bucket_work", "_bucket_launched", "_offsets", "_bucket_of"}
         return {"state": self._state, "vars": {k: v for k, v in vars(self).items() if k not in skip}}
 
@@ -119,11 +127,24 @@ class Optimizer:
         for p in self._parameters:
             p.grad = None
         self._reset_buckets()
+        self._synced = False
+
+    def sync_grads(self) -> None:
+        """Data-parallel runs: completes the gradient exchange NOW and leaves the world-MEAN gradient in every ``p.grad``
+        (``step()`` then skips the exchange).  Anything that reads or rescales gradients before ``step()`` — gradient
+        clipping, logging of gradient norms — must see the averaged global gradient, not this rank's shard gradient:
+        ``clip_grad_norm`` calls this itself.  No-op on one rank."""
+        if self._dp_world() == 1 or self._synced or self._arena is None:
+            return
+        scale = self._sync_grads()
+        self._arena *= float(scale)
+        self._synced = True
 
     def step(self) -> None:
         """Updates the parameters (one fused launch).  Inside a CUDA-graph capture the per-step scalars are read from device
         memory and ``t`` is advanced by ``upload_live_scalars`` at replay time instead."""
-        scale = self._sync_grads()
+        scale = 1.0 if self._synced else self._sync_grads()
+        self._synced = False
         if graph.is_capturing():
             self._launch(self._peek_scalars(), self._live_buffer().ptr, scale)
             return
@@ -170,6 +191,8 @@ class Optimizer:
             total += (p.size + 63) // 64 * 64
         self._arena = DeviceArray.zeros((total,), np.float32)
         self._offsets = offs
+        for ptr in [k for k, (ref, _) in _SLOT_OWNERS.items() if ref() is None or ref() is self]:
+            del _SLOT_OWNERS[ptr]  # slots of collected optimizers / of this optimizer's previous arena
         flat = self._arena._buf
         for i, (p, o) in enumerate(zip(cuda_params, offs)):
             p.grad_slot = DeviceArray(flat[o:o + p.size], p.shape, np.float32)

@@ -18,6 +18,14 @@ class Parameter(Tensor):
         super().__init__(data.data)
         self.grad_slot = None  # DeviceArray view into a flat gradient arena (data-parallel mode), else None
 
+    def __getstate__(self):
+        """Checkpoints (``cp.save(model.get_state_dict())``, utils.py:44-73) carry the value only: the gradient and its arena
+        slot belong to the running optimizer (a pickled slot would be a detached host copy of the whole gradient)."""
+        state = dict(self.__dict__)
+        state["grad_slot"] = None
+        state["grad"] = None
+        return state
+
 
 class Buffer(Tensor):
     """Non-trainable state (running statistics)."""

@@ -344,6 +344,11 @@ def workspace(nbytes: int) -> tuple[int, int]:
     return _ws.ptr, _ws.nbytes
 
 
+def current_workspace() -> Optional[DeviceArray]:
+    """The scratch buffer in use right now (a CUDA graph captured against it keeps this reference, see graph.CapturedStep)."""
+    return _ws
+
+
 def _device_of(data: Any) -> Device:
     return cuda if isinstance(data, DeviceArray) else cpu
 

@@ -102,6 +102,31 @@ int cpt_conv2d_dgrad_cl_supported(const cpt_conv2d_desc* d, int mode);
 int cpt_conv2d_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* dy_cl, float* dw,
                         int mode, void* ws, size_t ws_bytes, void* stream);
 
+/* Strip ("shared halo") path for stride-1, dilation-1, same-padded odd-K layers with Ci, Co multiples of 64 and <= 128
+ * (larger layers are tensor-pipe bound on the im2col path), bf16 mode.  Replaces the same reference computation as the
+ * *_cl entry points (convolution_funcs.py:222-241 forward, :390-403 dX, :405-408 dW); what changes is the operand layout:
+ * activations are staged ZERO-PADDED channels-last, act_pad[B][H+2P][W+2P][C] bf16, so that the K*K filter taps of 128
+ * consecutive output positions read ONE strip of input rows from shared memory (each activation crosses L2->SM once
+ * instead of once per tap) and the filter tiles stay resident in shared memory.
+ *   cpt_conv2d_strip_supported       1 when the geometry / mode is covered
+ *   cpt_channels_last_padded_bytes   bytes of act_pad
+ *   cpt_to_channels_last_padded      x (NCHW fp32) -> act_pad (+ optional per-channel sums = db when staging dy)
+ *   cpt_conv2d_fprop_strip           y = conv(x_pad, w) + bias; stats != NULL: also the batch-statistics partials of
+ *                                    cpt_conv2d_fprop_cl_stats
+ *   cpt_conv2d_dgrad_strip           dx from dy_pad (the forward strip with reversed taps)
+ *   cpt_conv2d_wgrad_padded          dw from x_pad and dy_pad (im2col maps over the padded tensors; split-K, fixed order) */
+int cpt_conv2d_strip_supported(const cpt_conv2d_desc* d, int mode);
+size_t cpt_channels_last_padded_bytes(int B, int C, int H, int W, int pad);
+int cpt_to_channels_last_padded(const float* src, void* dst, int B, int C, int H, int W, int pad, float* chan_sum, void* ws,
+                                size_t ws_bytes, void* stream);
+size_t cpt_conv2d_strip_workspace_size(int op, const cpt_conv2d_desc* d);
+int cpt_conv2d_fprop_strip(const cpt_conv2d_desc* d, const void* x_pad, const float* w, const float* bias, float* y, float* stats,
+                           void* ws, size_t ws_bytes, void* stream);
+int cpt_conv2d_dgrad_strip(const cpt_conv2d_desc* d, const void* dy_pad, const float* w, float* dx, void* ws, size_t ws_bytes,
+                           void* stream);
+int cpt_conv2d_wgrad_padded(const cpt_conv2d_desc* d, const void* x_pad, const void* dy_pad, float* dw, void* ws, size_t ws_bytes,
+                            void* stream);
+
 /* Packed-K path for first layers (Ci <= 16: ResNet stem 3->64 7x7/s2, VGG / MNIST conv1), bf16 mode.  The reference
  * evaluates these layers like any other (window view + einsum, convolution_funcs.py:357-408); the im2col-TMA path would
  * spend one 64-channel k-iteration per tap on 1-3 real channels.  Here the patches are written once as an explicit bf16

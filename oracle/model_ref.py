@@ -13,7 +13,32 @@ import numpy as np
 from . import compyute_ref as R
 
 
+def round_operand(a: np.ndarray, how: str) -> np.ndarray:
+    """Operand rounding of the tensor-core compute modes, emulated on fp32 bits: "bf16" = round to nearest even to 8
+    significand bits (cvt.rn.bf16), "tf32_rna" = round to nearest, ties away, to 11 bits (cvt.rna.tf32, the staging kernels of
+    the convolutions), "tf32_trunc" = the low 13 bits ignored (what tcgen05 kind::tf32 does with raw fp32 bits: Linear layers)."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    if how == "bf16":
+        u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    elif how == "tf32_rna":
+        u = (u + 0x1000) & 0xFFFFE000
+    elif how == "tf32_trunc":
+        u = u & 0xFFFFE000
+    else:
+        raise ValueError(how)
+    return u.astype(np.uint32).view(np.float32).reshape(a.shape)
+
+
+_ROUNDING = {None: (None, None), "bf16": ("bf16", "bf16"), "tf32": ("tf32_rna", "tf32_trunc")}  # mode -> (conv, linear)
+
+
 class _Layer:
+    rounding = None  # compute mode whose operand rounding the contractions emulate (None = the reference's fp32)
+
+    def _rnd(self, a):
+        how = _ROUNDING[self.rounding][0 if self.kind == "conv" else 1]
+        return a if how is None else round_operand(a, how)
+
     def __init__(self, spec, rng_params):
         self.spec = spec
         self.kind = spec[0]
@@ -38,10 +63,10 @@ class _Layer:
 
     def forward(self, x, training):
         k, s, c = self.kind, self.spec, self.cache
-        if k == "conv":
-            return R.conv2d_forward(c, x, self.params[0], self.params[1] if s[6] else None, s[4], s[5], 1)
+        if k == "conv":  # the cache keeps the (rounded) operands: backward contracts those, like the device path
+            return R.conv2d_forward(c, self._rnd(x), self._rnd(self.params[0]), self.params[1] if s[6] else None, s[4], s[5], 1)
         if k == "linear":
-            return R.linear_forward(c, x, self.params[0], self.params[1] if s[3] else None)
+            return R.linear_forward(c, self._rnd(x), self._rnd(self.params[0]), self.params[1] if s[3] else None)
         if k in ("bn2d", "bn1d"):
             y, rm, rv = R.batchnorm_forward(c, x, self.buffers[0], self.buffers[1], self.params[0], self.params[1], 0.1, 1e-5, training)
             self.buffers = [rm, rv]
@@ -71,11 +96,15 @@ class _Layer:
     def backward(self, dy):
         k, s, c = self.kind, self.spec, self.cache
         if k == "conv":
-            dx, dw, db = R.conv2d_backward(c, dy)
+            dx, dw, db = R.conv2d_backward(c, self._rnd(dy))
+            if self.rounding and s[6]:
+                db = dy.sum((0, 2, 3))  # the bias gradient is an fp32 reduction of the unrounded dy in every mode
             self.grads = [dw] + ([db] if s[6] else [])
             return dx
         if k == "linear":
-            dx, dw, db = R.linear_backward(c, dy)
+            dx, dw, db = R.linear_backward(c, self._rnd(dy))
+            if self.rounding and s[3]:
+                db = dy.reshape(-1, dy.shape[-1]).sum(0)
             self.grads = [dw] + ([db] if s[3] else [])
             return dx
         if k in ("bn2d", "bn1d"):
@@ -107,8 +136,13 @@ class _Layer:
 class RefModel:
     """Sequential model over a spec.  ``params`` / ``buffers``: flat lists in get_parameters() / get_buffers() order."""
 
-    def __init__(self, spec, params, buffers):
+    def __init__(self, spec, params, buffers, operand_rounding=None):
+        """``operand_rounding`` = "bf16" / "tf32": Conv2D / Linear round their operands (x, w, dy) like the device's tensor-core
+        modes before contracting in fp32 — the oracle for model-level parity in those modes (decisions such as ReLU masks and
+        max-pool winners then agree, so the comparison is tight); None = the reference's fp32 arithmetic."""
         self.layers = [_Layer(s, None) for s in spec]
+        for l in self.leaves():
+            l.rounding = operand_rounding
         pi, bi = iter(params), iter(buffers)
         for l in self.leaves():
             s = l.spec

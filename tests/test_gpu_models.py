@@ -70,16 +70,35 @@ def test_config_train_steps(name):
 
 # Tensor-core modes against the ORACLE (not against the repo's own fp32 run).  Widths are chosen so that the layers run on the
 # kernels the benchmarks use (im2col tcgen05 path for Ci >= 32, packed-K path for the first layer, fused Linear+ReLU
-# epilogues for the MLP).  Tolerances (stated per mode): the first loss, relative; every parameter gradient of the first
-# backward pass as ||g - g_ref||_2 / ||g_ref||_2 (gradients that are analytically zero — a conv bias feeding a BatchNorm —
-# are skipped: both sides hold rounding noise); the loss trace of 3 SGD-momentum steps.
+# epilogues for the MLP).  Two oracles, two stated tolerances per mode:
+#   (A) the oracle with the mode's OPERAND ROUNDING emulated (RefModel(operand_rounding=mode): x, w, dy rounded to bf16 /
+#       tf32 before each fp32 contraction).  Discrete decisions (ReLU masks, max-pool winners) then agree with the device, so
+#       this pins everything except the rounding itself: first loss 2e-4 relative, every parameter gradient
+#       ||g - g_ref||_2 / ||g_ref||_2 <= 1e-2, loss trace of 3 SGD-momentum steps 1e-3.
+#   (B) the reference's fp32 arithmetic.  The loss agrees to the mode's operand precision; parameter GRADIENTS differ by
+#       far more than a per-operation bound suggests, because rounding an operand flips the ReLU / max-pool decision of every
+#       pre-activation within ~2^-8 (bf16) / 2^-11 (tf32) relative of a tie, and a flipped unit changes its whole gradient
+#       contribution: a fraction f of flipped units moves the gradient by ~sqrt(f) in relative L2 (measured on B200, round 2:
+#       bf16 0.05-0.44, tf32 0.04-0.14 — PyTorch autocast shows the same).  Stated bound: 0.6 / 0.25, loss 1e-2 / 2e-3.
+# Gradients that are analytically zero (a conv bias feeding a BatchNorm) are skipped: both sides hold rounding noise.
 TC_CASES = {
     "c3_vgg_w32": (W.vgg(width=32, hw=32, hidden=64), (4, 3, 32, 32), 10),
     "c4_resnet18_w32": (W.resnet18(width=32, hw=64, classes=16), (4, 3, 64, 64), 16),
     "c5_mlp_w256": (W.mlp(width=256, depth=8), (64, 256), 256),
 }
 _ORACLE_RUNS = {}
-TC_TOL = {"bf16": dict(loss=2e-2, grad=8e-2, trace=5e-2), "tf32": dict(loss=3e-3, grad=1.5e-2, trace=1e-2)}
+TC_TOL_ROUNDED = dict(loss=2e-4, grad=1e-2, trace=1e-3)
+TC_TOL_FP32 = {"bf16": dict(loss=1e-2, grad=0.6, trace=0.1), "tf32": dict(loss=2e-3, grad=0.25, trace=3e-2)}
+
+
+def _oracle_run(spec, params0, bufs0, x, t, rounding):
+    from oracle import compyute_ref as R
+    gref = RefModel(spec, [p.copy() for p in params0], [b.copy() for b in bufs0], operand_rounding=rounding)
+    lc = []
+    loss0 = float(R.cross_entropy_forward(lc, gref.forward(x, True), t))
+    gref.backward(R.cross_entropy_backward(lc))
+    ref = RefModel(spec, [p.copy() for p in params0], [b.copy() for b in bufs0], operand_rounding=rounding)
+    return gref.gradients(), loss0, ref.train_steps(x, t, 3, lr=0.02, optimizer="sgd", momentum=0.9)
 
 
 @pytest.mark.parametrize("mode", ["bf16", "tf32"])
@@ -89,10 +108,8 @@ def test_config_train_steps_tensor_core_modes_vs_oracle(name, mode):
     import os
 
     import compyute_b200 as cp
-    from compyute_b200 import nn
-    from oracle import compyute_ref as R
+    from compyute_b200 import _lib, nn
     spec, xshape, classes = TC_CASES[name]
-    tol = TC_TOL[mode]
     np.random.seed(11)
     with cp.use_device(cp.cuda):
         model = W.build(spec)
@@ -102,47 +119,46 @@ def test_config_train_steps_tensor_core_modes_vs_oracle(name, mode):
     rng = np.random.RandomState(5)
     x = rng.normal(0, 1, xshape).astype(np.float32)
     t = rng.randint(0, classes, (xshape[0],))
-    if name not in _ORACLE_RUNS:  # the oracle run (seconds per step on the einsum path) is shared by the two modes
-        gref = RefModel(spec, [p.copy() for p in params0], [b.copy() for b in bufs0])
-        lc = []
-        loss_ref0 = R.cross_entropy_forward(lc, gref.forward(x, True), t)
-        gref.backward(R.cross_entropy_backward(lc))
-        ref = RefModel(spec, [p.copy() for p in params0], [b.copy() for b in bufs0])
-        _ORACLE_RUNS[name] = (gref, loss_ref0, ref.train_steps(x, t, 3, lr=0.02, optimizer="sgd", momentum=0.9), params0)
-    gref, loss_ref0, ref_losses, p_first = _ORACLE_RUNS[name]
-    assert all(np.array_equal(a, b) for a, b in zip(p_first, params0))  # same seed -> same initial parameters in both modes
+    for rounding in (mode, None):  # oracle runs cost seconds per step on the einsum path: the fp32 one is shared by the modes
+        if (name, rounding) not in _ORACLE_RUNS:
+            _ORACLE_RUNS[(name, rounding)] = _oracle_run(spec, params0, bufs0, x, t, rounding)
 
     opt = nn.optimizers.SGD(model.get_parameters(), lr=0.02, momentum=0.9)
     loss_fn = nn.CrossEntropyLoss()
     xt, tt = cp.tensor(x, device=cp.cuda), cp.tensor(t.astype(np.int32), device=cp.cuda)
-    losses, gerrs = [], []
+    losses, grads = [], None
     with cp.compute_mode(mode):
         for step in range(3):
             loss = loss_fn(model(xt), tt)
             opt.reset_grads()
             model.backward(loss_fn.backward())
             if step == 0:
-                gmax = max(np.abs(g).max() for g in gref.gradients())
-                for i, (p, g) in enumerate(zip(model.get_parameters(), gref.gradients())):
-                    if np.abs(g).max() <= 1e-5 * gmax:
-                        continue  # analytically zero gradient: noise on both sides
-                    got = p.grad.to_numpy().astype(np.float64)
-                    gerrs.append((i, float(np.linalg.norm(got - g) / np.linalg.norm(g))))
+                grads = [p.grad.to_numpy().astype(np.float64) for p in model.get_parameters()]
             opt.step()
             losses.append(loss.item())
-    from compyute_b200 import _lib
     assert _lib.lib().cpt_tc_check_status() == 0
-    loss_err = abs(losses[0] - float(loss_ref0)) / max(1.0, abs(float(loss_ref0)))
-    trace_err = float(np.max(np.abs(np.array(losses) - np.array(ref_losses)) / np.maximum(1.0, np.abs(ref_losses))))
-    worst = max(gerrs, key=lambda e: e[1])
+    report = {"case": name, "mode": mode}
+    failures = []
+    for tag, rounding, tol in (("rounded_oracle", mode, TC_TOL_ROUNDED), ("fp32_oracle", None, TC_TOL_FP32[mode])):
+        g_ref, loss0, ref_losses = _ORACLE_RUNS[(name, rounding)]
+        gmax = max(np.abs(g).max() for g in g_ref)
+        gerrs = [(i, float(np.linalg.norm(got - g) / np.linalg.norm(g))) for i, (got, g) in enumerate(zip(grads, g_ref))
+                 if np.abs(g).max() > 1e-5 * gmax]
+        loss_err = abs(losses[0] - loss0) / max(1.0, abs(loss0))
+        trace_err = float(np.max(np.abs(np.array(losses) - np.array(ref_losses)) / np.maximum(1.0, np.abs(ref_losses))))
+        worst = max(gerrs, key=lambda e: e[1])
+        report[tag] = {"loss_err": loss_err, "trace_err": trace_err, "worst_grad": worst, "median_grad": float(np.median([e for _, e in gerrs])), "tol": tol}
+        if loss_err > tol["loss"]:
+            failures.append(f"{tag}: first loss {losses[0]} vs {loss0}")
+        if worst[1] > tol["grad"]:
+            failures.append(f"{tag}: parameter {worst[0]} relative L2 gradient error {worst[1]:.3e} > {tol['grad']}")
+        if trace_err > tol["trace"]:
+            failures.append(f"{tag}: loss trace {losses} vs {ref_losses}")
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):  # measured margins, kept next to the run's other artefacts
         with open(os.path.join(out, "model_parity_tc_modes.jsonl"), "a") as f:
-            f.write(json.dumps({"case": name, "mode": mode, "loss_err": loss_err, "trace_err": trace_err, "worst_grad": worst,
-                                "median_grad": float(np.median([e for _, e in gerrs])), "tol": tol}) + "\n")
-    assert loss_err <= tol["loss"], (losses[0], float(loss_ref0))
-    assert worst[1] <= tol["grad"], f"parameter {worst[0]}: relative L2 gradient error {worst[1]:.3e}"
-    assert trace_err <= tol["trace"], (losses, ref_losses)
+            f.write(json.dumps(report) + "\n")
+    assert not failures, failures
 
 
 @pytest.mark.parametrize("mode", ["tf32", "bf16"])
