@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 
 SWEEP = (64, 128, 256, 512)
 BATCH, HW, KS = 256, 56, 3
-TOL = {"fp32": "allclose rtol=atol=1e-5 vs the NumPy reference (db 1e-4)", "fp32x3": "allclose rtol=atol=1e-5 vs the NumPy reference (db 1e-4)",
+TOL = {"fp32": "allclose rtol=atol=1e-5 vs the NumPy reference (db 1e-4)", "fp32_simt": "allclose rtol=atol=1e-5 vs the NumPy reference (db 1e-4)",
        "tf32": "max-abs err <= 2e-3*max|ref|",
        "bf16": "max-abs err <= 1e-2*max|ref|"}
 
@@ -238,7 +238,7 @@ def run_ours(args) -> None:
     sampler = ClockSampler(local)
     results = {}
     with cp.compute_mode(args.mode):
-        L.cpt_conv2d_fprop_cl = fprop_probe if args.mode != "fp32" else orig_fprop
+        L.cpt_conv2d_fprop_cl = fprop_probe if args.mode != "fp32_simt" else orig_fprop
         layers, opt = make_layers(args.mode)
         if rank == 0:
             sampler.start()
@@ -350,7 +350,7 @@ def run_ours(args) -> None:
     # ---- other compute modes (outside the headline timed region; same step, fewer iterations)
     modes = {}
     if rank == 0 and world == 1 and not args.no_extra_modes:
-        for m, (k, w) in {"bf16": (3, 2), "tf32": (3, 2), "fp32x3": (2, 1), "fp32": (1, 1)}.items():
+        for m, (k, w) in {"bf16": (3, 2), "tf32": (3, 2), "fp32": (2, 1), "fp32_simt": (1, 1)}.items():
             if m == args.mode:
                 continue
             with cp.compute_mode(m):
@@ -405,7 +405,7 @@ def run_ours(args) -> None:
     value = world * step_flops / ms / 1e9
     line = {"metric": "conv2d_fwd_bwd_tflops", "value": round(value, 2), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32", "fp32x3": "f32"}[args.mode], "data": "synthetic",
+            "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32", "fp32_simt": "f32"}[args.mode], "data": "synthetic",
             "config": workload_config(args, args.mode), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": {"value": round(cpu_tf, 7), "unit": "TFLOP/s", "cores": 1, "host_cores": os.cpu_count(),
                                                 "kind": "port", "sample": cpu_desc, "seconds": round(cpu_times[0], 2)},
@@ -440,7 +440,7 @@ def parity_check(layer, x_dev, dy_dev, x_t, dy_t, mode: str, samples: int = 96) 
     """One more forward + backward of the C=512 layer in the benchmarked mode; sampled entries of y, dx and dw against
     fp64 dot products.  Errors are relative to the largest magnitude of the tensor (the mode's tolerance convention)."""
     import torch
-    tol = {"bf16": 1e-2, "tf32": 2e-3, "fp32": 1e-5, "fp32x3": 1e-5}[mode]
+    tol = {"bf16": 1e-2, "tf32": 2e-3, "fp32": 1e-5, "fp32_simt": 1e-5}[mode]
     layer.w.grad = None  # first gradient of a step is stored by reference (module.py:392-400), later ones accumulate
     if layer.b is not None:
         layer.b.grad = None
@@ -672,7 +672,7 @@ def model_record(args, cpu: bool = True):
         cpu_note = f"cpu sample failed: {e}"
     line = {"metric": "cnn_train_images_per_s" if args.workload != "mlp" else "mlp_train_samples_per_s", "value": round(ips, 1), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": scaling,
-            "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32", "fp32x3": "f32"}[args.mode], "data": "synthetic",
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32", "fp32_simt": "f32"}[args.mode], "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "compute_mode": args.mode, "cuda_graph": bool(graphed), "tolerance": TOL[args.mode], "parallelism": f"dp{world}",
                        "grad_sync": ("bucketed all-reduce overlapped with backward" if opt.overlap_grad_sync else "one all-reduce at step()") if world > 1 else "n/a",
                        "batchnorm": "synchronised (global-batch statistics)" if distributed.sync_batchnorm_active() else "per-shard statistics",
@@ -713,7 +713,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("COMPYUTE_B200_MODE", "bf16"), choices=["bf16", "tf32", "fp32", "fp32x3"])
+    ap.add_argument("--mode", default=os.environ.get("COMPYUTE_B200_MODE", "bf16"), choices=["bf16", "tf32", "fp32", "fp32_simt"])
     ap.add_argument("--no-extra-modes", action="store_true")
     ap.add_argument("--no-models", action="store_true", help="skip the model sub-records (configs 2-4) of the default line")
     ap.add_argument("--model-steps", type=int, default=5, help="timed steps of each model sub-record")

@@ -1,0 +1,5 @@
+"""compyute/nn/modules/reshapes.py of the reference: in-scope layers from compyute_b200, the rest as raising stubs."""
+
+from compyute_b200.nn import Flatten  # noqa: F401
+
+from .._stubs import *  # noqa: F401,F403

@@ -85,9 +85,14 @@ def use_device(device: Device):
         _default_device = prev
 
 
-# ---- compute mode of the contractions (Conv2D / Linear): "fp32" exact FFMA, "tf32" / "bf16" tcgen05, "fp32x3" = fp32-exact on
-# tcgen05 (operands split into tf32 hi + lo planes, three MMAs per k-step; same 1e-5 contract as "fp32")
-_MODES = {"fp32": _lib.MODE_FP32, "tf32": _lib.MODE_TF32, "bf16": _lib.MODE_BF16, "fp32x3": _lib.MODE_FP32X3}
+# ---- compute mode of the contractions (Conv2D / Linear)
+#   "fp32"      the reference's contract, allclose(rtol=atol=1e-5): fp32-exact on tcgen05 — operands split into tf32 hi + lo
+#               planes, three MMAs per k-step, chunked fp32 accumulation (CPT_MODE_FP32X3); layers outside the TMA limits and
+#               convolutions with < 8 input channels run the FFMA kernels.  ~11x the FFMA path on the Conv2D sweep.
+#   "fp32_simt" every contraction on the exact FFMA kernels (CPT_MODE_FP32): the mode round 1 called "fp32"
+#   "tf32"      tcgen05 kind::tf32, 2e-3;   "bf16"  tcgen05 kind::f16 (bf16 operands, fp32 accumulate), 1e-2
+#   "fp32x3"    alias of "fp32"
+_MODES = {"fp32": _lib.MODE_FP32X3, "fp32x3": _lib.MODE_FP32X3, "fp32_simt": _lib.MODE_FP32, "tf32": _lib.MODE_TF32, "bf16": _lib.MODE_BF16}
 _mode = _MODES[os.environ.get("COMPYUTE_B200_MODE", "fp32")]
 
 

@@ -531,7 +531,10 @@ __global__ void __launch_bounds__(256) random_kernel(float* __restrict__ dst, in
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint64_t z = mix64(seed, (uint64_t)i);
     const float u = (float)(z >> 40) * (1.0f / 16777216.0f);  // [0, 1)
-    if (kind == 0) dst[i] = fminf(lo + (hi - lo) * u, nextafterf(hi, lo));
+    // uniform: drawn in double (53 random bits) and cast, like numpy.random.uniform(...).astype(float32) in the reference
+    // (random.py:118-150): every float32 of the interval can occur, so exact duplicates — ties in a max-pooling window, where
+    // the reference and torch disagree by design — are as rare as on the NumPy path (a 24-bit draw repeats values ~60x more often)
+    if (kind == 0) dst[i] = fminf((float)((double)lo + ((double)hi - (double)lo) * ((double)(z >> 11) * (1.0 / 9007199254740992.0))), nextafterf(hi, lo));
     else if (kind == 2) dst[i] = fminf(floorf(lo + (hi - lo) * u), hi - 1.f);
     else {
       const float u2 = (float)((z >> 16) & 0xffffff) * (1.0f / 16777216.0f);

@@ -57,8 +57,10 @@ class Conv2DFn(Function):
         mode = get_compute_mode()
         if mode != _lib.MODE_FP32 and (d.K * d.K > 64 or (d.K - 1) * d.dil > 255 or d.pad > 127 or d.stride > 8):
             mode = _lib.MODE_FP32  # outside the TMA im2col limits (8-bit corners, 64 taps): exact path for this layer
-        if mode == _lib.MODE_FP32X3 and d.Ci < 8:
-            mode = _lib.MODE_FP32  # a tap's k-slice is 32 channels wide: with < 8 real channels the FFMA kernel is the faster exact path
+        if mode == _lib.MODE_FP32X3:
+            emit_stats = False  # the exact mode keeps BatchNorm's own two-pass statistics (the epilogue sums are E[a^2] - E[a]^2)
+            if d.Ci < 8:
+                mode = _lib.MODE_FP32  # a tap's k-slice is 32 channels wide: with < 8 real channels the FFMA kernel is the faster exact path
         y = DeviceArray.empty((d.B, d.Co, ho, wo), np.float32)
         st = stream_ptr()
         x_cl = None

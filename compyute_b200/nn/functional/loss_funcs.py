@@ -16,7 +16,8 @@ def _targets_i32(targets: Tensor) -> DeviceArray:
     if targets.data.dtype == np.int32:
         return targets.data
     if targets.data.dtype == np.int64:  # labels arrive as int64 like in the reference; the kernels index with int32
-        return DeviceArray.from_numpy(targets.data.numpy().astype(np.int32))
+        from ... import device_ops as D
+        return D.astype(targets.data, np.int32)  # cast kernel on the device: no host round trip
     raise ValueError(f"Input must be an integer, got '{targets.data.dtype}'.")
 
 
@@ -27,25 +28,30 @@ class CrossEntropyLossFn(Function):
     @staticmethod
     def forward(cache: FunctionCache, logits: Tensor, targets: Tensor, eta: float) -> Tensor:
         require_cuda(logits)
-        if logits.ndim != 2:
-            raise ShapeError(f"Expected logits to be 2D (batch, classes), got {logits.ndim}D.")
-        B, NC = logits.shape
+        if logits.ndim < 2:
+            raise ShapeError(f"Expected logits to be at least 2D (..., classes), got {logits.ndim}D.")
+        # (..., classes): softmax over the last dim, mean over all leading dims (loss_funcs.py:57-64) == the 2-D case on
+        # the flattened rows; backward divides by the number of rows, math.prod(shape[:-1]) (:67-69)
+        NC = logits.shape[-1]
+        B = logits.size // NC
         t32 = _targets_i32(targets)
+        if t32.size != B:
+            raise ShapeError(f"Expected {B} targets for logits of shape {logits.shape}, got {targets.shape}.")
         probs = DeviceArray.empty((B, NC), np.float32)
         loss = DeviceArray.empty((1,), np.float32)
         rows = DeviceArray.empty((B,), np.float32)
         _lib.check(_lib.lib().cpt_softmax_ce_fwd(f32ptr(logits), t32.ptr, probs.ptr, loss.ptr, rows.ptr, B, NC, float(eta),
                                                  stream_ptr()))
-        cache.push(t32, probs)
+        cache.push(t32, probs, logits.shape)
         return Tensor(loss.reshape(()))
 
     @staticmethod
     def backward(cache: FunctionCache) -> Tensor:
-        t32, probs = cache.pop()
+        t32, probs, shape = cache.pop()
         B, NC = probs.shape
         d = DeviceArray.empty((B, NC), np.float32)
         _lib.check(_lib.lib().cpt_softmax_ce_bwd(probs.ptr, t32.ptr, d.ptr, B, NC, stream_ptr()))
-        return Tensor(d)
+        return Tensor(d.reshape(shape))
 
 
 def cross_entropy_loss(logits: Tensor, targets: Tensor, eta: float = 1e-8) -> Tensor:
@@ -55,7 +61,8 @@ def cross_entropy_loss(logits: Tensor, targets: Tensor, eta: float = 1e-8) -> Te
 def accuracy_score(logits: Tensor, targets: Tensor) -> float:
     """mean(argmax(logits, -1) == targets) (metric_funcs.py:10-25)."""
     require_cuda(logits)
-    B, NC = logits.shape
+    NC = logits.shape[-1]
+    B = logits.size // NC
     t32 = _targets_i32(targets)
     cnt = DeviceArray.empty((1,), np.int32)
     _lib.check(_lib.lib().cpt_accuracy_count(f32ptr(logits), t32.ptr, cnt.ptr, B, NC, stream_ptr()))

@@ -6,6 +6,7 @@ statistically equivalent to, not stream-identical with, NumPy's generator.  ``cp
 
 from __future__ import annotations
 
+from contextlib import contextmanager
 from typing import Optional
 
 import numpy as np
@@ -14,7 +15,7 @@ from . import device_ops as D
 from .backend import Device, select_device
 from .tensors import DeviceArray, Tensor
 
-__all__ = ["set_seed", "random", "normal", "uniform", "uniform_int", "permutation", "bernoulli", "shuffle"]
+__all__ = ["set_seed", "seed", "random", "normal", "uniform", "uniform_int", "permutation", "bernoulli", "shuffle"]
 
 
 def _shape(shape):
@@ -25,6 +26,16 @@ def set_seed(value: Optional[int] = None) -> None:
     """random.py:25-36: seeds the host (NumPy) and the device generator."""
     np.random.seed(value)
     D.set_seed(value)
+
+
+@contextmanager
+def seed(value: int):
+    """random.py:39-51: ``with seed(42): ...`` / ``@seed(42)`` — seeded inside, reset afterwards."""
+    set_seed(value)
+    try:
+        yield
+    finally:
+        set_seed()
 
 
 def _draw(shape, kind, p0, p1, dtype, device, host):

@@ -86,6 +86,30 @@ class DeviceArray:
         out._buf.copy_(src.reshape(out._buf.shape), non_blocking=False)  # cudaMemcpy H2D
         return out
 
+    @staticmethod
+    def from_cuda_array_interface(obj) -> "DeviceArray":
+        """Adopts foreign device memory WITHOUT a copy: any object exporting ``__cuda_array_interface__`` (a CuPy ndarray — what
+        the reference's ``cuda`` tensors hold, backend.py:169-173 —, a Numba device array, a torch tensor).  The array must be
+        C-contiguous and live on this process's device; the exporting object is kept alive by the returned handle."""
+        torch = _t()
+        if isinstance(obj, DeviceArray):
+            return obj
+        cai = obj.__cuda_array_interface__
+        shape, dtype = tuple(int(s) for s in cai["shape"]), np.dtype(cai["typestr"])
+        strides = cai.get("strides")
+        if strides is not None:
+            expect, acc = [], dtype.itemsize
+            for d in reversed(shape):
+                expect.append(acc); acc *= d
+            if tuple(strides) != tuple(reversed(expect)):
+                raise ShapeError("only C-contiguous device arrays can be adopted (call ascontiguousarray on the producer side)")
+        if dtype.name not in _NP2TORCH:
+            raise TypeError(f"unsupported device array dtype {dtype}")
+        buf = obj if isinstance(obj, torch.Tensor) else torch.as_tensor(obj, device=f"cuda:{cuda.index}")  # zero-copy
+        if buf.data_ptr() != int(cai["data"][0]):
+            raise DeviceError("device array could not be adopted in place (different device?)")
+        return DeviceArray(buf, shape, dtype)
+
     # -- attributes
     @property
     def ptr(self) -> int:
@@ -359,6 +383,8 @@ class Tensor:
     def __init__(self, data: Any) -> None:
         if isinstance(data, Tensor):
             data = data.data
+        if not isinstance(data, (np.ndarray, DeviceArray)) and hasattr(data, "__cuda_array_interface__"):
+            data = DeviceArray.from_cuda_array_interface(data)  # CuPy / Numba / torch device memory, adopted without a copy
         if not isinstance(data, (np.ndarray, DeviceArray)):
             data = np.asarray(data)
         self.data = data
@@ -549,7 +575,14 @@ def _unwrap_key(key: Any) -> Any:
 
 
 def tensor(data: Any, device: Optional[Device] = None, dtype=None) -> Tensor:
-    """``compyute.tensor`` (tensors.py:44-73): host data → Tensor on ``device`` (default: context / cpu)."""
+    """``compyute.tensor`` (tensors.py:44-73): host data → Tensor on ``device`` (default: context / cpu).  Device memory of
+    another library (``__cuda_array_interface__``: CuPy, Numba, torch) becomes a cuda Tensor without a copy."""
+    if not isinstance(data, (np.ndarray, Tensor)) and hasattr(data, "__cuda_array_interface__"):
+        t = Tensor(DeviceArray.from_cuda_array_interface(data))
+        if dtype is not None and np.dtype(dtype) != t.dtype:
+            from . import device_ops as D
+            t = Tensor(D.astype(t.data, dtype))
+        return t
     arr = np.asarray(data, dtype=dtype)
     if arr.dtype == np.float64 and dtype is None:
         arr = arr.astype(np.float32)

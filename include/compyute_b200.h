@@ -489,6 +489,45 @@ uint64_t cpt_launch_count(void);
  * finds an SM to run on; 0 restores the full grid.  Takes effect for subsequent launches. */
 int cpt_tc_reserve_sms(int n);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Data parallelism (the reference is single-device: compyute/backend.py:88-89).  One process per GPU.
+ *
+ * (1) Gradient exchange over NCCL: SUM all-reduce of the flat gradient arena before the update (hook points
+ *     compyute/nn/modules/module.py:392-400, nn/optimizers.py:152,241).  libnccl.so.2 is bound at run time (dlopen).
+ *     Rank 0 calls cpt_nccl_unique_id and ships the 128 bytes to the other ranks (any side channel), every rank calls
+ *     cpt_nccl_init; cpt_nccl_allreduce_sum_f32 is in place and asynchronous on `stream`. */
+int cpt_nccl_unique_id(void* out128);
+int cpt_nccl_init(int rank, int world, const void* unique_id128);
+int cpt_nccl_world_size(void);
+int cpt_nccl_allreduce_sum_f32(float* ptr, int64_t count, void* stream);
+int cpt_nccl_destroy(void);
+
+/* (2) Optimizer step fused with the exchange over NVLink / NVSwitch peer memory (csrc/dp_step.cu): the gradient arena G and
+ *     the parameter arena P are symmetric allocations (same layout on every rank, mapped into every peer and, on NVSwitch,
+ *     into a multicast object).  Rank r owns the shard [shard_off, shard_off + shard_elems) of both arenas; one kernel reads the
+ *     sum of its gradient shard over all ranks (multimem.ld_reduce through the multicast mapping, or `world` peer loads in rank
+ *     order when g_mc == NULL), applies SGD (optimizers.py:152-176) / Adam / AdamW (:241-271, :335-362) to its shard with moment
+ *     buffers that exist for the shard only, and writes the new parameters to every replica (multimem.st / peer stores).
+ *     Ordering across ranks is the caller's: all gradients written before the call, all replicas complete before P is read
+ *     again (a symmetric-memory barrier on `stream` before and after).  pre_reduced != 0: g_local already holds the averaged
+ *     global gradient (an earlier all-reduce, e.g. for gradient clipping); grad_scale is then applied to it as is. */
+typedef struct cpt_dp_view {
+  float* p_local;            /* this rank's parameter arena                                   */
+  float* p_mc;               /* multicast address of the parameter arenas, or NULL            */
+  const uint64_t* p_peers;   /* device array of `world` arena base addresses (used if !p_mc)  */
+  const float* g_local;      /* this rank's gradient arena                                    */
+  const float* g_mc;         /* multicast address of the gradient arenas, or NULL             */
+  const uint64_t* g_peers;   /* device array of `world` arena base addresses (used if !g_mc)  */
+  int64_t shard_off;         /* first element of this rank's shard (multiple of 4)            */
+  int64_t shard_elems;       /* elements in the shard (multiple of 4)                         */
+  int32_t world;
+  int32_t pre_reduced;
+} cpt_dp_view;
+int cpt_dp_adam_step(const cpt_dp_view* view, float* m, float* v, float lr, float beta1, float beta2, float eps, float weight_decay,
+                     float m_div, float v_div, float grad_scale, int decoupled, const float* live_scalars, void* stream);
+int cpt_dp_sgd_step(const cpt_dp_view* view, float* velocity, float lr, float momentum, int nesterov, float weight_decay,
+                    float grad_scale, const float* live_scalars, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,7 +64,7 @@ CONV_EXACT = [  # (B, Ci, Co, H, K, pad, stride, dil)
 ]
 
 
-@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_simt", "tf32", "bf16"])
 @pytest.mark.parametrize("shape", LINEAR_EXACT, ids=lambda s: "x".join(map(str, s)))
 def test_linear_exact_integer(cp, shape, mode):
     from compyute_b200.nn.functional import FunctionCache, LinearFn
@@ -95,7 +95,7 @@ def _torch_conv_ref(x, w, b, dy, P, s, d):
     return f(y), f(xt.grad), f(wt.grad), (f(bt.grad) if bt is not None else None)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_simt", "tf32", "bf16"])
 @pytest.mark.parametrize("shape", CONV_EXACT, ids=lambda s: "x".join(map(str, s)))
 def test_conv2d_exact_integer(cp, shape, mode):
     from compyute_b200.nn.functional import Conv2DFn, FunctionCache
@@ -125,15 +125,15 @@ def test_conv2d_exact_integer(cp, shape, mode):
 
 
 # ------------------------------------------------------------------ BASELINE configs[1] at full size
-@pytest.mark.parametrize("mode", ["bf16", "tf32", "fp32x3", "fp32"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32", "fp32", "fp32_simt"])
 @pytest.mark.parametrize("C", [64, 128, 256, 512])
 def test_conv2d_sweep_full_size_exact(cp, C, mode):
-    """The benchmarked shapes themselves: x = (256, C, 56, 56), 3x3 same.  fp32 mode is limited to C <= 128 (the exact
-    path needs seconds per pass at C = 512 and is covered as the cross-check of the other two modes)."""
+    """The benchmarked shapes themselves: x = (256, C, 56, 56), 3x3 same.  The FFMA mode is limited to C <= 128 (it needs
+    seconds per pass at C = 512) and runs at full size as the whole-tensor cross-check of the bf16 case."""
     import torch
     from compyute_b200.nn.functional import Conv2DFn, FunctionCache
-    if mode == "fp32" and C > 128:
-        pytest.skip("fp32 path at C >= 256 runs as the whole-tensor cross-check of the bf16 case")
+    if mode == "fp32_simt" and C > 128:
+        pytest.skip("the FFMA path at C >= 256 runs as the whole-tensor cross-check of the bf16 case")
     B, H, K = 256, 56, 3
     rng = np.random.RandomState(C)
     x, w, b, dy = ints(rng, (B, C, H, H), -2, 2), ints(rng, (C, C, K, K), -1, 1), ints(rng, (C,), -2, 2), ints(rng, (B, C, H, H), -1, 1)
@@ -162,7 +162,7 @@ def test_conv2d_sweep_full_size_exact(cp, C, mode):
     exact("db", dbh, dy.sum((0, 2, 3), dtype=np.float64).astype(np.float32))
     # (3) whole tensors against the exact FFMA path (itself pinned to the oracle and the goldens in test_gpu_parity.py)
     if mode == "bf16":
-        with cp.compute_mode("fp32"):
+        with cp.compute_mode("fp32_simt"):
             c = FunctionCache()
             y32 = Conv2DFn.forward(c, xt, wt, bt, 1, 1, 1)
             dx32, dw32, db32 = Conv2DFn.backward(c, dyt)
@@ -170,13 +170,15 @@ def test_conv2d_sweep_full_size_exact(cp, C, mode):
         exact("dw vs fp32 path", dwh, dw32.to_numpy()); exact("db vs fp32 path", dbh, db32.to_numpy())
 
 
-@pytest.mark.parametrize("mode,tol", [("bf16", 1e-2), ("tf32", 2e-3), ("fp32x3", 1e-5), ("fp32", 1e-5)])
+@pytest.mark.parametrize("mode,tol", [("bf16", 1e-2), ("tf32", 2e-3), ("fp32", 1e-5), ("fp32_simt", 1e-5)])
 @pytest.mark.parametrize("C", [128, 256, 512])
 def test_conv2d_sweep_real_valued(cp, C, mode, tol):
-    """Same shapes with real-valued data at B = 32 (enough pixels for every tile shape of the full-size run): complete
+    """(fp32_simt: C = 128 only — the FFMA kernels need seconds per pass beyond.)  Same shapes with real-valued data at B = 32 (enough pixels for every tile shape of the full-size run): complete
     planes of two images and sampled dw entries against fp64; tolerance = the mode's stated bound (bench.py TOL)."""
     import torch
     from compyute_b200.nn.functional import Conv2DFn, FunctionCache
+    if mode == "fp32_simt" and C > 128:
+        pytest.skip("FFMA path: covered at C = 128")
     B, H, K = 32, 56, 3
     rng = np.random.RandomState(7 + C)
     x = rng.uniform(-0.1, 0.1, (B, C, H, H)).astype(np.float32)
@@ -197,7 +199,7 @@ def test_conv2d_sweep_real_valued(cp, C, mode, tol):
     yh, dxh, dwh = y.to_numpy(), dx.to_numpy(), dw.to_numpy()
 
     def within(name, got, ref):
-        if mode in ("fp32", "fp32x3"):
+        if mode in ("fp32", "fp32_simt"):
             assert np.allclose(got, ref, rtol=tol, atol=tol), f"{name}: max abs err {np.abs(got - ref).max():.3e}"
         else:
             err = np.abs(got - ref).max() / np.abs(ref).max()
@@ -209,7 +211,7 @@ def test_conv2d_sweep_real_valued(cp, C, mode, tol):
     ref = np.array([np.dot(dy[:, o].reshape(-1).astype(np.float64), np.ascontiguousarray(xp[:, i, j:j + H, k:k + H]).reshape(-1)) for o, i, j, k in idx])
     got = np.array([dwh[t] for t in idx])
     scale = np.abs(dwh).max()
-    if mode in ("fp32", "fp32x3"):
+    if mode in ("fp32", "fp32_simt"):
         assert np.allclose(got, ref, rtol=2e-5, atol=2e-5 * scale), np.abs(got - ref).max()
     else:
         assert np.abs(got - ref).max() <= tol * scale

@@ -70,16 +70,21 @@ def test_config_train_steps(name):
 
 # Tensor-core modes against the ORACLE (not against the repo's own fp32 run).  Widths are chosen so that the layers run on the
 # kernels the benchmarks use (im2col tcgen05 path for Ci >= 32, packed-K path for the first layer, fused Linear+ReLU
-# epilogues for the MLP).  Two oracles, two stated tolerances per mode:
-#   (A) the oracle with the mode's OPERAND ROUNDING emulated (RefModel(operand_rounding=mode): x, w, dy rounded to bf16 /
-#       tf32 before each fp32 contraction).  Discrete decisions (ReLU masks, max-pool winners) then agree with the device, so
-#       this pins everything except the rounding itself: first loss 2e-4 relative, every parameter gradient
-#       ||g - g_ref||_2 / ||g_ref||_2 <= 1e-2, loss trace of 3 SGD-momentum steps 1e-3.
-#   (B) the reference's fp32 arithmetic.  The loss agrees to the mode's operand precision; parameter GRADIENTS differ by
-#       far more than a per-operation bound suggests, because rounding an operand flips the ReLU / max-pool decision of every
-#       pre-activation within ~2^-8 (bf16) / 2^-11 (tf32) relative of a tie, and a flipped unit changes its whole gradient
-#       contribution: a fraction f of flipped units moves the gradient by ~sqrt(f) in relative L2 (measured on B200, round 2:
-#       bf16 0.05-0.44, tf32 0.04-0.14 — PyTorch autocast shows the same).  Stated bound: 0.6 / 0.25, loss 1e-2 / 2e-3.
+# epilogues for the MLP).  Two oracles, two stated tolerances per case and mode:
+#   (A) "rounded": the oracle with the mode's OPERAND ROUNDING emulated (RefModel(operand_rounding=mode): x, w, dy rounded to
+#       bf16 / tf32 before each fp32 contraction — tools/rounding_probe.py pins the emulation per operation to ~1e-6 on the
+#       device: bf16 = RNE, tf32 convolutions = RNA in the staging kernels, tf32 Linear = the tensor core's truncation).
+#       For the MLP this reproduces the device run to rounding noise (loss bit-equal, gradients ~1e-6).  For the CNNs it
+#       cannot stay that tight, and the bound says by how much: rounding is DISCONTINUOUS.  An activation that differs from
+#       the oracle's by 1e-7 (fp32 summation order) rounds to the neighbouring bf16 value with probability |delta|/ulp; one
+#       such flip moves all 9*C outputs of the next convolution that read it by ulp*|w| ~ 2e-4 of their scale, which makes
+#       more inputs of the following layer flip, and BatchNorm over a batch of 4 (all the einsum oracle affords) divides by
+#       small standard deviations on the way.  tools/model_parity_probe.py shows the layer-by-layer growth (profiles/
+#       r02_model_parity_probe.log): 2e-7 after the first conv/BN/ReLU, 2e-4 after the second conv, 5e-3 at the logits (bf16).
+#   (B) "fp32": the reference's own arithmetic.  The loss agrees to the mode's operand precision; parameter gradients
+#       additionally see every ReLU / max-pool decision within one operand-rounding of a tie flipped (a flipped unit changes
+#       its whole gradient contribution; a fraction f of flipped units moves the gradient by ~sqrt(f) in relative L2).
+# Bounds are the measured values (B200, round 2, gpurun_out/model_parity_tc_modes.jsonl -> profiles/) with >= 2x margin.
 # Gradients that are analytically zero (a conv bias feeding a BatchNorm) are skipped: both sides hold rounding noise.
 TC_CASES = {
     "c3_vgg_w32": (W.vgg(width=32, hw=32, hidden=64), (4, 3, 32, 32), 10),
@@ -87,8 +92,12 @@ TC_CASES = {
     "c5_mlp_w256": (W.mlp(width=256, depth=8), (64, 256), 256),
 }
 _ORACLE_RUNS = {}
-TC_TOL_ROUNDED = dict(loss=2e-4, grad=1e-2, trace=1e-3)
-TC_TOL_FP32 = {"bf16": dict(loss=1e-2, grad=0.6, trace=0.1), "tf32": dict(loss=2e-3, grad=0.25, trace=3e-2)}
+TC_TOL_ROUNDED = {
+    ("c5_mlp_w256", "bf16"): dict(loss=1e-5, grad=5e-3, trace=1e-4), ("c5_mlp_w256", "tf32"): dict(loss=1e-5, grad=2e-2, trace=1e-4),
+    ("c3_vgg_w32", "bf16"): dict(loss=6e-4, grad=0.4, trace=2e-2), ("c3_vgg_w32", "tf32"): dict(loss=1e-4, grad=6e-2, trace=5e-3),
+    ("c4_resnet18_w32", "bf16"): dict(loss=1.5e-3, grad=0.5, trace=5e-2), ("c4_resnet18_w32", "tf32"): dict(loss=6e-4, grad=0.3, trace=6e-2),
+}
+TC_TOL_FP32 = {"bf16": dict(loss=1e-2, grad=0.8, trace=0.1), "tf32": dict(loss=2e-3, grad=0.3, trace=3e-2)}
 
 
 def _oracle_run(spec, params0, bufs0, x, t, rounding):
@@ -139,7 +148,7 @@ def test_config_train_steps_tensor_core_modes_vs_oracle(name, mode):
     assert _lib.lib().cpt_tc_check_status() == 0
     report = {"case": name, "mode": mode}
     failures = []
-    for tag, rounding, tol in (("rounded_oracle", mode, TC_TOL_ROUNDED), ("fp32_oracle", None, TC_TOL_FP32[mode])):
+    for tag, rounding, tol in (("rounded_oracle", mode, TC_TOL_ROUNDED[(name, mode)]), ("fp32_oracle", None, TC_TOL_FP32[mode])):
         g_ref, loss0, ref_losses = _ORACLE_RUNS[(name, rounding)]
         gmax = max(np.abs(g).max() for g in g_ref)
         gerrs = [(i, float(np.linalg.norm(got - g) / np.linalg.norm(g))) for i, (got, g) in enumerate(zip(grads, g_ref))

@@ -13,8 +13,8 @@ from tests.conftest import load_golden, manifest
 
 pytestmark = pytest.mark.gpu
 M = manifest()
-TOL = {"fp32": None, "fp32x3": None, "tf32": 2e-3, "bf16": 1e-2}
-EXACT_MODES = ("fp32", "fp32x3")  # both promise the reference's own allclose(1e-5)
+TOL = {"fp32": None, "fp32_simt": None, "tf32": 2e-3, "bf16": 1e-2}
+EXACT_MODES = ("fp32", "fp32_simt")  # tcgen05 3xTF32 and FFMA: both promise the reference's own allclose(1e-5)
 
 
 @pytest.fixture(scope="module")
@@ -50,7 +50,7 @@ def tc_ok():
 
 
 # ------------------------------------------------------------------ Conv2D
-@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_simt", "tf32", "bf16"])
 @pytest.mark.parametrize("case", M["conv2d"], ids=lambda c: f"conv{c['id']}")
 def test_conv2d_golden(cp, case, mode):
     from compyute_b200.nn.functional import Conv2DFn, FunctionCache
@@ -80,7 +80,7 @@ CONV_ORACLE = [  # (B, Ci, Co, H, K, pad, stride, dil, bias)
 ]
 
 
-@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_simt", "tf32", "bf16"])
 @pytest.mark.parametrize("shape", CONV_ORACLE, ids=lambda s: "x".join(map(str, s[:8])))
 def test_conv2d_oracle(cp, shape, mode):
     from compyute_b200.nn.functional import Conv2DFn, FunctionCache
@@ -115,7 +115,7 @@ def test_conv2d_errors(cp):
         conv2d(cp.tensor(np.zeros((2, 3, 8, 8), np.float32)), cp.tensor(np.zeros((4, 3, 3, 3), np.float32)))
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_simt", "bf16"])
 def test_conv2d_full_size_properties(cp, mode):
     """BASELINE config 2 at full size (B=256, C=64, 56x56, 3x3 same): sampled outputs against fp64 dot products,
     linearity in dy for the backward pass, and db == dy.sum by an independent reduction."""
@@ -127,7 +127,7 @@ def test_conv2d_full_size_properties(cp, mode):
     b = rng.uniform(-0.04, 0.04, (C,)).astype(np.float32)
     dy = rng.uniform(-0.1, 0.1, (B, C, H, H)).astype(np.float32)
     T = lambda a: cp.tensor(a, device=cp.cuda)
-    tol = 1e-5 if mode == "fp32" else TOL[mode]
+    tol = 1e-5 if mode in EXACT_MODES else TOL[mode]
     with cp.compute_mode(mode):
         c = FunctionCache()
         xt, wt, bt, dyt = T(x), T(w), T(b), T(dy)
@@ -145,21 +145,21 @@ def test_conv2d_full_size_properties(cp, mode):
     for _ in range(200):
         bi, o, p, q = rng.randint(B), rng.randint(C), rng.randint(H), rng.randint(H)
         ref = (xp[bi, :, p:p + 3, q:q + 3] * wf[o]).sum() + b[o]
-        assert abs(yh[bi, o, p, q] - ref) <= tol * max(scale_y, 1.0) + (1e-5 if mode == "fp32" else 0) * abs(ref)
+        assert abs(yh[bi, o, p, q] - ref) <= tol * max(scale_y, 1.0) + (1e-5 if mode in EXACT_MODES else 0) * abs(ref)
         i = rng.randint(C)
         ref = (dyp[bi, :, p:p + 3, q:q + 3] * wf[:, i, ::-1, ::-1]).sum()
         assert abs(dxh[bi, i, p, q] - ref) <= tol * max(scale_dx, 1.0) + 1e-6
     for _ in range(20):
         o, i, j, k = rng.randint(C), rng.randint(C), rng.randint(K), rng.randint(K)
         ref = (dy[:, o].astype(np.float64) * xp[:, i, j:j + H, k:k + H]).sum()
-        assert abs(dwh[o, i, j, k] - ref) <= (2e-5 if mode == "fp32" else tol) * max(np.abs(dwh).max(), abs(ref))
+        assert abs(dwh[o, i, j, k] - ref) <= (2e-5 if mode in EXACT_MODES else tol) * max(np.abs(dwh).max(), abs(ref))
     assert np.allclose(db.to_numpy(), dy.astype(np.float64).sum((0, 2, 3)), rtol=1e-4, atol=1e-3)
     # linearity of the backward pass: bwd(2 dy) == 2 bwd(dy) exactly (power-of-two scaling commutes with rounding)
     assert np.array_equal(dx2.to_numpy(), 2.0 * dxh) and np.allclose(dw2.to_numpy(), 2.0 * dwh, rtol=1e-6, atol=0)
 
 
 # ------------------------------------------------------------------ Linear
-@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_simt", "tf32", "bf16"])
 @pytest.mark.parametrize("case", M["linear"], ids=lambda c: f"lin{c['id']}")
 def test_linear_golden(cp, case, mode):
     from compyute_b200.nn.functional import FunctionCache, LinearFn
@@ -175,7 +175,7 @@ def test_linear_golden(cp, case, mode):
         check(db, g[f"c{n}_db"], mode)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_simt", "tf32", "bf16"])
 @pytest.mark.parametrize("shape", [(128, 576, 256, True), (300, 84, 10, True), (512, 1024, 768, False), (1000, 333, 130, True),
                                    (4096, 512, 1000, True)], ids=str)
 def test_linear_oracle(cp, shape, mode):

@@ -26,9 +26,11 @@ struct Cfg { int test, r, r2, variant; };
 struct Params {
   CUtensorMap tmS, tmB;
   float* out;  // [ncfg][128][64]
+  long long* cycles;  // [ncfg]: test 3 = cycles of TIMING_REPS x 4 MMAs (same descriptors as test 1 / 2, variant 0)
   int ncfg;
   Cfg cfg[NCFG_MAX];
 };
+constexpr int TIMING_REPS = 512;
 
 __device__ __forceinline__ uint64_t desc_with_base(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t base_off) {
   return make_smem_desc(saddr, lbo, sbo, 2) | ((uint64_t)(base_off & 7u) << 49);
@@ -87,6 +89,35 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
     tc_fence_before();
     __syncthreads();
   }
+  // ---- test 3: MMA issue rate as a function of the descriptor start row (is an unaligned start a slow path?)
+  for (int c = 0; c < p.ncfg; ++c) {
+    const Cfg cf = p.cfg[c];
+    if (cf.variant != 0) continue;
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const long long t0 = clock64();
+      for (int rep = 0; rep < TIMING_REPS; ++rep) {
+        for (int s = 0; s < 4; ++s) {
+          uint64_t da;
+          uint32_t idesc;
+          if (cf.test == 1) {
+            da = make_smem_desc(sS + cf.r * 128 + s * 32, 16, 1024);
+            idesc = make_idesc(true, false, false, 128, NB);
+          } else {
+            da = make_smem_desc(sS + cf.r * 128 + s * (16 * 128), (uint32_t)(cf.r2 - cf.r) * 128, 1024, 2);
+            idesc = make_idesc(true, true, false, 128, NB);
+          }
+          const uint64_t db = make_smem_desc(sB + s * 32, 16, 1024);
+          umma<true, false>(tmem_base, da, db, idesc, 1u);
+        }
+      }
+      umma_commit<false>(bar2);
+      mbar_wait(bar2, phase);
+      p.cycles[c] = clock64() - t0;
+    }
+    phase ^= 1;
+    __syncthreads();
+  }
   if (warp == 0) { tc_fence_after(); tmem_dealloc<false>(tmem_base, 64); }
 }
 
@@ -130,6 +161,10 @@ int main() {
   cudaMalloc(&dOut, (size_t)n * 128 * NB * 4);
   cudaMemset(dOut, 0xff, (size_t)n * 128 * NB * 4);
   p.out = dOut;
+  long long* dCyc;
+  cudaMalloc(&dCyc, NCFG_MAX * sizeof(long long));
+  cudaMemset(dCyc, 0, NCFG_MAX * sizeof(long long));
+  p.cycles = dCyc;
   const int smem = RS * 128 + NB * 128 + 1024 + 64;
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   probe_kernel<<<1, 128, smem>>>(p);
@@ -154,5 +189,11 @@ int main() {
     printf("test %d r=%3d r2=%3d base_offset=%s : %s (%d bad, first m=%d n=%d)\n", cf.test, cf.r, cf.r2, cf.variant ? "(addr>>7)&7" : "0",
            bad ? "MISMATCH" : "exact", bad, first < 0 ? -1 : first / NB, first < 0 ? -1 : first % NB);
   }
+  std::vector<long long> cyc(NCFG_MAX);
+  cudaMemcpy(cyc.data(), dCyc, NCFG_MAX * sizeof(long long), cudaMemcpyDeviceToHost);
+  for (int c = 0; c < n; ++c)
+    if (p.cfg[c].variant == 0)
+      printf("timing test %d r=%3d r2=%3d : %.1f cycles per MMA (M=128 N=64 K=16 bf16; floor 32)\n", p.cfg[c].test, p.cfg[c].r, p.cfg[c].r2,
+             (double)cyc[c] / (TIMING_REPS * 4));
   return 0;
 }
