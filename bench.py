@@ -165,6 +165,7 @@ def run_ours(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = distributed.bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa_bind else {"bound": False}
     if world > 1:
         distributed.init("nccl")
     dev = cp.cuda
@@ -177,6 +178,7 @@ def run_ours(args) -> None:
         for l in layers:
             l.training()
         opt = nn.optimizers.SGD([p for l in layers for p in l.get_parameters()], lr=1e-3)
+        opt.fused_dp_step = not args.no_fused_step
         return layers, opt
 
     # device-resident inputs (value) and pinned host copies (e2e)
@@ -244,6 +246,8 @@ def run_ours(args) -> None:
             sampler.start()
         ms, launches = timed(layers, opt, args.steps, args.warmup, with_probe=True)
         clocks = sampler.stop() if rank == 0 else {}
+        grad_sync = "n/a" if world == 1 else (("fused sharded step: " + opt.fused_dp_note()) if opt._fused is not None else
+                                              "one NCCL all-reduce of the gradient arena at step() + replicated update (" + opt.fused_dp_note() + ")")
         L.cpt_conv2d_fprop_cl = orig_fprop
         status = L.cpt_tc_check_status()
         # per-layer device times (separate short pass, for the report)
@@ -335,6 +339,8 @@ def run_ours(args) -> None:
                 dt = float(t.item())
             e2e = {"value": round(world * step_flops / dt / 1e12, 3), "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "steps": e2e_steps, "ms_per_step": round(dt * 1e3, 2),
+                   "host_link_gbs_per_rank_each_way": round(h2d / dt / 1e9, 1), "host_link_gbs_all_ranks_both_ways": round(world * (h2d + d2h) / dt / 1e9, 1),
+                   "numa": numa,
                    "note": "Conv2DFn.forward/backward per layer with pinned host buffers: H2D x,w,b,dy and D2H y,dx,dw,db inside the timed "
                            "region, copies on side streams overlapping the kernels (forward starts when x has landed, y returns while backward "
                            "runs); PCIe-bound (6.2 GB each way per step)"}
@@ -406,7 +412,7 @@ def run_ours(args) -> None:
     line = {"metric": "conv2d_fwd_bwd_tflops", "value": round(value, 2), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32", "fp32_simt": "f32"}[args.mode], "data": "synthetic",
-            "config": workload_config(args, args.mode), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "config": dict(workload_config(args, args.mode), grad_sync=grad_sync), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": {"value": round(cpu_tf, 7), "unit": "TFLOP/s", "cores": 1, "host_cores": os.cpu_count(),
                                                 "kind": "port", "sample": cpu_desc, "seconds": round(cpu_times[0], 2)},
             "images_per_s": round(world * BATCH * len(SWEEP) / (ms / 1e3), 1), "frac_of_bf16_peak": round(value / world / pk["bf16_tflops"], 4),
@@ -502,7 +508,9 @@ def model_record(args, cpu: bool = True):
     L = _lib.lib()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not distributed.is_initialized():
+        if not getattr(args, "no_numa_bind", False):
+            distributed.bind_to_gpu_numa_node(local)
         distributed.init("nccl")
     factory, xshape, classes, B, desc = MODEL_WORKLOADS[args.workload]
     B = args.batch or B
@@ -520,6 +528,7 @@ def model_record(args, cpu: bool = True):
     model.training()
     opt = nn.optimizers.Adam(model.get_parameters(), lr=1e-3)
     opt.overlap_grad_sync = world > 1 and args.overlap  # bucketed all-reduces launched during backward
+    opt.fused_dp_step = world > 1 and not args.no_fused_step  # exchange + update in one kernel over NVLS / peer memory
     distributed.set_sync_batchnorm(world > 1 and args.sync_bn)  # BatchNorm statistics over the global batch (optional)
     opt.reserve_sms = int(os.environ.get("CPT_DP_RESERVE_SMS", opt.reserve_sms))
     opt.bucket_bytes = int(os.environ.get("CPT_DP_BUCKET_BYTES", opt.bucket_bytes))
@@ -674,7 +683,8 @@ def model_record(args, cpu: bool = True):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32", "fp32_simt": "f32"}[args.mode], "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "compute_mode": args.mode, "cuda_graph": bool(graphed), "tolerance": TOL[args.mode], "parallelism": f"dp{world}",
-                       "grad_sync": ("bucketed all-reduce overlapped with backward" if opt.overlap_grad_sync else "one all-reduce at step()") if world > 1 else "n/a",
+                       "grad_sync": (("fused sharded step: " + opt.fused_dp_note()) if opt._fused is not None else
+                                     ("bucketed all-reduce overlapped with backward" if opt.overlap_grad_sync else "one NCCL all-reduce at step() + replicated update")) if world > 1 else "n/a",
                        "batchnorm": "synchronised (global-batch statistics)" if distributed.sync_batchnorm_active() else "per-shard statistics",
                        "l2_policy": "activations of one step exceed L2" if B * int(np.prod(xshape)) * 4 > 126e6 else "L2 flushed implicitly: per-step activation traffic exceeds L2"},
             "clocks": clocks, "e2e": {"value": round(world * B / (e2e_ms / 1e3), 1), "unit": "images/s", "h2d_bytes_per_step": int(hx.numel() * 4 + ht.numel() * 4),
@@ -726,6 +736,10 @@ def main() -> None:
                     help="data-parallel model runs: bucketed all-reduces launched during backward (Optimizer.overlap_grad_sync) "
                          "instead of one all-reduce of the whole gradient arena at step(); measured gain at 2 GPUs is ~1 %% because "
                          "the persistent GEMM grids leave NCCL little room, so it is opt-in")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU runs: do not pin each rank to its GPU's NUMA node")
+    ap.add_argument("--no-fused-step", action="store_true",
+                    help="data-parallel runs: classic NCCL all-reduce + replicated update instead of the fused sharded step over "
+                         "NVLS / peer memory (csrc/dp_step.cu)")
     ap.add_argument("--sync-bn", action="store_true",
                     help="data-parallel model runs: synchronised BatchNorm (distributed.set_sync_batchnorm): statistics and backward "
                          "sums over the global batch, one small all-gather / all-reduce per BatchNorm layer and pass")

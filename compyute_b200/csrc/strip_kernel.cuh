@@ -69,88 +69,88 @@ __global__ void __launch_bounds__(256, 1) strip_conv_kernel(const __grid_constan
   const int my_tiles = cta < total_tiles ? (total_tiles - cta + n_ctas - 1) / n_ctas : 0;
   const int T = p.T, cchunks = p.cchunks;
 
+  // Slot / phase counters of the two rings are advanced incrementally and every quantity of the role loops is derived from
+  // kernel parameters and loop counters only: no runtime division, so the compiler keeps addresses and descriptors on the
+  // uniform datapath (a `k % n_units` here put them in vector registers: R2UR per MMA operand, ~420 cycles per tap).
   if (warp == 0) {
     // =========================== TMA producer ===========================
     const int total_units = my_tiles * cchunks;
-    int u_issued = 0, b_cnt = 0;
+    int iu = 0, iu_slot = 0, iu_ti = 0, iu_cc = 0;      // next strip to issue: sequence index, ring slot, (tile, chunk)
+    uint32_t iu_phase = 0;
+    int bslot = 0;
+    uint32_t bphase = 0;
     bool ok = true;
-    auto issue_strip = [&](int k) -> bool {  // unit k of this CTA's sequence: (tile, chunk)
-      const int ti = k / cchunks, cc = k - ti * cchunks;
-      const int t = cta + ti * n_ctas;
+    auto issue_strip = [&]() -> bool {
+      const int t = cta + iu_ti * n_ctas;
       const int m0 = (t % p.m_tiles) * 128;
-      const int slot = k % p.n_units;
-      const uint32_t par = (uint32_t)((k / p.n_units) & 1);
-      if (!__all_sync(0xffffffffu, mbar_wait(uempty(slot), par ^ 1))) { atomicExch(p.status, 11); return false; }
+      if (!__all_sync(0xffffffffu, mbar_wait(uempty(iu_slot), iu_phase ^ 1))) { atomicExch(p.status, 11); return false; }
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(ufull(slot), (uint32_t)p.unit_bytes);
+        mbar_arrive_expect_tx(ufull(iu_slot), (uint32_t)p.unit_bytes);
         for (int l = 0; l < p.n_loads; ++l)
-          tma_load_2d<false>(&p.tmA, ufull(slot), unit_smem(slot) + (uint32_t)(l * p.box_rows * 128), cc * 64, m0 + l * p.box_rows);
+          tma_load_2d<false>(&p.tmA, ufull(iu_slot), unit_smem(iu_slot) + (uint32_t)(l * p.box_rows * 128), iu_cc * 64, m0 + l * p.box_rows);
       }
       __syncwarp();
+      ++iu;
+      if (++iu_slot == p.n_units) { iu_slot = 0; iu_phase ^= 1; }
+      if (++iu_cc == cchunks) { iu_cc = 0; ++iu_ti; }
       return true;
     };
     const int la = T > 1 ? 1 : 0;
-    if (total_units > 0) { ok = issue_strip(0); u_issued = 1; }
-    for (int k = 0; k < total_units && ok; ++k) {
-      const int ti = k / cchunks, cc = k - ti * cchunks;
+    if (total_units > 0) ok = issue_strip();
+    for (int ti = 0; ti < my_tiles && ok; ++ti) {
       const int t = cta + ti * n_ctas;
       const int n0 = (t / p.m_tiles) * BN;
       const bool load_b = !p.resident || ti == 0;
-      for (int tap = 0; tap < T && ok; ++tap) {
-        if (tap == la && u_issued < total_units) { ok = issue_strip(u_issued); ++u_issued; if (!ok) break; }
-        if (load_b) {
-          int slot;
-          uint32_t par;
-          if (p.resident) { slot = cc * T + tap; par = 0; }
-          else { slot = b_cnt % p.b_stages; par = (uint32_t)((b_cnt / p.b_stages) & 1); ++b_cnt; }
-          if (!p.resident && !__all_sync(0xffffffffu, mbar_wait(bempty(slot), par ^ 1))) { atomicExch(p.status, 12); ok = false; break; }
-          if (elect_one_sync()) {
-            mbar_arrive_expect_tx(bfull(slot), B_BYTES);
-            tma_load_2d<false>(&p.tmB, bfull(slot), b_smem(slot), tap * p.wk_cols + cc * 64, n0);
+      for (int cc = 0; cc < cchunks && ok; ++cc) {
+        for (int tap = 0; tap < T && ok; ++tap) {
+          if (tap == la && iu < total_units) { ok = issue_strip(); if (!ok) break; }
+          if (load_b) {
+            const int slot = p.resident ? cc * T + tap : bslot;
+            if (!p.resident && !__all_sync(0xffffffffu, mbar_wait(bempty(slot), bphase ^ 1))) { atomicExch(p.status, 12); ok = false; break; }
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(bfull(slot), B_BYTES);
+              tma_load_2d<false>(&p.tmB, bfull(slot), b_smem(slot), tap * p.wk_cols + cc * 64, n0);
+            }
+            __syncwarp();
+            if (!p.resident && ++bslot == p.b_stages) { bslot = 0; bphase ^= 1; }
           }
-          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    int acc = 0, k = 0, b_cnt = 0;
-    uint32_t acc_phase = 0;
+    int acc = 0, uslot = 0, bslot = 0;
+    uint32_t acc_phase = 0, uphase = 0, bphase = 0;
     bool ok = true;
     for (int ti = 0; ti < my_tiles && ok; ++ti) {
       if (!__all_sync(0xffffffffu, mbar_wait(tempty(acc), acc_phase ^ 1))) { atomicExch(p.status, 13); break; }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int cc = 0; cc < cchunks && ok; ++cc, ++k) {
-        const int uslot = k % p.n_units;
-        if (!__all_sync(0xffffffffu, mbar_wait(ufull(uslot), (uint32_t)((k / p.n_units) & 1)))) { atomicExch(p.status, 14); ok = false; break; }
+      for (int cc = 0; cc < cchunks && ok; ++cc) {
+        if (!__all_sync(0xffffffffu, mbar_wait(ufull(uslot), uphase))) { atomicExch(p.status, 14); ok = false; break; }
+        tc_fence_after();
         const uint32_t sa0 = unit_smem(uslot);
         for (int tap = 0; tap < T; ++tap) {
-          int bslot;
-          if (p.resident) {
-            bslot = cc * T + tap;
-            if (ti == 0 && !__all_sync(0xffffffffu, mbar_wait(bfull(bslot), 0))) { atomicExch(p.status, 15); ok = false; break; }
-          } else {
-            bslot = b_cnt % p.b_stages;
-            const uint32_t par = (uint32_t)((b_cnt / p.b_stages) & 1);
-            ++b_cnt;
-            if (!__all_sync(0xffffffffu, mbar_wait(bfull(bslot), par))) { atomicExch(p.status, 15); ok = false; break; }
+          const int bs = p.resident ? cc * T + tap : bslot;
+          if (!p.resident || ti == 0) {
+            if (!__all_sync(0xffffffffu, mbar_wait(bfull(bs), p.resident ? 0u : bphase))) { atomicExch(p.status, 15); ok = false; break; }
+            tc_fence_after();
           }
-          tc_fence_after();
           if (elect_one_sync()) {
-            const uint32_t sa = sa0 + (uint32_t)p.tap_off[tap] * 128u, sb = b_smem(bslot);
+            const uint32_t sa = sa0 + (uint32_t)p.tap_off[tap] * 128u, sb = b_smem(bs);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-              uint64_t da = make_smem_desc(sa + s * 32, 16, 1024);
-              if (p.base_offset_mode) da |= (uint64_t)(((sa + s * 32) >> 7) & 7u) << 49;
+              const uint64_t da = make_smem_desc(sa + s * 32, 16, 1024);
               const uint64_t db = make_smem_desc(sb + s * 32, 16, 1024);
               umma<true, false>(d_tmem, da, db, IDESC, (uint32_t)((cc | tap | s) != 0));
             }
-            if (!p.resident) umma_commit<false>(bempty(bslot));
+            if (!p.resident) umma_commit<false>(bempty(bs));
             if (tap == T - 1) umma_commit<false>(uempty(uslot));   // strip free once these MMAs have read it
           }
           __syncwarp();
+          if (!p.resident && ++bslot == p.b_stages) { bslot = 0; bphase ^= 1; }
         }
+        if (++uslot == p.n_units) { uslot = 0; uphase ^= 1; }
       }
       if (!ok) break;
       if (elect_one_sync()) umma_commit<false>(tfull(acc));

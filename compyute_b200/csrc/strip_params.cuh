@@ -25,7 +25,6 @@ struct alignas(64) StripParams {
   int unit_bytes;            // n_loads * box_rows * 128, multiple of 1024
   int n_units, b_stages;     // strip buffers, filter-tile slots
   int resident;              // 1: filter tiles are loaded once (slot = chunk*T + tap)
-  int base_offset_mode;      // 1: descriptors carry base_offset = (start >> 7) & 7
   long long col_stride, img_stride;  // H*W, N*H*W
   int tap_off[64];           // j*Wp + k
 };

@@ -1536,8 +1536,6 @@ static int conv_strip_gemm(const void* act_pad, int B, int Cact, int H, int W, i
   p.H = H; p.W = W; p.Wp = q.Wp; p.HpWp = q.Hp * q.Wp;
   p.box_rows = q.box_rows; p.n_loads = q.n_loads; p.unit_bytes = q.unit_bytes; p.n_units = q.n_units; p.b_stages = q.b_stages;
   p.resident = q.resident;
-  static const int base_mode = getenv("CPT_STRIP_BASE_OFFSET") ? atoi(getenv("CPT_STRIP_BASE_OFFSET")) : 0;
-  p.base_offset_mode = base_mode;
   p.col_stride = (long long)H * W; p.img_stride = (long long)Ncols * H * W;
   for (int j = 0; j < K; ++j)
     for (int k = 0; k < K; ++k) p.tap_off[j * K + k] = j * q.Wp + k;

@@ -73,6 +73,7 @@ class Optimizer:
     """Optimizer base class (optimizers.py:14-92)."""
 
     _state_keys: tuple[str, ...] = ()
+    _fused_dp_keys: Optional[tuple[str, ...]] = None  # state buffers of the fused data-parallel step (None: not supported)
 
     def __init__(self, parameters: Optional[Iterable[Parameter]] = None, lr: float = 1e-3) -> None:
         self.lr = lr
@@ -95,6 +96,10 @@ class Optimizer:
         self._bucket_launched: list[bool] = []
         self._live = None           # device float[8]: per-step scalars read by the update kernel in CUDA-graph replays
         self._synced = False        # sync_grads() already exchanged (and averaged) this step's gradients
+        # fused data-parallel step (csrc/dp_step.cu): gradient + parameter arenas in symmetric memory, each rank updates its
+        # shard from the in-switch gradient sum and multicasts the new parameters; None = classic all-reduce + replicated update
+        self.fused_dp_step = True   # use it whenever the process group supports it (set False before the first step to opt out)
+        self._fused, self._fused_checked = None, False
         if parameters is not None:
             self.set_parameters(parameters)
 
@@ -112,7 +117,9 @@ class Optimizer:
         self._build_arena()
 
     def get_state_dict(self) -> dict[str, dict[Any, Any]]:
-        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel", "_live", "_synced", "overlap_grad_sync",
+        if self._fused is not None:
+            self._materialize_fused_state()
+        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel", "_live", "_synced", "_fused", "fused_dp_step", "overlap_grad_sync",
                 "bucket_bytes", "reserve_sms", "_buckets", "_bucket_pending", "_bucket_work", "_bucket_launched", "_offsets", "_bucket_of"}
         return {"state": self._state, "vars": {k: v for k, v in vars(self).items() if k not in skip}}
 
@@ -121,6 +128,8 @@ class Optimizer:
         for k, v in state_dict["vars"].items():
             setattr(self, k, v)
         self._table_key = None
+        if self._fused is not None:
+            self._scatter_fused_state()
 
     def reset_grads(self) -> None:
         """``p.grad = None`` (optimizers.py:85-88); arena slots are simply overwritten by the next backward."""
@@ -136,13 +145,24 @@ class Optimizer:
         ``clip_grad_norm`` calls this itself.  No-op on one rank."""
         if self._dp_world() == 1 or self._synced or self._arena is None:
             return
-        scale = self._sync_grads()
+        if self._fused is not None:  # plain all-reduce of the symmetric gradient arena; the fused step then skips its own sum
+            distributed.all_reduce_sum(self._arena)
+            scale = 1.0 / self._dp_world()
+        else:
+            scale = self._sync_grads()
         self._arena *= float(scale)
         self._synced = True
 
     def step(self) -> None:
         """Updates the parameters (one fused launch).  Inside a CUDA-graph capture the per-step scalars are read from device
         memory and ``t`` is advanced by ``upload_live_scalars`` at replay time instead."""
+        if not self._fused_checked and not graph.is_capturing():
+            self._maybe_enable_fused()
+        if self._fused is not None and not graph.is_capturing() and self._dp_world() > 1:
+            self._fused_step()
+            self._synced = False
+            self.t += 1
+            return
         scale = 1.0 if self._synced else self._sync_grads()
         self._synced = False
         if graph.is_capturing():
@@ -189,6 +209,7 @@ class Optimizer:
         for p in cuda_params:
             offs.append(total)
             total += (p.size + 63) // 64 * 64
+        self._fused, self._fused_checked = None, False  # the symmetric arenas are built at the first data-parallel step()
         self._arena = DeviceArray.zeros((total,), np.float32)
         self._offsets = offs
         for ptr in [k for k, (ref, _) in _SLOT_OWNERS.items() if ref() is None or ref() is self]:
@@ -198,6 +219,99 @@ class Optimizer:
             p.grad_slot = DeviceArray(flat[o:o + p.size], p.shape, np.float32)
             _SLOT_OWNERS[p.grad_slot.ptr] = (weakref.ref(self), i)  # looked up by Module.update_parameter_grad
         self._buckets = None
+
+    # ---- fused data-parallel step ---------------------------------------------------------------
+    def _maybe_enable_fused(self) -> None:
+        """First data-parallel step(): move the gradient arena G and the parameters (arena P) into symmetric memory.  Collective —
+        every rank of the group reaches its first step() —, which is why it does not happen in set_parameters (an optimizer
+        built on one rank only, e.g. a single-process reference run next to a DP run, must not start a rendezvous).
+        ``p.data`` becomes a view of P (the fused step writes every replica's P through the multicast / peer mappings); this
+        rank owns ``[rank*S, (rank+1)*S)`` of both arenas and keeps the moments of that shard only."""
+        self._fused_checked = True
+        if not (self.fused_dp_step and self._fused_dp_keys is not None and self._arena is not None and self._dp_world() > 1
+                and distributed.symmetric_memory_available()):
+            return
+        if any(self._state[i] for i in self._state):
+            return  # moments already exist in the replicated layout (resumed run): keep the classic path
+        world, rank = distributed.world_size(), distributed.rank()
+        total = self._arena.size
+        padded, shard = distributed.plan_shards(total, world)
+        G, P = distributed.SymmetricArena(padded), distributed.SymmetricArena(padded)
+        G.tensor[:total].copy_(self._arena._buf)  # this step's gradients are already in the old arena
+        for ptr in [k for k, (ref, _) in _SLOT_OWNERS.items() if ref() is self]:
+            del _SLOT_OWNERS[ptr]
+        for i, (p, o) in enumerate(zip(self._parameters, self._offsets)):
+            P.tensor[o:o + p.size].copy_(p.data._buf.reshape(-1))
+            p.data = DeviceArray(P.tensor[o:o + p.size], p.shape, np.float32)
+            had_slot_grad = p.grad is not None and p.grad_slot is not None and p.grad.data.ptr == p.grad_slot.ptr
+            p.grad_slot = DeviceArray(G.tensor[o:o + p.size], p.shape, np.float32)
+            _SLOT_OWNERS[p.grad_slot.ptr] = (weakref.ref(self), i)
+            if had_slot_grad:
+                p.grad = Tensor(p.grad_slot)
+        self._arena = G.array
+        self._table_key = None
+        self._buckets = None
+        self._fused = {"G": G, "P": P, "shard": shard, "off": rank * shard, "world": world, "state": {}}
+
+    def _fused_view(self) -> "_lib.DpView":
+        f = self._fused
+        v = _lib.DpView()
+        v.p_local, v.g_local = f["P"].array.ptr, f["G"].array.ptr
+        v.p_mc, v.g_mc = f["P"].multicast_ptr or None, f["G"].multicast_ptr or None
+        v.p_peers, v.g_peers = f["P"].peer_ptrs_dev, f["G"].peer_ptrs_dev
+        v.shard_off, v.shard_elems, v.world = f["off"], f["shard"], f["world"]
+        v.pre_reduced = 1 if self._synced else 0
+        return v
+
+    def _fused_buffer(self, key: str) -> DeviceArray:
+        st = self._fused["state"]
+        if key not in st:
+            st[key] = DeviceArray.zeros((self._fused["shard"],), np.float32)  # the reference's moments start from 0
+        return st[key]
+
+    def _fused_step(self) -> None:
+        """barrier -> one kernel (in-switch gradient sum of this rank's shard, update, multicast of the new parameters) ->
+        barrier, all on the compute stream; no separate collective and no host synchronisation."""
+        if any(p.grad is None for p in self._parameters):
+            raise RuntimeError("fused data-parallel step: every parameter needs a gradient each step (parameters without one "
+                               "are skipped by the reference, optimizers.py:157; set optimizer.fused_dp_step = False before "
+                               "set_parameters for such models)")
+        self._gather_grads_into_arena()
+        f = self._fused
+        f["G"].barrier(0)   # every rank's backward has written its gradient arena
+        self._launch_fused(self._step_scalars(), 1.0 if self._synced else 1.0 / f["world"])
+        f["P"].barrier(0)   # every replica of the parameters is complete before the next forward reads it
+
+    def _launch_fused(self, sc: list[float], scale: float) -> None:
+        raise NotImplementedError
+
+    def fused_dp_note(self) -> str:
+        if self._fused is None:
+            return "off (" + (distributed.symmetric_memory_note() or "single rank / unsupported optimizer") + ")"
+        return "multimem (NVLS in-switch reduction + multicast store)" if self._fused["P"].multicast_ptr else "peer loads / stores (no multicast support)"
+
+    def _materialize_fused_state(self) -> None:
+        """Checkpoints keep the reference layout ``{i: {"m": Tensor, "v": Tensor}}``: the shards are gathered from all ranks and
+        cut at the parameter offsets (collective call)."""
+        f = self._fused
+        for key, shard in f["state"].items():
+            full = distributed.all_gather(shard).reshape(-1)
+            for i, (p, o) in enumerate(zip(self._parameters, self._offsets)):
+                self._state[i][key] = Tensor(DeviceArray(full._buf[o:o + p.size].clone(), p.shape, np.float32))
+
+    def _scatter_fused_state(self) -> None:
+        f = self._fused
+        lo, hi = f["off"], f["off"] + f["shard"]
+        for key in self._fused_dp_keys or ():
+            buf = self._fused_buffer(key)
+            buf.fill(0.0)
+            for i, (p, o) in enumerate(zip(self._parameters, self._offsets)):
+                st = self._state.get(i, {}).get(key)
+                a, b = max(o, lo), min(o + p.size, hi)
+                if st is None or a >= b:
+                    continue
+                src = st.data if isinstance(st.data, DeviceArray) else DeviceArray.from_numpy(np.asarray(st.data, np.float32))
+                buf._buf[a - lo:b - lo].copy_(src._buf.reshape(-1)[a - o:b - o])
 
     # ---- overlapped data-parallel exchange -----------------------------------------------------
     def _dp_world(self) -> int:
@@ -312,8 +426,16 @@ class SGD(Optimizer):
         super().__init__(parameters, lr)
         self.momentum, self.nesterov, self.weight_decay = momentum, nesterov, weight_decay
 
+    _fused_dp_keys = ("v",)
+
     def _step_scalars(self) -> list[float]:
         return [float(self.lr)]
+
+    def _launch_fused(self, sc, scale) -> None:
+        vel = self._fused_buffer("v").ptr if self.momentum > 0.0 else None
+        view = self._fused_view()
+        _lib.check(_lib.lib().cpt_dp_sgd_step(ctypes.byref(view), vel, sc[0], float(self.momentum), int(self.nesterov),
+                                              float(self.weight_decay), float(scale), None, stream_ptr()))
 
     def _launch(self, sc, live, scale) -> None:
         keys = ("v",) if self.momentum > 0.0 else ()
@@ -326,11 +448,18 @@ class Adam(Optimizer):
     """optimizers.py:179-271"""
 
     _decoupled = 0
+    _fused_dp_keys = ("m", "v")
 
     def __init__(self, parameters: Optional[Iterable[Parameter]] = None, lr: float = 1e-3, beta1: float = 0.9,
                  beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0) -> None:
         super().__init__(parameters, lr)
         self.beta1, self.beta2, self.eps, self.weight_decay = beta1, beta2, eps, weight_decay
+
+    def _launch_fused(self, sc, scale) -> None:
+        view = self._fused_view()
+        _lib.check(_lib.lib().cpt_dp_adam_step(ctypes.byref(view), self._fused_buffer("m").ptr, self._fused_buffer("v").ptr, sc[0],
+                                               float(self.beta1), float(self.beta2), float(self.eps), float(self.weight_decay), sc[1],
+                                               sc[2], float(scale), self._decoupled, None, stream_ptr()))
 
     def _step_scalars(self) -> list[float]:
         # python doubles, like optimizers.py:243-244

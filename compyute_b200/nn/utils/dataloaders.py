@@ -2,9 +2,16 @@
 
 ``Dataloader`` mirrors compyute/nn/utils/dataloaders.py:18-69 (same constructor, ``__call__`` yields tuples of batch
 Tensors on ``device``, ``__len__``).  It is the H2D boundary of a train step and the natural data-parallel shard point
-(SURVEY §8e, f3): batches are gathered on the host into PINNED staging buffers and uploaded with an asynchronous copy on
-a side stream one batch ahead of the consumer; with ``shard=True`` every rank takes its contiguous slice of each global
-batch (``distributed.shard_bounds``).
+(SURVEY §8e, f3).  Two paths:
+
+* data tensors already on ``cuda`` (the dataset fits in HBM — 180 GB): the shuffled batch is GATHERED ON THE DEVICE
+  (``cpt_gather_rows`` with the batch's index vector, a few KB of H2D per step); nothing else crosses PCIe.
+* data on the host: batches are gathered on the host into PINNED staging buffers and uploaded with an asynchronous copy on
+  a side stream one batch ahead of the consumer.  A pinned slot is rewritten only after the H2D copy that last read it has
+  finished (per-slot event, waited on the HOST: a device-side ``wait_event`` does not stop the host from running ahead
+  when the consumer's host time per step is tiny, e.g. CUDA-graph replay).
+
+With ``shard=True`` every rank takes its contiguous slice of each global batch (``distributed.shard_bounds``).
 """
 
 from __future__ import annotations
@@ -31,6 +38,7 @@ class Dataloader:
         self.shard = shard
         self._additional_batch = not drop_remaining and self._n % self.batch_size > 0
         self._pinned = None  # two sets of pinned staging buffers (double buffering)
+        self._slot_events = [None, None]  # H2D completion of the copy that last read each pinned slot
 
     def __len__(self) -> int:
         return max(1, self._n // self.batch_size + self._additional_batch)
@@ -49,6 +57,22 @@ class Dataloader:
             out.append(np.ascontiguousarray(a))
         return out
 
+    def _device_batches(self, batches) -> Iterator[tuple[Tensor, ...]]:
+        """Device-resident dataset: x[idx] on the device (dataloaders.py:65-66 does the same fancy index on CuPy arrays)."""
+        from ... import device_ops as D
+        for b in batches:
+            if self.shard:
+                lo, hi = distributed.shard_bounds(len(b))
+                b = b[lo:hi]
+            idx = DeviceArray.from_numpy(np.ascontiguousarray(b, dtype=np.int32))
+            out = []
+            for t in self.data:
+                a = D.getitem(t.data, idx)
+                if a.dtype == np.int64:  # labels are int32 on the device
+                    a = D.astype(a, np.int32)
+                out.append(Tensor(a))
+            yield tuple(out)
+
     def __call__(self) -> Iterator[tuple[Tensor, ...]]:
         # same index stream as the reference: numpy's legacy global RNG (random.py permutation)
         idx = np.random.permutation(self._n) if self.shuffle else np.arange(self._n, dtype=np.int64)
@@ -58,6 +82,9 @@ class Dataloader:
                 yield tuple(Tensor(a) for a in self._host_batch(b))
             return
         import torch
+        if all(isinstance(t.data, DeviceArray) for t in self.data):
+            yield from self._device_batches(batches)
+            return
         side = torch.cuda.Stream()
         main = torch.cuda.current_stream()
 
@@ -70,6 +97,8 @@ class Dataloader:
                 cap = [max(h.size, (self.batch_size * int(np.prod(h.shape[1:], dtype=np.int64)))) for h in host]
                 pins = [torch.empty(c, dtype=torch.from_numpy(h).dtype).pin_memory() for c, h in zip(cap, host)]
                 self._pinned[slot] = pins
+            if self._slot_events[slot] is not None:
+                self._slot_events[slot].synchronize()  # host-side: the previous H2D out of this slot's pinned buffers is done
             devs = []
             with torch.cuda.stream(side):
                 for p, h in zip(pins, host):
@@ -79,6 +108,7 @@ class Dataloader:
                     devs.append((d, h))
                 ev = torch.cuda.Event()
                 ev.record(side)
+            self._slot_events[slot] = ev
             return devs, ev
 
         pending = upload(batches[0], 0) if batches else None

@@ -142,3 +142,16 @@ def test_syncbn_protocol_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+def test_plan_shards_for_the_fused_step():
+    """Layout of the symmetric gradient / parameter arenas of the fused data-parallel step (csrc/dp_step.cu): equal
+    contiguous shards, 16-byte vectors never straddle a shard, padding only at the end, every element owned exactly once."""
+    from compyute_b200.distributed import plan_shards
+    for total in (1, 63, 64, 65, 1000, 12_345_677, 134_250_496):
+        for world in (1, 2, 3, 4, 8):
+            padded, shard = plan_shards(total, world)
+            assert padded == shard * world and padded >= total and shard % 64 == 0
+            assert padded - total < world * 64  # at most one alignment unit of padding per rank
+            owners = [(r * shard, (r + 1) * shard) for r in range(world)]
+            assert owners[0][0] == 0 and owners[-1][1] == padded and all(a[1] == b[0] for a, b in zip(owners, owners[1:]))

@@ -56,7 +56,8 @@ def test_config_train_steps(name):
             for i, (p, g) in enumerate(zip(model.get_parameters(), gref.gradients())):
                 got = p.grad.to_numpy()
                 assert got.shape == g.shape
-                assert np.abs(got - g).max() <= 2e-4 * max(np.abs(g).max(), 1e-3), f"grad {i}: {np.abs(got - g).max():.3e} vs max {np.abs(g).max():.3e}"
+                # floor 1e-2: the analytically ZERO gradients (conv bias feeding a BatchNorm) are ~1e-7 rounding noise on both sides
+                assert np.abs(got - g).max() <= 2e-4 * max(np.abs(g).max(), 1e-2), f"grad {i}: {np.abs(got - g).max():.3e} vs max {np.abs(g).max():.3e}"
         opt.step()
         losses.append(loss.item())
     assert np.allclose(losses, ref_losses, rtol=1e-4, atol=1e-5), (losses, ref_losses)

@@ -142,12 +142,17 @@ def test_optimizer_bookkeeping():
 
 
 def test_compute_mode_context():
-    assert cp.get_compute_mode() == _lib.MODE_FP32
+    # "fp32" (the default) is the fp32-exact tensor-core mode; "fp32_simt" the FFMA kernels; both keep the 1e-5 contract
+    assert cp.get_compute_mode() == _lib.MODE_FP32X3
     with cp.compute_mode("bf16"):
         assert cp.get_compute_mode() == _lib.MODE_BF16
         with cp.compute_mode("tf32"):
             assert cp.get_compute_mode() == _lib.MODE_TF32
-    assert cp.get_compute_mode() == _lib.MODE_FP32
+        with cp.compute_mode("fp32_simt"):
+            assert cp.get_compute_mode() == _lib.MODE_FP32
+    assert cp.get_compute_mode() == _lib.MODE_FP32X3
+    with cp.compute_mode("fp32x3"):
+        assert cp.get_compute_mode() == _lib.MODE_FP32X3
     with cp.use_device(cp.cuda):
         assert cp.select_device(None) == cp.cuda
     assert cp.select_device(None) == cp.cpu

@@ -42,6 +42,7 @@ def train(model, x, t, steps, dp):
     model.training()
     opt = nn.optimizers.SGD(model.get_parameters(), lr=5e-2, momentum=0.9) if SYNCBN else nn.optimizers.Adam(model.get_parameters(), lr=1e-2)
     opt._data_parallel = dp
+    opt.fused_dp_step = dp and os.environ.get("DP_FUSED", "1") == "1"  # NVLS / peer-memory fused exchange + update (default)
     opt.overlap_grad_sync = dp and os.environ.get("DP_OVERLAP", "0") == "1"  # bucketed all-reduces during backward
     opt.bucket_bytes = int(os.environ.get("DP_BUCKET_BYTES", 4096))           # tiny buckets: several of them even in this small model
     loss_fn = nn.CrossEntropyLoss()
@@ -56,6 +57,8 @@ def train(model, x, t, steps, dp):
             opt.step()
             losses.append(loss.item())
     D.set_sync_batchnorm(False)
+    if dp and D.rank() == 0:
+        print("gradient exchange:", "fused step, " + opt.fused_dp_note() if opt._fused is not None else "NCCL all-reduce + replicated update (" + opt.fused_dp_note() + ")")
     return losses
 
 
