@@ -154,6 +154,48 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const float* __restric
   }
 }
 
+// Global average (Ho = Wo = 1, the 7x7 head of the ResNet-shaped config): a warp per (image, channel) plane reads its H*W
+// contiguous floats coalesced and reduces them with shuffles — the generic kernel's thread-per-output reads each plane with
+// one lane (44 % of HBM peak, round 1).  Covers the k x k window at the top-left like the generic form (tail rows / columns
+// outside the window do not contribute, pooling_funcs.py:111-121).
+__global__ void __launch_bounds__(256) avgpool_global_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t planes,
+                                                                 int H, int W, int k) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float inv = 1.0f / (float)(k * k);
+  const bool full = (k == H && k == W);
+  for (int64_t pl = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pl < planes; pl += wstride) {
+    const float* src = x + pl * H * W;
+    float s = 0.f;
+    if (full) {
+      for (int i = lane; i < H * W; i += 32) s += src[i];
+    } else {
+      for (int i = lane; i < k * k; i += 32) s += src[(i / k) * W + (i % k)];
+    }
+    s = warp_sum(s);
+    if (lane == 0) y[pl] = s * inv;
+  }
+}
+
+// k = 2, W % 4 == 0: a thread makes two outputs from two 128-bit loads (rows 2p and 2p+1), like the max-pooling fast path
+__global__ void __launch_bounds__(256) avgpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n_pairs,
+                                                           int H, int W, int Ho, int Wo) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int wp = W >> 2;  // output pairs per row
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_pairs; o += stride) {
+    const int q2 = (int)(o % wp);
+    const int64_t t = o / wp;
+    const int p = (int)(t % Ho);
+    const int64_t bc = t / Ho;
+    const float4* r0 = reinterpret_cast<const float4*>(x + (bc * H + 2 * (int64_t)p) * W) + q2;
+    const float4 a = ld_stream(r0), b = ld_stream(r0 + wp);
+    float2 out;
+    out.x = ((a.x + a.y) + (b.x + b.y)) * 0.25f;
+    out.y = ((a.z + a.w) + (b.z + b.w)) * 0.25f;
+    *reinterpret_cast<float2*>(y + (bc * Ho + p) * Wo + 2 * q2) = out;
+  }
+}
+
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int64_t n_in,
                                                           int H, int W, int Ho, int Wo, int k) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -220,7 +262,15 @@ int cpt_avgpool2d_fwd(const float* x, float* y, int B, int C, int H, int W, int 
   if (int e = check_pool("avgpool2d_fwd", B, C, H, W, k)) return e;
   const int Ho = H / k, Wo = W / k;
   const int64_t n_out = (int64_t)B * C * Ho * Wo;
-  avgpool_fwd_kernel<<<ew_grid(n_out, 256), 256, 0, as_stream(stream)>>>(x, y, n_out, H, W, Ho, Wo, k);
+  if (Ho == 1 && Wo == 1 && k * k >= 16) {
+    const int64_t planes = (int64_t)B * C;
+    avgpool_global_fwd_kernel<<<ew_grid(planes * 32, 256), 256, 0, as_stream(stream)>>>(x, y, planes, H, W, k);
+  } else if (k == 2 && W % 4 == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(y) & 7) == 0) {
+    const int64_t n_pairs = n_out / 2;
+    avgpool2_fwd_kernel<<<ew_grid(n_pairs, 256), 256, 0, as_stream(stream)>>>(x, y, n_pairs, H, W, Ho, Wo);
+  } else {
+    avgpool_fwd_kernel<<<ew_grid(n_out, 256), 256, 0, as_stream(stream)>>>(x, y, n_out, H, W, Ho, Wo, k);
+  }
   CPT_LAUNCH_CHECK("avgpool2d_fwd");
   return CPT_OK;
 }

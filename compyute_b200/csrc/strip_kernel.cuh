@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(256, 1) strip_conv_kernel(const __grid_constan
     int acc = 0, uslot = 0, bslot = 0;
     uint32_t acc_phase = 0, uphase = 0, bphase = 0;
     bool ok = true;
+    const uint32_t a_lo_unit0 = smem_desc_lo(unit_smem(0), 16), b_lo_slot0 = smem_desc_lo(b_smem(0), 16);
     for (int ti = 0; ti < my_tiles && ok; ++ti) {
       if (!__all_sync(0xffffffffu, mbar_wait(tempty(acc), acc_phase ^ 1))) { atomicExch(p.status, 13); break; }
       tc_fence_after();
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256, 1) strip_conv_kernel(const __grid_constan
       for (int cc = 0; cc < cchunks && ok; ++cc) {
         if (!__all_sync(0xffffffffu, mbar_wait(ufull(uslot), uphase))) { atomicExch(p.status, 14); ok = false; break; }
         tc_fence_after();
-        const uint32_t sa0 = unit_smem(uslot);
+        const uint32_t a_lo0 = a_lo_unit0 + (uint32_t)uslot * ((uint32_t)p.unit_bytes >> 4);
         for (int tap = 0; tap < T; ++tap) {
           const int bs = p.resident ? cc * T + tap : bslot;
           if (!p.resident || ti == 0) {
@@ -137,13 +138,12 @@ __global__ void __launch_bounds__(256, 1) strip_conv_kernel(const __grid_constan
             tc_fence_after();
           }
           if (elect_one_sync()) {
-            const uint32_t sa = sa0 + (uint32_t)p.tap_off[tap] * 128u, sb = b_smem(bs);
+            constexpr uint32_t HI = smem_desc_hi(1024);
+            const uint32_t a_lo = a_lo0 + (uint32_t)p.tap_off[tap] * 8u;   // tap's row offset: rows x 128 B >> 4
+            const uint32_t b_lo = b_lo_slot0 + (uint32_t)bs * (B_BYTES >> 4);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              const uint64_t da = make_smem_desc(sa + s * 32, 16, 1024);
-              const uint64_t db = make_smem_desc(sb + s * 32, 16, 1024);
-              umma<true, false>(d_tmem, da, db, IDESC, (uint32_t)((cc | tap | s) != 0));
-            }
+            for (int s = 0; s < 4; ++s)
+              umma<true, false>(d_tmem, smem_desc_pack(a_lo + 2 * s, HI), smem_desc_pack(b_lo + 2 * s, HI), IDESC, (uint32_t)((cc | tap | s) != 0));
             if (!p.resident) umma_commit<false>(bempty(bs));
             if (tap == T - 1) umma_commit<false>(uempty(uslot));   // strip free once these MMAs have read it
           }

@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     bool ok = true;
+    const uint32_t a_lo_stage0 = smem_desc_lo(a_smem(0), A_MN ? CHUNK_BYTES : 16), b_lo_stage0 = smem_desc_lo(b_smem(0), B_MN ? CHUNK_BYTES : 16);
     for (int t = group; t < total_tiles && ok; t += n_groups) {
       const int z = (t / p.m_tiles) / p.n_tiles;
       const int iters = tile_k_iters(z);
@@ -231,21 +232,19 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
         if (!__all_sync(0xffffffffu, mbar_wait(full_bar(stage), phase))) { atomicExch(p.status, 3); ok = false; break; }
         tc_fence_after();
         if (elect_one_sync()) {
-        const uint32_t sa = a_smem(stage), sb = b_smem(stage);
+        // descriptor low words of this stage (start address + LBO); per k-step only a constant is added (see tc_ptx.cuh)
+        //   K-major : 32 B further inside the 128-B swizzle row;  MN-major: UMMA_K k-rows (x 128 B) further
+        //   MN-major tf32 uses the 32-byte-atom swizzle: k-groups of 4 rows (512 B) instead of 8 rows (1024 B)
+        constexpr uint32_t A_HI = A_MN ? smem_desc_hi(MN_SBO, MN_LAYOUT) : smem_desc_hi(1024), A_STEP = (A_MN ? E::UMMA_K * 128 : 32) >> 4;
+        constexpr uint32_t B_HI = B_MN ? smem_desc_hi(MN_SBO, MN_LAYOUT) : smem_desc_hi(1024), B_STEP = (B_MN ? E::UMMA_K * 128 : 32) >> 4;
+        const uint32_t a_lo = a_lo_stage0 + (uint32_t)stage * (S::STAGE_BYTES >> 4), b_lo = b_lo_stage0 + (uint32_t)stage * (S::STAGE_BYTES >> 4);
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          // K-major: advance 32 B inside the 128-B swizzle row; MN-major: advance UMMA_K k-rows (x128 B)
-          // MN-major tf32 uses the 32-byte-atom swizzle: k-groups of 4 rows (512 B) instead of 8 rows (1024 B)
-          auto desc_a = [&](uint32_t a0) {
-            return A_MN ? make_smem_desc(a0 + s * (E::UMMA_K * 128), CHUNK_BYTES, MN_SBO, MN_LAYOUT) : make_smem_desc(a0 + s * 32, 16, 1024);
-          };
-          auto desc_b = [&](uint32_t b0) {
-            return B_MN ? make_smem_desc(b0 + s * (E::UMMA_K * 128), CHUNK_BYTES, MN_SBO, MN_LAYOUT) : make_smem_desc(b0 + s * 32, 16, 1024);
-          };
-          const uint64_t da = desc_a(sa), db = desc_b(sb);
+          const uint64_t da = smem_desc_pack(a_lo + s * A_STEP, A_HI), db = smem_desc_pack(b_lo + s * B_STEP, B_HI);
           const uint32_t accumulate = (uint32_t)(((i - i0) | s) != 0);
           if (X3) {  // small terms first: lo*hi, hi*lo, then hi*hi
-            const uint64_t da2 = desc_a(sa + S::PLANE_BYTES), db2 = desc_b(sb + S::PLANE_BYTES);
+            const uint64_t da2 = smem_desc_pack(a_lo + (S::PLANE_BYTES >> 4) + s * A_STEP, A_HI);
+            const uint64_t db2 = smem_desc_pack(b_lo + (S::PLANE_BYTES >> 4) + s * B_STEP, B_HI);
             umma<BF16, CTA2>(d_tmem, da2, db, IDESC, accumulate);
             umma<BF16, CTA2>(d_tmem, da, db2, IDESC, 1u);
             umma<BF16, CTA2>(d_tmem, da, db, IDESC, 1u);

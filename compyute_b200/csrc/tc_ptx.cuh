@@ -197,6 +197,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
+// The same descriptor split into its two 32-bit halves.  Inside an MMA issue loop only the START ADDRESS field changes
+// (bits [0,14) of the low word: stage base, + 32 B per k-step, + a tap's row offset ...), so a loop builds `lo` once per
+// stage and adds small constants to it; `hi` (SBO, version, layout) is a compile-time constant.  One ADD per descriptor
+// instead of the shift / mask / or chain of make_smem_desc — the single issuing warp's instruction count per k-iteration is
+// what bounds small-N tiles.  The start field cannot carry: shared-memory addresses are < 2^18.
+__device__ __forceinline__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t layout_type = 2) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t smem_desc_pack(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
 // Instruction descriptor (kind::f16 / kind::tf32, fp32 accumulate):
 //   [4,6) D fmt (1 = f32) | [7,10) A fmt | [10,13) B fmt (1 = bf16, 2 = tf32) | 15 A MN-major | 16 B MN-major |
 //   [17,23) N>>3 | [24,29) M>>4

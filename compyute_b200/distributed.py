@@ -44,6 +44,12 @@ def init(backend: str | None = None) -> None:
     os.environ.setdefault("MASTER_PORT", "29500")
     d.init_process_group(backend=backend, rank=int(os.environ.get("RANK", "0")),
                          world_size=int(os.environ.get("WORLD_SIZE", "1")))
+    if backend == "nccl" and d.get_world_size() > 1 and os.environ.get("CPT_OWN_NCCL", "1") != "0":
+        try:  # gradient all-reduces go through the library's own communicator (C ABI cpt_nccl_*); the group stays the side channel
+            use_own_nccl(True)
+        except Exception as e:  # pragma: no cover - depends on the NCCL build
+            import warnings
+            warnings.warn(f"compyute_b200: own NCCL communicator unavailable ({e}); using torch.distributed for all-reduces")
 
 
 def bind_to_gpu_numa_node(device_index: int | None = None) -> dict:
