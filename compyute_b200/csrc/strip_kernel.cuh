@@ -23,7 +23,7 @@ namespace cpt {
 namespace tc {
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1) strip_conv_kernel(const __grid_constant__ StripParams p) {
+__global__ void __launch_bounds__((EpiCfg<BN>::THREADS), 1) strip_conv_kernel(const __grid_constant__ StripParams p) {
   constexpr uint32_t IDESC = make_idesc(true, false, false, 128, BN);
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   constexpr uint32_t B_BYTES = BN * 128;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256, 1) strip_conv_kernel(const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int u = 0; u < p.n_units; ++u) { mbar_init(ufull(u), 1); mbar_init(uempty(u), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), EpiCfg<BN>::WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -160,6 +160,8 @@ __global__ void __launch_bounds__(256, 1) strip_conv_kernel(const __grid_constan
   } else if (warp >= 4) {
     // =========================== epilogue ===========================
     const int ew = warp & 3;
+    constexpr int EPI_SPLIT = EpiCfg<BN>::WARPS / 4;  // warps sharing a TMEM lane quarter: each takes 1 / EPI_SPLIT of the columns
+    const int half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     __shared__ float stat_acc[4][BN][2];
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(256, 1) strip_conv_kernel(const __grid_constan
     auto stats_flush = [&]() {
       if (stat_n_tile >= 0) {
         float* dstp = p.stats + ((long long)(blockIdx.x * 4 + ew) * p.N) * 2;
-        for (int c = lane; c < BN; c += 32) {
+        for (int c = half * (BN / EPI_SPLIT) + lane; c < (half + 1) * (BN / EPI_SPLIT); c += 32) {
           const int col = stat_n_tile * BN + c;
           if (col < p.N) { dstp[2 * col] = stat_acc[ew][c][0]; dstp[2 * col + 1] = stat_acc[ew][c][1]; }
         }
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(256, 1) strip_conv_kernel(const __grid_constan
       if (do_stats && n_tile != stat_n_tile) {
         stats_flush();
         stat_n_tile = n_tile;
-        for (int c = lane; c < BN; c += 32) stat_acc[ew][c][0] = stat_acc[ew][c][1] = 0.f;
+        for (int c = half * (BN / EPI_SPLIT) + lane; c < (half + 1) * (BN / EPI_SPLIT); c += 32) stat_acc[ew][c][0] = stat_acc[ew][c][1] = 0.f;
         __syncwarp();
       }
       // lane -> (image, row, col) of the padded grid; pad rows / columns are dropped
@@ -193,8 +195,10 @@ __global__ void __launch_bounds__(256, 1) strip_conv_kernel(const __grid_constan
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
       constexpr int NCH = BN / 32;
+      constexpr int CPW = NCH / EPI_SPLIT;
+      const int c_lo = half * CPW;
       uint32_t va[32], vb[32];
-      tmem_ld_32x32(tbase, va);
+      tmem_ld_32x32(tbase + (uint32_t)(c_lo * 32), va);
       auto release_acc = [&]() {
         tc_fence_before();
         __syncwarp();
@@ -233,14 +237,17 @@ __global__ void __launch_bounds__(256, 1) strip_conv_kernel(const __grid_constan
         }
       };
 #pragma unroll 1
-      for (int c = 0; c < NCH; c += 2) {
+      for (int k = 0; k < CPW; k += 2) {
         tmem_ld_wait();
-        tmem_ld_32x32(tbase + (uint32_t)((c + 1) * 32), vb);
-        store_chunk(va, c);
-        tmem_ld_wait();
-        if (c + 2 < NCH) tmem_ld_32x32(tbase + (uint32_t)((c + 2) * 32), va);
-        if (c + 2 >= NCH) release_acc();
-        store_chunk(vb, c + 1);
+        if (k + 1 < CPW) tmem_ld_32x32(tbase + (uint32_t)((c_lo + k + 1) * 32), vb);
+        if (k + 1 >= CPW) release_acc();
+        store_chunk(va, c_lo + k);
+        if (k + 1 < CPW) {
+          tmem_ld_wait();
+          if (k + 2 < CPW) tmem_ld_32x32(tbase + (uint32_t)((c_lo + k + 2) * 32), va);
+          if (k + 2 >= CPW) release_acc();
+          store_chunk(vb, c_lo + k + 1);
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

@@ -3,6 +3,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "tc_params.cuh"
+
 namespace cpt {
 namespace tc {
 

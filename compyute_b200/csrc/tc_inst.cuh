@@ -23,7 +23,7 @@ static int launch_inst(const TcParams& p, const LaunchSel& s, cudaStream_t st) {
   if (groups < 1) return CPT_OK;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(groups * ncta);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(EpiCfg<BN, X3>::THREADS);
   cfg.dynamicSmemBytes = S::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -13,7 +13,7 @@ static int launch_strip_bn(const StripParams& p, int grid, size_t smem_bytes, cu
     CPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4 * BN * 2 * 4));
     configured = true;
   }
-  kern<<<grid, 256, smem_bytes, st>>>(p);
+  kern<<<grid, EpiCfg<BN>::THREADS, smem_bytes, st>>>(p);
   CPT_LAUNCH_CHECK("strip_conv_kernel");
   return CPT_OK;
 }

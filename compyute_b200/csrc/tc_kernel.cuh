@@ -46,7 +46,7 @@ __device__ __forceinline__ float col_sums_32x32(float (&a)[32], int lane) {
 // lo = rna_tf32(a - hi); a*b is evaluated as lo_a*hi_b + hi_a*lo_b + hi_a*hi_b (the dropped lo*lo term and the rounding of lo are
 // ~2^-22 relative), fp32 accumulation in TMEM: three MMAs per k-step over a stage that holds both planes of both operands.
 template <bool BF16, bool X3, bool A_MN, bool B_MN, int BN, int OP, bool CTA2>
-__global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__((EpiCfg<BN, X3>::THREADS), 1) tc_kernel(const __grid_constant__ TcParams p) {
   static_assert(!(BF16 && X3), "the hi/lo split applies to fp32 operands");
   using E = Elem<BF16>;
   using S = StageCfg<BN, CTA2, X3>;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4 * NCTA);  // one arrive per epilogue warp of every CTA of the group
+      mbar_init(tempty_bar(a), EpiCfg<BN, X3>::WARPS * NCTA);  // one arrive per epilogue warp of every CTA of the group
     }
     fence_barrier_init();
   }
@@ -266,6 +266,8 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
   } else if (warp >= 4) {
     // =========================== epilogue (every CTA: its own 128 TMEM lanes) ===========================
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    constexpr int EPI_SPLIT = EpiCfg<BN, X3>::WARPS / 4;  // warps sharing a lane quarter: each takes 1 / EPI_SPLIT of the columns
+    const int half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     // batch statistics for a consuming BatchNorm (only the K-major x K-major instantiations that produce activations)
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
     auto stats_flush = [&]() {  // this warp's column sums of the finished N-tile -> its slot of the partial buffer
       if (STATS_OK && stat_n_tile >= 0) {
         float* dstp = p.stats + ((long long)(blockIdx.x * 4 + ew) * p.N) * 2;
-        for (int c = lane; c < BN; c += 32) {
+        for (int c = half * (BN / EPI_SPLIT) + lane; c < (half + 1) * (BN / EPI_SPLIT); c += 32) {
           const int col = stat_n_tile * BN + c;
           if (col < p.N) {
             dstp[2 * col] = stat_acc[STATS_OK ? ew : 0][STATS_OK ? c : 0][0];
@@ -291,7 +293,8 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
       if (do_stats && n_tile != stat_n_tile) {
         stats_flush();
         stat_n_tile = n_tile;
-        for (int c = lane; c < BN; c += 32) stat_acc[STATS_OK ? ew : 0][STATS_OK ? c : 0][0] = stat_acc[STATS_OK ? ew : 0][STATS_OK ? c : 0][1] = 0.f;
+        for (int c = half * (BN / EPI_SPLIT) + lane; c < (half + 1) * (BN / EPI_SPLIT); c += 32)
+          stat_acc[STATS_OK ? ew : 0][STATS_OK ? c : 0][0] = stat_acc[STATS_OK ? ew : 0][STATS_OK ? c : 0][1] = 0.f;
         __syncwarp();
       }
       const int iters = tile_k_iters(z);
@@ -316,10 +319,11 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
       const long long cs = p.col_stride;
       const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
       constexpr int NCH = BN / 32;
-      static_assert(NCH % 2 == 0, "chunk pairs");
+      constexpr int CPW = NCH / EPI_SPLIT;  // 32-column chunks per warp
+      const int c_lo = half * CPW;
       const bool col_bias = p.bias_mode == BIAS_COL;
       uint32_t va[32], vb[32];
-      if (!X3 && iters > 0) tmem_ld_32x32(tbase, va);
+      if (!X3 && iters > 0) tmem_ld_32x32(tbase + (uint32_t)(c_lo * 32), va);
       auto release_acc = [&]() {
         tc_fence_before();
         __syncwarp();
@@ -457,22 +461,28 @@ __global__ void __launch_bounds__(256, 1) tc_kernel(const __grid_constant__ TcPa
         }
         continue;
       }
-#pragma unroll 1
-      for (int c = 0; c < NCH; c += 2) {
-        if (iters > 0) {
-          tmem_ld_wait();                                   // chunk c in va
-          tmem_ld_32x32(tbase + (uint32_t)((c + 1) * 32), vb);
-        } else {
+      if (iters == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) va[j] = vb[j] = 0u;
-        }
-        store_chunk(va, c);
+        for (int j = 0; j < 32; ++j) va[j] = vb[j] = 0u;
+      }
+      // this warp's chunks c_lo .. c_lo + CPW - 1, the next one in flight (tcgen05.ld) while the current one is stored; the
+      // accumulator stage goes back to the MMA warp as soon as the last chunk is in registers
+#pragma unroll 1
+      for (int k = 0; k < CPW; k += 2) {
         if (iters > 0) {
-          tmem_ld_wait();                                   // chunk c+1 in vb
-          if (c + 2 < NCH) tmem_ld_32x32(tbase + (uint32_t)((c + 2) * 32), va);
+          tmem_ld_wait();                                   // chunk k in va
+          if (k + 1 < CPW) tmem_ld_32x32(tbase + (uint32_t)((c_lo + k + 1) * 32), vb);
         }
-        if (c + 2 >= NCH) release_acc();
-        store_chunk(vb, c + 1);
+        if (k + 1 >= CPW) release_acc();
+        store_chunk(va, c_lo + k);
+        if (k + 1 < CPW) {
+          if (iters > 0) {
+            tmem_ld_wait();                                 // chunk k+1 in vb
+            if (k + 2 < CPW) tmem_ld_32x32(tbase + (uint32_t)((c_lo + k + 2) * 32), va);
+          }
+          if (k + 2 >= CPW) release_acc();
+          store_chunk(vb, c_lo + k + 1);
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

@@ -58,6 +58,18 @@ struct Elem {
   static constexpr int BK = KC;               // reduction elements per stage (also k-rows of an MN-major stage)
 };
 
+// Epilogue warps per CTA.  A warp drains its 32 TMEM lanes one column at a time (load, bias, predicated 128-byte store,
+// pointer step: ~5 dependent-issue instructions per column and ONE warp per scheduler), ~45 cycles per column: a 128 x 64 tile
+// costs ~2800 cycles of epilogue against 9 k-iterations of MMA at C = 64 — the small-channel layers were EPILOGUE-bound
+// (ncu round 2: epilogue warps busy 60-70 % of the kernel, tensor pipe 24-30 %).  Tiles of <= 128 columns therefore use two
+// warps per TMEM lane quarter, each taking half of the columns; 256-column tiles (tensor-pipe bound, and 160+ registers per
+// thread) keep four.  The X3 epilogue accumulates the whole tile in registers and keeps four as well.
+template <int BN, bool X3 = false>
+struct EpiCfg {
+  static constexpr int WARPS = (BN <= 128 && !X3) ? 8 : 4;
+  static constexpr int THREADS = 128 + 32 * WARPS;
+};
+
 template <int BN, bool CTA2, bool X3 = false>
 struct StageCfg {
   static constexpr int A_BYTES = 128 * 128;   // 128 lanes x 128 B (K-major) == (128/KC chunks) x BK rows x 128 B
