@@ -161,11 +161,15 @@ def run_ours(args) -> None:
     from compyute_b200 import _lib, distributed, nn
 
     L = _lib.lib()  # no fallback: raises if the CUDA library is missing
+    if args.strip:
+        cp.set_strip_conv_enabled(True)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    numa = distributed.bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa_bind else {"bound": False}
+    # pin the process (CPUs + preferred memory node) to the GPU's NUMA node before any pinned allocation: the e2e numbers are
+    # PCIe / host-memory bound (6.2 GB each way per step and rank)
+    numa = distributed.bind_to_gpu_numa_node(local) if not args.no_numa_bind else {"bound": False}
     if world > 1:
         distributed.init("nccl")
     dev = cp.cuda
@@ -508,9 +512,10 @@ def model_record(args, cpu: bool = True):
     L = _lib.lib()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    if not getattr(args, "no_numa_bind", False) and not getattr(model_record, "_bound", False):
+        distributed.bind_to_gpu_numa_node(local)
+        model_record._bound = True
     if world > 1 and not distributed.is_initialized():
-        if not getattr(args, "no_numa_bind", False):
-            distributed.bind_to_gpu_numa_node(local)
         distributed.init("nccl")
     factory, xshape, classes, B, desc = MODEL_WORKLOADS[args.workload]
     B = args.batch or B
@@ -736,7 +741,8 @@ def main() -> None:
                     help="data-parallel model runs: bucketed all-reduces launched during backward (Optimizer.overlap_grad_sync) "
                          "instead of one all-reduce of the whole gradient arena at step(); measured gain at 2 GPUs is ~1 %% because "
                          "the persistent GEMM grids leave NCCL little room, so it is opt-in")
-    ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU runs: do not pin each rank to its GPU's NUMA node")
+    ap.add_argument("--strip", action="store_true", help="enable the opt-in strip (shared-halo) convolution kernels for the C <= 128 layers")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's NUMA node")
     ap.add_argument("--no-fused-step", action="store_true",
                     help="data-parallel runs: classic NCCL all-reduce + replicated update instead of the fused sharded step over "
                          "NVLS / peer memory (csrc/dp_step.cu)")

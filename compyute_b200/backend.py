@@ -15,7 +15,7 @@ from dataclasses import dataclass
 from . import _lib
 
 __all__ = ["Device", "cpu", "cuda", "DeviceError", "gpu_available", "synchronize", "use_device", "select_device",
-           "compute_mode", "get_compute_mode", "set_compute_mode"]
+           "compute_mode", "get_compute_mode", "set_compute_mode", "set_strip_conv_enabled"]
 
 
 class DeviceError(Exception):
@@ -94,6 +94,12 @@ def use_device(device: Device):
 #   "fp32x3"    alias of "fp32"
 _MODES = {"fp32": _lib.MODE_FP32X3, "fp32x3": _lib.MODE_FP32X3, "fp32_simt": _lib.MODE_FP32, "tf32": _lib.MODE_TF32, "bf16": _lib.MODE_BF16}
 _mode = _MODES[os.environ.get("COMPYUTE_B200_MODE", "fp32")]
+
+
+def set_strip_conv_enabled(enabled: bool) -> bool:
+    """Opt-in switch of the strip ("shared halo") convolution kernels for stride-1 same-padded 64 / 128-channel layers in
+    bf16 mode (csrc/strip_kernel.cuh).  Returns the previous setting."""
+    return bool(_lib.lib().cpt_conv2d_set_strip_enabled(1 if enabled else 0))
 
 
 def get_compute_mode() -> int:

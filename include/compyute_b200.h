@@ -103,7 +103,8 @@ int cpt_conv2d_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* 
                         int mode, void* ws, size_t ws_bytes, void* stream);
 
 /* Strip ("shared halo") path for stride-1, dilation-1, same-padded odd-K layers with Ci, Co multiples of 64 and <= 128
- * (larger layers are tensor-pipe bound on the im2col path), bf16 mode.  Replaces the same reference computation as the
+ * (larger layers are tensor-pipe bound on the im2col path), bf16 mode.  OPT-IN (cpt_conv2d_set_strip_enabled): parity-green and
+ * 6x lighter on L2->SM traffic, but not faster than the im2col kernels on B200 (DESIGN.md §4 has the measurements).  Replaces the same reference computation as the
  * *_cl entry points (convolution_funcs.py:222-241 forward, :390-403 dX, :405-408 dW); what changes is the operand layout:
  * activations are staged ZERO-PADDED channels-last, act_pad[B][H+2P][W+2P][C] bf16, so that the K*K filter taps of 128
  * consecutive output positions read ONE strip of input rows from shared memory (each activation crosses L2->SM once
@@ -115,6 +116,7 @@ int cpt_conv2d_wgrad_cl(const cpt_conv2d_desc* d, const void* x_cl, const void* 
  *                                    cpt_conv2d_fprop_cl_stats
  *   cpt_conv2d_dgrad_strip           dx from dy_pad (the forward strip with reversed taps)
  *   cpt_conv2d_wgrad_padded          dw from x_pad and dy_pad (im2col maps over the padded tensors; split-K, fixed order) */
+int cpt_conv2d_set_strip_enabled(int enabled);   /* opt-in switch (default: env CPT_STRIP, off); returns the previous setting */
 int cpt_conv2d_strip_supported(const cpt_conv2d_desc* d, int mode);
 size_t cpt_channels_last_padded_bytes(int B, int C, int H, int W, int pad);
 int cpt_to_channels_last_padded(const float* src, void* dst, int B, int C, int H, int W, int pad, float* chan_sum, void* ws,

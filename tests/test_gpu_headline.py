@@ -124,6 +124,35 @@ def test_conv2d_exact_integer(cp, shape, mode):
     exact("y", y, y_ref); exact("dx", dx, dx_ref); exact("dw", dw, dw_ref); exact("db", db, db_ref)
 
 
+@pytest.mark.parametrize("shape", [(4, 64, 64, 56, 3, 1, 1, 1), (2, 128, 128, 28, 3, 1, 1, 1), (3, 64, 128, 20, 3, 1, 1, 1), (2, 128, 64, 17, 5, 2, 1, 1),
+                                   (1, 64, 64, 112, 3, 1, 1, 1)], ids=lambda s: "x".join(map(str, s)))
+def test_conv2d_strip_kernels_exact_integer(cp, shape):
+    """The opt-in strip ("shared halo") kernels (csrc/strip_kernel.cuh): zero-padded channels-last staging, one strip per 128
+    outputs with the K*K taps as descriptors into it, resident / streamed filter tiles, wgrad through im2col maps over the
+    padded tensors — exact on integer data against the fp64 convolution, like every other operand layout."""
+    from compyute_b200.nn.functional import Conv2DFn, FunctionCache
+    B, Ci, Co, H, K, P, s, d = shape
+    rng = np.random.RandomState(1)
+    x, w, b = ints(rng, (B, Ci, H, H), -2, 2), ints(rng, (Co, Ci, K, K), -1, 1), ints(rng, (Co,), -2, 2)
+    dy = ints(rng, (B, Co, H, H), -1, 1)
+    y_ref, dx_ref, dw_ref, db_ref = _torch_conv_ref(x, w, b, dy, P, s, d)
+    T = lambda a: cp.tensor(a, device=cp.cuda)
+    prev = cp.set_strip_conv_enabled(True)
+    try:
+        from compyute_b200 import _lib
+        import ctypes
+        desc = _lib.ConvDesc(B, Ci, H, H, Co, K, P, s, d)
+        assert _lib.lib().cpt_conv2d_strip_supported(ctypes.byref(desc), _lib.MODE_BF16) == 1
+        with cp.compute_mode("bf16"):
+            c = FunctionCache()
+            y = Conv2DFn.forward(c, T(x), T(w), T(b), P, s, d)
+            dx, dw, db = Conv2DFn.backward(c, T(dy))
+    finally:
+        cp.set_strip_conv_enabled(prev)
+    tc_ok()
+    exact("y", y, y_ref); exact("dx", dx, dx_ref); exact("dw", dw, dw_ref); exact("db", db, db_ref)
+
+
 # ------------------------------------------------------------------ BASELINE configs[1] at full size
 @pytest.mark.parametrize("mode", ["bf16", "tf32", "fp32", "fp32_simt"])
 @pytest.mark.parametrize("C", [64, 128, 256, 512])
