@@ -38,6 +38,8 @@ __device__ __forceinline__ void st_sys(float* p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+constexpr int DP_UNROLL = 4;
+
 // summed gradient of 4 consecutive arena elements at float offset `off`
 template <bool MC>
 __device__ __forceinline__ float4 grad_sum(const cpt_dp_view& d, int64_t off) {
@@ -71,16 +73,36 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(const cpt_dp_view d, float
     const float mh = mv / m_div, vh = vv / v_div;
     pv -= lr * mh / (sqrtf(vh) + eps);
   };
+  // U independent 16-byte gradient sums per thread are in flight before the first is used: a multimem.ld_reduce (or a peer
+  // load) takes a round trip through the NVSwitch (~2-3 us), so link bandwidth needs megabytes outstanding per SM
   const int64_t n4 = d.shard_elems / 4, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const int64_t off = d.shard_off + 4 * i;
-    const float4 g = grad_sum<MC>(d, off);
-    float4 p = *reinterpret_cast<const float4*>(d.p_local + off);
-    float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
-    upd(p.x, g.x, mv.x, vv.x); upd(p.y, g.y, mv.y, vv.y); upd(p.z, g.z, mv.z, vv.z); upd(p.w, g.w, mv.w, vv.w);
-    reinterpret_cast<float4*>(m)[i] = mv;
-    reinterpret_cast<float4*>(v)[i] = vv;
-    param_bcast<MC>(d, off, p);
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * DP_UNROLL) {
+    float4 g[DP_UNROLL], p[DP_UNROLL], mv[DP_UNROLL], vv[DP_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DP_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) g[u] = grad_sum<MC>(d, d.shard_off + 4 * i);
+    }
+#pragma unroll
+    for (int u = 0; u < DP_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) {
+        p[u] = *reinterpret_cast<const float4*>(d.p_local + d.shard_off + 4 * i);
+        mv[u] = reinterpret_cast<float4*>(m)[i];
+        vv[u] = reinterpret_cast<float4*>(v)[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < DP_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) {
+        upd(p[u].x, g[u].x, mv[u].x, vv[u].x); upd(p[u].y, g[u].y, mv[u].y, vv[u].y);
+        upd(p[u].z, g[u].z, mv[u].z, vv[u].z); upd(p[u].w, g[u].w, mv[u].w, vv[u].w);
+        reinterpret_cast<float4*>(m)[i] = mv[u];
+        reinterpret_cast<float4*>(v)[i] = vv[u];
+        param_bcast<MC>(d, d.shard_off + 4 * i, p[u]);
+      }
+    }
   }
   __threadfence_system();
 }
@@ -99,14 +121,30 @@ __global__ void __launch_bounds__(256) dp_sgd_kernel(const cpt_dp_view d, float*
     pv = pv - lr * gv;
   };
   const int64_t n4 = d.shard_elems / 4, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const int64_t off = d.shard_off + 4 * i;
-    const float4 g = grad_sum<MC>(d, off);
-    float4 p = *reinterpret_cast<const float4*>(d.p_local + off);
-    float4 vv = vel ? reinterpret_cast<float4*>(vel)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    upd(p.x, g.x, vv.x); upd(p.y, g.y, vv.y); upd(p.z, g.z, vv.z); upd(p.w, g.w, vv.w);
-    if (vel) reinterpret_cast<float4*>(vel)[i] = vv;
-    param_bcast<MC>(d, off, p);
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * DP_UNROLL) {
+    float4 g[DP_UNROLL], p[DP_UNROLL], vv[DP_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DP_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) g[u] = grad_sum<MC>(d, d.shard_off + 4 * i);
+    }
+#pragma unroll
+    for (int u = 0; u < DP_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) {
+        p[u] = *reinterpret_cast<const float4*>(d.p_local + d.shard_off + 4 * i);
+        vv[u] = vel ? reinterpret_cast<float4*>(vel)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < DP_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) {
+        upd(p[u].x, g[u].x, vv[u].x); upd(p[u].y, g[u].y, vv[u].y); upd(p[u].z, g[u].z, vv[u].z); upd(p[u].w, g[u].w, vv[u].w);
+        if (vel) reinterpret_cast<float4*>(vel)[i] = vv[u];
+        param_bcast<MC>(d, d.shard_off + 4 * i, p[u]);
+      }
+    }
   }
   __threadfence_system();
 }
@@ -119,7 +157,7 @@ static int check_view(const cpt_dp_view* d, const char* who) {
   return CPT_OK;
 }
 static int dp_grid(int64_t elems) {
-  int64_t g = (elems / 4 + 255) / 256, cap = (int64_t)sm_count() * 4;
+  int64_t g = (elems / 4 + 256 * DP_UNROLL - 1) / (256 * DP_UNROLL), cap = (int64_t)sm_count() * 4;
   if (g > cap) g = cap;
   return g < 1 ? 1 : (int)g;
 }
