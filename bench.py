@@ -457,10 +457,10 @@ def parity_check(layer, x_dev, dy_dev, x_t, dy_t, mode: str, samples: int = 96) 
     y = layer(x_t)
     dx = layer.backward(dy_t)
     yb, dxb = y.data._buf, dx.data._buf
-    w = layer.w.data._buf.double()
-    b = layer.b.data._buf.double()
     B, C, H, _ = x_dev.shape
-    dw = layer.w.grad.data._buf.view(C, C, 3, 3)  # a flat slice of the optimizer's gradient arena
+    w = layer.w.data._buf.reshape(C, C, 3, 3).double()  # a flat slice of the symmetric parameter arena in fused data-parallel runs
+    b = layer.b.data._buf.reshape(C).double()
+    dw = layer.w.grad.data._buf.reshape(C, C, 3, 3)  # a flat slice of the optimizer's gradient arena
     g = torch.Generator().manual_seed(0)
     r = lambda n: int(torch.randint(0, n, (1,), generator=g))
     xp = lambda t, bi, p, q: torch.nn.functional.pad(t[bi].double(), (1, 1, 1, 1))[:, p:p + 3, q:q + 3]

@@ -17,6 +17,7 @@ state layout ``{i: {"m": Tensor, "v": Tensor}}``.  What changes is *how* a step 
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 from typing import Any, Iterable, Optional
 
@@ -251,13 +252,18 @@ class Optimizer:
         self._arena = G.array
         self._table_key = None
         self._buckets = None
-        self._fused = {"G": G, "P": P, "shard": shard, "off": rank * shard, "world": world, "state": {}}
+        # multimem pulls EVERY member's copy through the switch, the requester's own included: at 2 ranks that is 1.5x the bytes
+        # of plain peer loads / stores (measured: 6.45 vs 6.5 ms MLP step), from 3 ranks on it is the cheaper path
+        env = os.environ.get("CPT_DP_MULTIMEM")
+        use_mc = bool(P.multicast_ptr and G.multicast_ptr) and (world > 2 if env is None else env != "0")
+        self._fused = {"G": G, "P": P, "shard": shard, "off": rank * shard, "world": world, "state": {}, "use_multimem": use_mc}
 
     def _fused_view(self) -> "_lib.DpView":
         f = self._fused
         v = _lib.DpView()
         v.p_local, v.g_local = f["P"].array.ptr, f["G"].array.ptr
-        v.p_mc, v.g_mc = f["P"].multicast_ptr or None, f["G"].multicast_ptr or None
+        mc = f["use_multimem"]
+        v.p_mc, v.g_mc = (f["P"].multicast_ptr if mc else None), (f["G"].multicast_ptr if mc else None)
         v.p_peers, v.g_peers = f["P"].peer_ptrs_dev, f["G"].peer_ptrs_dev
         v.shard_off, v.shard_elems, v.world = f["off"], f["shard"], f["world"]
         v.pre_reduced = 1 if self._synced else 0
@@ -278,6 +284,11 @@ class Optimizer:
                                "set_parameters for such models)")
         self._gather_grads_into_arena()
         f = self._fused
+        base = f["P"].array.ptr
+        for p, o in zip(self._parameters, self._offsets):  # a parameter rebound since (load_state_dict) moves back into the arena
+            if p.data.ptr != base + 4 * o:
+                f["P"].tensor[o:o + p.size].copy_(p.data._buf.reshape(-1))
+                p.data = DeviceArray(f["P"].tensor[o:o + p.size], p.shape, np.float32)
         f["G"].barrier(0)   # every rank's backward has written its gradient arena
         self._launch_fused(self._step_scalars(), 1.0 if self._synced else 1.0 / f["world"])
         f["P"].barrier(0)   # every replica of the parameters is complete before the next forward reads it
@@ -288,7 +299,9 @@ class Optimizer:
     def fused_dp_note(self) -> str:
         if self._fused is None:
             return "off (" + (distributed.symmetric_memory_note() or "single rank / unsupported optimizer") + ")"
-        return "multimem (NVLS in-switch reduction + multicast store)" if self._fused["P"].multicast_ptr else "peer loads / stores (no multicast support)"
+        if self._fused["use_multimem"]:
+            return "multimem (NVLS in-switch reduction + multicast store)"
+        return "peer loads / stores" + (" (2 ranks: cheaper than pulling both copies through the switch)" if self._fused["P"].multicast_ptr else " (no multicast support)")
 
     def _materialize_fused_state(self) -> None:
         """Checkpoints keep the reference layout ``{i: {"m": Tensor, "v": Tensor}}``: the shards are gathered from all ranks and
