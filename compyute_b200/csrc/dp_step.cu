@@ -13,6 +13,8 @@
 // second pass over the gradients, and replicas that are bit-identical by construction (one writer per element).
 // Cross-rank ordering (all gradients written before step 1; all parameters landed before the next forward) is the caller's:
 // a symmetric-memory barrier on the launching stream before and after (compyute_b200/distributed.py SymmetricArena.barrier).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cpt {
@@ -38,7 +40,6 @@ __device__ __forceinline__ void st_sys(float* p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-constexpr int DP_UNROLL = 4;
 
 // summed gradient of 4 consecutive arena elements at float offset `off`
 template <bool MC>
@@ -58,7 +59,7 @@ __device__ __forceinline__ void param_bcast(const cpt_dp_view& d, int64_t off, f
   for (int r = 0; r < d.world; ++r) st_sys(reinterpret_cast<float*>(d.p_peers[r]) + off, p);
 }
 
-template <bool MC>
+template <bool MC, int DP_UNROLL>
 __global__ void __launch_bounds__(256) dp_adam_kernel(const cpt_dp_view d, float* __restrict__ m, float* __restrict__ v, float lr,
                                                       float beta1, float beta2, float eps, float wd, float m_div, float v_div,
                                                       float grad_scale, int decoupled, const float* __restrict__ live) {
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(const cpt_dp_view d, float
   __threadfence_system();
 }
 
-template <bool MC>
+template <bool MC, int DP_UNROLL>
 __global__ void __launch_bounds__(256) dp_sgd_kernel(const cpt_dp_view d, float* __restrict__ vel, float lr, float momentum, int nesterov,
                                                      float wd, float grad_scale, const float* __restrict__ live) {
   if (live) lr = live[0];
@@ -156,8 +157,19 @@ static int check_view(const cpt_dp_view* d, const char* who) {
               "%s: shard offset / size must be multiples of 4 floats", who);
   return CPT_OK;
 }
-static int dp_grid(int64_t elems) {
-  int64_t g = (elems / 4 + 256 * DP_UNROLL - 1) / (256 * DP_UNROLL), cap = (int64_t)sm_count() * 4;
+// launch shape: CTAs per SM and 16-byte gradient sums in flight per thread (tools/dp_step_bench.py sweeps them on the box:
+// CPT_DP_CTAS_PER_SM, CPT_DP_UNROLL)
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static int dp_unroll() {
+  static const int u = env_int("CPT_DP_UNROLL", 4);
+  return u >= 8 ? 8 : (u <= 2 ? 2 : 4);
+}
+static int dp_grid(int64_t elems, int unroll) {
+  static const int per_sm = env_int("CPT_DP_CTAS_PER_SM", 4);
+  int64_t g = (elems / 4 + 256 * unroll - 1) / (256 * unroll), cap = (int64_t)sm_count() * (per_sm < 1 ? 1 : per_sm);
   if (g > cap) g = cap;
   return g < 1 ? 1 : (int)g;
 }
@@ -173,12 +185,13 @@ int cpt_dp_adam_step(const cpt_dp_view* view, float* m, float* v, float lr, floa
   if (int e = check_view(view, "dp_adam_step")) return e;
   CPT_REQUIRE(m && v, CPT_ERR_INVALID, "dp_adam_step: moment shards are NULL");
   if (view->shard_elems == 0) return CPT_OK;
-  if (view->p_mc && view->g_mc)
-    dp_adam_kernel<true><<<dp_grid(view->shard_elems), 256, 0, as_stream(stream)>>>(*view, m, v, lr, beta1, beta2, eps, weight_decay, m_div,
-                                                                                   v_div, grad_scale, decoupled, live_scalars);
-  else
-    dp_adam_kernel<false><<<dp_grid(view->shard_elems), 256, 0, as_stream(stream)>>>(*view, m, v, lr, beta1, beta2, eps, weight_decay, m_div,
-                                                                                    v_div, grad_scale, decoupled, live_scalars);
+  const bool mc = view->p_mc && view->g_mc;
+  const int u = dp_unroll();
+  const int grid = dp_grid(view->shard_elems, u);
+#define CPT_DP_ADAM(MC, U) dp_adam_kernel<MC, U><<<grid, 256, 0, as_stream(stream)>>>(*view, m, v, lr, beta1, beta2, eps, weight_decay, m_div, v_div, grad_scale, decoupled, live_scalars)
+  if (mc) { if (u == 8) CPT_DP_ADAM(true, 8); else if (u == 2) CPT_DP_ADAM(true, 2); else CPT_DP_ADAM(true, 4); }
+  else { if (u == 8) CPT_DP_ADAM(false, 8); else if (u == 2) CPT_DP_ADAM(false, 2); else CPT_DP_ADAM(false, 4); }
+#undef CPT_DP_ADAM
   CPT_LAUNCH_CHECK("dp_adam_step");
   return CPT_OK;
 }
@@ -188,12 +201,13 @@ int cpt_dp_sgd_step(const cpt_dp_view* view, float* velocity, float lr, float mo
   if (int e = check_view(view, "dp_sgd_step")) return e;
   CPT_REQUIRE(velocity || momentum <= 0.0f, CPT_ERR_INVALID, "dp_sgd_step: momentum needs the velocity shard");
   if (view->shard_elems == 0) return CPT_OK;
-  if (view->p_mc && view->g_mc)
-    dp_sgd_kernel<true><<<dp_grid(view->shard_elems), 256, 0, as_stream(stream)>>>(*view, velocity, lr, momentum, nesterov, weight_decay,
-                                                                                  grad_scale, live_scalars);
-  else
-    dp_sgd_kernel<false><<<dp_grid(view->shard_elems), 256, 0, as_stream(stream)>>>(*view, velocity, lr, momentum, nesterov, weight_decay,
-                                                                                   grad_scale, live_scalars);
+  const bool mc = view->p_mc && view->g_mc;
+  const int u = dp_unroll();
+  const int grid = dp_grid(view->shard_elems, u);
+#define CPT_DP_SGD(MC, U) dp_sgd_kernel<MC, U><<<grid, 256, 0, as_stream(stream)>>>(*view, velocity, lr, momentum, nesterov, weight_decay, grad_scale, live_scalars)
+  if (mc) { if (u == 8) CPT_DP_SGD(true, 8); else if (u == 2) CPT_DP_SGD(true, 2); else CPT_DP_SGD(true, 4); }
+  else { if (u == 8) CPT_DP_SGD(false, 8); else if (u == 2) CPT_DP_SGD(false, 2); else CPT_DP_SGD(false, 4); }
+#undef CPT_DP_SGD
   CPT_LAUNCH_CHECK("dp_sgd_step");
   return CPT_OK;
 }

@@ -159,8 +159,13 @@ class Optimizer:
         memory and ``t`` is advanced by ``upload_live_scalars`` at replay time instead."""
         if not self._fused_checked and not graph.is_capturing():
             self._maybe_enable_fused()
-        if self._fused is not None and not graph.is_capturing() and self._dp_world() > 1:
-            self._fused_step()
+        if self._fused is not None and self._dp_world() > 1:
+            if graph.is_capturing():
+                # captured data-parallel step: barriers and the fused kernel are ordinary launches on the capture stream; the
+                # per-step scalars come from the live buffer and ``t`` advances in upload_live_scalars at replay time
+                self._fused_step(self._peek_scalars(), self._live_buffer().ptr)
+                return
+            self._fused_step(self._step_scalars(), None)
             self._synced = False
             self.t += 1
             return
@@ -275,7 +280,7 @@ class Optimizer:
             st[key] = DeviceArray.zeros((self._fused["shard"],), np.float32)  # the reference's moments start from 0
         return st[key]
 
-    def _fused_step(self) -> None:
+    def _fused_step(self, scalars: list[float], live) -> None:
         """barrier -> one kernel (in-switch gradient sum of this rank's shard, update, multicast of the new parameters) ->
         barrier, all on the compute stream; no separate collective and no host synchronisation."""
         if any(p.grad is None for p in self._parameters):
@@ -290,10 +295,10 @@ class Optimizer:
                 f["P"].tensor[o:o + p.size].copy_(p.data._buf.reshape(-1))
                 p.data = DeviceArray(f["P"].tensor[o:o + p.size], p.shape, np.float32)
         f["G"].barrier(0)   # every rank's backward has written its gradient arena
-        self._launch_fused(self._step_scalars(), 1.0 if self._synced else 1.0 / f["world"])
+        self._launch_fused(scalars, 1.0 if self._synced else 1.0 / f["world"], live)
         f["P"].barrier(0)   # every replica of the parameters is complete before the next forward reads it
 
-    def _launch_fused(self, sc: list[float], scale: float) -> None:
+    def _launch_fused(self, sc: list[float], scale: float, live) -> None:
         raise NotImplementedError
 
     def fused_dp_note(self) -> str:
@@ -444,11 +449,11 @@ class SGD(Optimizer):
     def _step_scalars(self) -> list[float]:
         return [float(self.lr)]
 
-    def _launch_fused(self, sc, scale) -> None:
+    def _launch_fused(self, sc, scale, live) -> None:
         vel = self._fused_buffer("v").ptr if self.momentum > 0.0 else None
         view = self._fused_view()
         _lib.check(_lib.lib().cpt_dp_sgd_step(ctypes.byref(view), vel, sc[0], float(self.momentum), int(self.nesterov),
-                                              float(self.weight_decay), float(scale), None, stream_ptr()))
+                                              float(self.weight_decay), float(scale), live, stream_ptr()))
 
     def _launch(self, sc, live, scale) -> None:
         keys = ("v",) if self.momentum > 0.0 else ()
@@ -468,11 +473,11 @@ class Adam(Optimizer):
         super().__init__(parameters, lr)
         self.beta1, self.beta2, self.eps, self.weight_decay = beta1, beta2, eps, weight_decay
 
-    def _launch_fused(self, sc, scale) -> None:
+    def _launch_fused(self, sc, scale, live) -> None:
         view = self._fused_view()
         _lib.check(_lib.lib().cpt_dp_adam_step(ctypes.byref(view), self._fused_buffer("m").ptr, self._fused_buffer("v").ptr, sc[0],
                                                float(self.beta1), float(self.beta2), float(self.eps), float(self.weight_decay), sc[1],
-                                               sc[2], float(scale), self._decoupled, None, stream_ptr()))
+                                               sc[2], float(scale), self._decoupled, live, stream_ptr()))
 
     def _step_scalars(self) -> list[float]:
         # python doubles, like optimizers.py:243-244
