@@ -42,7 +42,7 @@ class DpView(ctypes.Structure):
 
     _fields_ = [("p_local", ctypes.c_void_p), ("p_mc", ctypes.c_void_p), ("p_peers", ctypes.c_void_p), ("g_local", ctypes.c_void_p),
                 ("g_mc", ctypes.c_void_p), ("g_peers", ctypes.c_void_p), ("shard_off", ctypes.c_int64), ("shard_elems", ctypes.c_int64),
-                ("world", ctypes.c_int32), ("pre_reduced", ctypes.c_int32)]
+                ("world", ctypes.c_int32), ("pre_reduced", ctypes.c_int32), ("max_ctas_per_sm", ctypes.c_int32), ("_pad", ctypes.c_int32)]
 
 
 _SCALARS = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,

@@ -167,8 +167,9 @@ static int dp_unroll() {
   static const int u = env_int("CPT_DP_UNROLL", 4);
   return u >= 8 ? 8 : (u <= 2 ? 2 : 4);
 }
-static int dp_grid(int64_t elems, int unroll) {
-  static const int per_sm = env_int("CPT_DP_CTAS_PER_SM", 4);
+static int dp_grid(int64_t elems, int unroll, int max_ctas_per_sm) {
+  static const int per_sm_env = env_int("CPT_DP_CTAS_PER_SM", 4);
+  const int per_sm = max_ctas_per_sm > 0 ? max_ctas_per_sm : per_sm_env;
   int64_t g = (elems / 4 + 256 * unroll - 1) / (256 * unroll), cap = (int64_t)sm_count() * (per_sm < 1 ? 1 : per_sm);
   if (g > cap) g = cap;
   return g < 1 ? 1 : (int)g;
@@ -187,7 +188,7 @@ int cpt_dp_adam_step(const cpt_dp_view* view, float* m, float* v, float lr, floa
   if (view->shard_elems == 0) return CPT_OK;
   const bool mc = view->p_mc && view->g_mc;
   const int u = dp_unroll();
-  const int grid = dp_grid(view->shard_elems, u);
+  const int grid = dp_grid(view->shard_elems, u, view->max_ctas_per_sm);
 #define CPT_DP_ADAM(MC, U) dp_adam_kernel<MC, U><<<grid, 256, 0, as_stream(stream)>>>(*view, m, v, lr, beta1, beta2, eps, weight_decay, m_div, v_div, grad_scale, decoupled, live_scalars)
   if (mc) { if (u == 8) CPT_DP_ADAM(true, 8); else if (u == 2) CPT_DP_ADAM(true, 2); else CPT_DP_ADAM(true, 4); }
   else { if (u == 8) CPT_DP_ADAM(false, 8); else if (u == 2) CPT_DP_ADAM(false, 2); else CPT_DP_ADAM(false, 4); }
@@ -203,7 +204,7 @@ int cpt_dp_sgd_step(const cpt_dp_view* view, float* velocity, float lr, float mo
   if (view->shard_elems == 0) return CPT_OK;
   const bool mc = view->p_mc && view->g_mc;
   const int u = dp_unroll();
-  const int grid = dp_grid(view->shard_elems, u);
+  const int grid = dp_grid(view->shard_elems, u, view->max_ctas_per_sm);
 #define CPT_DP_SGD(MC, U) dp_sgd_kernel<MC, U><<<grid, 256, 0, as_stream(stream)>>>(*view, velocity, lr, momentum, nesterov, weight_decay, grad_scale, live_scalars)
   if (mc) { if (u == 8) CPT_DP_SGD(true, 8); else if (u == 2) CPT_DP_SGD(true, 2); else CPT_DP_SGD(true, 4); }
   else { if (u == 8) CPT_DP_SGD(false, 8); else if (u == 2) CPT_DP_SGD(false, 2); else CPT_DP_SGD(false, 4); }

@@ -120,7 +120,7 @@ class Optimizer:
     def get_state_dict(self) -> dict[str, dict[Any, Any]]:
         if self._fused is not None:
             self._materialize_fused_state()
-        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel", "_live", "_synced", "_fused", "fused_dp_step", "overlap_grad_sync",
+        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel", "_live", "_synced", "_fused", "_fused_checked", "fused_dp_step", "overlap_grad_sync",
                 "bucket_bytes", "reserve_sms", "_buckets", "_bucket_pending", "_bucket_work", "_bucket_launched", "_offsets", "_bucket_of"}
         return {"state": self._state, "vars": {k: v for k, v in vars(self).items() if k not in skip}}
 
@@ -137,6 +137,7 @@ class Optimizer:
         for p in self._parameters:
             p.grad = None
         self._reset_buckets()
+        self._fused_reset_buckets()
         self._synced = False
 
     def sync_grads(self) -> None:
@@ -165,7 +166,7 @@ class Optimizer:
                 # per-step scalars come from the live buffer and ``t`` advances in upload_live_scalars at replay time
                 self._fused_step(self._peek_scalars(), self._live_buffer().ptr)
                 return
-            self._fused_step(self._step_scalars(), None)
+            self._fused_step(None, None)
             self._synced = False
             self.t += 1
             return
@@ -231,8 +232,12 @@ class Optimizer:
         """First data-parallel step(): move the gradient arena G and the parameters (arena P) into symmetric memory.  Collective —
         every rank of the group reaches its first step() —, which is why it does not happen in set_parameters (an optimizer
         built on one rank only, e.g. a single-process reference run next to a DP run, must not start a rendezvous).
-        ``p.data`` becomes a view of P (the fused step writes every replica's P through the multicast / peer mappings); this
-        rank owns ``[rank*S, (rank+1)*S)`` of both arenas and keeps the moments of that shard only."""
+
+        The arenas are cut into BUCKETS of whole parameters (one bucket without ``overlap_grad_sync``; ``plan_grad_buckets`` of
+        >= ``bucket_bytes`` each with it, in the order backward completes them), every bucket padded to a multiple of
+        world * 64 elements so that rank r owns the r-th equal slice of EVERY bucket and keeps the moments of those slices only.
+        ``p.data`` / ``p.grad_slot`` become views of P / G (the fused step writes every replica's P through the multicast /
+        peer mappings)."""
         self._fused_checked = True
         if not (self.fused_dp_step and self._fused_dp_keys is not None and self._arena is not None and self._dp_world() > 1
                 and distributed.symmetric_memory_available()):
@@ -240,13 +245,29 @@ class Optimizer:
         if any(self._state[i] for i in self._state):
             return  # moments already exist in the replicated layout (resumed run): keep the classic path
         world, rank = distributed.world_size(), distributed.rank()
-        total = self._arena.size
-        padded, shard = distributed.plan_shards(total, world)
-        G, P = distributed.SymmetricArena(padded), distributed.SymmetricArena(padded)
-        G.tensor[:total].copy_(self._arena._buf)  # this step's gradients are already in the old arena
+        sizes = [p.size for p in self._parameters]
+        if self.overlap_grad_sync:
+            plan = plan_grad_buckets(self._offsets, sizes, max(1, self.bucket_bytes // 4))
+        else:
+            plan = [(0, self._arena.size, list(range(len(sizes) - 1, -1, -1)))]
+        # new layout: buckets in arena order, parameters 64-aligned inside, bucket length a multiple of world * 64
+        new_off, buckets, cursor = [0] * len(sizes), [], 0
+        for lo, hi, members in sorted(plan, key=lambda b: b[0]):
+            b_lo = cursor
+            for i in sorted(members):
+                new_off[i] = cursor
+                cursor += (sizes[i] + 63) // 64 * 64
+            length, shard = distributed.plan_shards(cursor - b_lo, world)
+            cursor = b_lo + length
+            buckets.append({"lo": b_lo, "hi": cursor, "shard": shard, "off": b_lo + rank * shard, "members": sorted(members),
+                            "state": {}, "pending": len(members), "launched": False, "order": plan.index((lo, hi, members))})
+        buckets.sort(key=lambda b: b["order"])  # expected completion order of backward
+        G, P = distributed.SymmetricArena(cursor), distributed.SymmetricArena(cursor)
+        old = self._arena._buf
         for ptr in [k for k, (ref, _) in _SLOT_OWNERS.items() if ref() is self]:
             del _SLOT_OWNERS[ptr]
-        for i, (p, o) in enumerate(zip(self._parameters, self._offsets)):
+        for i, (p, o_old, o) in enumerate(zip(self._parameters, self._offsets, new_off)):
+            G.tensor[o:o + p.size].copy_(old[o_old:o_old + p.size])  # this step's gradients are already in the old arena
             P.tensor[o:o + p.size].copy_(p.data._buf.reshape(-1))
             p.data = DeviceArray(P.tensor[o:o + p.size], p.shape, np.float32)
             had_slot_grad = p.grad is not None and p.grad_slot is not None and p.grad.data.ptr == p.grad_slot.ptr
@@ -254,82 +275,135 @@ class Optimizer:
             _SLOT_OWNERS[p.grad_slot.ptr] = (weakref.ref(self), i)
             if had_slot_grad:
                 p.grad = Tensor(p.grad_slot)
-        self._arena = G.array
+        self._arena, self._offsets = G.array, new_off
         self._table_key = None
         self._buckets = None
         # multimem pulls EVERY member's copy through the switch, the requester's own included: at 2 ranks that is 1.5x the bytes
-        # of plain peer loads / stores (measured: 6.45 vs 6.5 ms MLP step), from 3 ranks on it is the cheaper path
+        # of plain peer loads / stores (measured, 537 MB: 1.43 vs 1.06 ms), from 3 ranks on it is the cheaper path
         env = os.environ.get("CPT_DP_MULTIMEM")
         use_mc = bool(P.multicast_ptr and G.multicast_ptr) and (world > 2 if env is None else env != "0")
-        self._fused = {"G": G, "P": P, "shard": shard, "off": rank * shard, "world": world, "state": {}, "use_multimem": use_mc}
+        self._fused = {"G": G, "P": P, "world": world, "buckets": buckets, "use_multimem": use_mc, "side": None, "scalars": None,
+                       "bucket_of": {i: b for b in buckets for i in b["members"]}}
 
-    def _fused_view(self) -> "_lib.DpView":
+    def _fused_view(self, bucket: dict, small_grid: bool) -> "_lib.DpView":
         f = self._fused
         v = _lib.DpView()
         v.p_local, v.g_local = f["P"].array.ptr, f["G"].array.ptr
         mc = f["use_multimem"]
         v.p_mc, v.g_mc = (f["P"].multicast_ptr if mc else None), (f["G"].multicast_ptr if mc else None)
         v.p_peers, v.g_peers = f["P"].peer_ptrs_dev, f["G"].peer_ptrs_dev
-        v.shard_off, v.shard_elems, v.world = f["off"], f["shard"], f["world"]
+        v.shard_off, v.shard_elems, v.world = bucket["off"], bucket["shard"], f["world"]
         v.pre_reduced = 1 if self._synced else 0
+        v.max_ctas_per_sm = 1 if small_grid else 0  # overlapped with backward: one small CTA next to each persistent GEMM CTA
         return v
 
-    def _fused_buffer(self, key: str) -> DeviceArray:
-        st = self._fused["state"]
+    def _fused_buffer(self, bucket: dict, key: str) -> DeviceArray:
+        st = bucket["state"]
         if key not in st:
-            st[key] = DeviceArray.zeros((self._fused["shard"],), np.float32)  # the reference's moments start from 0
+            st[key] = DeviceArray.zeros((bucket["shard"],), np.float32)  # the reference's moments start from 0
         return st[key]
 
-    def _fused_step(self, scalars: list[float], live) -> None:
-        """barrier -> one kernel (in-switch gradient sum of this rank's shard, update, multicast of the new parameters) ->
-        barrier, all on the compute stream; no separate collective and no host synchronisation."""
-        if any(p.grad is None for p in self._parameters):
-            raise RuntimeError("fused data-parallel step: every parameter needs a gradient each step (parameters without one "
-                               "are skipped by the reference, optimizers.py:157; set optimizer.fused_dp_step = False before "
-                               "set_parameters for such models)")
-        self._gather_grads_into_arena()
+    def _fused_rebind(self) -> None:
+        """A parameter rebound since (load_state_dict) moves back into the arena."""
         f = self._fused
         base = f["P"].array.ptr
-        for p, o in zip(self._parameters, self._offsets):  # a parameter rebound since (load_state_dict) moves back into the arena
+        for p, o in zip(self._parameters, self._offsets):
             if p.data.ptr != base + 4 * o:
                 f["P"].tensor[o:o + p.size].copy_(p.data._buf.reshape(-1))
                 p.data = DeviceArray(f["P"].tensor[o:o + p.size], p.shape, np.float32)
-        f["G"].barrier(0)   # every rank's backward has written its gradient arena
-        self._launch_fused(scalars, 1.0 if self._synced else 1.0 / f["world"], live)
-        f["P"].barrier(0)   # every replica of the parameters is complete before the next forward reads it
 
-    def _launch_fused(self, sc: list[float], scale: float, live) -> None:
+    def _fused_launch_bucket_async(self, bucket: dict) -> None:
+        """Overlapped form: as soon as backward has enqueued the last gradient of a bucket, its exchange + update goes to a
+        high-priority side stream (event wait -> cross-rank barrier -> fused kernel with a one-CTA-per-SM grid that co-resides
+        with the persistent GEMM kernels of the layers still in backward).  Every rank issues the buckets in the same order."""
+        import torch
+        f = self._fused
+        if f["side"] is None:
+            f["side"] = torch.cuda.Stream(priority=-1)
+        if f["scalars"] is None:
+            f["scalars"] = self._step_scalars()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(f["side"]):
+            f["side"].wait_event(ev)
+            f["G"].barrier(1)
+            self._launch_fused(f["scalars"], 1.0 / f["world"], None, bucket, True)
+        bucket["launched"] = True
+
+    def _fused_step(self, scalars, live) -> None:
+        """barrier -> one kernel per bucket (in-switch gradient sum of this rank's slice, update, multicast of the new parameters)
+        -> barrier; no separate collective and no host synchronisation.  Buckets already exchanged during backward
+        (``overlap_grad_sync``) are only waited for."""
+        import torch
+        if any(p.grad is None for p in self._parameters):
+            raise RuntimeError("fused data-parallel step: every parameter needs a gradient each step (parameters without one "
+                               "are skipped by the reference, optimizers.py:157; set optimizer.fused_dp_step = False before "
+                               "the first step for such models)")
+        self._gather_grads_into_arena()
+        self._fused_rebind()
+        f = self._fused
+        overlapped = any(b["launched"] for b in f["buckets"])
+        if overlapped:
+            if self._synced:
+                raise RuntimeError("overlap_grad_sync: gradients were synchronised by hand (clip_grad_norm / sync_grads) after "
+                                   "buckets had already been exchanged during backward; use one or the other")
+            for b in f["buckets"]:  # whatever backward did not complete goes behind the others on the side stream
+                if not b["launched"]:
+                    self._fused_launch_bucket_async(b)
+            done = torch.cuda.Event()
+            done.record(f["side"])
+            torch.cuda.current_stream().wait_event(done)
+        else:
+            if scalars is None:
+                scalars = self._step_scalars()
+            f["G"].barrier(0)   # every rank's backward has written its gradient arena
+            for b in f["buckets"]:
+                self._launch_fused(scalars, 1.0 if self._synced else 1.0 / f["world"], live, b, False)
+        f["P"].barrier(0)       # every replica of the parameters is complete before the next forward reads it
+        self._fused_reset_buckets()
+
+    def _fused_reset_buckets(self) -> None:
+        if self._fused is not None:
+            self._fused["scalars"] = None
+            for b in self._fused["buckets"]:
+                b["pending"], b["launched"] = len(b["members"]), False
+
+    def _launch_fused(self, sc: list[float], scale: float, live, bucket: dict, small_grid: bool) -> None:
         raise NotImplementedError
 
     def fused_dp_note(self) -> str:
         if self._fused is None:
             return "off (" + (distributed.symmetric_memory_note() or "single rank / unsupported optimizer") + ")"
+        nb = len(self._fused["buckets"])
+        how = f", {nb} buckets overlapped with backward" if self.overlap_grad_sync and nb > 1 else ""
         if self._fused["use_multimem"]:
-            return "multimem (NVLS in-switch reduction + multicast store)"
-        return "peer loads / stores" + (" (2 ranks: cheaper than pulling both copies through the switch)" if self._fused["P"].multicast_ptr else " (no multicast support)")
+            return "multimem (NVLS in-switch reduction + multicast store)" + how
+        return "peer loads / stores" + (" (2 ranks: cheaper than pulling both copies through the switch)" if self._fused["P"].multicast_ptr else " (no multicast support)") + how
 
     def _materialize_fused_state(self) -> None:
-        """Checkpoints keep the reference layout ``{i: {"m": Tensor, "v": Tensor}}``: the shards are gathered from all ranks and
+        """Checkpoints keep the reference layout ``{i: {"m": Tensor, "v": Tensor}}``: the slices are gathered from all ranks and
         cut at the parameter offsets (collective call)."""
-        f = self._fused
-        for key, shard in f["state"].items():
-            full = distributed.all_gather(shard).reshape(-1)
-            for i, (p, o) in enumerate(zip(self._parameters, self._offsets)):
-                self._state[i][key] = Tensor(DeviceArray(full._buf[o:o + p.size].clone(), p.shape, np.float32))
+        for b in self._fused["buckets"]:
+            for key, shard in b["state"].items():
+                full = distributed.all_gather(shard).reshape(-1)  # [world * shard] == the bucket's range [lo, hi)
+                for i in b["members"]:
+                    p, o = self._parameters[i], self._offsets[i] - b["lo"]
+                    self._state[i][key] = Tensor(DeviceArray(full._buf[o:o + p.size].clone(), p.shape, np.float32))
 
     def _scatter_fused_state(self) -> None:
-        f = self._fused
-        lo, hi = f["off"], f["off"] + f["shard"]
-        for key in self._fused_dp_keys or ():
-            buf = self._fused_buffer(key)
-            buf.fill(0.0)
-            for i, (p, o) in enumerate(zip(self._parameters, self._offsets)):
-                st = self._state.get(i, {}).get(key)
-                a, b = max(o, lo), min(o + p.size, hi)
-                if st is None or a >= b:
-                    continue
-                src = st.data if isinstance(st.data, DeviceArray) else DeviceArray.from_numpy(np.asarray(st.data, np.float32))
-                buf._buf[a - lo:b - lo].copy_(src._buf.reshape(-1)[a - o:b - o])
+        for bk in self._fused["buckets"]:
+            lo, hi = bk["off"], bk["off"] + bk["shard"]
+            for key in self._fused_dp_keys or ():
+                buf = self._fused_buffer(bk, key)
+                buf.fill(0.0)
+                for i in bk["members"]:
+                    p, o = self._parameters[i], self._offsets[i]
+                    st = self._state.get(i, {}).get(key)
+                    a, b = max(o, lo), min(o + p.size, hi)
+                    if st is None or a >= b:
+                        continue
+                    src = st.data if isinstance(st.data, DeviceArray) else DeviceArray.from_numpy(np.asarray(st.data, np.float32))
+                    buf._buf[a - lo:b - lo].copy_(src._buf.reshape(-1)[a - o:b - o])
 
     # ---- overlapped data-parallel exchange -----------------------------------------------------
     def _dp_world(self) -> int:
@@ -362,6 +436,18 @@ class Optimizer:
         (``first``) or accumulated into it again (shared parameter)."""
         if not self.overlap_grad_sync or self._arena is None or self._dp_world() == 1 or graph.is_capturing():
             return
+        if self._fused is not None:  # bucketed fused step on the side stream (the first step, which builds the arenas, is not overlapped)
+            bk = self._fused["bucket_of"][i]
+            if bk["launched"]:
+                raise RuntimeError("overlap_grad_sync: a parameter received a second gradient after its bucket was exchanged "
+                                   "(shared parameters need overlap_grad_sync = False)")
+            if first:
+                bk["pending"] -= 1
+                if bk["pending"] == 0 and len(self._fused["buckets"]) > 1:
+                    self._fused_launch_bucket_async(bk)
+            return
+        if self._fused_dp_keys is not None and self.fused_dp_step and not self._fused_checked:
+            return  # the first step() decides between the fused and the classic exchange
         self._ensure_buckets()
         b = self._bucket_of[i]
         if not first and not self._bucket_launched[b]:
@@ -449,9 +535,9 @@ class SGD(Optimizer):
     def _step_scalars(self) -> list[float]:
         return [float(self.lr)]
 
-    def _launch_fused(self, sc, scale, live) -> None:
-        vel = self._fused_buffer("v").ptr if self.momentum > 0.0 else None
-        view = self._fused_view()
+    def _launch_fused(self, sc, scale, live, bucket, small_grid) -> None:
+        vel = self._fused_buffer(bucket, "v").ptr if self.momentum > 0.0 else None
+        view = self._fused_view(bucket, small_grid)
         _lib.check(_lib.lib().cpt_dp_sgd_step(ctypes.byref(view), vel, sc[0], float(self.momentum), int(self.nesterov),
                                               float(self.weight_decay), float(scale), live, stream_ptr()))
 
@@ -473,9 +559,9 @@ class Adam(Optimizer):
         super().__init__(parameters, lr)
         self.beta1, self.beta2, self.eps, self.weight_decay = beta1, beta2, eps, weight_decay
 
-    def _launch_fused(self, sc, scale, live) -> None:
-        view = self._fused_view()
-        _lib.check(_lib.lib().cpt_dp_adam_step(ctypes.byref(view), self._fused_buffer("m").ptr, self._fused_buffer("v").ptr, sc[0],
+    def _launch_fused(self, sc, scale, live, bucket, small_grid) -> None:
+        view = self._fused_view(bucket, small_grid)
+        _lib.check(_lib.lib().cpt_dp_adam_step(ctypes.byref(view), self._fused_buffer(bucket, "m").ptr, self._fused_buffer(bucket, "v").ptr, sc[0],
                                                float(self.beta1), float(self.beta2), float(self.eps), float(self.weight_decay), sc[1],
                                                sc[2], float(scale), self._decoupled, live, stream_ptr()))
 

@@ -524,6 +524,8 @@ typedef struct cpt_dp_view {
   int64_t shard_elems;       /* elements in the shard (multiple of 4)                         */
   int32_t world;
   int32_t pre_reduced;
+  int32_t max_ctas_per_sm;   /* 0: default grid; n > 0: at most n CTAs per SM (a step overlapped with other kernels) */
+  int32_t reserved;
 } cpt_dp_view;
 int cpt_dp_adam_step(const cpt_dp_view* view, float* m, float* v, float lr, float beta1, float beta2, float eps, float weight_decay,
                      float m_div, float v_div, float grad_scale, int decoupled, const float* live_scalars, void* stream);

@@ -19,6 +19,8 @@ VARIANTS = {
     "fused_step": {},                                   # peer loads / stores at 2 ranks, multimem from 3 ranks on
     "fused_step_multimem": {"CPT_DP_MULTIMEM": "1"},    # multimem.ld_reduce / multimem.st through the NVSwitch at any world size
     "fused_step_peer": {"CPT_DP_MULTIMEM": "0"},
+    "fused_step_overlapped_buckets": {"DP_OVERLAP": "1"},                       # bucketed, on a side stream during backward
+    "fused_step_overlapped_multimem": {"DP_OVERLAP": "1", "CPT_DP_MULTIMEM": "1"},
     "nccl_allreduce": {"DP_FUSED": "0"},
     "nccl_overlapped_buckets": {"DP_FUSED": "0", "DP_OVERLAP": "1"},
     "torch_distributed_allreduce": {"DP_FUSED": "0", "CPT_OWN_NCCL": "0"},

@@ -50,7 +50,8 @@ def train(model, x, t, steps, dp):
     losses = []
     D.set_sync_batchnorm(SYNCBN and dp)
     with cp.compute_mode(MODE):
-        for _ in range(steps):
+        steps = max(steps, int(os.environ.get("DP_STEPS", steps)))
+    for _ in range(steps):
             loss = loss_fn(model(xt), tt)
             opt.reset_grads()
             model.backward(loss_fn.backward())
