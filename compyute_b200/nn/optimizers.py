@@ -327,7 +327,9 @@ class Optimizer:
         with torch.cuda.stream(f["side"]):
             f["side"].wait_event(ev)
             f["G"].barrier(1)
-            self._launch_fused(f["scalars"], 1.0 / f["world"], None, bucket, True)
+            # the bucket backward completes LAST (the first layers' parameters) has nothing left to hide behind: full grid
+            last = bucket["order"] == len(f["buckets"]) - 1
+            self._launch_fused(f["scalars"], 1.0 / f["world"], None, bucket, not last)
         bucket["launched"] = True
 
     def _fused_step(self, scalars, live) -> None:
