@@ -618,7 +618,7 @@ def model_record(args, cpu: bool = True):
         # configs 1 and 2 are launch-bound on one GPU (mnist: 645 launches of a few microseconds per step; vgg: 1000 launches in
         # 4.5 ms, 226-231 k images/s eager vs 246 k replayed): the step is replayed as one CUDA graph
         args.graph = True
-    if world > 1 and args.workload in ("mnist", "vgg") and not args.no_graph and not args.overlap:
+    if world > 1 and args.graph_dp and args.workload in ("mnist", "vgg") and not args.no_graph and not args.overlap:
         # data-parallel CUDA graph: needs the fused sharded step (its barriers and kernel are plain launches; an NCCL call would
         # be captured too, but only the fused form is validated).  One eager step first: it moves the arenas into symmetric memory.
         with cp.compute_mode(args.mode):
@@ -743,7 +743,9 @@ def main() -> None:
     ap.add_argument("--workload", default="conv2d_sweep", choices=["conv2d_sweep", "mnist", "vgg", "resnet18", "mlp"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of a model workload")
     ap.add_argument("--graph", action="store_true", help="model workloads: replay the train step as one CUDA graph (default for mnist and vgg on one GPU)")
-    ap.add_argument("--graph-dp", action="store_true", help="(default since round 2) mnist / vgg at N > 1: the data-parallel step, fused sharded step included, is replayed as one CUDA graph; --no-graph switches it off")
+    ap.add_argument("--graph-dp", action="store_true", help="mnist / vgg at N > 1: replay the data-parallel step (fused sharded step included) as one CUDA graph.  Opt-in: measured "
+                         "faster at 2 GPUs (4.28 vs 4.62 ms VGG) and for the launch-bound strong-scaling case at 8 (1.46 vs 3.69 ms), slower for "
+                         "weak-scaling VGG at 8 GPUs (6.7 vs 4.6 ms; not diagnosed)")
     ap.add_argument("--no-graph", action="store_true", help="mnist / vgg: eager launches instead of the default CUDA-graph replay")
     ap.add_argument("--overlap", action="store_true",
                     help="data-parallel model runs: bucketed all-reduces launched during backward (Optimizer.overlap_grad_sync) "

@@ -164,7 +164,7 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 static int dp_unroll() {
-  static const int u = env_int("CPT_DP_UNROLL", 4);
+  static const int u = env_int("CPT_DP_UNROLL", 8);  // 537 MB at 8 GPUs (tools/dp_step_bench.py): 1.48 ms with 4, 1.24 with 8
   return u >= 8 ? 8 : (u <= 2 ? 2 : 4);
 }
 static int dp_grid(int64_t elems, int unroll, int max_ctas_per_sm) {

@@ -17,7 +17,7 @@ import numpy as np
 
 __all__ = ["init", "is_initialized", "rank", "world_size", "all_reduce_sum", "all_reduce_sum_async", "all_gather", "broadcast_parameters",
            "shard_batch", "shard_bounds", "barrier", "set_sync_batchnorm", "sync_batchnorm_active", "SymmetricArena",
-           "symmetric_memory_available", "use_own_nccl", "plan_shards", "bind_to_gpu_numa_node"]
+           "symmetric_memory_available", "use_own_nccl", "plan_shards", "bind_to_gpu_numa_node", "shard_weight"]
 
 _dist = None
 
@@ -252,6 +252,14 @@ def shard_bounds(n: int, r: int | None = None, world: int | None = None) -> tupl
     base, rem = divmod(n, world)
     lo = r * base + min(r, rem)
     return lo, lo + base + (1 if r < rem else 0)
+
+
+def shard_weight(n_local: int, n_global: int, world: int | None = None) -> float:
+    """Weight of this rank's (local-mean) gradient in the global-batch mean when shards are uneven: n_local * world / n_global.
+    The exchange averages the ranks' gradients with equal weights (sum, then 1/world); a rank that holds more samples than the
+    others must count for more — set ``optimizer.local_weight = shard_weight(...)`` (1.0 for equal shards)."""
+    world = world_size() if world is None else world
+    return float(n_local) * world / float(n_global)
 
 
 def shard_batch(*arrays: np.ndarray):

@@ -99,6 +99,7 @@ class Optimizer:
         self._synced = False        # sync_grads() already exchanged (and averaged) this step's gradients
         # fused data-parallel step (csrc/dp_step.cu): gradient + parameter arenas in symmetric memory, each rank updates its
         # shard from the in-switch gradient sum and multicasts the new parameters; None = classic all-reduce + replicated update
+        self.local_weight = 1.0     # uneven data-parallel shards: distributed.shard_weight(n_local, n_global); 1.0 = equal shards
         self.fused_dp_step = True   # use it whenever the process group supports it (set False before the first step to opt out)
         self._fused, self._fused_checked = None, False
         if parameters is not None:
@@ -120,7 +121,7 @@ class Optimizer:
     def get_state_dict(self) -> dict[str, dict[Any, Any]]:
         if self._fused is not None:
             self._materialize_fused_state()
-        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel", "_live", "_synced", "_fused", "_fused_checked", "fused_dp_step", "overlap_grad_sync",
+        skip = {"_parameters", "_state", "_arena", "_table_dev", "_table_key", "_data_parallel", "_live", "_synced", "_fused", "_fused_checked", "fused_dp_step", "local_weight", "overlap_grad_sync",
                 "bucket_bytes", "reserve_sms", "_buckets", "_bucket_pending", "_bucket_work", "_bucket_launched", "_offsets", "_bucket_of"}
         return {"state": self._state, "vars": {k: v for k, v in vars(self).items() if k not in skip}}
 
@@ -148,6 +149,9 @@ class Optimizer:
         if self._dp_world() == 1 or self._synced or self._arena is None:
             return
         if self._fused is not None:  # plain all-reduce of the symmetric gradient arena; the fused step then skips its own sum
+            self._gather_grads_into_arena()
+            if self.local_weight != 1.0:
+                self._arena *= float(self.local_weight)
             distributed.all_reduce_sum(self._arena)
             scale = 1.0 / self._dp_world()
         else:
@@ -345,6 +349,10 @@ class Optimizer:
         self._fused_rebind()
         f = self._fused
         overlapped = any(b["launched"] for b in f["buckets"])
+        if self.local_weight != 1.0 and not self._synced:
+            if overlapped:
+                raise RuntimeError("overlap_grad_sync needs equal shards (local_weight == 1.0)")
+            self._arena *= float(self.local_weight)  # this rank's share of the global-batch mean (uneven shards)
         if overlapped:
             if self._synced:
                 raise RuntimeError("overlap_grad_sync: gradients were synchronised by hand (clip_grad_norm / sync_grads) after "
@@ -510,6 +518,10 @@ class Optimizer:
         if self._arena is None:
             raise RuntimeError("data-parallel step needs cuda parameters (gradient arena missing)")
         self._gather_grads_into_arena()
+        if self.local_weight != 1.0:
+            if self.overlap_grad_sync and self._buckets is not None and any(self._bucket_launched):
+                raise RuntimeError("overlap_grad_sync needs equal shards (local_weight == 1.0)")
+            self._arena *= float(self.local_weight)  # this rank's share of the global-batch mean (uneven shards)
         if self.overlap_grad_sync and self._buckets is not None and any(self._bucket_launched):
             for b in range(len(self._buckets)):  # whatever backward did not complete (e.g. parameters without gradient)
                 if not self._bucket_launched[b]:

@@ -155,3 +155,18 @@ def test_plan_shards_for_the_fused_step():
             assert padded - total < world * 64  # at most one alignment unit of padding per rank
             owners = [(r * shard, (r + 1) * shard) for r in range(world)]
             assert owners[0][0] == 0 and owners[-1][1] == padded and all(a[1] == b[0] for a, b in zip(owners, owners[1:]))
+
+
+def test_shard_weight_restores_the_global_mean():
+    """Uneven shards (shard_bounds spreads the remainder over the first ranks): averaging the ranks' local-mean gradients with
+    weights n_r * world / N before the sum / world exchange gives the global-batch mean exactly."""
+    from compyute_b200.distributed import shard_bounds, shard_weight
+    rng = np.random.RandomState(0)
+    g = rng.normal(0, 1, (11, 5))  # per-sample gradients
+    for world in (2, 3, 4):
+        acc = np.zeros(5)
+        for r in range(world):
+            lo, hi = shard_bounds(11, r, world)
+            acc += shard_weight(hi - lo, 11, world) * g[lo:hi].mean(0)
+        assert np.allclose(acc / world, g.mean(0), rtol=1e-12, atol=1e-12)
+    assert shard_weight(8, 32, 4) == 1.0
