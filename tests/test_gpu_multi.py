@@ -24,6 +24,8 @@ VARIANTS = {
     "nccl_allreduce": {"DP_FUSED": "0"},
     "nccl_overlapped_buckets": {"DP_FUSED": "0", "DP_OVERLAP": "1"},
     "torch_distributed_allreduce": {"DP_FUSED": "0", "CPT_OWN_NCCL": "0"},
+    "clip_grad_norm_fused": {"DP_CLIP": "0.05"},                                 # sync_grads() first, the fused kernel then skips its sum
+    "clip_grad_norm_nccl": {"DP_CLIP": "0.05", "DP_FUSED": "0"},
     "sync_batchnorm": {"DP_SYNCBN": "1"},
     "fused_step_bf16": {"DP_MODE": "bf16", "DP_SYNCBN": "1"},
 }

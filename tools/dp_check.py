@@ -9,7 +9,8 @@ parameters (1e-5) and the loss trace.  Prints DP_CHECK OK / FAIL.
 DP_SYNCBN=1: the model contains BatchNorm2D (+ fused ReLU) and BatchNorm1D layers and synchronised BatchNorm is switched on
 (``distributed.set_sync_batchnorm``): statistics and backward sums over the global batch make DP on shards equal to the
 single-GPU full-batch run again (SGD with momentum, 1e-4; per-shard statistics would differ at the 1e-1 level).  DP_MODE
-selects the compute mode (fp32 default; bf16 exercises the channels-last producer paths)."""
+selects the compute mode (fp32 default; bf16 exercises the channels-last producer paths).  DP_CLIP=<max_norm>: gradient clipping
+before every step — the data-parallel run must clip the averaged global gradient to stay equal to the single-process run."""
 import os
 import sys
 
@@ -24,6 +25,7 @@ from compyute_b200 import nn
 
 SYNCBN = os.environ.get("DP_SYNCBN", "0") == "1"
 MODE = os.environ.get("DP_MODE", "fp32")
+CLIP = float(os.environ.get("DP_CLIP", "0"))  # > 0: clip_grad_norm(max_norm) before every step, in the DP and the single-process run
 
 
 def build():
@@ -55,6 +57,8 @@ def train(model, x, t, steps, dp):
             loss = loss_fn(model(xt), tt)
             opt.reset_grads()
             model.backward(loss_fn.backward())
+            if CLIP > 0.0:  # clipping must see the GLOBAL-batch gradient on every rank (Optimizer.sync_grads)
+                nn.utils.clip_grad_norm(model.get_parameters(), CLIP)
             opt.step()
             losses.append(loss.item())
     D.set_sync_batchnorm(False)
