@@ -123,10 +123,14 @@ constexpr int CL_PX = 128, CL_CH = 64;
 // Zero-padded destination (strip convolution path): pixel (b, h, w) goes to row b*Hp*Wp + (h + P)*Wp + (w + P)
 struct PadGeom { int W, H, P; };
 
-template <bool BF16, bool PAD = false>
-__global__ void __launch_bounds__(256, 4) nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW,
+// GATE: every value is multiplied by (gate > 0) first, gate = a tensor of src's shape — the backward pass of a ReLU folded into
+// the staging of dy (dy * mask, activation_funcs.py:32-34, with the mask taken from the ReLU's own output): 10 B/elem instead
+// of 8 1/8 (ReLU backward) + 6 (staging); the channel sums (db) are those of the gated values.
+template <bool BF16, bool PAD = false, bool GATE = false>
+__global__ void __launch_bounds__(256, GATE ? 3 : 4) nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW,
                                                            int Cp, float* __restrict__ chan_sum, float* __restrict__ partial,
-                                                           int64_t Q, float* __restrict__ dst_lo, PadGeom pg = PadGeom{0, 0, 0}) {
+                                                           int64_t Q, float* __restrict__ dst_lo, PadGeom pg = PadGeom{0, 0, 0},
+                                                           const float* __restrict__ gate = nullptr) {
   // pixel tiles run over the flattened (image, pixel) index q in [0, Q = B*HW): small feature maps (HW < 128) fill the
   // 128-pixel tile with pixels of several images instead of leaving lanes idle
   __shared__ uint32_t tile[BF16 ? 32 : 64][CL_PX + 1];
@@ -160,6 +164,20 @@ __global__ void __launch_bounds__(256, 4) nchw_to_nhwc_kernel(const float* __res
           const bool okp = soff[pi] != PAST_END;
           v0[ci][pi] = (okp && c < C) ? s[soff[pi] + (uint32_t)(c * HW)] : 0.f;
           v1[ci][pi] = (okp && c + 1 < C) ? s[soff[pi] + (uint32_t)((c + 1) * HW)] : 0.f;
+        }
+      }
+      if (GATE) {
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = c0 + 2 * (warp + 8 * ci);
+#pragma unroll
+          for (int pi = 0; pi < 4; ++pi) {
+            const bool okp = soff[pi] != PAST_END;
+            const float g0 = (okp && c < C) ? gate[soff[pi] + (uint32_t)(c * HW)] : 0.f;
+            const float g1 = (okp && c + 1 < C) ? gate[soff[pi] + (uint32_t)((c + 1) * HW)] : 0.f;
+            v0[ci][pi] *= g0 > 0.f ? 1.f : 0.f;  // a product, like numpy's float * bool: NaN / inf gradients stay visible
+            v1[ci][pi] *= g1 > 0.f ? 1.f : 0.f;
+          }
         }
       }
 #pragma unroll
@@ -206,6 +224,17 @@ __global__ void __launch_bounds__(256, 4) nchw_to_nhwc_kernel(const float* __res
         const int c = c0 + warp + 8 * ci;
 #pragma unroll
         for (int pi = 0; pi < 4; ++pi) v[ci][pi] = (soff[pi] != PAST_END && c < C) ? s[soff[pi] + (uint32_t)(c * HW)] : 0.f;
+      }
+      if (GATE) {
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+          const int c = c0 + warp + 8 * ci;
+#pragma unroll
+          for (int pi = 0; pi < 4; ++pi) {
+            const float g = (soff[pi] != PAST_END && c < C) ? gate[soff[pi] + (uint32_t)(c * HW)] : 0.f;
+            v[ci][pi] *= g > 0.f ? 1.f : 0.f;
+          }
+        }
       }
 #pragma unroll
       for (int ci = 0; ci < 8; ++ci) {
@@ -395,6 +424,19 @@ static bool want_2cta(int BN, int64_t m_tiles128) {
   return true;  // measured: C=512 fprop 2.85 -> 2.65 ms, never slower for BN >= 128
 }
 
+// 64-column tiles of the K-major kernels (convolution fprop / dgrad with <= 64 output channels).  Such a tile is bound by the
+// ONE thread that issues its MMAs (~450 cycles per filter tap, twice what the tensor pipe needs); with
+// cta_group::2 the same instruction stream drives the tensor cores of two SMs (a 256 x 64 tile), halving the issue cost per pixel.
+static bool want_2cta_kmajor(int BN, int64_t m_tiles128, int mode) {
+  if (BN >= 128) return want_2cta(BN, m_tiles128);
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CPT_TC_2CTA_64");
+    on = e ? atoi(e) : 1;
+  }
+  return on && BN == 64 && m_tiles128 >= 2 && !is_x3(mode);
+}
+
 template <bool A_MN, bool B_MN, int OP>
 static int launch_bn(TcParams p, int mode, int BN, bool use2, cudaStream_t st) {
   if (use2) p.m_tiles = (p.m_tiles + 1) / 2;  // 256-row tiles
@@ -485,7 +527,7 @@ size_t to_channels_last_ws(int B, int C, int H, int W) {
 // chan_sum != NULL: per-channel sums of src.  With a workspace they are reduced deterministically (per-block partials +
 // fixed-order pass) and chan_sum is overwritten; without one they are atomically accumulated into chan_sum (pre-zeroed).
 int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, int mode, float* chan_sum, void* ws, size_t ws_bytes,
-                     cudaStream_t st) {
+                     cudaStream_t st, const float* gate = nullptr) {
   const int Cp = round_up(C, 8), HW = H * W;
   int gx, groups;
   cl_grid(B, C, H, W, gx, groups);
@@ -496,7 +538,12 @@ int to_channels_last(const float* src, void* dst, int B, int C, int H, int W, in
   if (chan_sum && ws && ws_bytes >= to_channels_last_ws(B, C, H, W)) partial = reinterpret_cast<float*>(ws);
   const int64_t Q = (int64_t)B * HW;
   float* dst_lo = is_x3(mode) ? reinterpret_cast<float*>(reinterpret_cast<char*>(dst) + cl_plane_bytes(B, C, H, W, mode)) : nullptr;
-  if (mode == CPT_MODE_BF16) nchw_to_nhwc_kernel<true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial, Q, nullptr);
+  if (gate) {
+    if (mode == CPT_MODE_BF16)
+      nchw_to_nhwc_kernel<true, false, true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial, Q, nullptr, PadGeom{0, 0, 0}, gate);
+    else
+      nchw_to_nhwc_kernel<false, false, true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial, Q, dst_lo, PadGeom{0, 0, 0}, gate);
+  } else if (mode == CPT_MODE_BF16) nchw_to_nhwc_kernel<true><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial, Q, nullptr);
   else nchw_to_nhwc_kernel<false><<<grid, 256, 0, st>>>(src, dst, C, HW, Cp, chan_sum, partial, Q, dst_lo);
   CPT_LAUNCH_CHECK("nchw_to_nhwc");
   if (partial) {
@@ -523,13 +570,14 @@ static size_t stats_bytes(int Ncols) { return (size_t)sm_count() * 4 * Ncols * 2
 
 // FP32X3: act_cl holds the hi and lo planes back to back (cl_bytes layout); wmat_lo is the lo plane of the filter matrix
 static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Win, const void* wmat, const void* wmat_lo, int Ncols,
-                            const ConvPlan& pl, const float* bias, float* out, int mode, cudaStream_t st, float* stats = nullptr) {
+                            const ConvPlan& pl, const float* bias, float* out, int mode, cudaStream_t st, float* stats = nullptr,
+                            bool relu = false) {
   const int kc = kc_of(mode), Cp = round_up(Cact, 8), Ck = round_up(Cact, kc), T = pl.ntaps;
   const int BN = pick_bn_mode(Ncols, mode);
   TcParams p{};
   const int64_t M = (int64_t)B * pl.sub_H * pl.sub_W;
   CPT_REQUIRE(M < (1LL << 31), CPT_ERR_UNSUPPORTED, "conv: pixel count exceeds int32");
-  const bool use2 = want_2cta(BN, (M + 127) / 128);
+  const bool use2 = want_2cta_kmajor(BN, (M + 127) / 128, mode);
   if (int e = make_map_im2col(&p.tmA, act_cl, mode, Cp, Win, Hin, B, pl.lower_w, pl.lower_h, pl.upper_w, pl.upper_h, pl.trav, kc, 128)) return e;
   if (int e = make_map_2d(&p.tmB, wmat, mode, (uint64_t)T * Ck, Ncols, (uint64_t)T * Ck, kc, use2 ? BN / 2 : BN)) return e;
   if (is_x3(mode)) {
@@ -540,6 +588,7 @@ static int conv_im2col_gemm(const void* act_cl, int B, int Cact, int Hin, int Wi
   p.out = out;
   p.bias = bias;
   p.bias_mode = bias ? BIAS_COL : BIAS_NONE;
+  p.relu = relu ? 3 : 0;
   if (stats) {  // slots of CTAs / N-tiles that never run stay zero
     CPT_CUDA(cudaMemsetAsync(stats, 0, stats_bytes(Ncols), st));
     p.stats = stats;
@@ -572,7 +621,7 @@ static bool fprop_tc_ok(const G& g) {
 }
 
 int conv_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w, const float* bias, float* y, int mode, void* ws,
-                  size_t ws_bytes, cudaStream_t st, float* stats = nullptr) {
+                  size_t ws_bytes, cudaStream_t st, float* stats = nullptr, bool relu = false) {
   const G g = geom(d);
   CPT_REQUIRE(fprop_tc_ok(g), CPT_ERR_UNSUPPORTED, "conv2d_fprop_cl: kernel %d / padding %d / dilation %d outside the TMA im2col limits", g.K, g.P, g.D);
   const size_t need = wmat_bytes(g.Co, g.T, g.Ci, mode);
@@ -594,7 +643,7 @@ int conv_fprop_cl(const cpt_conv2d_desc* d, const void* x_cl, const float* w, co
   pl.trav = g.S;
   pl.sub_H = g.Ho; pl.sub_W = g.Wo;
   pl.out_H = g.Ho; pl.out_W = g.Wo; pl.out_s = 1; pl.out_r0 = pl.out_c0 = 0;
-  return conv_im2col_gemm(x_cl, g.B, g.Ci, g.H, g.W, ws, w_lo, g.Co, pl, bias, y, mode, st, stats);
+  return conv_im2col_gemm(x_cl, g.B, g.Ci, g.H, g.W, ws, w_lo, g.Co, pl, bias, y, mode, st, stats, relu);
 }
 
 // taps (j, kk) of stride class (rh, rw) — same rule as the exact path (conv.cu class_taps)
@@ -1322,7 +1371,7 @@ int conv_im2col_pack(const cpt_conv2d_desc* d, const float* x, void* col, cudaSt
 }
 
 int conv_fprop_packed(const cpt_conv2d_desc* d, const void* col, const float* w, const float* bias, float* y, void* ws,
-                      size_t ws_bytes, cudaStream_t st, float* stats = nullptr) {
+                      size_t ws_bytes, cudaStream_t st, float* stats = nullptr, bool relu = false) {
   const G g = geom(d);
   const int mode = CPT_MODE_BF16;
   CPT_REQUIRE(packed_ok(g, mode), CPT_ERR_UNSUPPORTED, "conv2d_fprop_packed: geometry not covered by the packed-K path");
@@ -1335,6 +1384,7 @@ int conv_fprop_packed(const cpt_conv2d_desc* d, const void* col, const float* w,
   if (int e = make_map_2d(&p.tmA, col, mode, q.Kdim, (uint64_t)q.px, q.Kp, kc, 128)) return e;
   if (int e = make_map_2d(&p.tmB, ws, mode, q.Kdim, g.Co, q.Kp, kc, use2 ? BN / 2 : BN)) return e;
   p.out = y; p.bias = bias; p.bias_mode = bias ? BIAS_COL : BIAS_NONE;
+  p.relu = relu ? 3 : 0;
   if (stats) {
     CPT_CUDA(cudaMemsetAsync(stats, 0, stats_bytes(g.Co), st));
     p.stats = stats;
@@ -1772,6 +1822,26 @@ int cpt_conv2d_fprop_packed_stats(const cpt_conv2d_desc* d, const void* col, con
   if (int e = check_tc(d, CPT_MODE_BF16, "conv2d_fprop_packed_stats")) return e;
   CPT_REQUIRE(stats, CPT_ERR_INVALID, "conv2d_fprop_packed_stats: stats is NULL");
   return tc::conv_fprop_packed(d, col, w, bias, y, ws, ws_bytes, as_stream(stream), stats);
+}
+
+/* Conv2D -> ReLU pairs: the forward epilogue applies max(. , 0) (convolution_funcs.py:237-238 + activation_funcs.py:26-29);
+ * the backward pass stages dy * (y > 0) in one pass (activation_funcs.py:32-34 folded into the operand staging of dgrad / wgrad) */
+int cpt_conv2d_fprop_cl_relu(const cpt_conv2d_desc* d, const void* x_cl, const float* w, const float* bias, float* y, int mode,
+                             void* ws, size_t ws_bytes, void* stream) {
+  if (int e = check_tc(d, mode, "conv2d_fprop_cl_relu")) return e;
+  return tc::conv_fprop_cl(d, x_cl, w, bias, y, mode, ws, ws_bytes, as_stream(stream), nullptr, true);
+}
+int cpt_conv2d_fprop_packed_relu(const cpt_conv2d_desc* d, const void* col, const float* w, const float* bias, float* y, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  if (int e = check_tc(d, CPT_MODE_BF16, "conv2d_fprop_packed_relu")) return e;
+  return tc::conv_fprop_packed(d, col, w, bias, y, ws, ws_bytes, as_stream(stream), nullptr, true);
+}
+int cpt_to_channels_last_gated(const float* src, const float* gate, void* dst, int B, int C, int H, int W, int mode, float* chan_sum,
+                               void* ws, size_t ws_bytes, void* stream) {
+  CPT_REQUIRE(src && gate && dst && B > 0 && C > 0 && H > 0 && W > 0, CPT_ERR_INVALID, "to_channels_last_gated: bad arguments");
+  CPT_REQUIRE(mode == CPT_MODE_TF32 || mode == CPT_MODE_BF16 || mode == CPT_MODE_FP32X3, CPT_ERR_INVALID,
+              "to_channels_last_gated: mode must be TF32, BF16 or FP32X3");
+  return tc::to_channels_last(src, dst, B, C, H, W, mode, chan_sum, ws, ws_bytes, as_stream(stream), gate);
 }
 
 size_t cpt_cast_bf16_bytes(int64_t rows, int cols) { return rows > 0 && cols > 0 ? tc::cast_bytes(rows, cols) : 0; }

@@ -45,6 +45,10 @@ static int launch_layout(const TcParams& p, const LaunchSel& s, cudaStream_t st)
   } else {
     CPT_REQUIRE(s.BN <= 128, CPT_ERR_INVALID, "tc launch: FP32X3 tiles are at most 128 columns wide");
   }
+  if constexpr (!A_MN && !B_MN && !X3) {  // K-major operands only: half of a 64-column MN-major B tile is less than one swizzle chunk
+    if (s.use2 && s.BN == 64) return launch_inst<BF16, X3, A_MN, B_MN, 64, OP, true>(p, s, st);
+  }
+  CPT_REQUIRE(!s.use2 || s.BN == 128, CPT_ERR_INVALID, "tc launch: no cta_group::2 instantiation for %d-column tiles of this layout", s.BN);
   if (s.use2) return launch_inst<BF16, X3, A_MN, B_MN, 128, OP, true>(p, s, st);
   if (s.BN == 128) return launch_inst<BF16, X3, A_MN, B_MN, 128, OP, false>(p, s, st);
   return launch_inst<BF16, X3, A_MN, B_MN, 64, OP, false>(p, s, st);

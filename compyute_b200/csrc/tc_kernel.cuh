@@ -355,7 +355,7 @@ __global__ void __launch_bounds__((EpiCfg<BN, X3>::THREADS), 1) tc_kernel(const 
           return;
         }
         float* q = dst + (long long)(c * 32) * cs;
-        if (p.relu) {  // Linear forward + ReLU: one ballot per column gives the mask word of this warp's 32 features
+        if (p.relu == 1 || p.relu == 2) {  // Linear forward + ReLU: one ballot per column gives the mask word of this warp's 32 features
           __nv_bfloat16* lq = p.relu_lp ? reinterpret_cast<__nv_bfloat16*>(p.relu_lp) + z_off + lane_off + (long long)cbase * cs : nullptr;
           const int mw = m >> 5;  // m - lane is a multiple of 32: word index of this warp's features within a row
           if (p.relu == 2) {  // dgrad of the layer behind a ReLU: dx = acc * mask (activation_funcs.py:32-34)
@@ -397,25 +397,27 @@ __global__ void __launch_bounds__((EpiCfg<BN, X3>::THREADS), 1) tc_kernel(const 
         }
         float bl = 0.f;  // this lane's column bias; column j's value is fetched with a shuffle (one LDG per chunk)
         if (col_bias && cbase + lane < p.N) bl = __ldg(p.bias + cbase + lane);
+        // ReLU behind a convolution (relu == 3): one NaN-propagating max per value against 0, against -inf (identity) otherwise
+        const float floor_v = p.relu == 3 ? 0.f : -INFINITY;
         if (cbase + 32 <= p.N) {
           if (col_bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float val = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j);
+              const float val = max_nan(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j), floor_v);
               if (m_ok) *q = val;
               q += cs;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              if (m_ok) *q = __uint_as_float(v[j]) + lane_bias;
+              if (m_ok) *q = max_nan(__uint_as_float(v[j]) + lane_bias, floor_v);
               q += cs;
             }
           }
         } else {  // ragged last chunk of the N dimension
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float val = __uint_as_float(v[j]) + lane_bias + __shfl_sync(0xffffffffu, bl, j);
+            const float val = max_nan(__uint_as_float(v[j]) + lane_bias + __shfl_sync(0xffffffffu, bl, j), floor_v);
             if (m_ok && cbase + j < p.N) *q = val;
             q += cs;
           }

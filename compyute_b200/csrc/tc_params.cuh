@@ -25,6 +25,8 @@ struct alignas(64) TcParams {
   // relu == 2 is the backward counterpart on a Linear layer's dgrad (lanes = input features): out = acc * mask, with the mask
   // (READ here) of the ReLU that produced this layer's input, relu_lp = the same values as bf16 rows (dy operand of the
   // previous Linear layer's backward)
+  // relu == 3: ReLU behind a convolution (lanes = pixels, column bias): out = max(acc + bias, 0), nothing else is written — the
+  // backward pass takes the mask from the output itself (out > 0), see cpt_to_channels_last_gated
   int relu;
   void* relu_lp;
   unsigned int* relu_mask;

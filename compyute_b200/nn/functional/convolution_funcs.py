@@ -45,22 +45,23 @@ class Conv2DFn(Function):
 
     @staticmethod
     def forward(cache: FunctionCache, x: Tensor, f: Tensor, b: Optional[Tensor], padding: int, stride: int,
-                dilation: int, emit_stats: bool = False) -> Tensor:
+                dilation: int, emit_stats: bool = False, relu: bool = False) -> Tensor:
         """``emit_stats`` (extension, tensor-core modes): the epilogue also leaves per-channel Σy / Σy² partials on the
-        result (``y.data.stats``) for a BatchNorm that consumes it, which then skips its statistics pass."""
+        result (``y.data.stats``) for a BatchNorm that consumes it, which then skips its statistics pass.
+        ``relu`` (extension; the caller checked ``relu_fusable``): returns ``relu(conv(x))`` from the GEMM epilogue, and
+        ``backward`` expects the gradient w.r.t. that — ReLUFn.backward (activation_funcs.py:32-34) is applied while dy is staged,
+        with the mask taken from the returned tensor itself, which therefore must not be modified in place."""
         if x.ndim != 4:
             raise ShapeError(f"Expected input to be 4D, got {x.ndim}D.")
         require_cuda(x, f, b)
         L = _lib.lib()
         d = _desc(x.shape, f.shape, padding, stride, dilation)
         ho, wo = _out_hw(d)
-        mode = get_compute_mode()
-        if mode != _lib.MODE_FP32 and (d.K * d.K > 64 or (d.K - 1) * d.dil > 255 or d.pad > 127 or d.stride > 8):
-            mode = _lib.MODE_FP32  # outside the TMA im2col limits (8-bit corners, 64 taps): exact path for this layer
+        mode = _layer_mode(d)
         if mode == _lib.MODE_FP32X3:
             emit_stats = False  # the exact mode keeps BatchNorm's own two-pass statistics (the epilogue sums are E[a^2] - E[a]^2)
-            if d.Ci < 8:
-                mode = _lib.MODE_FP32  # a tap's k-slice is 32 channels wide: with < 8 real channels the FFMA kernel is the faster exact path
+        if relu and not _relu_path_ok(L, d, mode):
+            raise NotImplementedError("Conv2DFn.forward(relu=True): layer not covered, check Conv2DFn.relu_fusable first")
         y = DeviceArray.empty((d.B, d.Co, ho, wo), np.float32)
         st = stream_ptr()
         x_cl = None
@@ -76,10 +77,12 @@ class Conv2DFn(Function):
                 stats = DeviceArray.empty((L.cpt_conv2d_stats_bytes(ctypes.byref(d)),), np.uint8)
                 _lib.check(L.cpt_conv2d_fprop_packed_stats(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, stats.ptr, ws, wsb, st))
                 y.stats = (stats, L.cpt_conv2d_stats_slots(), b)
+            elif relu:
+                _lib.check(L.cpt_conv2d_fprop_packed_relu(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, ws, wsb, st))
             else:
                 _lib.check(L.cpt_conv2d_fprop_packed(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, ws, wsb, st))
             mode = _MODE_PACKED
-        elif L.cpt_conv2d_strip_supported(ctypes.byref(d), mode) and not _has_dense_shadow(x, mode):
+        elif not relu and L.cpt_conv2d_strip_supported(ctypes.byref(d), mode) and not _has_dense_shadow(x, mode):
             # stride-1 same-padded small-channel layer: zero-padded channels-last operand, one strip per 128 outputs
             shadow = getattr(x.data, "cl", None)
             if shadow is not None and shadow[0] == (_MODE_STRIP, d.pad):
@@ -108,16 +111,27 @@ class Conv2DFn(Function):
                 stats = DeviceArray.empty((L.cpt_conv2d_stats_bytes(ctypes.byref(d)),), np.uint8)
                 _lib.check(L.cpt_conv2d_fprop_cl_stats(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, stats.ptr, mode, ws, wsb, st))
                 y.stats = (stats, L.cpt_conv2d_stats_slots(), b)
+            elif relu:
+                _lib.check(L.cpt_conv2d_fprop_cl_relu(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, mode, ws, wsb, st))
             else:
                 _lib.check(L.cpt_conv2d_fprop_cl(ctypes.byref(d), x_cl.ptr, f32ptr(f), f32ptr(b), y.ptr, mode, ws, wsb, st))
-        cache.push(x, f, b is not None, d, mode, x_cl)
+        cache.push(x, f, b is not None, d, mode, x_cl, y if relu else None)
         return Tensor(y)
+
+    @staticmethod
+    def relu_fusable(x: Tensor, f: Tensor, padding: int, stride: int, dilation: int) -> bool:
+        """Can ``forward(..., relu=True)`` serve this layer?  Tensor-core modes on the dense / packed paths, with the input
+        gradient on the tensor-core path as well (the exact fallbacks read dy unstaged)."""
+        if x.ndim != 4 or not isinstance(x.data, DeviceArray) or f.ndim != 4 or f.shape[1] != x.shape[1] or f.shape[2] != f.shape[3]:
+            return False
+        d = _desc(x.shape, f.shape, padding, stride, dilation)
+        return _relu_path_ok(_lib.lib(), d, _layer_mode(d))
 
     @staticmethod
     def backward(cache: FunctionCache, dy: Tensor, df_out: Optional[DeviceArray] = None,
                  db_out: Optional[DeviceArray] = None) -> tuple[Tensor, Tensor, Optional[Tensor]]:
         """``df_out``/``db_out``: optional preallocated gradient slots (flat DP arena); extension of the reference API."""
-        x, f, has_bias, d, mode, x_cl = cache.pop()
+        x, f, has_bias, d, mode, x_cl, gate = cache.pop()
         require_cuda(dy)
         L = _lib.lib()
         st = stream_ptr()
@@ -130,7 +144,7 @@ class Conv2DFn(Function):
         dbp = db.ptr if db is not None else None
         ho, wo = dy.shape[2], dy.shape[3]
         if mode == _MODE_PACKED:
-            dy_cl = _staged_dy(L, dy, d, ho, wo, _lib.MODE_BF16, db, st)
+            dy_cl = _staged_dy(L, dy, d, ho, wo, _lib.MODE_BF16, db, st, gate)
             ws, wsb = workspace(L.cpt_conv2d_packed_workspace_size(_lib.OP_DGRAD, dref))
             _lib.check(L.cpt_conv2d_dgrad_packed(dref, dy_cl.ptr, f32ptr(f), dx.ptr, ws, wsb, st))
             ws, wsb = workspace(L.cpt_conv2d_packed_workspace_size(_lib.OP_WGRAD, dref))
@@ -151,7 +165,7 @@ class Conv2DFn(Function):
             _lib.check(L.cpt_conv2d_wgrad(dref, f32ptr(x), f32ptr(dy), df.ptr, dbp, mode, ws, wsb, st))
         else:
             # dy staged once (db fused into the staging pass), shared by dgrad and wgrad
-            dy_cl = _staged_dy(L, dy, d, ho, wo, mode, db, st)
+            dy_cl = _staged_dy(L, dy, d, ho, wo, mode, db, st, gate)
             if tc_dgrad:
                 ws, wsb = workspace(L.cpt_conv2d_workspace_size(_lib.OP_DGRAD, dref, mode))
                 _lib.check(L.cpt_conv2d_dgrad_cl(dref, dy_cl.ptr, f32ptr(f), dx.ptr, mode, ws, wsb, st))
@@ -163,9 +177,34 @@ class Conv2DFn(Function):
         return Tensor(dx), Tensor(df), (Tensor(db) if db is not None else None)
 
 
-def _staged_dy(L, dy: Tensor, d, ho: int, wo: int, mode: int, db: Optional[DeviceArray], st) -> DeviceArray:
+def _layer_mode(d) -> int:
+    """Compute mode of one layer: the global mode, or the exact FFMA kernels where the tensor-core path does not apply."""
+    mode = get_compute_mode()
+    if mode != _lib.MODE_FP32 and (d.K * d.K > 64 or (d.K - 1) * d.dil > 255 or d.pad > 127 or d.stride > 8):
+        return _lib.MODE_FP32  # outside the TMA im2col limits (8-bit corners, 64 taps): exact path for this layer
+    if mode == _lib.MODE_FP32X3 and d.Ci < 8:
+        return _lib.MODE_FP32  # a tap's k-slice is 32 channels wide: with < 8 real channels the FFMA kernel is the faster exact path
+    return mode
+
+
+def _relu_path_ok(L, d, mode: int) -> bool:
+    if mode == _lib.MODE_FP32:
+        return False
+    dref = ctypes.byref(d)
+    return bool(L.cpt_conv2d_packed_bytes(dref, mode)) or bool(L.cpt_conv2d_dgrad_cl_supported(dref, mode))
+
+
+def _staged_dy(L, dy: Tensor, d, ho: int, wo: int, mode: int, db: Optional[DeviceArray], st,
+               gate: Optional[DeviceArray] = None) -> DeviceArray:
     """Channels-last copy of dy (+ db = dy.sum((0, 2, 3)), convolution_funcs.py:252).  When dy was produced by a
-    BatchNorm backward pass that already emitted it (``dy.data.cl``), nothing is staged."""
+    BatchNorm backward pass that already emitted it (``dy.data.cl``), nothing is staged.  ``gate``: the layer ran with its ReLU
+    in the epilogue — dy is the gradient behind that ReLU, and ``dy * (gate > 0)`` is what gets staged and summed."""
+    if gate is not None:
+        dy_cl = DeviceArray.empty((L.cpt_channels_last_bytes(d.B, d.Co, ho, wo, mode),), np.uint8)
+        ws, wsb = workspace(L.cpt_to_channels_last_workspace_size(d.B, d.Co, ho, wo))
+        _lib.check(L.cpt_to_channels_last_gated(f32ptr(dy), gate.ptr, dy_cl.ptr, d.B, d.Co, ho, wo, mode,
+                                                db.ptr if db is not None else None, ws, wsb, st))
+        return dy_cl
     shadow = getattr(dy.data, "cl", None)
     if shadow is not None and shadow[0] == mode:
         if db is not None:

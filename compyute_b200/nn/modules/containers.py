@@ -137,6 +137,21 @@ class Sequential(Module):
         return (not lin.retain_values and not relu.retain_values and lin.is_training == relu.is_training
                 and LinearFn.relu_fusable(x, lin.w))
 
+    def _conv_relu_fusable(self, i: int, x: Tensor) -> bool:
+        """layers[i : i + 2] is Conv2D -> ReLU on the tensor-core path, followed by another layer of this container: the ReLU
+        comes out of the convolution's epilogue and its backward is folded into the staging of dy (cpt_conv2d_fprop_cl_relu,
+        cpt_to_channels_last_gated) — bit-identical, 12 B/element less traffic.  The backward mask is the fused output itself
+        (y > 0), so the pair must not end the container: an enclosing ResidualConnection adds the skip branch in place."""
+        from ..functional.convolution_funcs import Conv2DFn
+        from .layers import Conv2D, ReLU
+        if not _fusion or i + 2 >= len(self.layers) or get_debug_mode() or not isinstance(x.data, DeviceArray):
+            return False
+        conv, relu = self.layers[i], self.layers[i + 1]
+        if type(conv) is not Conv2D or type(relu) is not ReLU:
+            return False
+        return (not conv.retain_values and not relu.retain_values and conv.is_training == relu.is_training
+                and Conv2DFn.relu_fusable(x, conv.w, conv.padding, conv.stride, conv.dilation))
+
     def _run(self, x: Tensor, tail=None) -> Tensor:
         """The layer walk.  ``tail = (skip_fn, relu)``: this container is the block of a fused residual connection — its last
         BatchNorm2D evaluates ``relu(bn(x) + skip_fn())``."""
@@ -162,6 +177,10 @@ class Sequential(Module):
                 i += 2
             elif self._linear_relu_fusable(i, x):
                 x = layer.forward_relu(x, self.layers[i + 1])
+                i += 2
+            elif self._conv_relu_fusable(i, x):
+                x = layer.forward_relu(x)
+                self.layers[i + 1].fcache.push(FUSED_INTO_PRODUCER)  # its backward is folded into the convolution's dy staging
                 i += 2
             elif self._residual_fusable(i, x):
                 x = layer.forward_relu(x, self.layers[i + 1])

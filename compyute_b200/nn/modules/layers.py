@@ -64,6 +64,11 @@ class Conv2D(Module):
         return Conv2DFn.forward(self.fcache, x, self.w, self.b, self.padding, self.stride, self.dilation,
                                 self._emit_stats and self._is_training)
 
+    def forward_relu(self, x: Tensor) -> Tensor:
+        """``relu(self(x))`` from the convolution's epilogue (called by ``Sequential`` for Conv2D -> ReLU, which also marks the
+        ReLU's cache so that its backward passes dy through): the ReLU's backward is folded into this layer's staging of dy."""
+        return Conv2DFn.forward(self.fcache, x, self.w, self.b, self.padding, self.stride, self.dilation, False, relu=True)
+
     @Module.register_backward
     def backward(self, dy: Tensor) -> Tensor:
         dx, dw, db = Conv2DFn.backward(self.fcache, dy, self.grad_slot(self.w), self.grad_slot(self.b))

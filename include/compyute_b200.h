@@ -253,6 +253,21 @@ int cpt_conv2d_fprop_cl_stats(const cpt_conv2d_desc* d, const void* x_cl, const 
 int cpt_conv2d_fprop_packed_stats(const cpt_conv2d_desc* d, const void* col, const float* w,
                                   const float* bias, float* y, float* stats, void* ws, size_t ws_bytes,
                                   void* stream);
+/* ---- Conv2D -> ReLU pairs ----
+ * Replaces ReLUFn.forward behind Conv2DFn.forward (compyute/nn/functional/activation_funcs.py:26-29 after
+ * convolution_funcs.py:237-238) and ReLUFn.backward in front of Conv2DFn.backward (activation_funcs.py:32-34 before
+ * convolution_funcs.py:244-252):
+ *   cpt_conv2d_fprop_cl_relu / _packed_relu   y = max(conv(x, w) + bias, 0) from the GEMM epilogue (NaN propagates like
+ *                                             numpy.maximum); nothing else is written — the mask is y > 0
+ *   cpt_to_channels_last_gated                staging of dy for dgrad / wgrad with dy * (gate > 0) applied in the same pass
+ *                                             (gate = the y above); chan_sum = db of the gated values
+ * Bit-identical to the two separate layers. */
+int cpt_conv2d_fprop_cl_relu(const cpt_conv2d_desc* d, const void* x_cl, const float* w, const float* bias, float* y, int mode,
+                             void* ws, size_t ws_bytes, void* stream);
+int cpt_conv2d_fprop_packed_relu(const cpt_conv2d_desc* d, const void* col, const float* w, const float* bias, float* y, void* ws,
+                                 size_t ws_bytes, void* stream);
+int cpt_to_channels_last_gated(const float* src, const float* gate, void* dst, int B, int C, int H, int W, int mode,
+                               float* chan_sum, void* ws, size_t ws_bytes, void* stream);
 int cpt_bn_act_fwd_train_presum(const float* x, const float* w, const float* b, const float* rmean,
                                 const float* rvar, float* y, void* y_cl, float* rmean_out,
                                 float* rvar_out, float* save_mean, float* save_rstd, int N, int C, int HW,

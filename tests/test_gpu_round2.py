@@ -174,3 +174,99 @@ def test_checkpoint_does_not_carry_gradient_arena(cp):
         assert v.grad is None and getattr(v, "grad_slot", None) is None
         assert np.array_equal(v.to_numpy(), m.get_state_dict()[k].to_numpy())
     opt.step()
+
+
+# ------------------------------------------------------------------ Conv2D -> ReLU from the convolution's epilogue (f4)
+@pytest.mark.parametrize("mode", ["bf16", "tf32", "fp32"])
+def test_conv_relu_epilogue_fusion_is_bit_exact(cp, mode):
+    """Conv2D -> ReLU inside a Sequential: the ReLU comes out of the convolution's GEMM epilogue (cpt_conv2d_fprop_cl_relu /
+    _packed_relu) and its backward is folded into the staging of dy (cpt_to_channels_last_gated, mask = fused output > 0).
+    Outputs, input gradient and every parameter gradient must equal the layer-by-layer evaluation bit for bit — packed first
+    layer (Ci = 1), ragged sizes, stride, dilation, with and without bias, NaN inputs, inference mode — and the fused walk
+    launches fewer kernels.  A pair that ENDS a container (the block of a ResidualConnection) is left alone."""
+    from compyute_b200 import _lib, nn
+    from compyute_b200.nn.functional.activation_funcs import FUSED_INTO_PRODUCER
+    rng = np.random.RandomState(17)
+    for B, H, nan in ((5, 28, False), (3, 19, True)):
+        x = rng.normal(0, 1, (B, 1, H, H)).astype(np.float32)
+        if nan:
+            x[1, 0, 4, 7] = np.nan
+
+        def build():
+            np.random.seed(23)
+            with cp.use_device(cp.cuda):
+                return nn.Sequential(
+                    nn.Conv2D(1, 32, 5), nn.ReLU(),                                    # packed first layer (bf16 mode)
+                    nn.Conv2D(32, 32, 5, bias=False), nn.ReLU(), nn.MaxPooling2D(1),
+                    nn.Conv2D(32, 64, 3, stride=2, padding=1), nn.ReLU(),
+                    nn.ResidualConnection(nn.Conv2D(64, 64, 3, padding="same"), nn.ReLU()),  # ends its container: not fused
+                    nn.Conv2D(64, 40, 3, dilation=2, padding="same"), nn.ReLU(),
+                    nn.Conv2D(40, 8, 3, padding="same"))
+
+        def run(fused):
+            nn.set_fusion_enabled(fused)
+            try:
+                model = build()
+                model.training()
+                n0 = _lib.lib().cpt_launch_count()
+                with cp.compute_mode(mode):
+                    y = model(cp.tensor(x, device=cp.cuda))
+                    marks = sum(1 for m in model.get_modules() if type(m) is nn.ReLU and m.fcache.cache
+                                and m.fcache.cache[-1][0] is FUSED_INTO_PRODUCER)
+                    dy = np.random.RandomState(6).normal(0, 1, y.shape).astype(np.float32)
+                    dx = model.backward(cp.tensor(dy, device=cp.cuda))
+                    launches = _lib.lib().cpt_launch_count() - n0
+                    assert _lib.lib().cpt_tc_check_status() == 0
+                    assert all(not m.fcache.cache for m in model.get_modules())
+                    out = [y.to_numpy(), dx.to_numpy()] + [p.grad.to_numpy() for p in model.get_parameters()]
+                    model.inference()
+                    out.append(model(cp.tensor(x, device=cp.cuda)).to_numpy())
+                return out, launches, marks
+            finally:
+                nn.set_fusion_enabled(True)
+
+        (a, la, ma), (b, lb, mb) = run(True), run(False)
+        # fp32 mode: the Ci = 1 layer runs on the exact FFMA kernels (not fusable), the other three pairs are
+        assert ma == (3 if mode == "fp32" else 4) and mb == 0, (ma, mb)
+        for k, (u, v) in enumerate(zip(a, b)):
+            assert np.array_equal(u, v, equal_nan=True), (mode, H, k, u.shape, float(np.nanmax(np.abs(u - v))))
+        assert la < lb, (la, lb)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_conv_relu_function_vs_oracle(cp, mode):
+    """``Conv2DFn.forward(..., relu=True)`` / ``backward`` against the oracle's Conv2D and ReLU functions chained
+    (convolution_funcs.py:218-254, activation_funcs.py:26-34): 1e-5 in the exact mode, the bf16 tolerance otherwise."""
+    from compyute_b200.nn.functional import Conv2DFn, FunctionCache
+    rng = np.random.RandomState(3)
+    for (B, Ci, Co, H, K, P, s, d, bias) in ((4, 16, 24, 14, 3, 1, 1, 1, True), (2, 40, 72, 17, 3, 2, 2, 1, False), (3, 8, 130, 9, 5, 4, 1, 2, True)):
+        x = rng.uniform(-1, 1, (B, Ci, H, H)).astype(np.float32)
+        w = (rng.uniform(-1, 1, (Co, Ci, K, K)) / np.sqrt(Ci * K * K)).astype(np.float32)
+        b = rng.uniform(-0.3, 0.3, (Co,)).astype(np.float32) if bias else None
+        rc, rr = [], []
+        a_ref = R.conv2d_forward(rc, x, w, b, P, s, d)
+        y_ref = R.relu_forward(rr, a_ref)
+        dy = rng.uniform(-1, 1, y_ref.shape).astype(np.float32)
+        dx_ref, dw_ref, db_ref = R.conv2d_backward(rc, R.relu_backward(rr, dy))
+        T = lambda t: cp.tensor(t, device=cp.cuda)
+        with cp.compute_mode(mode):
+            assert Conv2DFn.relu_fusable(T(x), T(w), P, s, d)
+            c = FunctionCache()
+            y = Conv2DFn.forward(c, T(x), T(w), None if b is None else T(b), P, s, d, False, relu=True)
+            dx, dw, db = Conv2DFn.backward(c, T(dy))
+        yv = y.to_numpy()
+        # an activation within rounding distance of 0 may land on the other side of the ReLU: the forward is compared where |a|
+        # is clear of it, the backward against the oracle evaluated with the mask the device produced
+        clear = np.abs(a_ref) > (1e-5 if mode == "fp32" else 2e-2)
+        tol = 1e-5 if mode == "fp32" else 1e-2
+        assert np.allclose(yv[clear], y_ref[clear], rtol=tol, atol=tol * max(1.0, float(np.abs(y_ref).max())))
+        assert ((yv > 0) == (a_ref > 0))[clear].all()
+        rc2 = []
+        R.conv2d_forward(rc2, x, w, b, P, s, d)
+        dx_ref, dw_ref, db_ref = R.conv2d_backward(rc2, dy * (yv > 0))
+        for got, ref, t32 in ((dx, dx_ref, 1e-5), (dw, dw_ref, 2e-5)) + (((db, db_ref, 1e-4),) if bias else ()):
+            if mode == "fp32":
+                assert np.allclose(got.to_numpy(), ref, rtol=t32, atol=t32), float(np.abs(got.to_numpy() - ref).max())
+            else:
+                assert np.abs(got.to_numpy() - ref).max() <= 1e-2 * max(float(np.abs(ref).max()), 1e-30)
+        assert (y.to_numpy() >= 0).all()
