@@ -163,6 +163,10 @@ def run_ours(args) -> None:
     L = _lib.lib()  # no fallback: raises if the CUDA library is missing
     if args.strip:
         cp.set_strip_conv_enabled(True)
+    if args.no_fusion:
+        nn.set_fusion_enabled(False)
+    if args.no_conv_relu_fusion:
+        nn.set_conv_relu_fusion_enabled(False)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -752,6 +756,8 @@ def main() -> None:
                          "instead of one all-reduce of the whole gradient arena at step(); measured gain at 2 GPUs is ~1 %% because "
                          "the persistent GEMM grids leave NCCL little room, so it is opt-in")
     ap.add_argument("--strip", action="store_true", help="enable the opt-in strip (shared-halo) convolution kernels for the C <= 128 layers")
+    ap.add_argument("--no-fusion", action="store_true", help="model workloads: evaluate layer by layer (no Sequential peephole fusions), for A/B runs")
+    ap.add_argument("--no-conv-relu-fusion", action="store_true", help="model workloads: Conv2D -> ReLU pairs as two layers (A/B of that one fusion)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's NUMA node")
     ap.add_argument("--no-fused-step", action="store_true",
                     help="data-parallel runs: classic NCCL all-reduce + replicated update instead of the fused sharded step over "

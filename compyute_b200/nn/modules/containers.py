@@ -25,6 +25,20 @@ def get_epilogue_stats_enabled() -> bool:
     return _epilogue_stats
 
 
+_conv_relu = True
+
+
+def set_conv_relu_fusion_enabled(enabled: bool) -> None:
+    """Conv2D -> ReLU pairs from the convolution's epilogue (``Sequential._conv_relu_fusable``).  On by default; a separate
+    switch so that its effect can be measured on its own (``bench.py --no-conv-relu-fusion``)."""
+    global _conv_relu
+    _conv_relu = bool(enabled)
+
+
+def get_conv_relu_fusion_enabled() -> bool:
+    return _conv_relu
+
+
 def set_fusion_enabled(enabled: bool) -> None:
     """Peephole fusion inside ``Sequential`` (BatchNorm -> ReLU in one pass).  On by default; results are identical to the
     unfused layers (the mask is recomputed from the forward's own expression), it only removes memory passes."""
@@ -36,7 +50,7 @@ def get_fusion_enabled() -> bool:
     return _fusion
 
 __all__ = ["Sequential", "ResidualConnection", "EmptyContainerError", "set_fusion_enabled", "get_fusion_enabled",
-           "set_epilogue_stats_enabled", "get_epilogue_stats_enabled"]
+           "set_epilogue_stats_enabled", "get_epilogue_stats_enabled", "set_conv_relu_fusion_enabled", "get_conv_relu_fusion_enabled"]
 
 
 class EmptyContainerError(Exception):
@@ -144,7 +158,7 @@ class Sequential(Module):
         (y > 0), so the pair must not end the container: an enclosing ResidualConnection adds the skip branch in place."""
         from ..functional.convolution_funcs import Conv2DFn
         from .layers import Conv2D, ReLU
-        if not _fusion or i + 2 >= len(self.layers) or get_debug_mode() or not isinstance(x.data, DeviceArray):
+        if not _fusion or not _conv_relu or i + 2 >= len(self.layers) or get_debug_mode() or not isinstance(x.data, DeviceArray):
             return False
         conv, relu = self.layers[i], self.layers[i + 1]
         if type(conv) is not Conv2D or type(relu) is not ReLU:
