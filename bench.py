@@ -522,6 +522,10 @@ def model_record(args, cpu: bool = True):
         model_record._bound = True
     if world > 1 and not distributed.is_initialized():
         distributed.init("nccl")
+    if getattr(args, "no_fusion", False):
+        nn.set_fusion_enabled(False)
+    if getattr(args, "no_conv_relu_fusion", False):
+        nn.set_conv_relu_fusion_enabled(False)
     factory, xshape, classes, B, desc = MODEL_WORKLOADS[args.workload]
     B = args.batch or B
     scaling = "weak"
