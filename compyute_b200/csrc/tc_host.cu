@@ -127,7 +127,7 @@ struct PadGeom { int W, H, P; };
 // the staging of dy (dy * mask, activation_funcs.py:32-34, with the mask taken from the ReLU's own output): 10 B/elem instead
 // of 8 1/8 (ReLU backward) + 6 (staging); the channel sums (db) are those of the gated values.
 template <bool BF16, bool PAD = false, bool GATE = false>
-__global__ void __launch_bounds__(256, GATE ? 3 : 4) nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW,
+__global__ void __launch_bounds__(256, 4) nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW,
                                                            int Cp, float* __restrict__ chan_sum, float* __restrict__ partial,
                                                            int64_t Q, float* __restrict__ dst_lo, PadGeom pg = PadGeom{0, 0, 0},
                                                            const float* __restrict__ gate = nullptr) {
